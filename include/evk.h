@@ -1,0 +1,237 @@
+/* evk.h — C-ABI boundary of the B200-native event-cloud downsample + k-means path.
+ *
+ * This header is the drop-in boundary for ONE hot path of the reference
+ * (LogicTronixInc/Event-Camera-Clustering-and-Optical-Flow-Estimation):
+ *
+ *     load events -> voxel-hash downsample -> k-means assign + centroid update
+ *                 -> return labels and centroids
+ *
+ * The reference has no library / plugin API for this path: every call is inlined in main()
+ * of three sample programs.  Each entry point below therefore cites the reference call site it
+ * replaces (paths relative to the reference root; abbreviations:
+ *   ACCEL = event-cam-clustering-accel/event-cam-clustering-downsampling-accel
+ *   SAMP  = event-cam-pre-processing-opencl/event-cam-sampling
+ *   KM    = event-cam-clustering-accel/event-cam-k-means-clustering
+ *   store.cpp = metavision_sdk_get_started5_opencl_store.cpp ).
+ *
+ * Conventions
+ *  - plain C, plain pointers and sizes; no C++ / torch / CUDA types in any signature;
+ *  - every function returns EVK_OK (0) or a negative evk_status; nothing calls exit() and no
+ *    exception crosses the boundary (the reference does perror()+exit(1), ACCEL/store.cpp:64-68);
+ *  - the caller owns every host pointer; the handle owns all device memory (arena sized in
+ *    evk_create; the hot calls never allocate — the reference leaks a cl_mem per slice,
+ *    ACCEL/store.cpp:389);
+ *  - one handle is used from one thread at a time (the reference does pack -> launch -> wait ->
+ *    consume on the single SDK decoding thread, ACCEL/store.cpp:370-615);
+ *  - there is NO CPU fallback: without a CUDA device evk_create fails with EVK_ERR_CUDA.
+ */
+#ifndef EVK_H_
+#define EVK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define EVK_API
+#else
+#define EVK_API __attribute__((visibility("default")))
+#endif
+
+typedef enum evk_status {
+    EVK_OK = 0,
+    EVK_ERR_INVALID = -1,  /* bad argument / parameter combination                      */
+    EVK_ERR_CUDA = -2,     /* CUDA runtime error (see evk_last_error)                    */
+    EVK_ERR_NOMEM = -3,    /* device or host allocation failed                           */
+    EVK_ERR_STATE = -4,    /* call order violated (e.g. kmeans before downsample)        */
+    EVK_ERR_CAPACITY = -5, /* more events / voxels than the handle was created for       */
+    EVK_ERR_IO = -6,       /* file could not be read / parsed                            */
+    EVK_ERR_COMM = -7      /* NCCL error or communicator not initialised                 */
+} evk_status;
+
+/* 16-byte packed event == layout of Metavision::EventCD {uint16 x; uint16 y; int16 p; int64 t}
+ * as consumed at ACCEL/store.cpp:575-590 (ev->x, ev->y, ev->t, ev->p).  Kernels read this record
+ * directly with one 128-bit load; the reference's int[2] repack loop (ACCEL/store.cpp:587-599) is
+ * gone. */
+typedef struct evk_event {
+    uint16_t x, y;
+    int16_t p;      /* polarity: > 0 is "on" */
+    uint16_t _pad;
+    int64_t t;      /* microseconds */
+} evk_event;
+
+enum { EVK_KEY_VOXEL = 0, EVK_KEY_REF_HASH8192 = 1 };
+/* downsample algorithm selector */
+enum {
+    EVK_ALGO_AUTO = 0,  /* time-slab kernel when the stream allows it, else the table        */
+    EVK_ALGO_TABLE = 1, /* global open-addressing table, 64-bit keys, atomicCAS insert       */
+    EVK_ALGO_SORT = 2,  /* radix sort + unique (cross-check variant)                         */
+    EVK_ALGO_SLAB = 3   /* per-time-bin shared-memory kernel; fails over to TABLE if the
+                           stream is not partitioned by time bin                            */
+};
+
+/* Downsample parameters.  Replaces the compile-time constants of the reference kernel
+ * (sensor bounds, bucket count: ACCEL/build/coordinate_processor.cl:7-12,29-30,56) and the unused
+ * width/height kernel arguments (:24-25).
+ *   keyfn = EVK_KEY_VOXEL:  key = ((tbin*NY + ybin)*NX + xbin) * (use_polarity?2:1) + pbit
+ *           xbin = x / vx, ybin = y / vy, tbin = (t - t0_us) / vt_us (vt_us <= 0: one bin),
+ *           NX = ceil(width / vx), NY = ceil(height / vy); gate x < width, y < height, t >= t0_us.
+ *   keyfn = EVK_KEY_REF_HASH8192: key = (1619*x + 31*y) mod 8192, gate x <= width, y <= height
+ *           (inclusive as coordinate_processor.cl:56); vx, vy, vt_us, t0_us, use_polarity ignored. */
+typedef struct evk_ds_params {
+    int32_t width, height;
+    int32_t vx, vy;
+    int64_t vt_us;
+    int64_t t0_us;
+    int32_t use_polarity;
+    int32_t keyfn;
+    int32_t algo;
+    int32_t count_repeated; /* 0: n_repeated is not computed (returned as 0) */
+} evk_ds_params;
+
+/* K-means parameters.  Replaces K=8 / D=2 / threshold 50 hard-wired in
+ * KM/assign_to_centers.cl:11,14 and the error_max > 10 loop of KM/assign_to_centers2.c:545.
+ * Point features, fixed order: x, y, (t - t0_us) * t_scale, pbit * p_scale  (D = 2, 3 or 4). */
+typedef struct evk_km_params {
+    int32_t K, D;
+    float max_dist; /* <= 0 or +inf: no gate; reference: 50.0f */
+    int32_t iters;  /* maximum Lloyd iterations (>= 1) */
+    float tol;      /* stop when max_k |delta c_k|_inf <= tol; < 0: always run `iters` */
+    float t_scale, p_scale;
+    int32_t on_events; /* 0: cluster the downsampled voxel representatives; 1: the raw events */
+} evk_km_params;
+
+/* Synthetic stream.  Counter-based: event i depends on (seed, i) only, so any
+ * index shard can be generated independently, bit-identically on CPU and GPU (evk_synth.h). */
+typedef struct evk_synth_params {
+    uint64_t seed;
+    uint64_t first_index; /* global index of the first generated event */
+    uint64_t n_events;    /* number of events to generate            */
+    uint64_t rate_eps;    /* events per second: t_i = i * 1e6 / rate */
+    int32_t width, height;
+    int32_t n_blobs;      /* moving Gaussian blobs                   */
+    int32_t sigma_q8;     /* blob sigma in 1/256 px (6 px = 1536)    */
+    int32_t noise_q16;    /* P(background event) * 65536 (25 % = 16384) */
+    int32_t vmax_pps;     /* max |blob velocity| per axis, px/s      */
+} evk_synth_params;
+
+/* Per-stage device times of the last evk_downsample / evk_kmeans call, in milliseconds, measured
+ * with CUDA events on the handle's stream when profiling is enabled.  Mirrors the reference's
+ * CL_QUEUE_PROFILING_ENABLE + clGetEventProfilingInfo use (ACCEL/store.cpp:277-278,450-454). */
+typedef struct evk_stage_times {
+    float ds_total_ms;    /* all downsample kernels                          */
+    float ds_main_ms;     /* dominant downsample kernel (insert or slab)     */
+    float ds_compact_ms;  /* table compaction (TABLE) / 0                    */
+    float km_total_ms;    /* all k-means kernels of the last evk_kmeans call */
+    float km_assign_ms;   /* sum over iterations of the fused assign+accumulate kernel */
+    int32_t ds_algo_used; /* EVK_ALGO_* actually run                         */
+    int32_t km_iters;
+    int32_t ds_launches;  /* kernels launched by the last evk_downsample     */
+    int32_t km_launches;  /* kernels launched by the last evk_kmeans         */
+} evk_stage_times;
+
+typedef struct evk_handle evk_handle;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* Replaces create_device/clCreateContext/build_program/clCreateBuffer x5 (ACCEL/store.cpp:55-139,
+ * 237-268; KM/assign_to_centers2.c:151-197).  Kernels are precompiled for sm_100a. */
+EVK_API int evk_create(evk_handle** out, int device, size_t max_events);
+EVK_API int evk_destroy(evk_handle* h);
+EVK_API const char* evk_last_error(const evk_handle* h); /* never NULL */
+EVK_API const char* evk_version(void);
+
+/* ---- load events --------------------------------------------------------------------------- */
+/* Replaces the event callback + packing loop aggregate_events_fct(begin,end)
+ * (ACCEL/store.cpp:570-611, SAMP/store.cpp:419-460) and the per-slice COPY_HOST_PTR upload
+ * (ACCEL/store.cpp:389).  Borrowed host range, copied H2D; the stream held by the handle is
+ * replaced. evk_append_events adds to it (the callback may fire several times per slice). */
+EVK_API int evk_load_events(evk_handle* h, const evk_event* begin, const evk_event* end);
+EVK_API int evk_append_events(evk_handle* h, const evk_event* begin, const evk_event* end);
+EVK_API int evk_load_events_soa(evk_handle* h, const uint16_t* x, const uint16_t* y,
+                                const int64_t* t, const uint8_t* p, size_t n);
+/* Reference-literal input: interleaved int32 (x0,y0,x1,y1,...) exactly as the kernel argument
+ * input_coords of process_coordinates (coordinate_processor.cl:17-18); t = 0, p = 0.
+ * Coordinates outside [0,65535] are carried as invalid events (always gated out). */
+EVK_API int evk_load_coords_i32(evk_handle* h, const int32_t* xy, size_t n_pairs);
+/* rows "x,y,t,p" as ACCEL-era dumps (optics-clustering/test/event_raw_data8.csv) */
+EVK_API int evk_load_csv(evk_handle* h, const char* path);
+/* generate on device (benchmarks; no host copy) */
+EVK_API int evk_synth(evk_handle* h, const evk_synth_params* sp);
+EVK_API int evk_num_events(const evk_handle* h, size_t* n);
+EVK_API int evk_get_events(evk_handle* h, evk_event* out, size_t first, size_t count);
+
+/* ---- downsample ---------------------------------------------------------------------------- */
+/* Replaces clSetKernelArg + clEnqueueNDRangeKernel(process_coordinates) + clFinish + the two
+ * blocking reads of unique_count (ACCEL/store.cpp:397-430; kernel coordinate_processor.cl:16-89).
+ * Counts are per call (the reference's counters are cumulative and never reset, :267-268,557).
+ * n_unique / n_repeated may be NULL. */
+EVK_API int evk_downsample(evk_handle* h, const evk_ds_params* p, size_t* n_unique,
+                           size_t* n_repeated);
+/* Replaces clEnqueueReadBuffer(unique_buffer) (ACCEL/store.cpp:412-413).  Canonical order =
+ * ascending first stream index (what a sequential run of the reference kernel produces).
+ * Any of keys / reps / first_idx may be NULL.  cap = capacity of the arrays in records. */
+EVK_API int evk_get_voxels(evk_handle* h, uint64_t* keys, evk_event* reps, uint32_t* first_idx,
+                           size_t cap);
+
+/* ---- cluster ------------------------------------------------------------------------------- */
+/* Replaces the host-initialised float centroids[16] (KM/assign_to_centers2.c:131). K*D floats. */
+EVK_API int evk_set_centroids(evk_handle* h, const float* c, int K, int D);
+/* Deterministic initialisation: the first K voxel representatives in canonical order. */
+EVK_API int evk_init_centroids_first_k(evk_handle* h, const evk_km_params* p);
+/* Replaces one or more trips round KERNEL_RESTART: assign_to_centers -> assign_data_cluster ->
+ * reduction_scalar -> host centroid update (KM/assign_to_centers2.c:184-548; kernels
+ * KM/assign_to_centers.cl:1-140) by a fused assign+accumulate kernel and a finalise kernel. */
+EVK_API int evk_kmeans(evk_handle* h, const evk_km_params* p, int* iters_done);
+
+/* ---- return labels and centroids ----------------------------------------------------------- */
+/* Replaces clEnqueueReadBuffer(assign_buffer) (KM/assign_to_centers2.c:259-265).  labels[i] in
+ * [0,K) or -1 (unassigned; the reference writes 2k or 255, assign_to_centers.cl:12,22,26), in the
+ * same canonical order as evk_get_voxels (or stream order when on_events = 1). */
+EVK_API int evk_get_labels(evk_handle* h, int32_t* labels, size_t cap);
+/* Replaces new_centroids / cluster_index of KM/assign_to_centers2.c:500-512.  counts may be NULL */
+EVK_API int evk_get_centroids(evk_handle* h, float* c, uint64_t* counts);
+
+/* ---- streaming windows --------------------------------------------------------------------- */
+/* Replaces the 50 ms reslicer + on_new_slice callback (ACCEL/store.cpp:329,349-352,370-568):
+ * events are appended; whenever window_us of event time is complete the window is downsampled
+ * and clustered with centroids warm-started from the previous window.  *windows_done receives
+ * the number of windows completed by this call (may be NULL). */
+EVK_API int evk_window_config(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
+                              int64_t window_us);
+EVK_API int evk_window_push(evk_handle* h, const evk_event* begin, const evk_event* end,
+                            int* windows_done);
+EVK_API int evk_window_flush(evk_handle* h, int* windows_done);
+
+/* ---- profiling / measurement --------------------------------------------------------------- */
+EVK_API int evk_set_profiling(evk_handle* h, int enabled);
+EVK_API int evk_get_stage_times(const evk_handle* h, evk_stage_times* out);
+/* CUDA-event stopwatch on the handle's stream (bench.py times the HBM-resident step with it) */
+EVK_API int evk_timer_start(evk_handle* h);
+EVK_API int evk_timer_stop(evk_handle* h, float* elapsed_ms);
+EVK_API int evk_sync(evk_handle* h);
+/* write `bytes` of device memory (L2 flush between timed iterations) */
+EVK_API int evk_flush_l2(evk_handle* h);
+
+/* ---- multi-GPU (one process per GPU, NCCL over NVLink / NVSwitch) --------------------------- */
+enum { EVK_OWNER_TIME_RANGE = 0, EVK_OWNER_MIX64 = 1 };
+EVK_API int evk_comm_unique_id(uint8_t* id128);                 /* rank 0: ncclGetUniqueId */
+EVK_API int evk_comm_init(evk_handle* h, int rank, int world, const uint8_t* id128);
+EVK_API int evk_comm_destroy(evk_handle* h);
+/* index offset of this rank's shard in the global stream (first_idx becomes global) */
+EVK_API int evk_set_shard(evk_handle* h, uint64_t first_global_index);
+/* local downsample -> all-to-all of (key, first_idx) by ownership -> owner-side merge.
+ * n_unique_local = voxels owned by this rank; n_unique_global = allreduced total. */
+EVK_API int evk_downsample_sharded(evk_handle* h, const evk_ds_params* p, int owner_mode,
+                                   size_t* n_unique_local, size_t* n_unique_global);
+/* k-means on the local voxel shard with an allreduce of the K*(D+1) exact partial sums */
+EVK_API int evk_kmeans_sharded(evk_handle* h, const evk_km_params* p, int* iters_done);
+/* broadcast-free deterministic init: the K globally lowest first indices */
+EVK_API int evk_init_centroids_first_k_sharded(evk_handle* h, const evk_km_params* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVK_H_ */

@@ -1,0 +1,537 @@
+/* evk_oracle.c — CPU ORACLE (test infrastructure only; see evk_oracle.h for the rules).
+ *
+ * Build: gcc -O2 -std=c11 -ffp-contract=off -fopenmp -shared -fPIC (oracle/Makefile).
+ * -ffp-contract=off matters: the contract arithmetic is "dx*dx rounded, then ONE fmaf", and gcc
+ * must not fuse or split anything on its own.
+ */
+#include "evk_oracle.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "../include/evk_synth.h"
+
+/* ============================================================================================
+ * 1. Literal restatements
+ * ========================================================================================== */
+
+/* coordinate_processor.cl:3-14 — hash_coordinate(); the dead locals width/height are omitted */
+static int ref_hash_coordinate(int x, int y) { return (x * 1619 + y * 31) % 8192; }
+
+int orc_ref_process_coordinates(const int* input_coords, int total_coords, int* unique_coords,
+                                int* repeated_count, int* unique_count) {
+    /* :29-44 — __local int coordinate_map[8192] zeroed, local counters zeroed */
+    static int coordinate_map[8192];
+    int local_repeated_count = 0, local_unique_count = 0;
+    memset(coordinate_map, 0, sizeof coordinate_map);
+    /* :50-78 — the grid-stride loop, run for one work-item after the other (i ascending) */
+    for (int i = 0; i < total_coords; i++) {
+        int x = input_coords[i * 2];     /* :52 */
+        int y = input_coords[i * 2 + 1]; /* :53 */
+        if (x >= 0 && x <= 1280 && y >= 0 && y <= 720) { /* :56, inclusive as written */
+            int hash = ref_hash_coordinate(x, y);         /* :58 */
+            int prev_value = coordinate_map[hash]++;      /* :62 atomic_inc returns old */
+            if (prev_value == 0) {                        /* :65 first occurrence */
+                int index = local_unique_count++;         /* :66 */
+                unique_coords[index * 2] = x;             /* :68 */
+                unique_coords[index * 2 + 1] = y;         /* :69 */
+            } else if (prev_value == 1) {                 /* :73 second occurrence */
+                local_repeated_count++;                   /* :74 */
+            }
+        }
+    }
+    *repeated_count += local_repeated_count; /* :85 atomic_add to a never-reset counter */
+    *unique_count += local_unique_count;     /* :86 */
+    return local_unique_count;
+}
+
+int orc_ref_analyze_coordinates(const int* data, int n_ints, int* xs, int* ys, int* counts) {
+    /* FCT/metavision_time_surface_periodic.cpp:72-98 with findCoordinate (:57-67) inlined */
+    int uniqueCount = 0;
+    for (int i = 0; i + 1 < n_ints; i += 2) {
+        int x = data[i], y = data[i + 1];
+        int existingIndex = -1;
+        for (int j = 0; j < uniqueCount; j++)
+            if (xs[j] == x && ys[j] == y) {
+                existingIndex = j;
+                break;
+            }
+        if (existingIndex != -1) {
+            counts[existingIndex]++;
+        } else {
+            xs[uniqueCount] = x;
+            ys[uniqueCount] = y;
+            counts[uniqueCount] = 1;
+            uniqueCount++;
+        }
+    }
+    return uniqueCount;
+}
+
+float orc_ref_kmeans_trip(const float* data, float* centroids, float* output, int* assign,
+                          int* cluster_index, float* scalar_sum, float* new_centroids) {
+    enum { ARRAY_SIZE = 4096, P = ARRAY_SIZE / 2, CLUSTER_NUM = 8 };
+    /* assign_to_centers2.c:186-188 */
+    for (int i = 0; i < 8; i++) cluster_index[i] = 0;
+
+    /* K1 assign_to_centers, assign_to_centers.cl:1-34, global size 2048 */
+    for (int g = 0; g < P; g++) {
+        unsigned gx = (unsigned)g * 2;
+        float data_x = data[gx], data_y = data[gx + 1];
+        float threshold_dd = 50.0f;
+        unsigned char indMin = (unsigned char)-1; /* :12 */
+        for (int i = 0; i < 16; i += 2) {
+            float localDx = centroids[i] - data_x;
+            float localDy = centroids[i + 1] - data_y;
+            /* length((float3)(dx,dy,0)) :17-18 */
+            float localD = sqrtf(localDx * localDx + localDy * localDy + 0.0f);
+            if (localD < threshold_dd) {
+                indMin = (unsigned char)i;
+                threshold_dd = localD;
+            }
+            assign[gx / 2] = indMin; /* :26 */
+        }
+    }
+    /* K2 assign_data_cluster, assign_to_centers.cl:36-119, work-items in gid order */
+    for (int g = 0; g < P; g++) {
+        unsigned gid = (unsigned)g * 2;
+        unsigned assign_cluster = (unsigned)assign[gid / 2] / 2; /* :43 */
+        unsigned address_offset = assign_cluster * 4096;          /* :45 */
+        unsigned address_offset_y = address_offset + 2048;        /* :46 */
+        if (assign_cluster < 8) {                                 /* the if-chain :48-111 */
+            int index = cluster_index[assign_cluster]++;          /* atomic_fetch_add */
+            output[address_offset + index] = data[gid];
+            output[address_offset_y + index] = data[gid + 1];
+        }
+    }
+    /* K3 reduction_scalar, assign_to_centers.cl:121-140: 32 groups of 1024, fp32 tree */
+    for (int grp = 0; grp < 32; grp++) {
+        float partial[1024];
+        for (int l = 0; l < 1024; l++) partial[l] = output[grp * 1024 + l];
+        for (int i = 512; i > 0; i >>= 1)
+            for (int l = 0; l < i; l++) partial[l] += partial[l + i];
+        scalar_sum[grp] = partial[0];
+    }
+    /* host: assign_to_centers2.c:500-512 (stride-2 indexing, as written) */
+    unsigned y_offset = 2;
+    for (int j = 0; j < CLUSTER_NUM * 2; j += 2) {
+        new_centroids[j] = (scalar_sum[j] + scalar_sum[j + 1]) / cluster_index[j / 2];
+        new_centroids[j + 1] =
+            (scalar_sum[j + y_offset] + scalar_sum[j + 1 + y_offset]) / cluster_index[j / 2];
+    }
+    /* :514-532 */
+    float error[16];
+    float error_max = 0.0f;
+    for (int j = 0; j < CLUSTER_NUM * 2; j += 2) {
+        error[j] = new_centroids[j] - centroids[j];
+        error[j + 1] = new_centroids[j + 1] - centroids[j + 1];
+    }
+    for (int j = 0; j < CLUSTER_NUM * 2; j++) {
+        if (abs((int)error[j]) > error_max) { /* C int abs() on a float, :526 */
+            error_max = (float)abs((int)error[j]);
+            centroids[j] = new_centroids[j];
+        }
+    }
+    return error_max;
+}
+
+/* ============================================================================================
+ * 2. Contract semantics
+ * ========================================================================================== */
+
+int orc_event_key(const evk_event* e, const evk_ds_params* p, uint64_t* key) {
+    if (p->keyfn == EVK_KEY_REF_HASH8192) {
+        /* coordinate_processor.cl:56 gate (inclusive) and :12 hash */
+        int x = e->x, y = e->y;
+        if (!(x >= 0 && x <= p->width && y >= 0 && y <= p->height)) return 0;
+        *key = (uint64_t)((x * 1619 + y * 31) % 8192);
+        return 1;
+    }
+    /* VOXEL(vx,vy,vt,use_p): SURVEY.md 8a */
+    if ((int)e->x >= p->width || (int)e->y >= p->height) return 0;
+    if (e->t < p->t0_us) return 0;
+    uint64_t NX = (uint64_t)((p->width + p->vx - 1) / p->vx);
+    uint64_t NY = (uint64_t)((p->height + p->vy - 1) / p->vy);
+    uint64_t xbin = (uint64_t)(e->x / p->vx), ybin = (uint64_t)(e->y / p->vy);
+    uint64_t tbin = p->vt_us > 0 ? (uint64_t)((e->t - p->t0_us) / p->vt_us) : 0;
+    uint64_t k = (tbin * NY + ybin) * NX + xbin;
+    if (p->use_polarity) k = k * 2 + (e->p > 0 ? 1u : 0u);
+    *key = k;
+    return 1;
+}
+
+static inline uint64_t mix64(uint64_t z) {
+    z = (z ^ (z >> 33)) * 0xFF51AFD7ED558CCDull;
+    z = (z ^ (z >> 33)) * 0xC4CEB9FE1A85EC53ull;
+    return z ^ (z >> 33);
+}
+
+typedef struct {
+    uint64_t* keys;  /* EMPTY = ~0 */
+    uint32_t* first;
+    uint8_t* rep;
+    size_t mask;
+} orc_map;
+
+static int map_init(orc_map* m, size_t n) {
+    size_t cap = 16;
+    while (cap < 2 * n + 2) cap <<= 1;
+    m->keys = (uint64_t*)malloc(cap * sizeof(uint64_t));
+    m->first = (uint32_t*)malloc(cap * sizeof(uint32_t));
+    m->rep = (uint8_t*)calloc(cap, 1);
+    if (!m->keys || !m->first || !m->rep) return -1;
+    memset(m->keys, 0xFF, cap * sizeof(uint64_t));
+    m->mask = cap - 1;
+    return 0;
+}
+static void map_free(orc_map* m) {
+    free(m->keys);
+    free(m->first);
+    free(m->rep);
+}
+/* returns slot; *fresh = 1 when the key was inserted by this call */
+static inline size_t map_put(orc_map* m, uint64_t key, int* fresh) {
+    size_t s = (size_t)mix64(key) & m->mask;
+    for (;;) {
+        if (m->keys[s] == key) {
+            *fresh = 0;
+            return s;
+        }
+        if (m->keys[s] == ~0ull) {
+            m->keys[s] = key;
+            *fresh = 1;
+            return s;
+        }
+        s = (s + 1) & m->mask;
+    }
+}
+
+size_t orc_downsample(const evk_event* ev, size_t n, const evk_ds_params* p, uint64_t* keys,
+                      uint32_t* first_idx, size_t* n_repeated) {
+    orc_map m;
+    if (map_init(&m, n)) return 0;
+    size_t U = 0, R = 0;
+    /* the reference kernel's loop body (coordinate_processor.cl:50-78) for i ascending: the
+     * first event that finds its bucket empty is emitted, in arrival order */
+    for (size_t i = 0; i < n; i++) {
+        uint64_t k;
+        if (!orc_event_key(&ev[i], p, &k)) continue;
+        int fresh;
+        size_t s = map_put(&m, k, &fresh);
+        if (fresh) {
+            m.first[s] = (uint32_t)i;
+            keys[U] = k;
+            first_idx[U] = (uint32_t)i;
+            U++;
+        } else if (!m.rep[s]) { /* prev_value == 1 branch, :73-75 */
+            m.rep[s] = 1;
+            R++;
+        }
+    }
+    map_free(&m);
+    if (n_repeated) *n_repeated = R;
+    return U;
+}
+
+typedef struct {
+    uint64_t key;
+    uint32_t first;
+    uint32_t rep;
+} orc_rec;
+
+static int cmp_first(const void* a, const void* b) {
+    uint32_t x = ((const orc_rec*)a)->first, y = ((const orc_rec*)b)->first;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+size_t orc_downsample_mt(const evk_event* ev, size_t n, const evk_ds_params* p, int threads,
+                         int canonical, uint64_t* keys, uint32_t* first_idx,
+                         size_t* n_repeated) {
+    if (threads < 1) threads = 1;
+    const int T = threads;
+    orc_rec** lists = (orc_rec**)calloc((size_t)T, sizeof(orc_rec*));
+    size_t* lens = (size_t*)calloc((size_t)T, sizeof(size_t));
+    orc_rec** outs = (orc_rec**)calloc((size_t)T, sizeof(orc_rec*));
+    size_t* olens = (size_t*)calloc((size_t)T, sizeof(size_t));
+    /* phase 1: every thread de-duplicates its contiguous index range */
+#pragma omp parallel num_threads(T)
+    {
+#ifdef _OPENMP
+        int tid = omp_get_thread_num();
+#else
+        int tid = 0;
+#endif
+        size_t lo = n * (size_t)tid / (size_t)T, hi = n * (size_t)(tid + 1) / (size_t)T;
+        orc_map m;
+        map_init(&m, hi - lo);
+        orc_rec* L = (orc_rec*)malloc((hi - lo + 1) * sizeof(orc_rec));
+        size_t u = 0;
+        for (size_t i = lo; i < hi; i++) {
+            uint64_t k;
+            if (!orc_event_key(&ev[i], p, &k)) continue;
+            int fresh;
+            size_t s = map_put(&m, k, &fresh);
+            if (fresh) {
+                m.first[s] = (uint32_t)u; /* position in L */
+                L[u].key = k;
+                L[u].first = (uint32_t)i;
+                L[u].rep = 0;
+                u++;
+            } else {
+                L[m.first[s]].rep = 1;
+            }
+        }
+        map_free(&m);
+        lists[tid] = L;
+        lens[tid] = u;
+    }
+    size_t total = 0;
+    for (int t = 0; t < T; t++) total += lens[t];
+    /* phase 2: thread q merges the keys it owns (mix64(key) % T == q) from all ranges, in range
+     * order, so the lowest stream index wins */
+#pragma omp parallel num_threads(T)
+    {
+#ifdef _OPENMP
+        int q = omp_get_thread_num();
+#else
+        int q = 0;
+#endif
+        size_t mine = 0;
+        for (int t = 0; t < T; t++)
+            for (size_t j = 0; j < lens[t]; j++)
+                if ((int)(mix64(lists[t][j].key ^ 0x5bd1e995u) % (uint64_t)T) == q) mine++;
+        orc_map m;
+        map_init(&m, mine);
+        orc_rec* O = (orc_rec*)malloc((mine + 1) * sizeof(orc_rec));
+        size_t u = 0;
+        for (int t = 0; t < T; t++)
+            for (size_t j = 0; j < lens[t]; j++) {
+                const orc_rec* r = &lists[t][j];
+                if ((int)(mix64(r->key ^ 0x5bd1e995u) % (uint64_t)T) != q) continue;
+                int fresh;
+                size_t s = map_put(&m, r->key, &fresh);
+                if (fresh) {
+                    m.first[s] = (uint32_t)u;
+                    O[u] = *r;
+                    u++;
+                } else {
+                    O[m.first[s]].rep = 1;
+                }
+            }
+        map_free(&m);
+        outs[q] = O;
+        olens[q] = u;
+    }
+    (void)total;
+    size_t U = 0, R = 0;
+    for (int q = 0; q < T; q++) U += olens[q];
+    orc_rec* all = (orc_rec*)malloc((U + 1) * sizeof(orc_rec));
+    size_t w = 0;
+    for (int q = 0; q < T; q++) {
+        memcpy(all + w, outs[q], olens[q] * sizeof(orc_rec));
+        w += olens[q];
+    }
+    if (canonical) qsort(all, U, sizeof(orc_rec), cmp_first);
+    for (size_t i = 0; i < U; i++) {
+        keys[i] = all[i].key;
+        first_idx[i] = all[i].first;
+        R += all[i].rep;
+    }
+    if (n_repeated) *n_repeated = R;
+    for (int t = 0; t < T; t++) {
+        free(lists[t]);
+        free(outs[t]);
+    }
+    free(all);
+    free(lists);
+    free(lens);
+    free(outs);
+    free(olens);
+    return U;
+}
+
+void orc_points(const evk_event* ev, const uint32_t* first_idx, size_t U, int D, int64_t t0_us,
+                float t_scale, float p_scale, float* pts) {
+    for (size_t i = 0; i < U; i++) {
+        const evk_event* e = &ev[first_idx ? first_idx[i] : i];
+        float* q = pts + i * (size_t)D;
+        q[0] = (float)e->x;
+        q[1] = (float)e->y;
+        if (D > 2) q[2] = (float)(e->t - t0_us) * t_scale;
+        if (D > 3) q[3] = (e->p > 0 ? 1.0f : 0.0f) * p_scale;
+    }
+}
+
+static inline int32_t assign_one(const float* q, int D, const float* cent, int K, float best,
+                                 int use_sqrt) {
+    int32_t lab = -1;
+    for (int k = 0; k < K; k++) {
+        const float* c = cent + (size_t)k * (size_t)D;
+        float dx = c[0] - q[0]; /* operand order of assign_to_centers.cl:15-16 */
+        float dy = c[1] - q[1];
+        float d = fmaf(dy, dy, dx * dx);
+        for (int j = 2; j < D; j++) {
+            float dj = c[j] - q[j];
+            d = fmaf(dj, dj, d);
+        }
+        if (use_sqrt) d = sqrtf(d); /* length(), :17-18 */
+        if (d < best) {             /* strict '<' :21 => lowest k wins ties */
+            lab = k;
+            best = d;
+        }
+    }
+    return lab;
+}
+
+static float gate_value(float max_dist, int use_sqrt) {
+    if (!(max_dist > 0.0f) || isinf(max_dist)) return INFINITY;
+    return use_sqrt ? max_dist : max_dist * max_dist;
+}
+
+void orc_kmeans_assign(const float* pts, size_t P, int D, const float* cent, int K,
+                       float max_dist, int use_sqrt, int32_t* labels) {
+    float best = gate_value(max_dist, use_sqrt);
+    for (size_t i = 0; i < P; i++)
+        labels[i] = assign_one(pts + i * (size_t)D, D, cent, K, best, use_sqrt);
+}
+
+static float finalise(int K, int D, const double* sums, const uint64_t* counts, float* cent) {
+    float shift = 0.0f;
+    for (int k = 0; k < K; k++) {
+        if (counts[k] == 0) continue; /* empty cluster keeps its centroid (contract, D15) */
+        for (int j = 0; j < D; j++) {
+            float nc = (float)(sums[(size_t)k * D + j] / (double)counts[k]);
+            float d = fabsf(nc - cent[(size_t)k * D + j]);
+            if (d > shift) shift = d;
+            cent[(size_t)k * D + j] = nc;
+        }
+    }
+    return shift;
+}
+
+float orc_kmeans_update(const float* pts, size_t P, int D, const int32_t* labels, int K,
+                        float* cent, uint64_t* counts, double* sums) {
+    double* s = (double*)calloc((size_t)K * D, sizeof(double));
+    uint64_t* c = (uint64_t*)calloc((size_t)K, sizeof(uint64_t));
+    for (size_t i = 0; i < P; i++) {
+        int32_t l = labels[i];
+        if (l < 0) continue; /* unassigned points contribute nothing (a8 skip) */
+        c[l]++;
+        for (int j = 0; j < D; j++) s[(size_t)l * D + j] += (double)pts[i * (size_t)D + j];
+    }
+    float shift = finalise(K, D, s, c, cent);
+    if (counts) memcpy(counts, c, (size_t)K * sizeof(uint64_t));
+    if (sums) memcpy(sums, s, (size_t)K * D * sizeof(double));
+    free(s);
+    free(c);
+    return shift;
+}
+
+int orc_kmeans(const float* pts, size_t P, int D, float* cent, int K, float max_dist, int iters,
+               float tol, int32_t* labels, uint64_t* counts) {
+    int it = 0;
+    while (it < iters) {
+        orc_kmeans_assign(pts, P, D, cent, K, max_dist, 0, labels);
+        float shift = orc_kmeans_update(pts, P, D, labels, K, cent, counts, NULL);
+        it++;
+        if (tol >= 0.0f && shift <= tol) break;
+    }
+    return it;
+}
+
+int orc_kmeans_mt(const float* pts, size_t P, int D, float* cent, int K, float max_dist,
+                  int iters, float tol, int threads, int32_t* labels, uint64_t* counts) {
+    if (threads < 1) threads = 1;
+    const int T = threads;
+    float best = gate_value(max_dist, 0);
+    double* S = (double*)malloc((size_t)T * K * D * sizeof(double));
+    uint64_t* C = (uint64_t*)malloc((size_t)T * K * sizeof(uint64_t));
+    double* s = (double*)malloc((size_t)K * D * sizeof(double));
+    uint64_t* c = (uint64_t*)malloc((size_t)K * sizeof(uint64_t));
+    int it = 0;
+    while (it < iters) {
+        memset(S, 0, (size_t)T * K * D * sizeof(double));
+        memset(C, 0, (size_t)T * K * sizeof(uint64_t));
+#pragma omp parallel num_threads(T)
+        {
+#ifdef _OPENMP
+            int tid = omp_get_thread_num();
+#else
+            int tid = 0;
+#endif
+            size_t lo = P * (size_t)tid / (size_t)T, hi = P * (size_t)(tid + 1) / (size_t)T;
+            double* ms = S + (size_t)tid * K * D;
+            uint64_t* mc = C + (size_t)tid * K;
+            for (size_t i = lo; i < hi; i++) {
+                int32_t l = assign_one(pts + i * (size_t)D, D, cent, K, best, 0);
+                labels[i] = l;
+                if (l < 0) continue;
+                mc[l]++;
+                for (int j = 0; j < D; j++) ms[(size_t)l * D + j] += (double)pts[i * (size_t)D + j];
+            }
+        }
+        memset(s, 0, (size_t)K * D * sizeof(double));
+        memset(c, 0, (size_t)K * sizeof(uint64_t));
+        for (int t = 0; t < T; t++) {
+            for (int k = 0; k < K * D; k++) s[k] += S[(size_t)t * K * D + k];
+            for (int k = 0; k < K; k++) c[k] += C[(size_t)t * K + k];
+        }
+        float shift = finalise(K, D, s, c, cent);
+        it++;
+        if (tol >= 0.0f && shift <= tol) break;
+    }
+    if (counts) memcpy(counts, c, (size_t)K * sizeof(uint64_t));
+    free(S);
+    free(C);
+    free(s);
+    free(c);
+    return it;
+}
+
+/* ============================================================================================
+ * 3. Inputs
+ * ========================================================================================== */
+
+void orc_synth(const evk_synth_params* sp, evk_event* out) {
+    for (uint64_t j = 0; j < sp->n_events; j++) out[j] = evk_synth_event(sp, sp->first_index + j);
+}
+
+void orc_synth_mt(const evk_synth_params* sp, evk_event* out, int threads) {
+    if (threads < 1) threads = 1;
+#pragma omp parallel for num_threads(threads) schedule(static)
+    for (int64_t j = 0; j < (int64_t)sp->n_events; j++)
+        out[j] = evk_synth_event(sp, sp->first_index + (uint64_t)j);
+}
+
+long orc_load_csv(const char* path, evk_event* out, size_t cap) {
+    /* same row shape as optics-clustering/test/cluster_event_data.cpp:21-55 reads: x,y,t,p */
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    char line[256];
+    size_t n = 0;
+    while (n < cap && fgets(line, sizeof line, f)) {
+        long x, y, p;
+        long long t;
+        if (sscanf(line, "%ld,%ld,%lld,%ld", &x, &y, &t, &p) != 4) continue;
+        out[n].x = (uint16_t)x;
+        out[n].y = (uint16_t)y;
+        out[n].p = (int16_t)p;
+        out[n]._pad = 0;
+        out[n].t = (int64_t)t;
+        n++;
+    }
+    fclose(f);
+    return (long)n;
+}
+
+int orc_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
