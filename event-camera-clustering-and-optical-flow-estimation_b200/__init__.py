@@ -1,0 +1,353 @@
+"""evk_b200 — Python view (ctypes) of the C-ABI library libevk.so (include/evk.h).
+
+The product is the CUDA library; this module only binds it for the tests and bench.py.  The
+directory name is not an importable identifier, so load it with `evk_loader.load()` from the
+repo root (registers it as module `evk_b200`).  There is no CPU fallback: if libevk.so is missing
+or no CUDA device is present every call fails loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libevk.so")
+
+EVENT_DTYPE = np.dtype(
+    [("x", "<u2"), ("y", "<u2"), ("p", "<i2"), ("_pad", "<u2"), ("t", "<i8")], align=True
+)
+assert EVENT_DTYPE.itemsize == 16
+
+KEY_VOXEL, KEY_REF_HASH8192 = 0, 1
+ALGO_AUTO, ALGO_TABLE, ALGO_SORT, ALGO_SLAB = 0, 1, 2, 3
+OWNER_TIME_RANGE, OWNER_MIX64 = 0, 1
+STATUS = {0: "EVK_OK", -1: "EVK_ERR_INVALID", -2: "EVK_ERR_CUDA", -3: "EVK_ERR_NOMEM",
+          -4: "EVK_ERR_STATE", -5: "EVK_ERR_CAPACITY", -6: "EVK_ERR_IO", -7: "EVK_ERR_COMM"}
+
+
+class EvkError(RuntimeError):
+    def __init__(self, status, msg=""):
+        self.status = status
+        super().__init__(f"{STATUS.get(status, status)}: {msg}")
+
+
+class DsParams(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("vx", C.c_int32), ("vy", C.c_int32),
+        ("vt_us", C.c_int64), ("t0_us", C.c_int64), ("use_polarity", C.c_int32),
+        ("keyfn", C.c_int32), ("algo", C.c_int32), ("count_repeated", C.c_int32),
+    ]
+
+
+class KmParams(C.Structure):
+    _fields_ = [
+        ("K", C.c_int32), ("D", C.c_int32), ("max_dist", C.c_float), ("iters", C.c_int32),
+        ("tol", C.c_float), ("t_scale", C.c_float), ("p_scale", C.c_float),
+        ("on_events", C.c_int32),
+    ]
+
+
+class SynthParams(C.Structure):
+    _fields_ = [
+        ("seed", C.c_uint64), ("first_index", C.c_uint64), ("n_events", C.c_uint64),
+        ("rate_eps", C.c_uint64), ("width", C.c_int32), ("height", C.c_int32),
+        ("n_blobs", C.c_int32), ("sigma_q8", C.c_int32), ("noise_q16", C.c_int32),
+        ("vmax_pps", C.c_int32),
+    ]
+
+
+class StageTimes(C.Structure):
+    _fields_ = [
+        ("ds_total_ms", C.c_float), ("ds_main_ms", C.c_float), ("ds_compact_ms", C.c_float),
+        ("km_total_ms", C.c_float), ("km_assign_ms", C.c_float), ("ds_algo_used", C.c_int32),
+        ("km_iters", C.c_int32), ("ds_launches", C.c_int32), ("km_launches", C.c_int32),
+    ]
+
+
+# every symbol include/evk.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "evk_create", "evk_destroy", "evk_last_error", "evk_version", "evk_load_events",
+    "evk_append_events", "evk_load_events_soa", "evk_load_coords_i32", "evk_load_csv", "evk_synth",
+    "evk_num_events", "evk_get_events", "evk_downsample", "evk_get_voxels", "evk_set_centroids",
+    "evk_init_centroids_first_k", "evk_kmeans", "evk_get_labels", "evk_get_centroids",
+    "evk_window_config", "evk_window_push", "evk_window_flush", "evk_set_profiling",
+    "evk_get_stage_times", "evk_timer_start", "evk_timer_stop", "evk_sync", "evk_flush_l2",
+    "evk_comm_unique_id", "evk_comm_init", "evk_comm_destroy", "evk_set_shard",
+    "evk_downsample_sharded", "evk_kmeans_sharded", "evk_init_centroids_first_k_sharded",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads libevk.so.  Raises if it has not been built — there is no fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise EvkError(-2, f"{LIB_PATH} is missing: run __graft_entry__.build() "
+                           "(nvcc, sm_100a); this package has no CPU or PyTorch fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+    psz = C.POINTER(sz)
+    sig = {
+        "evk_create": [C.POINTER(vp), i32, sz],
+        "evk_destroy": [vp],
+        "evk_load_events": [vp, vp, vp],
+        "evk_append_events": [vp, vp, vp],
+        "evk_load_events_soa": [vp, vp, vp, vp, vp, sz],
+        "evk_load_coords_i32": [vp, vp, sz],
+        "evk_load_csv": [vp, C.c_char_p],
+        "evk_synth": [vp, C.POINTER(SynthParams)],
+        "evk_num_events": [vp, psz],
+        "evk_get_events": [vp, vp, sz, sz],
+        "evk_downsample": [vp, C.POINTER(DsParams), psz, psz],
+        "evk_get_voxels": [vp, vp, vp, vp, sz],
+        "evk_set_centroids": [vp, vp, i32, i32],
+        "evk_init_centroids_first_k": [vp, C.POINTER(KmParams)],
+        "evk_kmeans": [vp, C.POINTER(KmParams), C.POINTER(i32)],
+        "evk_get_labels": [vp, vp, sz],
+        "evk_get_centroids": [vp, vp, vp],
+        "evk_window_config": [vp, C.POINTER(DsParams), C.POINTER(KmParams), C.c_int64],
+        "evk_window_push": [vp, vp, vp, C.POINTER(i32)],
+        "evk_window_flush": [vp, C.POINTER(i32)],
+        "evk_set_profiling": [vp, i32],
+        "evk_get_stage_times": [vp, C.POINTER(StageTimes)],
+        "evk_timer_start": [vp],
+        "evk_timer_stop": [vp, C.POINTER(C.c_float)],
+        "evk_sync": [vp],
+        "evk_flush_l2": [vp],
+        "evk_comm_unique_id": [vp],
+        "evk_comm_init": [vp, i32, i32, vp],
+        "evk_comm_destroy": [vp],
+        "evk_set_shard": [vp, C.c_uint64],
+        "evk_downsample_sharded": [vp, C.POINTER(DsParams), i32, psz, psz],
+        "evk_kmeans_sharded": [vp, C.POINTER(KmParams), C.POINTER(i32)],
+        "evk_init_centroids_first_k_sharded": [vp, C.POINTER(KmParams)],
+    }
+    for name, args in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = i32
+    L.evk_last_error.argtypes = [vp]
+    L.evk_last_error.restype = C.c_char_p
+    L.evk_version.argtypes = []
+    L.evk_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def ds_params(width, height, vx=1, vy=1, vt_us=0, t0_us=0, use_polarity=0, keyfn=KEY_VOXEL,
+              algo=ALGO_AUTO, count_repeated=1):
+    return DsParams(width, height, vx, vy, vt_us, t0_us, use_polarity, keyfn, algo,
+                    count_repeated)
+
+
+def km_params(K, D=2, max_dist=0.0, iters=1, tol=-1.0, t_scale=1e-3, p_scale=1.0, on_events=0):
+    return KmParams(K, D, max_dist, iters, tol, t_scale, p_scale, on_events)
+
+
+def synth_params(seed, n_events, width, height, rate_eps, n_blobs, first_index=0,
+                 sigma_q8=1536, noise_q16=16384, vmax_pps=200):
+    return SynthParams(seed, first_index, n_events, rate_eps, width, height, n_blobs, sigma_q8,
+                       noise_q16, vmax_pps)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Evk:
+    """One handle = one GPU stream of work, used from one thread (as the reference's single SDK
+    thread does pack -> launch -> wait -> consume, ACCEL/store.cpp:370-615).  Method names follow
+    the reference's call order: load events -> downsample -> cluster -> labels / centroids."""
+
+    def __init__(self, max_events, device=0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        st = self._L.evk_create(C.byref(self._h), device, max_events)
+        if st != 0:
+            raise EvkError(st, "evk_create failed (no CUDA device? there is no CPU fallback)")
+        self.max_events = max_events
+
+    def _ck(self, st):
+        if st != 0:
+            raise EvkError(st, self._L.evk_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self._L.evk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- load events
+    def load_events(self, ev, append=False):
+        ev = np.ascontiguousarray(ev, dtype=EVENT_DTYPE)
+        b = ev.ctypes.data
+        fn = self._L.evk_append_events if append else self._L.evk_load_events
+        self._ck(fn(self._h, b, b + ev.nbytes))
+        self._ck(self._L.evk_sync(self._h))  # ev is borrowed only for the duration of the call
+
+    def load_events_ptr(self, addr, n, append=False):
+        """pinned host buffer at `addr` holding n records; asynchronous (caller keeps it alive)"""
+        fn = self._L.evk_append_events if append else self._L.evk_load_events
+        self._ck(fn(self._h, addr, addr + 16 * n))
+
+    def load_events_soa(self, x, y, t=None, p=None):
+        x = np.ascontiguousarray(x, dtype=np.uint16)
+        y = np.ascontiguousarray(y, dtype=np.uint16)
+        t = None if t is None else np.ascontiguousarray(t, dtype=np.int64)
+        p = None if p is None else np.ascontiguousarray(p, dtype=np.uint8)
+        self._ck(self._L.evk_load_events_soa(self._h, _p(x), _p(y), None if t is None else _p(t),
+                                             None if p is None else _p(p), len(x)))
+        self._ck(self._L.evk_sync(self._h))
+
+    def load_coords_i32(self, xy):
+        xy = np.ascontiguousarray(xy, dtype=np.int32)
+        self._ck(self._L.evk_load_coords_i32(self._h, _p(xy), xy.size // 2))
+        self._ck(self._L.evk_sync(self._h))
+
+    def load_csv(self, path):
+        self._ck(self._L.evk_load_csv(self._h, path.encode()))
+
+    def synth(self, sp):
+        self._ck(self._L.evk_synth(self._h, C.byref(sp)))
+
+    @property
+    def num_events(self):
+        n = C.c_size_t(0)
+        self._ck(self._L.evk_num_events(self._h, C.byref(n)))
+        return n.value
+
+    def get_events(self, first=0, count=None):
+        count = self.num_events - first if count is None else count
+        out = np.zeros(count, dtype=EVENT_DTYPE)
+        self._ck(self._L.evk_get_events(self._h, _p(out), first, count))
+        return out
+
+    # ---- downsample
+    def downsample(self, p):
+        u, r = C.c_size_t(0), C.c_size_t(0)
+        self._ck(self._L.evk_downsample(self._h, C.byref(p), C.byref(u), C.byref(r)))
+        self.n_unique = u.value
+        return u.value, r.value
+
+    def get_voxels(self, keys=True, reps=True, first=True):
+        n = self.n_unique
+        k = np.zeros(n, dtype=np.uint64) if keys else None
+        r = np.zeros(n, dtype=EVENT_DTYPE) if reps else None
+        f = np.zeros(n, dtype=np.uint32) if first else None
+        self._ck(self._L.evk_get_voxels(self._h, None if k is None else _p(k),
+                                        None if r is None else _p(r),
+                                        None if f is None else _p(f), n))
+        return k, r, f
+
+    # ---- cluster
+    def set_centroids(self, c):
+        c = np.ascontiguousarray(c, dtype=np.float32)
+        self._ck(self._L.evk_set_centroids(self._h, _p(c), c.shape[0], c.shape[1]))
+
+    def init_centroids_first_k(self, km):
+        self._ck(self._L.evk_init_centroids_first_k(self._h, C.byref(km)))
+
+    def kmeans(self, km):
+        it = C.c_int(0)
+        self._ck(self._L.evk_kmeans(self._h, C.byref(km), C.byref(it)))
+        self._km = km
+        return it.value
+
+    def get_labels(self, n=None):
+        if n is None:
+            n = self.num_events if self._km.on_events else self.n_unique
+        out = np.zeros(n, dtype=np.int32)
+        self._ck(self._L.evk_get_labels(self._h, _p(out), n))
+        return out
+
+    def get_centroids(self, K, D):
+        c = np.zeros((K, D), dtype=np.float32)
+        counts = np.zeros(K, dtype=np.uint64)
+        self._ck(self._L.evk_get_centroids(self._h, _p(c), _p(counts)))
+        return c, counts
+
+    # ---- streaming windows
+    def window_config(self, ds, km, window_us):
+        self._ck(self._L.evk_window_config(self._h, C.byref(ds), C.byref(km), window_us))
+        self._km = km
+
+    def window_push(self, ev):
+        ev = np.ascontiguousarray(ev, dtype=EVENT_DTYPE)
+        done = C.c_int(0)
+        b = ev.ctypes.data
+        self._ck(self._L.evk_window_push(self._h, b, b + ev.nbytes, C.byref(done)))
+        return done.value
+
+    def window_flush(self):
+        done = C.c_int(0)
+        self._ck(self._L.evk_window_flush(self._h, C.byref(done)))
+        return done.value
+
+    # ---- measurement
+    def set_profiling(self, on=True):
+        self._ck(self._L.evk_set_profiling(self._h, int(on)))
+
+    def stage_times(self):
+        t = StageTimes()
+        self._ck(self._L.evk_get_stage_times(self._h, C.byref(t)))
+        return t
+
+    def timer_start(self):
+        self._ck(self._L.evk_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        self._ck(self._L.evk_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def sync(self):
+        self._ck(self._L.evk_sync(self._h))
+
+    def flush_l2(self):
+        self._ck(self._L.evk_flush_l2(self._h))
+
+    # ---- multi-GPU
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_uint8 * 128)()
+        st = lib().evk_comm_unique_id(buf)
+        if st != 0:
+            raise EvkError(st, "ncclGetUniqueId failed")
+        return bytes(buf)
+
+    def comm_init(self, rank, world, uid):
+        buf = (C.c_uint8 * 128).from_buffer_copy(uid)
+        self._ck(self._L.evk_comm_init(self._h, rank, world, buf))
+
+    def set_shard(self, first_global_index):
+        self._ck(self._L.evk_set_shard(self._h, first_global_index))
+
+    def downsample_sharded(self, p, owner_mode=OWNER_TIME_RANGE):
+        ul, ug = C.c_size_t(0), C.c_size_t(0)
+        self._ck(self._L.evk_downsample_sharded(self._h, C.byref(p), owner_mode, C.byref(ul),
+                                                C.byref(ug)))
+        self.n_unique = ul.value
+        return ul.value, ug.value
+
+    def init_centroids_first_k_sharded(self, km):
+        self._ck(self._L.evk_init_centroids_first_k_sharded(self._h, C.byref(km)))
+
+    def kmeans_sharded(self, km):
+        it = C.c_int(0)
+        self._ck(self._L.evk_kmeans_sharded(self._h, C.byref(km), C.byref(it)))
+        self._km = km
+        return it.value

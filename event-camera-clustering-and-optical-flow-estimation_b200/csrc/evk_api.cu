@@ -1,0 +1,690 @@
+// evk_api.cu — the C-ABI of include/evk.h: handle, arena, loaders, downsample dispatch, k-means
+// loop, streaming windows, profiling.  Host orchestration only; kernels are in the other .cu files.
+// Replaces the OpenCL host code of ACCEL/store.cpp:55-139,219-326,370-568 and
+// KM/assign_to_centers2.c:105-568.  There is no CPU path: every entry point needs the device.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "evk_internal.cuh"
+
+int evk_fail(evk_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf;
+    return code;
+}
+
+namespace {
+
+size_t next_pow2(size_t v) {
+    size_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+void prof_rec(evk_handle* h, int i) {
+    if (h->profiling) cudaEventRecord(h->ev[i], h->stream);
+}
+float prof_ms(evk_handle* h, int a, int b) {
+    float ms = 0.f;
+    if (h->profiling) cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]);
+    return ms;
+}
+
+int check_handle(evk_handle* h) { return h ? EVK_OK : EVK_ERR_INVALID; }
+
+void invalidate_results(evk_handle* h) {
+    h->have_voxels = false;
+    h->perm_valid = false;
+    h->reps_valid = false;
+    h->n_unique = h->n_repeated = 0;
+    h->n_labels = 0;
+}
+
+int km_validate(evk_handle* h, const evk_km_params* p) {
+    if (!p) return evk_fail(h, EVK_ERR_INVALID, "km params are NULL");
+    if (p->K < 1 || p->K > EVK_MAX_K) return evk_fail(h, EVK_ERR_INVALID, "K must be in [1,%d]", EVK_MAX_K);
+    if (p->D < 2 || p->D > EVK_MAX_D) return evk_fail(h, EVK_ERR_INVALID, "D must be 2, 3 or 4");
+    if (p->iters < 1) return evk_fail(h, EVK_ERR_INVALID, "iters must be >= 1");
+    return EVK_OK;
+}
+
+KmLaunch km_launch_params(const evk_handle* h, const evk_km_params* p) {
+    KmLaunch kl;
+    kl.K = p->K;
+    kl.D = p->D;
+    kl.best2 = (p->max_dist > 0.f && !isinf(p->max_dist)) ? p->max_dist * p->max_dist : INFINITY;
+    kl.t_scale = p->t_scale;
+    kl.p_scale = p->p_scale;
+    kl.t0 = h->have_ds ? h->ds.t0_us : 0;
+    kl.write_labels = 1;
+    return kl;
+}
+
+}  // namespace
+
+int evk_make_key_params(evk_handle* h, const evk_ds_params* p, KeyParams* kp) {
+    if (!p) return evk_fail(h, EVK_ERR_INVALID, "ds params are NULL");
+    if (p->width < 1 || p->height < 1 || p->width > 65536 || p->height > 65536)
+        return evk_fail(h, EVK_ERR_INVALID, "width/height must be in [1,65536]");
+    memset(kp, 0, sizeof *kp);
+    kp->keyfn = p->keyfn;
+    kp->width = p->width;
+    kp->height = p->height;
+    if (p->keyfn == EVK_KEY_REF_HASH8192) {
+        kp->use_p = 0;
+        kp->mx = kp->my = 1ull << 32;
+        kp->NX = kp->NY = kp->P = 1;
+        kp->vt = 0;
+        kp->vt_shift = -1;
+        kp->cells = 8192;
+        return EVK_OK;
+    }
+    if (p->keyfn != EVK_KEY_VOXEL) return evk_fail(h, EVK_ERR_INVALID, "unknown keyfn %d", p->keyfn);
+    if (p->vx < 1 || p->vy < 1 || p->vx > 65536 || p->vy > 65536)
+        return evk_fail(h, EVK_ERR_INVALID, "vx/vy must be in [1,65536]");
+    kp->use_p = p->use_polarity ? 1 : 0;
+    kp->P = kp->use_p ? 2 : 1;
+    kp->mx = ((1ull << 32) + (uint64_t)p->vx - 1) / (uint64_t)p->vx;
+    kp->my = ((1ull << 32) + (uint64_t)p->vy - 1) / (uint64_t)p->vy;
+    kp->NX = (uint32_t)((p->width + p->vx - 1) / p->vx);
+    kp->NY = (uint32_t)((p->height + p->vy - 1) / p->vy);
+    kp->cells = (uint64_t)kp->NX * kp->NY * kp->P;
+    kp->t0 = p->t0_us;
+    kp->vt = p->vt_us > 0 ? p->vt_us : 0;
+    kp->vt_shift = -1;
+    if (kp->vt > 0) {
+        uint64_t v = (uint64_t)kp->vt;
+        if ((v & (v - 1)) == 0) {
+            int s = 0;
+            while ((1ull << s) < v) s++;
+            kp->vt_shift = s;
+        } else {
+            kp->vt_limit = 0xFFFFFFFFFFFFFFFFull / v;      // dt <= limit: magic quotient exact
+            kp->vt_magic = 0xFFFFFFFFFFFFFFFFull / v + 1;  // ceil(2^64 / v) (v not a power of 2)
+        }
+    }
+    return EVK_OK;
+}
+
+extern "C" {
+
+const char* evk_version(void) { return "evk-b200 0.1 (sm_100a)"; }
+
+const char* evk_last_error(const evk_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int evk_create(evk_handle** out, int device, size_t max_events) {
+    if (!out) return EVK_ERR_INVALID;
+    *out = nullptr;
+    if (max_events == 0 || max_events >= 0xFFFFFFF0ull) return EVK_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return EVK_ERR_CUDA;  // no fallback
+    if (device < 0 || device >= ndev) return EVK_ERR_INVALID;
+    evk_handle* h = new (std::nothrow) evk_handle();
+    if (!h) return EVK_ERR_NOMEM;
+    h->device = device;
+    h->max_events = max_events;
+    auto bail = [&](int code) {
+        evk_destroy(h);
+        return code;
+    };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(EVK_ERR_CUDA);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(EVK_ERR_CUDA);
+    h->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(EVK_ERR_CUDA);
+    const size_t m = max_events;
+    h->table_cap = next_pow2(2 * m + 2);
+    h->max_bins = 1u << 22;
+    h->cand_cap = 1u << 16;
+    h->flush_bytes = 256ull << 20;
+#define ALLOC(ptr, bytes)                                                          \
+    if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) return bail(EVK_ERR_NOMEM)
+    ALLOC(h->d_events, m * sizeof(evk_event));
+    ALLOC(h->d_tkeys, h->table_cap * sizeof(uint64_t));
+    ALLOC(h->d_tfirst, h->table_cap * sizeof(uint32_t));
+    ALLOC(h->d_keys, m * sizeof(uint64_t));
+    ALLOC(h->d_first, m * sizeof(uint32_t));
+    ALLOC(h->d_xy, m * sizeof(uint32_t));
+    ALLOC(h->d_labels, m * sizeof(int32_t));
+    ALLOC(h->d_bin_start, (h->max_bins + 2) * sizeof(uint32_t));
+    ALLOC(h->d_cnt, sizeof(DsCounters));
+    ALLOC(h->d_cent, EVK_MAX_K * EVK_MAX_D * sizeof(float));
+    ALLOC(h->d_acc, EVK_MAX_K * 5 * sizeof(unsigned long long));
+    ALLOC(h->d_counts, EVK_MAX_K * sizeof(unsigned long long));
+    ALLOC(h->d_shift, sizeof(float));
+    ALLOC(h->d_cand, 2 * h->cand_cap * sizeof(uint32_t));
+    ALLOC(h->d_flush, h->flush_bytes);
+#undef ALLOC
+    if (cudaMallocHost((void**)&h->h_cnt, sizeof(DsCounters)) != cudaSuccess) return bail(EVK_ERR_NOMEM);
+    if (cudaMallocHost((void**)&h->h_shift, sizeof(float)) != cudaSuccess) return bail(EVK_ERR_NOMEM);
+    for (auto& e : h->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) return bail(EVK_ERR_CUDA);
+    for (auto& e : h->ev_timer)
+        if (cudaEventCreate(&e) != cudaSuccess) return bail(EVK_ERR_CUDA);
+    if (evk_launch_table_clear(h->d_tkeys, h->d_tfirst, h->table_cap, h->stream) != cudaSuccess)
+        return bail(EVK_ERR_CUDA);
+    cudaMemsetAsync(h->d_acc, 0, EVK_MAX_K * 5 * sizeof(unsigned long long), h->stream);
+    cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream);
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(EVK_ERR_CUDA);
+    *out = h;
+    return EVK_OK;
+}
+
+int evk_comm_destroy(evk_handle* h);
+
+int evk_destroy(evk_handle* h) {
+    if (!h) return EVK_OK;
+    DeviceGuard g(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    evk_comm_destroy(h);
+    void* ptrs[] = {h->d_events, h->d_tkeys,  h->d_tfirst, h->d_keys,   h->d_first,  h->d_xy,
+                    h->d_reps,   h->d_labels, h->d_perm,   h->d_sort_tmp, h->d_sort_a, h->d_sort_b,
+                    h->d_sort_c, h->d_sk_in,  h->d_sk_out, h->d_si_in,  h->d_si_out, h->d_sv_tmp,
+                    h->d_bin_start, h->d_cnt, h->d_cent,   h->d_acc,    h->d_counts, h->d_shift,
+                    h->d_cand,   h->d_flush};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (h->h_cnt) cudaFreeHost(h->h_cnt);
+    if (h->h_shift) cudaFreeHost(h->h_shift);
+    for (auto& e : h->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : h->ev_timer)
+        if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return EVK_OK;
+}
+
+// ---- load ---------------------------------------------------------------------------------
+static int append_host(evk_handle* h, const evk_event* begin, const evk_event* end, bool replace) {
+    EVK_TRY(check_handle(h));
+    if ((!begin && end != begin) || end < begin) return evk_fail(h, EVK_ERR_INVALID, "bad event range");
+    DeviceGuard g(h->device);
+    const size_t n = (size_t)(end - begin);
+    const size_t at = replace ? 0 : h->n_events;
+    if (at + n > h->max_events)
+        return evk_fail(h, EVK_ERR_CAPACITY, "%zu events exceed the handle capacity %zu", at + n,
+                        h->max_events);
+    if (n)
+        EVK_CUDA(h, cudaMemcpyAsync(h->d_events + at, begin, n * sizeof(evk_event),
+                                    cudaMemcpyHostToDevice, h->stream));
+    h->n_events = at + n;
+    invalidate_results(h);
+    return EVK_OK;
+}
+
+int evk_load_events(evk_handle* h, const evk_event* begin, const evk_event* end) {
+    return append_host(h, begin, end, true);
+}
+int evk_append_events(evk_handle* h, const evk_event* begin, const evk_event* end) {
+    return append_host(h, begin, end, false);
+}
+
+int evk_load_events_soa(evk_handle* h, const uint16_t* x, const uint16_t* y, const int64_t* t,
+                        const uint8_t* p, size_t n) {
+    EVK_TRY(check_handle(h));
+    if (n && (!x || !y)) return evk_fail(h, EVK_ERR_INVALID, "x / y are NULL");
+    if (n > h->max_events) return evk_fail(h, EVK_ERR_CAPACITY, "too many events");
+    DeviceGuard g(h->device);
+    invalidate_results(h);
+    h->n_events = n;
+    if (!n) return EVK_OK;
+    // stage the columns in the (idle) label / key buffers, then pack on the device
+    uint16_t* dx = reinterpret_cast<uint16_t*>(h->d_labels);
+    uint16_t* dy = dx + n;
+    int64_t* dt = reinterpret_cast<int64_t*>(h->d_keys);
+    uint8_t* dp = reinterpret_cast<uint8_t*>(h->d_first);
+    EVK_CUDA(h, cudaMemcpyAsync(dx, x, n * 2, cudaMemcpyHostToDevice, h->stream));
+    EVK_CUDA(h, cudaMemcpyAsync(dy, y, n * 2, cudaMemcpyHostToDevice, h->stream));
+    if (t) EVK_CUDA(h, cudaMemcpyAsync(dt, t, n * 8, cudaMemcpyHostToDevice, h->stream));
+    if (p) EVK_CUDA(h, cudaMemcpyAsync(dp, p, n, cudaMemcpyHostToDevice, h->stream));
+    EVK_CUDA(h, evk_launch_soa_pack(dx, dy, t ? dt : nullptr, p ? dp : nullptr, n, h->d_events,
+                                    h->stream));
+    return EVK_OK;
+}
+
+int evk_load_coords_i32(evk_handle* h, const int32_t* xy, size_t n_pairs) {
+    EVK_TRY(check_handle(h));
+    if (n_pairs && !xy) return evk_fail(h, EVK_ERR_INVALID, "xy is NULL");
+    if (n_pairs > h->max_events) return evk_fail(h, EVK_ERR_CAPACITY, "too many coordinates");
+    DeviceGuard g(h->device);
+    invalidate_results(h);
+    h->n_events = n_pairs;
+    if (!n_pairs) return EVK_OK;
+    int32_t* d = reinterpret_cast<int32_t*>(h->d_keys);
+    EVK_CUDA(h, cudaMemcpyAsync(d, xy, n_pairs * 8, cudaMemcpyHostToDevice, h->stream));
+    EVK_CUDA(h, evk_launch_coords_pack(d, n_pairs, h->d_events, h->stream));
+    return EVK_OK;
+}
+
+int evk_load_csv(evk_handle* h, const char* path) {
+    EVK_TRY(check_handle(h));
+    if (!path) return evk_fail(h, EVK_ERR_INVALID, "path is NULL");
+    FILE* f = fopen(path, "r");
+    if (!f) return evk_fail(h, EVK_ERR_IO, "cannot open %s", path);
+    std::vector<evk_event> ev;
+    char line[256];
+    while (fgets(line, sizeof line, f)) {
+        long x, y, p;
+        long long t;
+        if (sscanf(line, "%ld,%ld,%lld,%ld", &x, &y, &t, &p) != 4) continue;
+        evk_event e;
+        e.x = (uint16_t)x;
+        e.y = (uint16_t)y;
+        e.p = (int16_t)p;
+        e._pad = 0;
+        e.t = (int64_t)t;
+        ev.push_back(e);
+    }
+    fclose(f);
+    int st = evk_load_events(h, ev.data(), ev.data() + ev.size());
+    if (st == EVK_OK) cudaStreamSynchronize(h->stream);  // ev goes out of scope
+    return st;
+}
+
+int evk_synth(evk_handle* h, const evk_synth_params* sp) {
+    EVK_TRY(check_handle(h));
+    if (!sp || sp->rate_eps == 0 || sp->width < 1 || sp->height < 1 || sp->n_blobs < 1)
+        return evk_fail(h, EVK_ERR_INVALID, "bad synth params");
+    if (sp->n_events > h->max_events) return evk_fail(h, EVK_ERR_CAPACITY, "too many events");
+    DeviceGuard g(h->device);
+    invalidate_results(h);
+    h->n_events = (size_t)sp->n_events;
+    if (sp->n_events) EVK_CUDA(h, evk_launch_synth(*sp, h->d_events, h->stream));
+    return EVK_OK;
+}
+
+int evk_num_events(const evk_handle* h, size_t* n) {
+    if (!h || !n) return EVK_ERR_INVALID;
+    *n = h->n_events;
+    return EVK_OK;
+}
+
+int evk_get_events(evk_handle* h, evk_event* out, size_t first, size_t count) {
+    EVK_TRY(check_handle(h));
+    if (first + count > h->n_events) return evk_fail(h, EVK_ERR_INVALID, "range beyond stream");
+    if (!count) return EVK_OK;
+    if (!out) return evk_fail(h, EVK_ERR_INVALID, "out is NULL");
+    DeviceGuard g(h->device);
+    EVK_CUDA(h, cudaMemcpyAsync(out, h->d_events + first, count * sizeof(evk_event),
+                                cudaMemcpyDeviceToHost, h->stream));
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EVK_OK;
+}
+
+// ---- downsample -----------------------------------------------------------------------------
+int evk_downsample_local(evk_handle* h, const evk_ds_params* p) {
+    KeyParams kp;
+    EVK_TRY(evk_make_key_params(h, p, &kp));
+    DeviceGuard g(h->device);
+    invalidate_results(h);
+    h->ds = *p;
+    h->kp = kp;
+    h->have_ds = true;
+    h->times.ds_total_ms = h->times.ds_main_ms = h->times.ds_compact_ms = 0.f;
+    int launches = 0;
+    EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
+    prof_rec(h, 0);
+    int algo = p->algo;
+    if (algo == EVK_ALGO_AUTO) algo = evk_slab_supported(h, kp) ? EVK_ALGO_SLAB : EVK_ALGO_TABLE;
+    if (algo == EVK_ALGO_SLAB) {
+        bool ok = false;
+        if (evk_slab_supported(h, kp)) EVK_TRY(evk_downsample_slab(h, kp, p->count_repeated, &ok, &launches));
+        if (!ok) {  // not partitioned by time bin (or unsupported shape): general path
+            algo = EVK_ALGO_TABLE;
+            EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
+            prof_rec(h, 0);
+        } else {
+            prof_rec(h, 1);
+            prof_rec(h, 2);
+        }
+    }
+    if (algo == EVK_ALGO_TABLE) {
+        EVK_CUDA(h, evk_launch_table_insert(kp, h->d_events, h->n_events, h->d_tkeys, h->d_tfirst,
+                                            h->table_cap, p->count_repeated, h->sm_count,
+                                            h->stream));
+        prof_rec(h, 1);
+        EVK_CUDA(h, evk_launch_table_compact(h->d_events, h->d_tkeys, h->d_tfirst, h->table_cap,
+                                             h->d_keys, h->d_first, h->d_xy, h->d_cnt,
+                                             h->sm_count, h->stream));
+        prof_rec(h, 2);
+        launches += 2;
+    } else if (algo == EVK_ALGO_SORT) {
+        EVK_TRY(evk_downsample_sort(h, kp, &launches));
+        prof_rec(h, 1);
+        prof_rec(h, 2);
+    } else if (algo != EVK_ALGO_SLAB) {
+        return evk_fail(h, EVK_ERR_INVALID, "unknown algo %d", p->algo);
+    }
+    EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,
+                                h->stream));
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->n_unique = (size_t)h->h_cnt->n_unique;
+    h->n_repeated = p->count_repeated ? (size_t)h->h_cnt->n_repeated : 0;
+    h->have_voxels = true;
+    h->times.ds_algo_used = algo;
+    h->times.ds_launches = launches;
+    if (h->profiling) {
+        h->times.ds_total_ms = prof_ms(h, 0, 2);
+        h->times.ds_main_ms = prof_ms(h, 0, 1);
+        h->times.ds_compact_ms = prof_ms(h, 1, 2);
+    }
+    return EVK_OK;
+}
+
+int evk_downsample(evk_handle* h, const evk_ds_params* p, size_t* n_unique, size_t* n_repeated) {
+    EVK_TRY(check_handle(h));
+    h->shard_first = h->comm ? h->shard_first : 0;
+    EVK_TRY(evk_downsample_local(h, p));
+    if (n_unique) *n_unique = h->n_unique;
+    if (n_repeated) *n_repeated = h->n_repeated;
+    return EVK_OK;
+}
+
+int evk_get_voxels(evk_handle* h, uint64_t* keys, evk_event* reps, uint32_t* first_idx, size_t cap) {
+    EVK_TRY(check_handle(h));
+    if (!h->have_voxels) return evk_fail(h, EVK_ERR_STATE, "evk_downsample has not run");
+    const size_t n = h->n_unique;
+    if (cap < n) return evk_fail(h, EVK_ERR_CAPACITY, "cap %zu < %zu voxels", cap, n);
+    if (!n) return EVK_OK;
+    DeviceGuard g(h->device);
+    EVK_TRY(evk_ensure_perm(h));
+    // gather into the (now idle) sort-variant / scratch buffers, one column at a time
+    if (!h->d_sort_c) EVK_CUDA(h, cudaMalloc(&h->d_sort_c, h->max_events * sizeof(evk_event)));
+    void* scratch = h->d_sort_c;
+    if (keys) {
+        EVK_CUDA(h, evk_launch_gather_voxels(h, (uint64_t*)scratch, nullptr, nullptr, n));
+        EVK_CUDA(h, cudaMemcpyAsync(keys, scratch, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (first_idx) {
+        EVK_CUDA(h, evk_launch_gather_voxels(h, nullptr, nullptr, (uint32_t*)scratch, n));
+        EVK_CUDA(h, cudaMemcpyAsync(first_idx, scratch, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (reps) {
+        EVK_CUDA(h, evk_launch_gather_voxels(h, nullptr, (evk_event*)scratch, nullptr, n));
+        EVK_CUDA(h, cudaMemcpyAsync(reps, scratch, n * 16, cudaMemcpyDeviceToHost, h->stream));
+    }
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EVK_OK;
+}
+
+// ---- k-means --------------------------------------------------------------------------------
+int evk_set_centroids(evk_handle* h, const float* c, int K, int D) {
+    EVK_TRY(check_handle(h));
+    if (!c || K < 1 || K > EVK_MAX_K || D < 2 || D > EVK_MAX_D)
+        return evk_fail(h, EVK_ERR_INVALID, "bad centroids (K=%d, D=%d)", K, D);
+    DeviceGuard g(h->device);
+    EVK_CUDA(h, cudaMemcpyAsync(h->d_cent, c, (size_t)K * D * sizeof(float), cudaMemcpyHostToDevice,
+                                h->stream));
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));  // c is borrowed
+    h->K = K;
+    h->D = D;
+    h->have_centroids = true;
+    return EVK_OK;
+}
+
+int evk_init_centroids_first_k(evk_handle* h, const evk_km_params* p) {
+    EVK_TRY(check_handle(h));
+    EVK_TRY(km_validate(h, p));
+    if (!h->have_voxels) return evk_fail(h, EVK_ERR_STATE, "evk_downsample has not run");
+    if (h->n_unique < (size_t)p->K)
+        return evk_fail(h, EVK_ERR_INVALID, "only %zu voxels for K=%d", h->n_unique, p->K);
+    DeviceGuard g(h->device);
+    KmLaunch kl = km_launch_params(h, p);
+    unsigned long long* d_count = &h->d_cnt->scratch[0];
+    // voxels with first index below `bound` are the only candidates for the K lowest ones;
+    // first indices are global in sharded mode, so the bound starts at the shard offset
+    uint64_t span = 2048 + 32ull * p->K;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        uint64_t bound64 = h->shard_first + span;
+        uint32_t bound = bound64 > 0xFFFFFFFEull ? 0xFFFFFFFEu : (uint32_t)bound64;
+        EVK_CUDA(h, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), h->stream));
+        EVK_CUDA(h, evk_launch_collect_below(h->d_first, h->n_unique, bound, h->d_cand,
+                                             (uint32_t)h->cand_cap, d_count, h->stream));
+        EVK_CUDA(h, cudaMemcpyAsync(&h->h_cnt->scratch[0], d_count, sizeof(unsigned long long),
+                                    cudaMemcpyDeviceToHost, h->stream));
+        EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+        const unsigned long long c = h->h_cnt->scratch[0];
+        if (c >= (unsigned long long)p->K && c <= h->cand_cap) {
+            const evk_event* ev0 = h->d_events - h->shard_first;  // indexable by global index
+            EVK_CUDA(h, evk_launch_init_from_cand(kl, h->d_cand, (uint32_t)c, h->d_xy, ev0,
+                                                  h->reps_valid ? h->d_reps : nullptr, h->d_cent,
+                                                  h->stream));
+            h->K = p->K;
+            h->D = p->D;
+            h->have_centroids = true;
+            return EVK_OK;
+        }
+        if (c > h->cand_cap) break;
+        span *= 16;
+    }
+    return evk_fail(h, EVK_ERR_CAPACITY, "centroid initialisation found no compact candidate set");
+}
+
+int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_done,
+                   int (*reduce)(evk_handle*, int K, int D)) {
+    EVK_TRY(km_validate(h, p));
+    if (!h->have_centroids || h->K != p->K || h->D != p->D)
+        return evk_fail(h, EVK_ERR_STATE, "centroids for K=%d, D=%d have not been set", p->K, p->D);
+    if (!p->on_events && !h->have_voxels)
+        return evk_fail(h, EVK_ERR_STATE, "evk_downsample has not run");
+    DeviceGuard g(h->device);
+    KmLaunch kl = km_launch_params(h, p);
+    const size_t n = p->on_events ? h->n_events : h->n_unique;
+    const uint32_t* xy = p->on_events ? nullptr : h->d_xy;
+    const evk_event* ev = p->on_events ? h->d_events : h->d_events - h->shard_first;
+    if (!p->on_events && p->D > 2 && h->reps_valid)
+        return evk_fail(h, EVK_ERR_INVALID, "D > 2 is not supported on a sharded voxel table");
+    h->times.km_total_ms = h->times.km_assign_ms = 0.f;
+    int it = 0, launches = 0;
+    prof_rec(h, 3);
+    while (it < p->iters) {
+        kl.write_labels = (p->tol >= 0.f || it == p->iters - 1) ? 1 : 0;
+        EVK_CUDA(h, evk_launch_km_assign(kl, xy, ev, h->d_first, n, h->d_cent, h->d_acc,
+                                         h->d_labels, h->sm_count, h->stream));
+        if (reduce) EVK_TRY(reduce(h, p->K, p->D));
+        EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
+                                           h->stream));
+        launches += n ? 2 : 1;
+        it++;
+        if (p->tol >= 0.f) {
+            EVK_CUDA(h, cudaMemcpyAsync(h->h_shift, h->d_shift, sizeof(float),
+                                        cudaMemcpyDeviceToHost, h->stream));
+            EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+            if (*h->h_shift <= p->tol) break;
+        }
+    }
+    prof_rec(h, 4);
+    h->n_labels = n;
+    h->labels_on_events = p->on_events != 0;
+    h->km_last = *p;
+    h->times.km_iters = it;
+    h->times.km_launches = launches;
+    if (h->profiling) {
+        EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+        h->times.km_total_ms = prof_ms(h, 3, 4);
+        h->times.km_assign_ms = h->times.km_total_ms;  // finalise is a single tiny block
+    }
+    if (iters_done) *iters_done = it;
+    return EVK_OK;
+}
+
+int evk_kmeans(evk_handle* h, const evk_km_params* p, int* iters_done) {
+    EVK_TRY(check_handle(h));
+    return evk_kmeans_run(h, p, iters_done, nullptr);
+}
+
+int evk_get_labels(evk_handle* h, int32_t* labels, size_t cap) {
+    EVK_TRY(check_handle(h));
+    if (!h->km_last.K) return evk_fail(h, EVK_ERR_STATE, "evk_kmeans has not run");
+    const size_t n = h->n_labels;
+    if (cap < n) return evk_fail(h, EVK_ERR_CAPACITY, "cap %zu < %zu labels", cap, n);
+    if (!n) return EVK_OK;
+    if (!labels) return evk_fail(h, EVK_ERR_INVALID, "labels is NULL");
+    DeviceGuard g(h->device);
+    if (h->labels_on_events) {
+        EVK_CUDA(h, cudaMemcpyAsync(labels, h->d_labels, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        EVK_TRY(evk_ensure_perm(h));
+        int32_t* scratch = reinterpret_cast<int32_t*>(h->d_sort_b);
+        EVK_CUDA(h, evk_launch_gather_labels(h->d_labels, h->d_perm, scratch, n, h->stream));
+        EVK_CUDA(h, cudaMemcpyAsync(labels, scratch, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EVK_OK;
+}
+
+int evk_get_centroids(evk_handle* h, float* c, uint64_t* counts) {
+    EVK_TRY(check_handle(h));
+    if (!h->have_centroids) return evk_fail(h, EVK_ERR_STATE, "no centroids");
+    DeviceGuard g(h->device);
+    if (c)
+        EVK_CUDA(h, cudaMemcpyAsync(c, h->d_cent, (size_t)h->K * h->D * sizeof(float),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    if (counts)
+        EVK_CUDA(h, cudaMemcpyAsync(counts, h->d_counts, (size_t)h->K * sizeof(uint64_t),
+                                    cudaMemcpyDeviceToHost, h->stream));
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EVK_OK;
+}
+
+// ---- streaming windows ----------------------------------------------------------------------
+int evk_window_config(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
+                      int64_t window_us) {
+    EVK_TRY(check_handle(h));
+    KeyParams kp;
+    EVK_TRY(evk_make_key_params(h, ds, &kp));
+    EVK_TRY(km_validate(h, km));
+    if (window_us <= 0) return evk_fail(h, EVK_ERR_INVALID, "window_us must be > 0");
+    if (km->on_events) return evk_fail(h, EVK_ERR_INVALID, "windows cluster voxels, not raw events");
+    h->win_ds = *ds;
+    h->win_km = *km;
+    h->win_us = window_us;
+    h->win_cfg = true;
+    h->win_started = false;
+    h->win_buf.clear();
+    h->win_count = 0;
+    h->have_centroids = false;
+    return EVK_OK;
+}
+
+static int window_run(evk_handle* h) {
+    // one slice: the body of on_new_slice (ACCEL/store.cpp:370-568) minus consumer and drawing
+    const evk_event* b = h->win_buf.data();
+    EVK_TRY(evk_load_events(h, b, b + h->win_buf.size()));
+    evk_ds_params ds = h->win_ds;
+    ds.t0_us = h->win_start;  // time bins restart with every window
+    size_t U = 0;
+    EVK_TRY(evk_downsample(h, &ds, &U, nullptr));
+    if (U >= (size_t)h->win_km.K) {
+        if (!h->have_centroids) EVK_TRY(evk_init_centroids_first_k(h, &h->win_km));  // else warm start
+        EVK_TRY(evk_kmeans(h, &h->win_km, nullptr));
+    }
+    h->win_count++;
+    return EVK_OK;
+}
+
+int evk_window_push(evk_handle* h, const evk_event* begin, const evk_event* end, int* windows_done) {
+    EVK_TRY(check_handle(h));
+    if (!h->win_cfg) return evk_fail(h, EVK_ERR_STATE, "evk_window_config has not been called");
+    if ((!begin && end != begin) || end < begin) return evk_fail(h, EVK_ERR_INVALID, "bad event range");
+    int done = 0;
+    for (const evk_event* e = begin; e != end; ++e) {
+        if (!h->win_started) {
+            h->win_started = true;
+            h->win_start = e->t - (e->t % h->win_us);
+        }
+        while (e->t >= h->win_start + h->win_us) {  // window complete (possibly an empty one)
+            if (!h->win_buf.empty()) {
+                EVK_TRY(window_run(h));
+                done++;
+                h->win_buf.clear();
+            }
+            h->win_start += h->win_us;
+        }
+        if (h->win_buf.size() >= h->max_events)
+            return evk_fail(h, EVK_ERR_CAPACITY, "window exceeds the handle capacity");
+        h->win_buf.push_back(*e);
+    }
+    if (windows_done) *windows_done = done;
+    return EVK_OK;
+}
+
+int evk_window_flush(evk_handle* h, int* windows_done) {
+    EVK_TRY(check_handle(h));
+    if (!h->win_cfg) return evk_fail(h, EVK_ERR_STATE, "evk_window_config has not been called");
+    int done = 0;
+    if (!h->win_buf.empty()) {
+        EVK_TRY(window_run(h));
+        done = 1;
+        h->win_buf.clear();
+        h->win_start += h->win_us;
+    }
+    if (windows_done) *windows_done = done;
+    return EVK_OK;
+}
+
+// ---- profiling / measurement ----------------------------------------------------------------
+int evk_set_profiling(evk_handle* h, int enabled) {
+    EVK_TRY(check_handle(h));
+    h->profiling = enabled != 0;
+    return EVK_OK;
+}
+int evk_get_stage_times(const evk_handle* h, evk_stage_times* out) {
+    if (!h || !out) return EVK_ERR_INVALID;
+    *out = h->times;
+    return EVK_OK;
+}
+int evk_timer_start(evk_handle* h) {
+    EVK_TRY(check_handle(h));
+    DeviceGuard g(h->device);
+    EVK_CUDA(h, cudaEventRecord(h->ev_timer[0], h->stream));
+    return EVK_OK;
+}
+int evk_timer_stop(evk_handle* h, float* elapsed_ms) {
+    EVK_TRY(check_handle(h));
+    DeviceGuard g(h->device);
+    EVK_CUDA(h, cudaEventRecord(h->ev_timer[1], h->stream));
+    EVK_CUDA(h, cudaEventSynchronize(h->ev_timer[1]));
+    float ms = 0.f;
+    EVK_CUDA(h, cudaEventElapsedTime(&ms, h->ev_timer[0], h->ev_timer[1]));
+    if (elapsed_ms) *elapsed_ms = ms;
+    return EVK_OK;
+}
+int evk_sync(evk_handle* h) {
+    EVK_TRY(check_handle(h));
+    DeviceGuard g(h->device);
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EVK_OK;
+}
+int evk_flush_l2(evk_handle* h) {
+    EVK_TRY(check_handle(h));
+    DeviceGuard g(h->device);
+    EVK_CUDA(h, evk_launch_fill_u8(h->d_flush, 0, h->flush_bytes, h->stream));
+    return EVK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,249 @@
+// evk_internal.cuh — shared declarations of the B200 (sm_100a) implementation behind include/evk.h.
+//
+// Data layout in HBM (all owned by the handle, allocated once in evk_create):
+//   d_events   evk_event[max_events]   16-B packed AoS records, read with one 128-bit load
+//   d_tkeys    u64[table_cap]          open-addressing table keys (EMPTY = ~0; bit 63 = "hit twice")
+//   d_tfirst   u32[table_cap]          lowest stream index per slot (atomicMin)
+//   d_keys     u64[max_events]         voxel keys, emission order            \  SoA voxel shard:
+//   d_first    u32[max_events]         lowest stream index of each voxel      | 16 B per voxel
+//   d_xy       u32[max_events]         representative's x | y << 16          /
+//   d_labels   i32[max_events]         k-means label of each voxel (or event)
+//   d_cent     f32[K*D], d_acc u64[K*(D+1)]  centroids and exact integer partial sums
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/evk.h"
+
+#define EVK_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define EVK_REP_FLAG 0x8000000000000000ull
+#define EVK_EMPTY_IDX 0xFFFFFFFFu
+#define EVK_MAX_K 1024
+#define EVK_MAX_D 4
+
+// ---- key arithmetic -------------------------------------------------------------------------
+struct KeyParams {
+    int32_t keyfn, width, height, use_p;
+    uint64_t mx, my;  // ceil(2^32 / vx), ceil(2^32 / vy): exact quotients for x, y < 65536
+    uint32_t NX, NY, P;
+    int32_t vt_shift;  // >= 0: vt is a power of two
+    int64_t t0, vt;    // vt <= 0: one time bin
+    uint64_t vt_magic, vt_limit;
+    uint64_t cells;    // NX * NY * P  (keys per time bin)
+};
+
+__host__ __device__ __forceinline__ uint64_t evk_mix64(uint64_t z) {
+    z = (z ^ (z >> 33)) * 0xFF51AFD7ED558CCDull;
+    z = (z ^ (z >> 33)) * 0xC4CEB9FE1A85EC53ull;
+    return z ^ (z >> 33);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ uint4 ld_event(const evk_event* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+// fields of the 16-B record held in a uint4: x = .x & 0xffff, y = .x >> 16, p = (int16).y, t = .z|.w<<32
+__device__ __forceinline__ uint32_t ev_x(const uint4& e) { return e.x & 0xFFFFu; }
+__device__ __forceinline__ uint32_t ev_y(const uint4& e) { return e.x >> 16; }
+__device__ __forceinline__ uint32_t ev_pbit(const uint4& e) {
+    return ((int32_t)(int16_t)(e.y & 0xFFFFu)) > 0 ? 1u : 0u;
+}
+__device__ __forceinline__ int64_t ev_t(const uint4& e) {
+    return (int64_t)((uint64_t)e.z | ((uint64_t)e.w << 32));
+}
+
+__device__ __forceinline__ uint64_t evk_tbin(const KeyParams& kp, int64_t t) {
+    if (kp.vt <= 0) return 0;
+    uint64_t dt = (uint64_t)(t - kp.t0);
+    if (kp.vt_shift >= 0) return dt >> kp.vt_shift;
+    if (dt <= kp.vt_limit) return __umul64hi(dt, kp.vt_magic);
+    return dt / (uint64_t)kp.vt;
+}
+
+// spatial cell index inside one time bin: (ybin * NX + xbin) * P + pbit
+__device__ __forceinline__ uint32_t evk_cell(const KeyParams& kp, const uint4& e) {
+    uint32_t xb = (uint32_t)((ev_x(e) * kp.mx) >> 32);
+    uint32_t yb = (uint32_t)((ev_y(e) * kp.my) >> 32);
+    uint32_t c = yb * kp.NX + xb;
+    return kp.use_p ? c * 2u + ev_pbit(e) : c;
+}
+
+// full key; returns false when the event is gated out
+__device__ __forceinline__ bool evk_key(const KeyParams& kp, const uint4& e, uint64_t& key) {
+    const uint32_t x = ev_x(e), y = ev_y(e);
+    if (kp.keyfn == EVK_KEY_REF_HASH8192) {
+        if (x > (uint32_t)kp.width || y > (uint32_t)kp.height) return false;
+        key = (uint64_t)((x * 1619u + y * 31u) & 8191u);
+        return true;
+    }
+    const int64_t t = ev_t(e);
+    if (x >= (uint32_t)kp.width || y >= (uint32_t)kp.height || t < kp.t0) return false;
+    key = evk_tbin(kp, t) * kp.cells + evk_cell(kp, e);
+    return true;
+}
+#endif
+
+// ---- handle ---------------------------------------------------------------------------------
+struct DsCounters {  // device-side counters, mirrored into pinned host memory after each call
+    unsigned long long n_unique;
+    unsigned long long n_repeated;
+    unsigned long long n_valid;
+    unsigned int slab_violation;  // slab kernel found an event outside its bin's index range
+    unsigned int overflow;
+    unsigned long long scratch[3];
+};
+
+struct CommState;
+
+struct evk_handle {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    size_t max_events = 0, n_events = 0;
+    evk_event* d_events = nullptr;
+    // table
+    size_t table_cap = 0;
+    uint64_t* d_tkeys = nullptr;
+    uint32_t* d_tfirst = nullptr;
+    // voxel shard (emission order)
+    uint64_t* d_keys = nullptr;
+    uint32_t* d_first = nullptr;
+    uint32_t* d_xy = nullptr;
+    evk_event* d_reps = nullptr;  // only materialised in sharded mode (voxels received from peers)
+    int32_t* d_labels = nullptr;
+    size_t n_unique = 0, n_repeated = 0;
+    bool have_voxels = false;
+    bool reps_valid = false;
+    // canonical order (lazy): d_perm[i] = emission position of the i-th voxel by first index
+    uint32_t* d_perm = nullptr;
+    bool perm_valid = false;
+    void* d_sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
+    uint32_t *d_sort_a = nullptr, *d_sort_b = nullptr, *d_sort_c = nullptr;  // perm scratch
+    // sort-variant scratch (lazy)
+    uint64_t *d_sk_in = nullptr, *d_sk_out = nullptr;
+    uint32_t *d_si_in = nullptr, *d_si_out = nullptr;
+    void* d_sv_tmp = nullptr;
+    size_t sv_tmp_bytes = 0;
+    // slab scratch
+    uint32_t* d_bin_start = nullptr;  // [max_bins + 1]
+    size_t max_bins = 0;
+    // counters
+    DsCounters* d_cnt = nullptr;
+    DsCounters* h_cnt = nullptr;  // pinned
+    // k-means
+    evk_ds_params ds{};
+    KeyParams kp{};
+    bool have_ds = false;
+    int K = 0, D = 0;
+    bool have_centroids = false;
+    float* d_cent = nullptr;                 // [EVK_MAX_K * EVK_MAX_D]
+    unsigned long long* d_acc = nullptr;     // [EVK_MAX_K * (EVK_MAX_D + 1)]
+    unsigned long long* d_counts = nullptr;  // [EVK_MAX_K] counts of the last iteration
+    float* d_shift = nullptr;                // [1]
+    float* h_shift = nullptr;                // pinned
+    size_t n_labels = 0;
+    bool labels_on_events = false;
+    evk_km_params km_last{};
+    // init-centroid scratch
+    uint32_t* d_cand = nullptr;  // pairs (first, pos)
+    size_t cand_cap = 0;
+    // profiling
+    bool profiling = false;
+    evk_stage_times times{};
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_timer[2] = {};
+    // L2 flush buffer
+    void* d_flush = nullptr;
+    size_t flush_bytes = 0;
+    // streaming windows
+    bool win_cfg = false;
+    evk_ds_params win_ds{};
+    evk_km_params win_km{};
+    int64_t win_us = 0, win_start = 0;
+    bool win_started = false;
+    std::vector<evk_event> win_buf;
+    size_t win_count = 0;
+    // multi-GPU
+    CommState* comm = nullptr;
+    uint64_t shard_first = 0;
+    std::string err;
+};
+
+// ---- error handling -------------------------------------------------------------------------
+int evk_fail(evk_handle* h, int code, const char* fmt, ...);
+#define EVK_CUDA(h, expr)                                                                    \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess)                                                               \
+            return evk_fail((h), EVK_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #expr,    \
+                            cudaGetErrorString(_e));                                         \
+    } while (0)
+#define EVK_TRY(expr)                 \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != EVK_OK) return _s;  \
+    } while (0)
+
+// ---- internal entry points shared between translation units ----------------------------------
+extern "C" int evk_downsample_local(evk_handle* h, const evk_ds_params* p);
+extern "C" int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_done,
+                              int (*reduce)(evk_handle*, int K, int D));
+
+// ---- kernel launchers (implemented in the .cu files) ----------------------------------------
+int evk_make_key_params(evk_handle* h, const evk_ds_params* p, KeyParams* kp);
+// synth
+cudaError_t evk_launch_synth(const evk_synth_params& sp, evk_event* out, cudaStream_t s);
+cudaError_t evk_launch_soa_pack(const uint16_t* x, const uint16_t* y, const int64_t* t,
+                                const uint8_t* p, size_t n, evk_event* out, cudaStream_t s);
+cudaError_t evk_launch_coords_pack(const int32_t* xy, size_t n, evk_event* out, cudaStream_t s);
+// downsample: table
+cudaError_t evk_launch_table_clear(uint64_t* tkeys, uint32_t* tfirst, size_t cap, cudaStream_t s);
+cudaError_t evk_launch_table_insert(const KeyParams& kp, const evk_event* ev, size_t n,
+                                    uint64_t* tkeys, uint32_t* tfirst, size_t cap,
+                                    int count_repeated, int sm_count, cudaStream_t s);
+cudaError_t evk_launch_table_compact(const evk_event* ev, uint64_t* tkeys, uint32_t* tfirst,
+                                     size_t cap, uint64_t* keys, uint32_t* first, uint32_t* xy,
+                                     DsCounters* cnt, int sm_count, cudaStream_t s);
+// downsample: sort + unique
+int evk_downsample_sort(evk_handle* h, const KeyParams& kp, int* launches);
+// downsample: time-slab kernel
+int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, bool* ok,
+                        int* launches);
+bool evk_slab_supported(const evk_handle* h, const KeyParams& kp);
+// canonical order
+int evk_ensure_perm(evk_handle* h);
+cudaError_t evk_launch_gather_voxels(const evk_handle* h, uint64_t* keys, evk_event* reps,
+                                     uint32_t* first, size_t n);
+cudaError_t evk_launch_gather_labels(const int32_t* labels, const uint32_t* perm, int32_t* out,
+                                     size_t n, cudaStream_t s);
+// k-means
+struct KmLaunch {
+    int K, D;
+    float best2;  // gate on the squared distance (+inf: none)
+    float t_scale, p_scale;
+    int64_t t0;
+    int write_labels;
+};
+cudaError_t evk_launch_km_assign(const KmLaunch& kl, const uint32_t* xy, const evk_event* ev,
+                                 const uint32_t* first, size_t n, const float* cent,
+                                 unsigned long long* acc, int32_t* labels, int sm_count,
+                                 cudaStream_t s);
+cudaError_t evk_launch_km_finalise(const KmLaunch& kl, float* cent, unsigned long long* acc,
+                                   unsigned long long* counts, float* shift, cudaStream_t s);
+cudaError_t evk_launch_collect_below(const uint32_t* first, size_t n, uint32_t bound,
+                                     uint32_t* cand, uint32_t cand_cap, unsigned long long* count,
+                                     cudaStream_t s);
+cudaError_t evk_launch_init_from_cand(const KmLaunch& kl, const uint32_t* cand, uint32_t n_cand,
+                                      const uint32_t* xy, const evk_event* ev,
+                                      const evk_event* reps, float* cent, cudaStream_t s);
+cudaError_t evk_launch_fill_u8(void* p, int v, size_t bytes, cudaStream_t s);

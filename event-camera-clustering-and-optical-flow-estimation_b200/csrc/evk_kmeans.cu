@@ -1,0 +1,314 @@
+// evk_kmeans.cu — fused k-means assign + accumulate and centroid finalise for sm_100a.
+//
+// Replaces the reference's three launches + four blocking reads per iteration
+// (KM/assign_to_centers.cl:1-140, KM/assign_to_centers2.c:218-512):
+//   assign_to_centers   -> argmin in registers, centroids broadcast from shared memory
+//   assign_data_cluster -> gone: no scatter into 4096-float slabs (D12, D13)
+//   reduction_scalar    -> block-private INTEGER partial sums in shared memory (coordinates are
+//                          integers, so sums are exact and independent of summation order),
+//                          merged with K*(D+1) 64-bit global atomics per 32 Ki points
+//   host centroid update-> k_km_finalise on the device (exact sum / count, rounded once to fp32)
+// Arithmetic contract: d2 = fmaf(dy,dy, dx*dx) (+ one fmaf per extra dimension),
+// dx = c.x - p.x, strict '<' so the lowest k wins ties, gate d2 < max_dist^2, label -1 if none.
+#include "evk_internal.cuh"
+
+namespace {
+
+constexpr int kBlock = 256;
+constexpr int kPPT = 4;                        // points per thread per pass
+constexpr int kChunk = kBlock * kPPT * 32;     // 32768 points between flushes: sums fit u32
+
+// accumulator slots per cluster in global memory
+enum { ACC_CNT = 0, ACC_X = 1, ACC_Y = 2, ACC_T = 3, ACC_P = 4, ACC_STRIDE = 5 };
+
+// SRC: 0 = packed xy[i] (voxels, D == 2), 1 = raw events ev[i], 2 = gather ev[first[i]]
+template <int D, int SRC>
+__global__ void __launch_bounds__(kBlock)
+    k_km_assign(KmLaunch kl, const uint32_t* __restrict__ xy, const evk_event* __restrict__ ev,
+                const uint32_t* __restrict__ first, size_t n, const float* __restrict__ cent,
+                unsigned long long* __restrict__ acc, int32_t* __restrict__ labels) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = kl.K;
+    float* s_c = reinterpret_cast<float*>(smem_raw);                         // [K * D]
+    unsigned long long* s_t = reinterpret_cast<unsigned long long*>(s_c + ((K * D + 3) & ~3));
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_t + K);                  // [K]
+    uint32_t* s_x = s_cnt + K;
+    uint32_t* s_y = s_x + K;
+    uint32_t* s_p = s_y + K;
+
+    for (int i = threadIdx.x; i < K * D; i += kBlock) s_c[i] = cent[i];
+    for (int i = threadIdx.x; i < K; i += kBlock) {
+        s_t[i] = 0;
+        s_cnt[i] = 0;
+        s_x[i] = 0;
+        s_y[i] = 0;
+        s_p[i] = 0;
+    }
+    __syncthreads();
+
+    const size_t n_chunks = (n + kChunk - 1) / kChunk;
+    for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const size_t cbase = c * (size_t)kChunk;
+        for (int r = 0; r < kChunk / (kBlock * kPPT); r++) {
+            const size_t base = cbase + (size_t)r * (kBlock * kPPT);
+            if (base >= n) break;
+            float px[kPPT], py[kPPT], pt[kPPT], pp[kPPT];
+            uint32_t ix[kPPT], iy[kPPT], ip[kPPT];
+            long long it[kPPT];
+            bool ok[kPPT];
+#pragma unroll
+            for (int q = 0; q < kPPT; q++) {
+                const size_t i = base + (size_t)q * kBlock + threadIdx.x;
+                ok[q] = i < n;
+                uint32_t w = 0;
+                ip[q] = 0;
+                it[q] = 0;
+                if (ok[q]) {
+                    if (SRC == 0) {
+                        w = xy[i];
+                    } else {
+                        const evk_event* src = SRC == 2 ? ev + first[i] : ev + i;
+                        if (D == 2) {
+                            w = *reinterpret_cast<const uint32_t*>(src);
+                        } else {
+                            uint4 e = ld_event(src);
+                            w = e.x;
+                            ip[q] = ev_pbit(e);
+                            it[q] = ev_t(e) - kl.t0;
+                        }
+                    }
+                }
+                ix[q] = w & 0xFFFFu;
+                iy[q] = w >> 16;
+                px[q] = (float)ix[q];
+                py[q] = (float)iy[q];
+                pt[q] = D > 2 ? __fmul_rn((float)it[q], kl.t_scale) : 0.f;
+                pp[q] = D > 3 ? __fmul_rn(ip[q] ? 1.0f : 0.0f, kl.p_scale) : 0.f;
+            }
+            float best[kPPT];
+            int lab[kPPT];
+#pragma unroll
+            for (int q = 0; q < kPPT; q++) {
+                best[q] = kl.best2;
+                lab[q] = -1;
+            }
+#pragma unroll 4
+            for (int k = 0; k < K; k++) {
+                float cx, cy, ct = 0.f, cp = 0.f;
+                if (D == 2) {
+                    float2 c2 = reinterpret_cast<const float2*>(s_c)[k];
+                    cx = c2.x;
+                    cy = c2.y;
+                } else if (D == 4) {
+                    float4 c4 = reinterpret_cast<const float4*>(s_c)[k];
+                    cx = c4.x;
+                    cy = c4.y;
+                    ct = c4.z;
+                    cp = c4.w;
+                } else {
+                    cx = s_c[k * 3];
+                    cy = s_c[k * 3 + 1];
+                    ct = s_c[k * 3 + 2];
+                }
+#pragma unroll
+                for (int q = 0; q < kPPT; q++) {
+                    float dx = __fsub_rn(cx, px[q]);
+                    float dy = __fsub_rn(cy, py[q]);
+                    float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+                    if (D > 2) {
+                        float dt = __fsub_rn(ct, pt[q]);
+                        d2 = __fmaf_rn(dt, dt, d2);
+                    }
+                    if (D > 3) {
+                        float dp = __fsub_rn(cp, pp[q]);
+                        d2 = __fmaf_rn(dp, dp, d2);
+                    }
+                    if (d2 < best[q]) {
+                        best[q] = d2;
+                        lab[q] = k;
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kPPT; q++) {
+                if (!ok[q]) continue;
+                const size_t i = base + (size_t)q * kBlock + threadIdx.x;
+                if (kl.write_labels) labels[i] = lab[q];
+                if (lab[q] >= 0) {
+                    atomicAdd(&s_cnt[lab[q]], 1u);
+                    atomicAdd(&s_x[lab[q]], ix[q]);
+                    atomicAdd(&s_y[lab[q]], iy[q]);
+                    if (D > 2) atomicAdd(&s_t[lab[q]], (unsigned long long)it[q]);
+                    if (D > 3) atomicAdd(&s_p[lab[q]], ip[q]);
+                }
+            }
+        }
+        // flush the block-private sums (u32 cannot overflow within one chunk: 32768 * 65535)
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += kBlock) {
+            if (s_cnt[k]) {
+                atomicAdd(&acc[k * ACC_STRIDE + ACC_CNT], (unsigned long long)s_cnt[k]);
+                atomicAdd(&acc[k * ACC_STRIDE + ACC_X], (unsigned long long)s_x[k]);
+                atomicAdd(&acc[k * ACC_STRIDE + ACC_Y], (unsigned long long)s_y[k]);
+                if (D > 2) atomicAdd(&acc[k * ACC_STRIDE + ACC_T], s_t[k]);
+                if (D > 3) atomicAdd(&acc[k * ACC_STRIDE + ACC_P], (unsigned long long)s_p[k]);
+                s_cnt[k] = 0;
+                s_x[k] = 0;
+                s_y[k] = 0;
+                s_t[k] = 0;
+                s_p[k] = 0;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// centroid = exact sum / count rounded once to fp32; empty clusters keep their centroid;
+// shift = max_k |delta c_k|_inf; accumulators are zeroed for the next iteration
+__global__ void __launch_bounds__(EVK_MAX_K)
+    k_km_finalise(KmLaunch kl, float* cent, unsigned long long* acc, unsigned long long* counts,
+                  float* shift) {
+    __shared__ unsigned int s_shift;
+    if (threadIdx.x == 0) s_shift = 0;
+    __syncthreads();
+    const int k = threadIdx.x;
+    if (k < kl.K) {
+        unsigned long long c = acc[k * ACC_STRIDE + ACC_CNT];
+        counts[k] = c;
+        float mx = 0.f;
+        if (c) {
+            const double inv = 1.0 / (double)c;
+            (void)inv;
+            for (int d = 0; d < kl.D; d++) {
+                double s;
+                if (d == 0) s = (double)acc[k * ACC_STRIDE + ACC_X];
+                else if (d == 1) s = (double)acc[k * ACC_STRIDE + ACC_Y];
+                else if (d == 2) s = (double)(long long)acc[k * ACC_STRIDE + ACC_T];
+                else s = (double)acc[k * ACC_STRIDE + ACC_P];
+                double m = s / (double)c;
+                if (d == 2) m *= (double)kl.t_scale;
+                if (d == 3) m *= (double)kl.p_scale;
+                float nc = (float)m;
+                float dl = fabsf(nc - cent[k * kl.D + d]);
+                mx = fmaxf(mx, dl);
+                cent[k * kl.D + d] = nc;
+            }
+        }
+        atomicMax(&s_shift, __float_as_uint(mx));  // non-negative floats order like uints
+#pragma unroll
+        for (int j = 0; j < ACC_STRIDE; j++) acc[k * ACC_STRIDE + j] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *shift = __uint_as_float(s_shift);
+}
+
+// candidates for "first K voxels in canonical order": voxels whose first index is below `bound`
+__global__ void __launch_bounds__(kBlock)
+    k_collect_below(const uint32_t* __restrict__ first, size_t n, uint32_t bound, uint32_t* cand,
+                    uint32_t cand_cap, unsigned long long* count) {
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint32_t f = first[i];
+        if (f < bound) {
+            unsigned long long o = atomicAdd(count, 1ull);
+            if (o < cand_cap) {
+                cand[2 * o] = f;
+                cand[2 * o + 1] = (uint32_t)i;
+            }
+        }
+    }
+}
+
+// rank the candidates by first index (all distinct) and write the K lowest as centroids
+__global__ void __launch_bounds__(1024)
+    k_init_from_cand(KmLaunch kl, const uint32_t* __restrict__ cand, uint32_t n_cand,
+                     const uint32_t* __restrict__ xy, const evk_event* __restrict__ ev,
+                     const evk_event* __restrict__ reps, uint64_t first_offset, float* cent) {
+    for (uint32_t i = threadIdx.x; i < n_cand; i += blockDim.x) {
+        const uint32_t f = cand[2 * i];
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < n_cand; j++) rank += cand[2 * j] < f;
+        if (rank < (uint32_t)kl.K) {
+            const uint32_t pos = cand[2 * i + 1];
+            const uint32_t w = xy[pos];
+            float* c = cent + rank * kl.D;
+            c[0] = (float)(w & 0xFFFFu);
+            c[1] = (float)(w >> 16);
+            if (kl.D > 2) {
+                const evk_event e = reps ? reps[pos] : ev[(uint64_t)f - first_offset];
+                c[2] = __fmul_rn((float)(e.t - kl.t0), kl.t_scale);
+                if (kl.D > 3) c[3] = __fmul_rn(e.p > 0 ? 1.0f : 0.0f, kl.p_scale);
+            }
+        }
+    }
+}
+
+size_t km_smem_bytes(int K, int D) {
+    return (size_t)((K * D + 3) & ~3) * sizeof(float) + (size_t)K * sizeof(unsigned long long) +
+           (size_t)K * 4 * sizeof(uint32_t);
+}
+
+template <int D, int SRC>
+cudaError_t launch_assign(const KmLaunch& kl, const uint32_t* xy, const evk_event* ev,
+                          const uint32_t* first, size_t n, const float* cent,
+                          unsigned long long* acc, int32_t* labels, int sm_count,
+                          cudaStream_t s) {
+    size_t chunks = (n + kChunk - 1) / kChunk;
+    size_t cap = (size_t)sm_count * 8;
+    int grid = (int)(chunks < cap ? chunks : cap);
+    k_km_assign<D, SRC><<<grid, kBlock, km_smem_bytes(kl.K, D), s>>>(kl, xy, ev, first, n, cent,
+                                                                      acc, labels);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// xy != nullptr: D == 2 reads the packed voxel coordinates; D > 2 gathers ev[first[i]].
+// xy == nullptr: points are the raw events ev[i].
+cudaError_t evk_launch_km_assign(const KmLaunch& kl, const uint32_t* xy, const evk_event* ev,
+                                 const uint32_t* first, size_t n, const float* cent,
+                                 unsigned long long* acc, int32_t* labels, int sm_count,
+                                 cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const bool on_events = xy == nullptr;
+    switch (kl.D) {
+        case 2:
+            return on_events
+                       ? launch_assign<2, 1>(kl, xy, ev, first, n, cent, acc, labels, sm_count, s)
+                       : launch_assign<2, 0>(kl, xy, ev, first, n, cent, acc, labels, sm_count, s);
+        case 3:
+            return on_events
+                       ? launch_assign<3, 1>(kl, xy, ev, first, n, cent, acc, labels, sm_count, s)
+                       : launch_assign<3, 2>(kl, xy, ev, first, n, cent, acc, labels, sm_count, s);
+        case 4:
+            return on_events
+                       ? launch_assign<4, 1>(kl, xy, ev, first, n, cent, acc, labels, sm_count, s)
+                       : launch_assign<4, 2>(kl, xy, ev, first, n, cent, acc, labels, sm_count, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t evk_launch_km_finalise(const KmLaunch& kl, float* cent, unsigned long long* acc,
+                                   unsigned long long* counts, float* shift, cudaStream_t s) {
+    int threads = ((kl.K + 31) / 32) * 32;
+    k_km_finalise<<<1, threads, 0, s>>>(kl, cent, acc, counts, shift);
+    return cudaGetLastError();
+}
+
+cudaError_t evk_launch_collect_below(const uint32_t* first, size_t n, uint32_t bound,
+                                     uint32_t* cand, uint32_t cand_cap, unsigned long long* count,
+                                     cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    size_t need = (n + kBlock - 1) / kBlock;
+    int grid = (int)(need < 148 * 8 ? need : 148 * 8);
+    k_collect_below<<<grid, kBlock, 0, s>>>(first, n, bound, cand, cand_cap, count);
+    return cudaGetLastError();
+}
+
+cudaError_t evk_launch_init_from_cand(const KmLaunch& kl, const uint32_t* cand, uint32_t n_cand,
+                                      const uint32_t* xy, const evk_event* ev,
+                                      const evk_event* reps, float* cent, cudaStream_t s) {
+    // first_offset is folded into ev by the caller (ev points at global index 0 of the shard)
+    k_init_from_cand<<<1, 1024, 0, s>>>(kl, cand, n_cand, xy, ev, reps, 0, cent);
+    return cudaGetLastError();
+}

@@ -1,0 +1,73 @@
+"""CPU tests of the drop-in boundary: libevk.so builds for sm_100a, loads, exports every symbol
+include/evk.h declares, and refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import evk_loader
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def evk():
+    evk_loader.build()
+    return evk_loader.load()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "evk.h")).read()
+    return sorted(set(re.findall(r"EVK_API\s+[\w\s\*]+?\b(evk_\w+)\s*\(", src)))
+
+
+def test_header_and_binding_agree(evk):
+    syms = header_symbols()
+    assert len(syms) >= 30
+    assert sorted(evk.SYMBOLS) == syms
+
+
+def test_library_exports_every_declared_symbol(evk):
+    L = evk.lib()
+    for s in header_symbols():
+        assert hasattr(L, s), s
+    out = subprocess.check_output(["nm", "-D", "--defined-only", evk.LIB_PATH], text=True)
+    exported = set(re.findall(r" T (evk_\w+)", out))
+    assert set(header_symbols()) <= exported
+    assert b"sm_100a" in L.evk_version()
+
+
+def test_library_is_sm100a_only(evk):
+    out = subprocess.run(["cuobjdump", "--list-elf", evk.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = set(re.findall(r"sm_\d+a?", out.stdout))
+    assert archs == {"sm_100a"}, archs
+
+
+def test_struct_layouts(evk):
+    assert evk.EVENT_DTYPE.itemsize == 16 and evk.EVENT_DTYPE.fields["t"][1] == 8
+    assert C.sizeof(evk.DsParams) == 48 and C.sizeof(evk.KmParams) == 32
+    assert C.sizeof(evk.SynthParams) == 56 and C.sizeof(evk.StageTimes) == 36
+
+
+def test_no_cpu_fallback(evk):
+    """without a CUDA device evk_create must fail with EVK_ERR_CUDA — never compute on the host"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(evk.EvkError) as e:
+        evk.Evk(1024)
+    assert e.value.status == -2
+
+
+def test_product_does_not_reference_the_oracle():
+    pkg = evk_loader.PKG_DIR
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".cu", ".cuh", ".py", ".hpp", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle/" not in txt and "liborc" not in txt and "import orc" not in txt, f
