@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — Mevents/s of the fused hot path: voxel-hash downsample + one k-means iteration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl evk|reference]
+
+Workload at N=1 (BASELINE.json configs[2], the config the metric is quoted on): 100 M synthetic
+Prophesee Gen4 (1280x720) events at 100 Mev/s, 2x2 px x 500 us voxels (+ polarity), k-means K=64,
+D=2.  A step = downsample -> first-K centroid initialisation -> one fused assign+accumulate
+iteration (+ finalise).  N>1: weak scaling, each rank owns a contiguous 100 M-event index shard of
+an N x 100 M-event stream (configs[3]); voxels are exchanged by ownership with an NCCL all-to-all
+and the K x (D+1) partial sums are allreduced.
+
+`value`  : events resident in HBM, timed with CUDA events on the library's stream.
+`e2e`    : the same step through the C-ABI from pinned HOST memory: H2D of the events and D2H of
+           centroids + counts inside the timed region.
+`roofline`: dominant kernel, algorithmic bytes / its CUDA-event duration, against
+           MEASURED_PEAKS.json hbm_gbs (fallback 6650 GB/s).
+`cpu_baseline`: the CPU oracle (a port of the reference's semantics; the reference's own OpenCL
+           code cannot be built here) on all host threads over a bounded prefix of the workload.
+--impl reference times that same oracle as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H = 1280, 720
+RATE = 100_000_000
+VOX = (2, 2, 500, 1)
+K, D = 64, 2
+SEED = 0xE7CA0003
+N_BLOBS = 64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="evk", choices=["evk", "reference"])
+    ap.add_argument("--events", type=int, default=100_000_000, help="events per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=20_000_000)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--owner", default="time", choices=["time", "mix64"])
+    ap.add_argument("--algo", default="auto", choices=["auto", "table", "sort", "slab"])
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi SM clock / throttle reasons sampled DURING the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu summary, if any"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def cpu_port(n_sample, steps, threads):
+    """CPU oracle (port) on a bounded prefix of the same stream. Returns Mev/s, description."""
+    from oracle import orc
+    orc.build()
+    threads = threads or orc.max_threads()
+    ev = orc.synth(orc.synth_params(SEED, n_sample, W, H, RATE, N_BLOBS), threads=threads)
+    p = orc.ds_params(W, H, VOX[0], VOX[1], VOX[2], 0, VOX[3])
+    best = None
+    U = 0
+    for _ in range(max(1, steps)):
+        t0 = time.perf_counter()
+        keys, first, rep = orc.downsample(ev, p, threads=threads, canonical=False)
+        pts = orc.points(ev, first, D)
+        # first-K initialisation needs the K lowest first indices only
+        import numpy as np
+        init = pts[np.argsort(first, kind="stable")[:K]]
+        orc.kmeans(pts, init, iters=1, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        U = len(keys)
+    return n_sample / best / 1e6, threads, U, best
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n_sample = min(args.cpu_sample, args.events)
+    mev, threads, U, best = cpu_port(n_sample, args.steps + args.warmup, 0)
+    sample = (f"first {n_sample} events of the workload stream (U={U}), best of "
+              f"{args.steps + args.warmup} passes, generation excluded")
+    line = {
+        "impl": "reference", "metric": "Mevents/s downsample+k-means iteration", "value": mev,
+        "unit": "Mevents/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": best * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 keys / f32 distances", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": mev, "unit": "Mevents/s", "cores": threads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": mev, "unit": "Mevents/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference's OpenCL/Metavision code cannot be built here; this is the CPU oracle "
+                "port of its semantics on all host threads",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"C3 synthetic Prophesee Gen4 {W}x{H}, {args.events} events/GPU at "
+                        f"{RATE // 1_000_000} Mev/s, voxels {VOX[0]}x{VOX[1]} px x {VOX[2]} us"
+                        f"{' x polarity' if VOX[3] else ''}, k-means K={K} D={D}, 1 iteration",
+            "events_per_gpu": args.events, "events_total": args.events * world, "K": K, "D": D,
+            "voxel": list(VOX), "seed": hex(SEED), "parallelism": f"index-sharded x{world}",
+            "l2_policy": "inputs (1.6 GB/GPU) larger than L2; no flush needed"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import evk_loader
+    evk = evk_loader.load()
+    evk.lib()  # fails loudly when libevk.so is missing: there is no fallback
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.events
+    algo = {"auto": evk.ALGO_AUTO, "table": evk.ALGO_TABLE, "sort": evk.ALGO_SORT,
+            "slab": evk.ALGO_SLAB}[args.algo]
+    ds = evk.ds_params(W, H, VOX[0], VOX[1], VOX[2], 0, VOX[3], algo=algo)
+    km = evk.km_params(K, D, iters=1)
+    h = evk.Evk(n, device=local_rank)
+    h.synth(evk.synth_params(SEED, n, W, H, RATE, N_BLOBS, first_index=rank * n))
+    h.sync()
+    if world > 1:
+        uid = [evk.Evk.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        h.comm_init(rank, world, uid[0])
+        h.set_shard(rank * n)
+    owner = evk.OWNER_TIME_RANGE if args.owner == "time" else evk.OWNER_MIX64
+
+    state = {}
+
+    def step():
+        if world > 1:
+            ul, ug = h.downsample_sharded(ds, owner)
+            h.init_centroids_first_k_sharded(km)
+            h.kmeans_sharded(km)
+            state["U_local"], state["U"] = ul, ug
+        else:
+            u, r = h.downsample(ds)
+            h.init_centroids_first_k(km)
+            h.kmeans(km)
+            state["U_local"] = state["U"] = u
+            state["R"] = r
+
+    h.set_profiling(True)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ds_main = ds_total = km_total = 0.0
+    launches = 0
+    h.timer_start()
+    for _ in range(args.steps):
+        step()
+        t = h.stage_times()
+        ds_main += t.ds_main_ms; ds_total += t.ds_total_ms; km_total += t.km_total_ms
+        launches += t.ds_launches + t.km_launches + 2
+    total_ms = h.timer_stop()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    algo_used = h.stage_times().ds_algo_used
+    tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tt.item()) / args.steps
+    value = n * world / (ms_per_step * 1e-3) / 1e6
+
+    # ---- end to end from pinned host memory through the C-ABI --------------------------------
+    host = torch.empty(n * 16, dtype=torch.uint8, pin_memory=True)
+    host_np = host.numpy().view(evk.EVENT_DTYPE)
+    host_np[:] = h.get_events()
+    cent = np.zeros((K, D), np.float32)
+    e2e_steps = max(1, args.e2e_steps)
+
+    def e2e_step():
+        h.load_events_ptr(host.data_ptr(), n)
+        step()
+        c, cnt = h.get_centroids(K, D)   # D2H + sync
+        return c
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        cent = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = n * world / float(te.item()) / 1e6
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        U = state["U_local"]
+        ds_ms, km_ms = ds_main / args.steps, km_total / args.steps
+        ds_bytes, km_bytes = 16.0 * n + 16.0 * U, 20.0 * U
+        names = {evk.ALGO_SLAB: "k_slab_main", evk.ALGO_TABLE: "k_table_insert",
+                 evk.ALGO_SORT: "sort+unique"}
+        traffic = ncu_traffic()
+        if ds_ms >= km_ms:
+            kern, a_bytes, a_ms = names.get(algo_used, "?"), ds_bytes, ds_ms
+        else:
+            kern, a_bytes, a_ms = "k_km_assign", km_bytes, km_ms
+        achieved = a_bytes / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0
+        step_bytes = 16.0 * n + 36.0 * U
+        line = {
+            "metric": "Mevents/s downsample+k-means iteration", "value": value,
+            "unit": "Mevents/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64 keys / f32 distances / exact u64 sums",
+            "data": "synthetic", "config": workload_config(args, world),
+            "unique_voxels_per_gpu": U, "repeated": state.get("R"),
+            "ds_algo": {1: "table", 2: "sort", 3: "slab"}.get(algo_used, str(algo_used)),
+            "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                         "frac_of_8000_nominal": achieved / 8000.0,
+                         "algorithmic_bytes_per_launch": a_bytes, "kernel_ms": a_ms,
+                         "traffic": traffic.get(kern)},
+            "stage_ms": {"downsample_dominant_kernel": ds_ms, "downsample_total": ds_total / args.steps,
+                         "kmeans_iteration": km_ms},
+            "step_roofline": {"algorithmic_bytes": step_bytes,
+                              "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                              "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                              "note": "16N+36U bytes over the whole step incl. host syncs"},
+            "e2e": {"value": e2e_val, "unit": "Mevents/s", "h2d_bytes_per_step": 16 * n,
+                    "d2h_bytes_per_step": K * D * 4 + K * 8 + 64, "steps": e2e_steps,
+                    "ms_per_step": float(te.item()) * 1e3,
+                    "result_read": "centroids + counts (+ voxel counters)"},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            n_sample = min(args.cpu_sample, n)
+            mev, threads, Us, best = cpu_port(n_sample, 2, 0)
+            line["cpu_baseline"] = {
+                "value": mev, "unit": "Mevents/s", "cores": threads, "kind": "port",
+                "sample": f"first {n_sample} events of the workload stream (U={Us}), best of 2 "
+                          f"passes ({best:.2f} s each), generation excluded"}
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -389,7 +389,7 @@ int evk_downsample_local(evk_handle* h, const evk_ds_params* p) {
     h->times.ds_launches = launches;
     if (h->profiling) {
         h->times.ds_total_ms = prof_ms(h, 0, 2);
-        h->times.ds_main_ms = prof_ms(h, 0, 1);
+        h->times.ds_main_ms = algo == EVK_ALGO_SLAB ? prof_ms(h, 5, 6) : prof_ms(h, 0, 1);
         h->times.ds_compact_ms = prof_ms(h, 1, 2);
     }
     return EVK_OK;

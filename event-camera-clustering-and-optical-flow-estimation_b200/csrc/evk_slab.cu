@@ -275,11 +275,13 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
                                          (int)kSmemLimit));
     k_slab_bins<<<h->sm_count, 256, 0, h->stream>>>(a);
     EVK_CUDA(h, cudaGetLastError());
+    if (h->profiling) cudaEventRecord(h->ev[5], h->stream);
     if (count_repeated)
         k_slab_main<true><<<h->sm_count, kThreads, smem, h->stream>>>(a);
     else
         k_slab_main<false><<<h->sm_count, kThreads, smem, h->stream>>>(a);
     EVK_CUDA(h, cudaGetLastError());
+    if (h->profiling) cudaEventRecord(h->ev[6], h->stream);
     *launches += 2;
     // the verification flag decides whether the result stands
     EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,
