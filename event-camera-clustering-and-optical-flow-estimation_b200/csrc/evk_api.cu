@@ -94,7 +94,8 @@ int evk_make_key_params(evk_handle* h, const evk_ds_params* p, KeyParams* kp) {
     kp->height = p->height;
     if (p->keyfn == EVK_KEY_REF_HASH8192) {
         kp->use_p = 0;
-        kp->mx = kp->my = 1ull << 32;
+        kp->mx = kp->my = 0;
+        kp->sx = kp->sy = 0;
         kp->NX = kp->NY = kp->P = 1;
         kp->vt = 0;
         kp->vt_shift = -1;
@@ -106,8 +107,19 @@ int evk_make_key_params(evk_handle* h, const evk_ds_params* p, KeyParams* kp) {
         return evk_fail(h, EVK_ERR_INVALID, "vx/vy must be in [1,65536]");
     kp->use_p = p->use_polarity ? 1 : 0;
     kp->P = kp->use_p ? 2 : 1;
-    kp->mx = ((1ull << 32) + (uint64_t)p->vx - 1) / (uint64_t)p->vx;
-    kp->my = ((1ull << 32) + (uint64_t)p->vy - 1) / (uint64_t)p->vy;
+    auto magic = [](int v, uint32_t* m, int32_t* s) {
+        *s = -1;
+        *m = 0;
+        if ((v & (v - 1)) == 0) {
+            int k = 0;
+            while ((1 << k) < v) k++;
+            *s = k;
+        } else {
+            *m = (uint32_t)(((1ull << 32) + (uint64_t)v - 1) / (uint64_t)v);
+        }
+    };
+    magic(p->vx, &kp->mx, &kp->sx);
+    magic(p->vy, &kp->my, &kp->sy);
     kp->NX = (uint32_t)((p->width + p->vx - 1) / p->vx);
     kp->NY = (uint32_t)((p->height + p->vy - 1) / p->vy);
     kp->cells = (uint64_t)kp->NX * kp->NY * kp->P;
@@ -137,7 +149,7 @@ const char* evk_last_error(const evk_handle* h) { return h ? h->err.c_str() : "n
 int evk_create(evk_handle** out, int device, size_t max_events) {
     if (!out) return EVK_ERR_INVALID;
     *out = nullptr;
-    if (max_events == 0 || max_events >= 0xFFFFFFF0ull) return EVK_ERR_INVALID;
+    if (max_events == 0 || max_events >= 0xFF000000ull) return EVK_ERR_INVALID;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return EVK_ERR_CUDA;  // no fallback
     if (device < 0 || device >= ndev) return EVK_ERR_INVALID;
@@ -165,9 +177,12 @@ int evk_create(evk_handle** out, int device, size_t max_events) {
     ALLOC(h->d_events, m * sizeof(evk_event));
     ALLOC(h->d_tkeys, h->table_cap * sizeof(uint64_t));
     ALLOC(h->d_tfirst, h->table_cap * sizeof(uint32_t));
-    ALLOC(h->d_keys, m * sizeof(uint64_t));
-    ALLOC(h->d_first, m * sizeof(uint32_t));
-    ALLOC(h->d_xy, m * sizeof(uint32_t));
+    // the slab kernel hands out output slots in CTA-private chunks: room for the unfilled tails
+    h->out_cap = m + (size_t)EVK_SLAB_CHUNK * (2 * (size_t)h->sm_count + 4);
+    ALLOC(h->d_keys, h->out_cap * sizeof(uint64_t));
+    ALLOC(h->d_first, h->out_cap * sizeof(uint32_t));
+    ALLOC(h->d_xy, h->out_cap * sizeof(uint32_t));
+    ALLOC(h->d_slab_scratch, evk_slab_scratch_bytes(h->sm_count));
     ALLOC(h->d_labels, m * sizeof(int32_t));
     ALLOC(h->d_bin_start, (h->max_bins + 2) * sizeof(uint32_t));
     ALLOC(h->d_cnt, sizeof(DsCounters));
@@ -203,7 +218,7 @@ int evk_destroy(evk_handle* h) {
     void* ptrs[] = {h->d_events, h->d_tkeys,  h->d_tfirst, h->d_keys,   h->d_first,  h->d_xy,
                     h->d_reps,   h->d_labels, h->d_perm,   h->d_sort_tmp, h->d_sort_a, h->d_sort_b,
                     h->d_sort_c, h->d_sk_in,  h->d_sk_out, h->d_si_in,  h->d_si_out, h->d_sv_tmp,
-                    h->d_bin_start, h->d_cnt, h->d_cent,   h->d_acc,    h->d_counts, h->d_shift,
+                    h->d_bin_start, h->d_slab_scratch, h->d_cnt, h->d_cent,   h->d_acc,    h->d_counts, h->d_shift,
                     h->d_cand,   h->d_flush};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -368,8 +383,9 @@ int evk_downsample_local(evk_handle* h, const evk_ds_params* p) {
                                             h->stream));
         prof_rec(h, 1);
         EVK_CUDA(h, evk_launch_table_compact(h->d_events, h->d_tkeys, h->d_tfirst, h->table_cap,
-                                             h->d_keys, h->d_first, h->d_xy, h->d_cnt,
-                                             h->sm_count, h->stream));
+                                             h->d_keys, h->d_first, h->d_xy,
+                                             (uint32_t)h->shard_first, h->d_cnt, h->sm_count,
+                                             h->stream));
         prof_rec(h, 2);
         launches += 2;
     } else if (algo == EVK_ALGO_SORT) {
@@ -455,7 +471,22 @@ int evk_init_centroids_first_k(evk_handle* h, const evk_km_params* p) {
     DeviceGuard g(h->device);
     KmLaunch kl = km_launch_params(h, p);
     unsigned long long* d_count = &h->d_cnt->scratch[0];
-    // voxels with first index below `bound` are the only candidates for the K lowest ones;
+    // fast path: walk the head of the stream until K distinct keys have been met
+    if (!h->reps_valid && h->n_events) {
+        const size_t n_scan = h->n_events < (1u << 20) ? h->n_events : (1u << 20);
+        EVK_CUDA(h, evk_launch_init_first_k_walk(h->kp, kl, h->d_events, n_scan, h->d_cent, d_count,
+                                                 h->stream));
+        EVK_CUDA(h, cudaMemcpyAsync(&h->h_cnt->scratch[0], d_count, sizeof(unsigned long long),
+                                    cudaMemcpyDeviceToHost, h->stream));
+        EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (h->h_cnt->scratch[0] == (unsigned long long)p->K) {
+            h->K = p->K;
+            h->D = p->D;
+            h->have_centroids = true;
+            return EVK_OK;
+        }
+    }
+    // general path: voxels with first index below `bound` are the only candidates for the K lowest ones;
     // first indices are global in sharded mode, so the bound starts at the shard offset
     uint64_t span = 2048 + 32ull * p->K;
     for (int attempt = 0; attempt < 8; attempt++) {

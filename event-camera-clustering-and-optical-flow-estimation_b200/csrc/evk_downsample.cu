@@ -111,7 +111,7 @@ constexpr int kCmpPer = 8;
 __global__ void __launch_bounds__(kBlock)
     k_table_compact(const evk_event* __restrict__ ev, uint64_t* tkeys, uint32_t* tfirst,
                     size_t cap, uint64_t* __restrict__ keys, uint32_t* __restrict__ first,
-                    uint32_t* __restrict__ xy, DsCounters* cnt) {
+                    uint32_t* __restrict__ xy, uint32_t first_offset, DsCounters* cnt) {
     __shared__ int s_warp[kBlock / 32 + 1];
     __shared__ unsigned long long s_base;
     const size_t tile = (size_t)kBlock * kCmpPer;
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kBlock)
                 size_t s = base + (size_t)j * kBlock + threadIdx.x;
                 uint32_t f = tfirst[s];
                 keys[o] = k[j] & ~EVK_REP_FLAG;
-                first[o] = f;
+                first[o] = f + first_offset;
                 xy[o] = *reinterpret_cast<const uint32_t*>(ev + f);  // x | y << 16
                 o++;
                 tkeys[s] = EVK_EMPTY_KEY;  // leave the table clean for the next call
@@ -171,7 +171,8 @@ __global__ void __launch_bounds__(kBlock)
 __global__ void __launch_bounds__(kBlock)
     k_unique_heads(const evk_event* __restrict__ ev, const uint64_t* __restrict__ sk,
                    const uint32_t* __restrict__ si, size_t n, uint64_t* __restrict__ keys,
-                   uint32_t* __restrict__ first, uint32_t* __restrict__ xy, DsCounters* cnt) {
+                   uint32_t* __restrict__ first, uint32_t* __restrict__ xy, uint32_t first_offset,
+                   DsCounters* cnt) {
     __shared__ int s_warp[kBlock / 32 + 1];
     __shared__ unsigned long long s_base;
     for (size_t base = (size_t)blockIdx.x * kBlock; base < n; base += (size_t)gridDim.x * kBlock) {
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(kBlock)
             size_t o = (size_t)s_base + off;
             uint32_t f = si[j];
             keys[o] = k;
-            first[o] = f;
+            first[o] = f + first_offset;
             xy[o] = *reinterpret_cast<const uint32_t*>(ev + f);
         }
         __syncthreads();
@@ -269,9 +270,11 @@ cudaError_t evk_launch_table_insert(const KeyParams& kp, const evk_event* ev, si
 
 cudaError_t evk_launch_table_compact(const evk_event* ev, uint64_t* tkeys, uint32_t* tfirst,
                                      size_t cap, uint64_t* keys, uint32_t* first, uint32_t* xy,
-                                     DsCounters* cnt, int sm_count, cudaStream_t s) {
+                                     uint32_t first_offset, DsCounters* cnt, int sm_count,
+                                     cudaStream_t s) {
     int grid = grid_for(cap, kBlock * kCmpPer, sm_count);
-    k_table_compact<<<grid, kBlock, 0, s>>>(ev, tkeys, tfirst, cap, keys, first, xy, cnt);
+    k_table_compact<<<grid, kBlock, 0, s>>>(ev, tkeys, tfirst, cap, keys, first, xy, first_offset,
+                                            cnt);
     return cudaGetLastError();
 }
 
@@ -299,7 +302,8 @@ int evk_downsample_sort(evk_handle* h, const KeyParams& kp, int* launches) {
                                                 h->d_si_in, h->d_si_out, (int64_t)n, 0, 64,
                                                 h->stream));
     k_unique_heads<<<grid, kBlock, 0, h->stream>>>(h->d_events, h->d_sk_out, h->d_si_out, n,
-                                                   h->d_keys, h->d_first, h->d_xy, h->d_cnt);
+                                                   h->d_keys, h->d_first, h->d_xy,
+                                                   (uint32_t)h->shard_first, h->d_cnt);
     EVK_CUDA(h, cudaGetLastError());
     *launches += 2 + 8;  // key build, head compaction, ~8 radix passes (library kernels)
     return EVK_OK;

@@ -25,11 +25,13 @@
 #define EVK_EMPTY_IDX 0xFFFFFFFFu
 #define EVK_MAX_K 1024
 #define EVK_MAX_D 4
+#define EVK_SLAB_CHUNK 8192u  // output slots per CTA-private chunk of the slab kernel
 
 // ---- key arithmetic -------------------------------------------------------------------------
 struct KeyParams {
     int32_t keyfn, width, height, use_p;
-    uint64_t mx, my;  // ceil(2^32 / vx), ceil(2^32 / vy): exact quotients for x, y < 65536
+    uint32_t mx, my;  // ceil(2^32 / v) for v >= 2: __umulhi(x, m) == x / v exactly for x < 65536
+    int32_t sx, sy;   // >= 0: v is a power of two, quotient is a shift
     uint32_t NX, NY, P;
     int32_t vt_shift;  // >= 0: vt is a power of two
     int64_t t0, vt;    // vt <= 0: one time bin
@@ -71,8 +73,8 @@ __device__ __forceinline__ uint64_t evk_tbin(const KeyParams& kp, int64_t t) {
 
 // spatial cell index inside one time bin: (ybin * NX + xbin) * P + pbit
 __device__ __forceinline__ uint32_t evk_cell(const KeyParams& kp, const uint4& e) {
-    uint32_t xb = (uint32_t)((ev_x(e) * kp.mx) >> 32);
-    uint32_t yb = (uint32_t)((ev_y(e) * kp.my) >> 32);
+    uint32_t xb = kp.sx >= 0 ? ev_x(e) >> kp.sx : __umulhi(ev_x(e), kp.mx);
+    uint32_t yb = kp.sy >= 0 ? ev_y(e) >> kp.sy : __umulhi(ev_y(e), kp.my);
     uint32_t c = yb * kp.NX + xb;
     return kp.use_p ? c * 2u + ev_pbit(e) : c;
 }
@@ -99,7 +101,7 @@ struct DsCounters {  // device-side counters, mirrored into pinned host memory a
     unsigned long long n_valid;
     unsigned int slab_violation;  // slab kernel found an event outside its bin's index range
     unsigned int overflow;
-    unsigned long long scratch[3];
+    unsigned long long scratch[6];
 };
 
 struct CommState;
@@ -136,6 +138,8 @@ struct evk_handle {
     size_t sv_tmp_bytes = 0;
     // slab scratch
     uint32_t* d_bin_start = nullptr;  // [max_bins + 1]
+    void* d_slab_scratch = nullptr;   // fix-up plan + per-CTA chunk list
+    size_t out_cap = 0;               // capacity of d_keys / d_first / d_xy (max_events + slack)
     size_t max_bins = 0;
     // counters
     DsCounters* d_cnt = nullptr;
@@ -213,13 +217,15 @@ cudaError_t evk_launch_table_insert(const KeyParams& kp, const evk_event* ev, si
                                     int count_repeated, int sm_count, cudaStream_t s);
 cudaError_t evk_launch_table_compact(const evk_event* ev, uint64_t* tkeys, uint32_t* tfirst,
                                      size_t cap, uint64_t* keys, uint32_t* first, uint32_t* xy,
-                                     DsCounters* cnt, int sm_count, cudaStream_t s);
+                                     uint32_t first_offset, DsCounters* cnt, int sm_count,
+                                     cudaStream_t s);
 // downsample: sort + unique
 int evk_downsample_sort(evk_handle* h, const KeyParams& kp, int* launches);
 // downsample: time-slab kernel
 int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, bool* ok,
                         int* launches);
 bool evk_slab_supported(const evk_handle* h, const KeyParams& kp);
+size_t evk_slab_scratch_bytes(int sm_count);
 // canonical order
 int evk_ensure_perm(evk_handle* h);
 cudaError_t evk_launch_gather_voxels(const evk_handle* h, uint64_t* keys, evk_event* reps,
@@ -246,4 +252,7 @@ cudaError_t evk_launch_collect_below(const uint32_t* first, size_t n, uint32_t b
 cudaError_t evk_launch_init_from_cand(const KmLaunch& kl, const uint32_t* cand, uint32_t n_cand,
                                       const uint32_t* xy, const evk_event* ev,
                                       const evk_event* reps, float* cent, cudaStream_t s);
+cudaError_t evk_launch_init_first_k_walk(const KeyParams& kp, const KmLaunch& kl,
+                                         const evk_event* ev, size_t n_scan, float* cent,
+                                         unsigned long long* found, cudaStream_t s);
 cudaError_t evk_launch_fill_u8(void* p, int v, size_t bytes, cudaStream_t s);

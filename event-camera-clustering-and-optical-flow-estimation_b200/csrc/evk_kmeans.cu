@@ -243,6 +243,49 @@ __global__ void __launch_bounds__(1024)
     }
 }
 
+// "first K voxel representatives in canonical order" == the first K distinct keys met when the
+// stream is walked in order.  One warp walks the head of the stream: lane l holds event base+l,
+// the 32 events are committed one after the other, the list of keys found so far is compared
+// 32 entries at a time.  A few hundred events suffice for realistic streams; `found` tells the
+// host when the walk ran out (it then falls back to the rank-by-first-index path).
+__global__ void __launch_bounds__(32)
+    k_init_first_k_walk(KeyParams kp, KmLaunch kl, const evk_event* __restrict__ ev, size_t n_scan,
+                        float* cent, unsigned long long* found_out) {
+    __shared__ uint64_t s_keys[EVK_MAX_K];
+    const int lane = threadIdx.x;
+    int found = 0;
+    for (size_t base = 0; base < n_scan && found < kl.K; base += 32) {
+        const size_t i = base + lane;
+        uint4 e = make_uint4(0, 0, 0, 0);
+        uint64_t key = 0;
+        bool valid = false;
+        if (i < n_scan) {
+            e = ld_event(ev + i);
+            valid = evk_key(kp, e, key);
+        }
+        const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+        for (int l = 0; l < 32 && found < kl.K; l++) {
+            if (!((vmask >> l) & 1u)) continue;
+            const uint64_t kl_key = __shfl_sync(0xffffffffu, key, l);
+            bool match = false;
+            for (int q = lane; q < found; q += 32) match |= s_keys[q] == kl_key;
+            if (!__any_sync(0xffffffffu, match)) {
+                if (lane == l) {
+                    s_keys[found] = key;
+                    float* c = cent + found * kl.D;
+                    c[0] = (float)ev_x(e);
+                    c[1] = (float)ev_y(e);
+                    if (kl.D > 2) c[2] = __fmul_rn((float)(ev_t(e) - kl.t0), kl.t_scale);
+                    if (kl.D > 3) c[3] = __fmul_rn(ev_pbit(e) ? 1.0f : 0.0f, kl.p_scale);
+                }
+                found++;
+                __syncwarp();
+            }
+        }
+    }
+    if (lane == 0) *found_out = (unsigned long long)found;
+}
+
 size_t km_smem_bytes(int K, int D) {
     return (size_t)((K * D + 3) & ~3) * sizeof(float) + (size_t)K * sizeof(unsigned long long) +
            (size_t)K * 4 * sizeof(uint32_t);
@@ -310,5 +353,12 @@ cudaError_t evk_launch_init_from_cand(const KmLaunch& kl, const uint32_t* cand, 
                                       const evk_event* reps, float* cent, cudaStream_t s) {
     // first_offset is folded into ev by the caller (ev points at global index 0 of the shard)
     k_init_from_cand<<<1, 1024, 0, s>>>(kl, cand, n_cand, xy, ev, reps, 0, cent);
+    return cudaGetLastError();
+}
+
+cudaError_t evk_launch_init_first_k_walk(const KeyParams& kp, const KmLaunch& kl,
+                                         const evk_event* ev, size_t n_scan, float* cent,
+                                         unsigned long long* found, cudaStream_t s) {
+    k_init_first_k_walk<<<1, 32, 0, s>>>(kp, kl, ev, n_scan, cent, found);
     return cudaGetLastError();
 }

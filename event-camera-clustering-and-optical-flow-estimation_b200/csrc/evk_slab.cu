@@ -8,23 +8,34 @@
 //            ACCEL/build/coordinate_processor.cl:73-75)
 //   s_hash   a 4096-slot tile table of packed (cell << 11 | index-in-tile) words: a 32-bit
 //            atomicCAS claims, a 32-bit atomicMin keeps the LOWEST stream index
-// Global memory sees each event read once (128-bit loads) and each voxel written once (16 B SoA);
-// no table lives in HBM.  This is the "perfect-hash" specialisation of the mandated
-// open-addressing table (evk_downsample.cu), which remains the general path: the slab kernel
-// verifies on the fly that [bin_start[b], bin_start[b+1]) holds only events of bin b and that the
-// ranges partition the stream; any violation makes the host fall back to the table.
+//   s_ev     a 2-stage ring of 2048-event tiles (32 KB each) filled by TMA bulk copies
+//            (cp.async.bulk + mbarrier complete_tx) issued one tile ahead by an elected thread
+// Per tile there are two block barriers and no global atomic: output slots come from a CTA-private
+// chunk of the output arrays (chunks are claimed from a global counter one chunk ahead, so the
+// round trip is never waited for); a tiny fix-up pass moves the tail of the last chunks into the
+// holes so the voxel shard is dense.  HBM sees each event read once and each voxel written once
+// (16 B SoA); no table lives in HBM.
+//
+// This is the "perfect-hash" specialisation of the mandated open-addressing table
+// (evk_downsample.cu), which remains the general path: the kernel verifies on the fly that
+// [bin_start[b], bin_start[b+1]) holds only events of bin b and that the ranges partition the
+// stream; any violation makes the host fall back to the table.
 #include "evk_internal.cuh"
 
 namespace {
 
 constexpr int kThreads = 1024;
 constexpr int kLogTile = 11;
-constexpr int kTile = 1 << kLogTile;       // events per tile
-constexpr int kPer = kTile / kThreads;     // events per thread per tile
-constexpr int kLogHash = 12;
-constexpr int kHash = 1 << kLogHash;       // tile table slots (load <= 0.5)
+constexpr int kTile = 1 << kLogTile;    // events per tile
+constexpr int kPer = kTile / kThreads;  // events per thread per tile
+constexpr int kLogHash = kLogTile + 1;
+constexpr int kHash = 1 << kLogHash;    // tile table slots (load <= 0.5)
 constexpr int kSlotsPer = kHash / kThreads;
+constexpr int kStages = 2;
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
+constexpr uint32_t kChunk = EVK_SLAB_CHUNK;  // output slots per CTA-private chunk (>= 2 tiles)
+constexpr uint32_t kNoChunk = 0xFFFFFFFFu;
+static_assert(kChunk >= 2 * kTile, "a fresh chunk must absorb a whole tile");
 
 struct SlabArgs {
     KeyParams kp;
@@ -35,13 +46,48 @@ struct SlabArgs {
     uint32_t* first;
     uint32_t* xy;
     DsCounters* cnt;
-    uint32_t words;  // bitmap words per bin
+    uint32_t* chunk_list;   // [2 * grid] pairs (base, filled)
+    uint32_t first_offset;  // added to every emitted first index (global index of event 0)
+    uint32_t words;         // bitmap words per bin
     uint32_t max_bins;
     uint32_t min_bins;
-    int count_repeated;
 };
 
-// scratch[0] = n_bins, scratch[1] = work counter, scratch[2] = tb0
+// ---- PTX helpers: mbarrier + 1-D TMA bulk copy ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "EVK_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra EVK_DONE_%=;\n\t"
+        "bra EVK_WAIT_%=;\n\t"
+        "EVK_DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes,
+                                            uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// scratch[0] = n_bins, scratch[1] = bin work counter, scratch[2] = tb0, scratch[3] = chunk counter
 __global__ void __launch_bounds__(256) k_slab_bins(SlabArgs a) {
     DsCounters* cnt = a.cnt;
     const KeyParams& kp = a.kp;
@@ -86,26 +132,41 @@ __device__ __forceinline__ uint32_t hash_slot(uint32_t cell) {
 
 template <bool COUNT_REP>
 __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
-    extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t* s_seen = smem;
-    uint32_t* s_rep = s_seen + a.words;                          // only touched when COUNT_REP
-    uint32_t* s_hash = s_rep + (COUNT_REP ? a.words : 0);        // [kHash]
-    uint32_t* s_xy = s_hash + kHash;                             // [kTile]
-    __shared__ int s_warp[kThreads / 32 + 1];
-    __shared__ unsigned long long s_base;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint4* s_ev = reinterpret_cast<uint4*>(smem_raw);                        // [kStages][kTile]
+    uint32_t* s_hash = reinterpret_cast<uint32_t*>(s_ev + kStages * kTile);  // [kHash]
+    uint32_t* s_seen = s_hash + kHash;                                       // [words]
+    uint32_t* s_rep = s_seen + a.words;                                      // [words] if COUNT_REP
+    __shared__ __align__(8) uint64_t s_bar[kStages];
     __shared__ uint32_t s_bin;
+    __shared__ uint32_t s_new[2];     // voxels claimed by the current tile (by tile parity)
+    __shared__ uint32_t s_cursor[2];  // slots handed out to warps within the tile
+    __shared__ uint32_t s_chunk_pos, s_chunk_end, s_next_base;
 
     DsCounters* cnt = a.cnt;
     if (cnt->slab_violation) return;
     const KeyParams& kp = a.kp;
     const uint32_t nb = (uint32_t)cnt->scratch[0];
     const uint64_t tb0 = cnt->scratch[2];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
 
     for (int i = tid; i < kHash; i += kThreads) s_hash[i] = kEmpty;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) mbar_init(&s_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_new[0] = s_new[1] = 0;
+        s_cursor[0] = s_cursor[1] = 0;
+        // two chunks up front: the current one and the one after it
+        const uint32_t c0 = (uint32_t)atomicAdd(&cnt->scratch[3], 2ull);
+        s_chunk_pos = c0 * kChunk;
+        s_chunk_end = s_chunk_pos + kChunk;
+        s_next_base = (c0 + 1) * kChunk;
+    }
+    uint32_t pend_chunk = kNoChunk;  // thread 0: chunk index requested but not yet published
+    uint32_t tile_seq = 0;           // tiles consumed by this CTA (stage = seq % kStages)
 
     for (;;) {
-        __syncthreads();  // previous bin fully retired (also orders the s_hash init)
+        __syncthreads();
         if (tid == 0) s_bin = (uint32_t)atomicAdd(&cnt->scratch[1], 1ull);
         __syncthreads();
         const uint32_t b = s_bin;
@@ -117,31 +178,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
         }
         if (hi == lo) continue;
         const uint64_t tb = tb0 + b;
+        const int64_t t_lo = kp.t0 + (int64_t)(tb * (uint64_t)kp.vt);
+        if (tid == 0) {  // first tile of the bin
+            const uint32_t cntev = min((uint32_t)kTile, hi - lo);
+            uint64_t* bar = &s_bar[tile_seq % kStages];
+            mbar_expect_tx(bar, cntev * 16u);
+            tma_load_1d(s_ev + (tile_seq % kStages) * kTile, a.ev + lo, cntev * 16u, bar);
+        }
         for (uint32_t i = tid; i < a.words; i += kThreads) {
             s_seen[i] = 0;
             if (COUNT_REP) s_rep[i] = 0;
         }
-        // prefetch the first tile
-        uint4 e[kPer];
-#pragma unroll
-        for (int j = 0; j < kPer; j++) {
-            uint32_t i = lo + j * kThreads + tid;
-            if (i < hi) e[j] = ld_event(a.ev + i);
-        }
         __syncthreads();
 
-        for (uint32_t base = lo; base < hi; base += kTile) {
+        for (uint32_t base = lo; base < hi; base += kTile, tile_seq++) {
+            const uint32_t stage = tile_seq % kStages, par = tile_seq & 1;
+            const uint4* tile = s_ev + stage * kTile;
+            // the next tile goes into the other stage, which every thread left before the barrier
+            // that ended the previous tile
+            if (tid == 0 && base + kTile < hi) {
+                const uint32_t nxt = base + kTile;
+                const uint32_t cntev = min((uint32_t)kTile, hi - nxt);
+                uint64_t* bar = &s_bar[(tile_seq + 1) % kStages];
+                mbar_expect_tx(bar, cntev * 16u);
+                tma_load_1d(s_ev + ((tile_seq + 1) % kStages) * kTile, a.ev + nxt, cntev * 16u,
+                            bar);
+            }
+            mbar_wait(&s_bar[stage], (tile_seq / kStages) & 1);
             // ---- phase A: classify against the bin bitmap, insert candidates in the tile table
+            uint32_t claimed = 0;
 #pragma unroll
             for (int j = 0; j < kPer; j++) {
                 const uint32_t li = j * kThreads + tid;
-                const uint32_t i = base + li;
-                if (i >= hi) continue;
-                const uint4 ev = e[j];
-                s_xy[li] = ev.x;
-                const int64_t t = ev_t(ev);
+                if (base + li >= hi) continue;
+                const uint4 ev = tile[li];
                 if (ev_x(ev) >= (uint32_t)kp.width || ev_y(ev) >= (uint32_t)kp.height) continue;
-                if (t < kp.t0 || evk_tbin(kp, t) != tb) {
+                if ((uint64_t)(ev_t(ev) - t_lo) >= (uint64_t)kp.vt) {  // not an event of this bin
                     atomicOr(&cnt->slab_violation, 1u);
                     continue;
                 }
@@ -154,8 +226,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
                 const uint32_t v = (cell << kLogTile) | li;
                 uint32_t s = hash_slot(cell);
                 for (;;) {
-                    uint32_t old = atomicCAS(&s_hash[s], kEmpty, v);
-                    if (old == kEmpty) break;
+                    const uint32_t old = atomicCAS(&s_hash[s], kEmpty, v);
+                    if (old == kEmpty) {
+                        claimed++;
+                        break;
+                    }
                     if ((old >> kLogTile) == cell) {
                         atomicMin(&s_hash[s], v);
                         if (COUNT_REP && !(s_rep[w] & bit)) atomicOr(&s_rep[w], bit);
@@ -164,16 +239,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
                     s = (s + 1) & (kHash - 1);
                 }
             }
-            // prefetch the next tile while the table is drained
-#pragma unroll
-            for (int j = 0; j < kPer; j++) {
-                uint32_t i = base + kTile + j * kThreads + tid;
-                if (i < hi) e[j] = ld_event(a.ev + i);
-            }
-            __syncthreads();
+            claimed = __reduce_add_sync(0xffffffffu, claimed);
+            if (lane == 0 && claimed) atomicAdd(&s_new[par], claimed);
+            __syncthreads();  // S1: tile table complete, s_new final
             // ---- phase B: every occupied slot is one new voxel with its lowest index
             uint32_t v[kSlotsPer];
-            int mine = 0;
+            uint32_t mine = 0;
 #pragma unroll
             for (int j = 0; j < kSlotsPer; j++) {
                 const int s = j * kThreads + tid;
@@ -185,64 +256,182 @@ __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
                     atomicOr(&s_seen[cell >> 5], 1u << (cell & 31));
                 }
             }
-            // block exclusive scan of `mine`
-            int inc = mine;
+            // warp-level slot allocation inside the tile (order within a tile is irrelevant)
+            uint32_t inc = mine;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                int nn = __shfl_up_sync(0xffffffffu, inc, o);
+                const uint32_t nn = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += nn;
             }
-            if (lane == 31) s_warp[warp] = inc;
-            __syncthreads();
-            if (warp == 0) {
-                int wv = s_warp[lane];
-                int winc = wv;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    int nn = __shfl_up_sync(0xffffffffu, winc, o);
-                    if (lane >= o) winc += nn;
-                }
-                s_warp[lane] = winc - wv;
-                if (lane == 31) {
-                    s_warp[32] = winc;
-                    if (winc) s_base = atomicAdd(&cnt->n_unique, (unsigned long long)winc);
-                }
-            }
-            __syncthreads();
-            if (s_warp[32]) {
-                size_t o = (size_t)s_base + s_warp[warp] + inc - mine;
+            const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
+            uint32_t wbase = 0;
+            if (lane == 0 && wtot) wbase = atomicAdd(&s_cursor[par], wtot);
+            wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            if (mine) {
+                const uint32_t pos0 = s_chunk_pos, nxt0 = s_next_base;
+                const uint32_t room = s_chunk_end - pos0;  // slots left in the current chunk
+                uint32_t o = wbase + inc - mine;
 #pragma unroll
                 for (int j = 0; j < kSlotsPer; j++) {
                     if (v[j] != kEmpty) {
                         const uint32_t cell = v[j] >> kLogTile, li = v[j] & (kTile - 1);
-                        a.keys[o] = tb * kp.cells + cell;
-                        a.first[o] = base + li;
-                        a.xy[o] = s_xy[li];
+                        const uint32_t p = o < room ? pos0 + o : nxt0 + (o - room);
+                        a.keys[p] = tb * kp.cells + cell;
+                        a.first[p] = base + li + a.first_offset;
+                        a.xy[p] = tile[li].x;
                         o++;
                     }
                 }
             }
-            __syncthreads();  // s_xy / s_hash / s_warp reusable
+            __syncthreads();  // S2: bitmap marked, table reset, tile and chunk state consumed
+            if (tid == 0) {
+                if (pend_chunk != kNoChunk) {  // requested one tile ago: has arrived by now
+                    s_next_base = pend_chunk * kChunk;
+                    pend_chunk = kNoChunk;
+                }
+                const uint32_t c = s_new[par];
+                const uint32_t room = s_chunk_end - s_chunk_pos;
+                if (c >= room) {  // spilled into the next chunk: make it current, request another
+                    const uint32_t nb0 = s_next_base;
+                    s_chunk_pos = nb0 + (c - room);
+                    s_chunk_end = nb0 + kChunk;
+                    s_next_base = kNoChunk;
+                    pend_chunk = (uint32_t)atomicAdd(&cnt->scratch[3], 1ull);
+                } else {
+                    s_chunk_pos += c;
+                }
+                s_new[par] = 0;
+                s_cursor[par] = 0;
+            }
         }
         if (COUNT_REP) {
-            int r = 0;
+            uint32_t r = 0;
             for (uint32_t i = tid; i < a.words; i += kThreads) r += __popc(s_rep[i]);
             r = __reduce_add_sync(0xffffffffu, r);
             if (lane == 0 && r) atomicAdd(&cnt->n_repeated, (unsigned long long)r);
         }
     }
+    if (tid == 0) {  // publish the two chunks this CTA leaves partly filled
+        if (pend_chunk != kNoChunk) s_next_base = pend_chunk * kChunk;
+        uint32_t* cl = a.chunk_list + 4 * blockIdx.x;
+        cl[0] = s_chunk_end - kChunk;
+        cl[1] = kChunk - (s_chunk_end - s_chunk_pos);
+        cl[2] = s_next_base;
+        cl[3] = 0;
+    }
+}
+
+// ---- fix-up: make the voxel shard dense -------------------------------------------------------
+// Chunks not listed are full.  U = total filled.  Every live slot at a position >= U is moved into
+// a hole (unfilled slot of a listed chunk) below U; the counts match by construction.
+constexpr int kMaxList = 1024;
+struct FixPlan {
+    uint32_t n_src, n_dst, total, pad;
+    uint32_t src_start[kMaxList + 2], src_prefix[kMaxList + 2];
+    uint32_t dst_start[kMaxList + 2], dst_prefix[kMaxList + 2];
+};
+
+__global__ void __launch_bounds__(kMaxList)
+    k_slab_fix_plan(const uint32_t* chunk_list, uint32_t n_list, DsCounters* cnt, FixPlan* plan) {
+    __shared__ uint32_t s_base[kMaxList], s_fill[kMaxList];
+    __shared__ uint32_t s_len[2][kMaxList + 2];
+    __shared__ unsigned long long s_holes;
+    if (cnt->slab_violation) return;
+    const uint32_t M = (uint32_t)cnt->scratch[3];  // chunks handed out
+    const uint32_t i = threadIdx.x;
+    if (i == 0) s_holes = 0;
+    __syncthreads();
+    if (i < n_list) {
+        s_base[i] = chunk_list[2 * i];
+        s_fill[i] = chunk_list[2 * i + 1];
+        atomicAdd(&s_holes, (unsigned long long)(kChunk - s_fill[i]));
+    }
+    __syncthreads();
+    const uint64_t U = (uint64_t)M * kChunk - s_holes;
+    const uint32_t m0 = (uint32_t)(U / kChunk);  // first chunk that may hold slots >= U
+    const uint32_t n_src = M - m0;               // <= n_list + 1 by construction
+    // destination segments: the part of each listed chunk's hole that lies below U
+    if (i < n_list) {
+        const uint64_t h0 = (uint64_t)s_base[i] + s_fill[i], h1 = (uint64_t)s_base[i] + kChunk;
+        const uint64_t e = h1 < U ? h1 : U;
+        plan->dst_start[i] = (uint32_t)h0;
+        s_len[1][i] = h0 < e ? (uint32_t)(e - h0) : 0;
+    }
+    // source segments: live slots at positions >= U, chunk by chunk
+    if (i < n_src && i <= kMaxList) {
+        const uint32_t m = m0 + i;
+        uint32_t fill = kChunk;
+        for (uint32_t q = 0; q < n_list; q++)
+            if (s_base[q] == m * kChunk) fill = s_fill[q];
+        const uint64_t l0 = (uint64_t)m * kChunk, l1 = l0 + fill;
+        const uint64_t s = l0 > U ? l0 : U;
+        plan->src_start[i] = (uint32_t)s;
+        s_len[0][i] = s < l1 ? (uint32_t)(l1 - s) : 0;
+    }
+    __syncthreads();
+    if (i == 0) {
+        cnt->n_unique = U;
+        uint32_t sp = 0, dp = 0;
+        const uint32_t ns = n_src <= kMaxList ? n_src : kMaxList;
+        for (uint32_t q = 0; q < ns; q++) {
+            plan->src_prefix[q] = sp;
+            sp += s_len[0][q];
+        }
+        plan->src_prefix[ns] = sp;
+        for (uint32_t q = 0; q < n_list; q++) {
+            plan->dst_prefix[q] = dp;
+            dp += s_len[1][q];
+        }
+        plan->dst_prefix[n_list] = dp;
+        plan->n_src = ns;
+        plan->n_dst = n_list;
+        plan->total = sp < dp ? sp : dp;
+        if (sp != dp || n_src > kMaxList) cnt->overflow = 1;  // cannot happen; checked by host
+    }
+}
+
+__device__ __forceinline__ uint32_t plan_locate(const uint32_t* start, const uint32_t* prefix,
+                                                uint32_t n, uint32_t j) {
+    uint32_t lo = 0, hi = n;  // last segment with prefix <= j (skips empty segments)
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (prefix[mid] <= j) lo = mid;
+        else hi = mid;
+    }
+    return start[lo] + (j - prefix[lo]);
+}
+
+__global__ void __launch_bounds__(256)
+    k_slab_fix_move(const FixPlan* plan, const DsCounters* cnt, uint64_t* keys, uint32_t* first,
+                    uint32_t* xy) {
+    if (cnt->slab_violation) return;
+    const uint32_t total = plan->total;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total;
+         j += gridDim.x * blockDim.x) {
+        const uint32_t s = plan_locate(plan->src_start, plan->src_prefix, plan->n_src, j);
+        const uint32_t d = plan_locate(plan->dst_start, plan->dst_prefix, plan->n_dst, j);
+        keys[d] = keys[s];
+        first[d] = first[s];
+        xy[d] = xy[s];
+    }
 }
 
 size_t slab_smem_bytes(uint32_t words, bool count_rep) {
-    return ((size_t)words * (count_rep ? 2 : 1) + kHash + kTile) * sizeof(uint32_t);
+    return (size_t)kStages * kTile * 16 + (size_t)kHash * 4 +
+           (size_t)words * (count_rep ? 2 : 1) * 4;
 }
-constexpr size_t kSmemLimit = 200 * 1024;
+constexpr size_t kSmemLimit = 220 * 1024;
 
 }  // namespace
+
+size_t evk_slab_scratch_bytes(int sm_count) {
+    return sizeof(FixPlan) + (size_t)sm_count * 4 * sizeof(uint32_t);
+}
 
 bool evk_slab_supported(const evk_handle* h, const KeyParams& kp) {
     if (kp.keyfn != EVK_KEY_VOXEL || kp.vt <= 0 || h->n_events == 0) return false;
     if (kp.cells >= (1ull << (32 - kLogTile))) return false;  // packed (cell, index) word
+    if (2 * h->sm_count > kMaxList) return false;
     const uint32_t words = (uint32_t)((kp.cells + 31) / 32);
     return slab_smem_bytes(words, true) <= kSmemLimit;
 }
@@ -250,6 +439,7 @@ bool evk_slab_supported(const evk_handle* h, const KeyParams& kp) {
 int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, bool* ok,
                         int* launches) {
     *ok = false;
+    const int grid = h->sm_count;
     SlabArgs a;
     a.kp = kp;
     a.ev = h->d_events;
@@ -259,11 +449,13 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
     a.first = h->d_first;
     a.xy = h->d_xy;
     a.cnt = h->d_cnt;
+    FixPlan* plan = reinterpret_cast<FixPlan*>(h->d_slab_scratch);
+    a.chunk_list = reinterpret_cast<uint32_t*>(plan + 1);
+    a.first_offset = (uint32_t)h->shard_first;
     a.words = (uint32_t)((kp.cells + 31) / 32);
     a.max_bins = (uint32_t)h->max_bins;
     // a single CTA walks a bin sequentially: with few bins and many events the table is faster
     a.min_bins = h->n_events > (1u << 22) ? 32 : 1;
-    a.count_repeated = count_repeated;
     const size_t smem = slab_smem_bytes(a.words, count_repeated != 0);
     if (count_repeated)
         EVK_CUDA(h, cudaFuncSetAttribute(k_slab_main<true>,
@@ -273,20 +465,23 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
         EVK_CUDA(h, cudaFuncSetAttribute(k_slab_main<false>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)kSmemLimit));
-    k_slab_bins<<<h->sm_count, 256, 0, h->stream>>>(a);
+    k_slab_bins<<<grid, 256, 0, h->stream>>>(a);
     EVK_CUDA(h, cudaGetLastError());
     if (h->profiling) cudaEventRecord(h->ev[5], h->stream);
     if (count_repeated)
-        k_slab_main<true><<<h->sm_count, kThreads, smem, h->stream>>>(a);
+        k_slab_main<true><<<grid, kThreads, smem, h->stream>>>(a);
     else
-        k_slab_main<false><<<h->sm_count, kThreads, smem, h->stream>>>(a);
+        k_slab_main<false><<<grid, kThreads, smem, h->stream>>>(a);
     EVK_CUDA(h, cudaGetLastError());
     if (h->profiling) cudaEventRecord(h->ev[6], h->stream);
-    *launches += 2;
+    k_slab_fix_plan<<<1, kMaxList, 0, h->stream>>>(a.chunk_list, 2 * grid, h->d_cnt, plan);
+    k_slab_fix_move<<<grid, 256, 0, h->stream>>>(plan, h->d_cnt, h->d_keys, h->d_first, h->d_xy);
+    EVK_CUDA(h, cudaGetLastError());
+    *launches += 4;
     // the verification flag decides whether the result stands
     EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,
                                 h->stream));
     EVK_CUDA(h, cudaStreamSynchronize(h->stream));
-    *ok = h->h_cnt->slab_violation == 0;
+    *ok = h->h_cnt->slab_violation == 0 && h->h_cnt->overflow == 0;
     return EVK_OK;
 }
