@@ -190,6 +190,7 @@ int evk_create(evk_handle** out, int device, size_t max_events) {
     ALLOC(h->d_acc, EVK_MAX_K * 5 * sizeof(unsigned long long));
     ALLOC(h->d_counts, EVK_MAX_K * sizeof(unsigned long long));
     ALLOC(h->d_shift, sizeof(float));
+    ALLOC(h->d_prune_lists, EVK_PRUNE_TILES * 16);
     ALLOC(h->d_cand, 2 * h->cand_cap * sizeof(uint32_t));
     ALLOC(h->d_flush, h->flush_bytes);
 #undef ALLOC
@@ -219,7 +220,7 @@ int evk_destroy(evk_handle* h) {
                     h->d_reps,   h->d_labels, h->d_perm,   h->d_sort_tmp, h->d_sort_a, h->d_sort_b,
                     h->d_sort_c, h->d_sk_in,  h->d_sk_out, h->d_si_in,  h->d_si_out, h->d_sv_tmp,
                     h->d_bin_start, h->d_slab_scratch, h->d_cnt, h->d_cent,   h->d_acc,    h->d_counts, h->d_shift,
-                    h->d_cand,   h->d_flush};
+                    h->d_cand,   h->d_flush, h->d_prune_lists};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
@@ -534,8 +535,15 @@ int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_done,
     prof_rec(h, 3);
     while (it < p->iters) {
         kl.write_labels = (p->tol >= 0.f || it == p->iters - 1) ? 1 : 0;
-        EVK_CUDA(h, evk_launch_km_assign(kl, xy, ev, h->d_first, n, h->d_cent, h->d_acc,
-                                         h->d_labels, h->sm_count, h->stream));
+        cudaError_t ce = cudaErrorNotSupported;
+        if (xy && h->have_ds)  // voxels are gated to the frame: exact candidate pruning applies
+            ce = evk_launch_km_assign_pruned(kl, h->ds.width, h->ds.height, h->d_prune_lists, xy, n,
+                                             h->d_cent, h->d_acc, h->d_labels, h->sm_count,
+                                             h->stream);
+        if (ce == cudaErrorNotSupported)
+            ce = evk_launch_km_assign(kl, xy, ev, h->d_first, n, h->d_cent, h->d_acc, h->d_labels,
+                                      h->sm_count, h->stream);
+        EVK_CUDA(h, ce);
         if (reduce) EVK_TRY(reduce(h, p->K, p->D));
         EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
                                            h->stream));

@@ -153,6 +153,7 @@ struct evk_handle {
     float* d_cent = nullptr;                 // [EVK_MAX_K * EVK_MAX_D]
     unsigned long long* d_acc = nullptr;     // [EVK_MAX_K * (EVK_MAX_D + 1)]
     unsigned long long* d_counts = nullptr;  // [EVK_MAX_K] counts of the last iteration
+    void* d_prune_lists = nullptr;           // [EVK_PRUNE_TILES] uint4 candidate lists
     float* d_shift = nullptr;                // [1]
     float* h_shift = nullptr;                // pinned
     size_t n_labels = 0;
@@ -244,6 +245,11 @@ cudaError_t evk_launch_km_assign(const KmLaunch& kl, const uint32_t* xy, const e
                                  const uint32_t* first, size_t n, const float* cent,
                                  unsigned long long* acc, int32_t* labels, int sm_count,
                                  cudaStream_t s);
+#define EVK_PRUNE_TILES 4096
+cudaError_t evk_launch_km_assign_pruned(const KmLaunch& kl, int width, int height, void* lists,
+                                        const uint32_t* xy, size_t n, const float* cent,
+                                        unsigned long long* acc, int32_t* labels, int sm_count,
+                                        cudaStream_t s);
 cudaError_t evk_launch_km_finalise(const KmLaunch& kl, float* cent, unsigned long long* acc,
                                    unsigned long long* counts, float* shift, cudaStream_t s);
 cudaError_t evk_launch_collect_below(const uint32_t* first, size_t n, uint32_t bound,

@@ -243,6 +243,164 @@ __global__ void __launch_bounds__(1024)
     }
 }
 
+// ---- exact candidate pruning (D == 2, voxels) ------------------------------------------------
+// The frame is cut into G x G pixel tiles.  For a tile T and centroid k let dmin(k) / dmax(k) be
+// the smallest / largest distance from c_k to any pixel of T.  With ub = min_k dmax(k), the
+// nearest centroid of EVERY pixel of T has dmin(k) <= ub, so only those k (ascending, which keeps
+// the lowest-k tie rule) need the contract arithmetic.  The test carries a relative + absolute
+// slack far above fp32 rounding, so the labels are bit-identical to the full scan; tiles with
+// more than 16 candidates are marked and scanned in full.
+constexpr int kListLen = 16;
+struct PruneGrid {
+    int32_t width, height, shift, tx, ty;
+};
+
+__global__ void __launch_bounds__(128)
+    k_km_candidates(KmLaunch kl, PruneGrid pg, const float* __restrict__ cent, uint4* lists) {
+    extern __shared__ float2 s_cc[];
+    for (int i = threadIdx.x; i < kl.K; i += blockDim.x)
+        s_cc[i] = reinterpret_cast<const float2*>(cent)[i];
+    __syncthreads();
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= pg.tx * pg.ty) return;
+    const int ty = t / pg.tx, tx = t - ty * pg.tx;
+    const float x0 = (float)(tx << pg.shift), y0 = (float)(ty << pg.shift);
+    const float x1 = (float)min(pg.width - 1, ((tx + 1) << pg.shift) - 1);
+    const float y1 = (float)min(pg.height - 1, ((ty + 1) << pg.shift) - 1);
+    float ub = INFINITY;
+    for (int k = 0; k < kl.K; k++) {
+        const float2 c = s_cc[k];
+        const float ax = fmaxf(fabsf(c.x - x0), fabsf(c.x - x1));
+        const float ay = fmaxf(fabsf(c.y - y0), fabsf(c.y - y1));
+        ub = fminf(ub, ax * ax + ay * ay);
+    }
+    const float lim = ub * 1.0001f + 0.01f;
+    unsigned char out[kListLen];
+#pragma unroll
+    for (int i = 0; i < kListLen; i++) out[i] = 0xFF;
+    int cnt = 0;
+    for (int k = 0; k < kl.K; k++) {
+        const float2 c = s_cc[k];
+        const float ix = fmaxf(0.f, fmaxf(x0 - c.x, c.x - x1));
+        const float iy = fmaxf(0.f, fmaxf(y0 - c.y, c.y - y1));
+        if (ix * ix + iy * iy <= lim) {
+#pragma unroll
+            for (int i = 0; i < kListLen; i++)
+                if (i == cnt) out[i] = (unsigned char)k;
+            cnt++;
+        }
+    }
+    if (cnt > kListLen) out[0] = 0xFE;  // too many candidates: full scan for this tile
+    uint4 w;
+    w.x = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
+    w.y = out[4] | (out[5] << 8) | (out[6] << 16) | ((uint32_t)out[7] << 24);
+    w.z = out[8] | (out[9] << 8) | (out[10] << 16) | ((uint32_t)out[11] << 24);
+    w.w = out[12] | (out[13] << 8) | (out[14] << 16) | ((uint32_t)out[15] << 24);
+    lists[t] = w;
+}
+
+constexpr int kRep = 8;  // accumulator copies: lane l adds into copy l % 8 (fewer same-address hits)
+__global__ void __launch_bounds__(kBlock)
+    k_km_assign_pruned(KmLaunch kl, PruneGrid pg, const uint4* __restrict__ lists,
+                       const uint32_t* __restrict__ xy, size_t n, const float* __restrict__ cent,
+                       unsigned long long* __restrict__ acc, int32_t* __restrict__ labels) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = kl.K;
+    float2* s_c = reinterpret_cast<float2*>(smem_raw);            // [K]
+    uint32_t* s_acc = reinterpret_cast<uint32_t*>(s_c + K);       // [kRep][3][K]
+    for (int i = threadIdx.x; i < K; i += kBlock) s_c[i] = reinterpret_cast<const float2*>(cent)[i];
+    for (int i = threadIdx.x; i < kRep * 3 * K; i += kBlock) s_acc[i] = 0;
+    __syncthreads();
+    uint32_t* my_acc = s_acc + (threadIdx.x & (kRep - 1)) * 3 * K;
+
+    const size_t n_chunks = (n + kChunk - 1) / kChunk;
+    for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const size_t cbase = c * (size_t)kChunk;
+        for (int r = 0; r < kChunk / (kBlock * kPPT); r++) {
+            const size_t base = cbase + (size_t)r * (kBlock * kPPT);
+            if (base >= n) break;
+            uint32_t w[kPPT];
+            uint4 lst[kPPT];
+#pragma unroll
+            for (int q = 0; q < kPPT; q++) {
+                const size_t i = base + (size_t)q * kBlock + threadIdx.x;
+                w[q] = i < n ? xy[i] : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < kPPT; q++) {
+                const uint32_t t = ((w[q] >> 16) >> pg.shift) * pg.tx + ((w[q] & 0xFFFFu) >> pg.shift);
+                lst[q] = __ldg(lists + t);
+            }
+#pragma unroll
+            for (int q = 0; q < kPPT; q++) {
+                const size_t i = base + (size_t)q * kBlock + threadIdx.x;
+                const bool ok = i < n;
+                const uint32_t ix = w[q] & 0xFFFFu, iy = w[q] >> 16;
+                const float px = (float)ix, py = (float)iy;
+                float best = kl.best2;
+                int lab = -1;
+                const bool full = (lst[q].x & 0xFFu) == 0xFEu;
+                if (__any_sync(0xffffffffu, full)) {
+                    if (full) {
+                        for (int k = 0; k < K; k++) {
+                            const float2 cc = s_c[k];
+                            const float dx = __fsub_rn(cc.x, px), dy = __fsub_rn(cc.y, py);
+                            const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+                            if (d2 < best) {
+                                best = d2;
+                                lab = k;
+                            }
+                        }
+                    }
+                }
+                if (!full) {
+                    const uint32_t lw[4] = {lst[q].x, lst[q].y, lst[q].z, lst[q].w};
+#pragma unroll
+                    for (int s = 0; s < kListLen; s++) {
+                        const uint32_t k = (lw[s >> 2] >> (8 * (s & 3))) & 0xFFu;
+                        if (k == 0xFFu) break;
+                        const float2 cc = s_c[k];
+                        const float dx = __fsub_rn(cc.x, px), dy = __fsub_rn(cc.y, py);
+                        const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+                        if (d2 < best) {
+                            best = d2;
+                            lab = (int)k;
+                        }
+                    }
+                }
+                if (ok) {
+                    if (kl.write_labels) labels[i] = lab;
+                    if (lab >= 0) {
+                        atomicAdd(&my_acc[lab], 1u);
+                        atomicAdd(&my_acc[K + lab], ix);
+                        atomicAdd(&my_acc[2 * K + lab], iy);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += kBlock) {
+            unsigned long long sc = 0, sx = 0, sy = 0;
+#pragma unroll
+            for (int rr = 0; rr < kRep; rr++) {
+                uint32_t* a = s_acc + rr * 3 * K;
+                sc += a[k];
+                sx += a[K + k];
+                sy += a[2 * K + k];
+                a[k] = 0;
+                a[K + k] = 0;
+                a[2 * K + k] = 0;
+            }
+            if (sc) {
+                atomicAdd(&acc[k * ACC_STRIDE + ACC_CNT], sc);
+                atomicAdd(&acc[k * ACC_STRIDE + ACC_X], sx);
+                atomicAdd(&acc[k * ACC_STRIDE + ACC_Y], sy);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // "first K voxel representatives in canonical order" == the first K distinct keys met when the
 // stream is walked in order.  One warp walks the head of the stream: lane l holds event base+l,
 // the 32 events are committed one after the other, the list of keys found so far is compared
@@ -329,6 +487,36 @@ cudaError_t evk_launch_km_assign(const KmLaunch& kl, const uint32_t* xy, const e
                        : launch_assign<4, 2>(kl, xy, ev, first, n, cent, acc, labels, sm_count, s);
     }
     return cudaErrorInvalidValue;
+}
+
+// D == 2 on the voxel shard with 16 < K <= 254: candidate lists per tile, then the pruned scan.
+// lists must hold EVK_PRUNE_TILES uint4.  Returns cudaErrorNotSupported when the shape does not fit.
+cudaError_t evk_launch_km_assign_pruned(const KmLaunch& kl, int width, int height, void* lists,
+                                        const uint32_t* xy, size_t n, const float* cent,
+                                        unsigned long long* acc, int32_t* labels, int sm_count,
+                                        cudaStream_t s) {
+    if (kl.D != 2 || kl.K <= 16 || kl.K > 254) return cudaErrorNotSupported;
+    PruneGrid pg;
+    pg.width = width;
+    pg.height = height;
+    pg.shift = 2;
+    for (;;) {
+        pg.tx = (width + (1 << pg.shift) - 1) >> pg.shift;
+        pg.ty = (height + (1 << pg.shift) - 1) >> pg.shift;
+        if ((long long)pg.tx * pg.ty <= EVK_PRUNE_TILES) break;
+        pg.shift++;
+    }
+    if (n == 0) return cudaSuccess;
+    const int tiles = pg.tx * pg.ty;
+    k_km_candidates<<<(tiles + 127) / 128, 128, kl.K * sizeof(float2), s>>>(
+        kl, pg, cent, reinterpret_cast<uint4*>(lists));
+    size_t chunks = (n + kChunk - 1) / kChunk;
+    size_t cap = (size_t)sm_count * 8;
+    int grid = (int)(chunks < cap ? chunks : cap);
+    size_t smem = (size_t)kl.K * sizeof(float2) + (size_t)kRep * 3 * kl.K * sizeof(uint32_t);
+    k_km_assign_pruned<<<grid, kBlock, smem, s>>>(kl, pg, reinterpret_cast<const uint4*>(lists),
+                                                  xy, n, cent, acc, labels);
+    return cudaGetLastError();
 }
 
 cudaError_t evk_launch_km_finalise(const KmLaunch& kl, float* cent, unsigned long long* acc,

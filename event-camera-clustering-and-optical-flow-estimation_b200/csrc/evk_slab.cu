@@ -3,11 +3,12 @@
 // Event streams are time-ordered (the SDK delivers them so: ACCEL/store.cpp:614-615), and the time
 // bin is the most significant part of the voxel key, so all events of one time bin are contiguous.
 // One CTA owns one time bin at a time and keeps the WHOLE key space of that bin on chip:
-//   s_seen   1 bit per spatial cell (NX*NY*P bits; 57.6 KB for Gen4 2x2 px + polarity)
-//   s_rep    1 bit per cell "hit at least twice" (the kernel's repeated_count semantics,
-//            ACCEL/build/coordinate_processor.cl:73-75)
-//   s_hash   a 4096-slot tile table of packed (cell << 11 | index-in-tile) words: a 32-bit
-//            atomicCAS claims, a 32-bit atomicMin keeps the LOWEST stream index
+//   s_map    2 bits per spatial cell: "seen" and "hit at least twice" (the kernel's
+//            repeated_count semantics, ACCEL/build/coordinate_processor.cl:73-75), 16 cells per
+//            word so one load answers both (115 KB for Gen4 2x2 px + polarity)
+//   s_hash   an 8192-slot tile table of packed (cell << 11 | index-in-tile) words: a 32-bit
+//            atomicCAS claims, a 32-bit atomicMin keeps the LOWEST stream index;
+//            after the barrier each candidate re-reads its slot: the survivor is the new voxel
 //   s_ev     a 2-stage ring of 2048-event tiles (32 KB each) filled by TMA bulk copies
 //            (cp.async.bulk + mbarrier complete_tx) issued one tile ahead by an elected thread
 // Per tile there are two block barriers and no global atomic: output slots come from a CTA-private
@@ -28,9 +29,8 @@ constexpr int kThreads = 1024;
 constexpr int kLogTile = 11;
 constexpr int kTile = 1 << kLogTile;    // events per tile
 constexpr int kPer = kTile / kThreads;  // events per thread per tile
-constexpr int kLogHash = kLogTile + 1;
-constexpr int kHash = 1 << kLogHash;    // tile table slots (load <= 0.5)
-constexpr int kSlotsPer = kHash / kThreads;
+constexpr int kLogHash = kLogTile + 2;
+constexpr int kHash = 1 << kLogHash;    // tile table slots (load <= 0.25)
 constexpr int kStages = 2;
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kChunk = EVK_SLAB_CHUNK;  // output slots per CTA-private chunk (>= 2 tiles)
@@ -135,12 +135,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* s_ev = reinterpret_cast<uint4*>(smem_raw);                        // [kStages][kTile]
     uint32_t* s_hash = reinterpret_cast<uint32_t*>(s_ev + kStages * kTile);  // [kHash]
-    uint32_t* s_seen = s_hash + kHash;                                       // [words]
-    uint32_t* s_rep = s_seen + a.words;                                      // [words] if COUNT_REP
+    // bin bitmap.  COUNT_REP: 16 cells per word, bit c = "seen", bit 16 + c = "hit at least twice"
+    // (one load answers both questions); else 32 cells per word, "seen" only.
+    uint32_t* s_map = s_hash + kHash;  // [words]
     __shared__ __align__(8) uint64_t s_bar[kStages];
     __shared__ uint32_t s_bin;
-    __shared__ uint32_t s_new[2];     // voxels claimed by the current tile (by tile parity)
-    __shared__ uint32_t s_cursor[2];  // slots handed out to warps within the tile
+    __shared__ uint32_t s_cursor[2];  // voxels emitted by the current tile (by tile parity)
     __shared__ uint32_t s_chunk_pos, s_chunk_end, s_next_base;
 
     DsCounters* cnt = a.cnt;
@@ -154,7 +154,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) mbar_init(&s_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_new[0] = s_new[1] = 0;
         s_cursor[0] = s_cursor[1] = 0;
         // two chunks up front: the current one and the one after it
         const uint32_t c0 = (uint32_t)atomicAdd(&cnt->scratch[3], 2ull);
@@ -185,10 +184,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
             mbar_expect_tx(bar, cntev * 16u);
             tma_load_1d(s_ev + (tile_seq % kStages) * kTile, a.ev + lo, cntev * 16u, bar);
         }
-        for (uint32_t i = tid; i < a.words; i += kThreads) {
-            s_seen[i] = 0;
-            if (COUNT_REP) s_rep[i] = 0;
-        }
+        for (uint32_t i = tid; i < a.words; i += kThreads) s_map[i] = 0;
         __syncthreads();
 
         for (uint32_t base = lo; base < hi; base += kTile, tile_seq++) {
@@ -206,9 +202,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
             }
             mbar_wait(&s_bar[stage], (tile_seq / kStages) & 1);
             // ---- phase A: classify against the bin bitmap, insert candidates in the tile table
-            uint32_t claimed = 0;
+            uint32_t cv[kPer], cslot[kPer], cxy[kPer];  // candidate word, its slot, its x|y<<16
+            bool cand[kPer];
 #pragma unroll
             for (int j = 0; j < kPer; j++) {
+                cand[j] = false;
+                cv[j] = cslot[j] = cxy[j] = 0;
                 const uint32_t li = j * kThreads + tid;
                 if (base + li >= hi) continue;
                 const uint4 ev = tile[li];
@@ -218,69 +217,65 @@ __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
                     continue;
                 }
                 const uint32_t cell = evk_cell(kp, ev);
-                const uint32_t w = cell >> 5, bit = 1u << (cell & 31);
-                if (s_seen[w] & bit) {  // seen in an earlier tile: duplicate
-                    if (COUNT_REP && !(s_rep[w] & bit)) atomicOr(&s_rep[w], bit);
+                const uint32_t w = COUNT_REP ? cell >> 4 : cell >> 5;
+                const uint32_t sbit = COUNT_REP ? 1u << (cell & 15) : 1u << (cell & 31);
+                const uint32_t rbit = sbit << 16;
+                const uint32_t wv = s_map[w];
+                if (wv & sbit) {  // emitted by an earlier tile: duplicate
+                    if (COUNT_REP && !(wv & rbit)) atomicOr(&s_map[w], rbit);
                     continue;
                 }
                 const uint32_t v = (cell << kLogTile) | li;
                 uint32_t s = hash_slot(cell);
                 for (;;) {
                     const uint32_t old = atomicCAS(&s_hash[s], kEmpty, v);
-                    if (old == kEmpty) {
-                        claimed++;
-                        break;
-                    }
-                    if ((old >> kLogTile) == cell) {
+                    if (old == kEmpty) break;
+                    if ((old >> kLogTile) == cell) {  // same cell inside this tile: keep the lowest
                         atomicMin(&s_hash[s], v);
-                        if (COUNT_REP && !(s_rep[w] & bit)) atomicOr(&s_rep[w], bit);
+                        if (COUNT_REP && !(wv & rbit)) atomicOr(&s_map[w], rbit);
                         break;
                     }
                     s = (s + 1) & (kHash - 1);
                 }
+                cand[j] = true;
+                cv[j] = v;
+                cslot[j] = s;
+                cxy[j] = ev.x;
             }
-            claimed = __reduce_add_sync(0xffffffffu, claimed);
-            if (lane == 0 && claimed) atomicAdd(&s_new[par], claimed);
-            __syncthreads();  // S1: tile table complete, s_new final
-            // ---- phase B: every occupied slot is one new voxel with its lowest index
-            uint32_t v[kSlotsPer];
-            uint32_t mine = 0;
+            __syncthreads();  // S1: tile table complete
+            // ---- phase B: a candidate whose word survived in its slot is a new voxel (lowest
+            // index of its cell in this tile, and no earlier tile had the cell)
+            uint32_t bal[kPer], wtot = 0;
 #pragma unroll
-            for (int j = 0; j < kSlotsPer; j++) {
-                const int s = j * kThreads + tid;
-                v[j] = s_hash[s];
-                if (v[j] != kEmpty) {
-                    mine++;
-                    s_hash[s] = kEmpty;
-                    const uint32_t cell = v[j] >> kLogTile;
-                    atomicOr(&s_seen[cell >> 5], 1u << (cell & 31));
+            for (int j = 0; j < kPer; j++) {
+                const bool win = cand[j] && s_hash[cslot[j]] == cv[j];
+                if (win) {
+                    s_hash[cslot[j]] = kEmpty;
+                    const uint32_t cell = cv[j] >> kLogTile;
+                    if (COUNT_REP) atomicOr(&s_map[cell >> 4], 1u << (cell & 15));
+                    else atomicOr(&s_map[cell >> 5], 1u << (cell & 31));
                 }
+                cand[j] = win;
+                bal[j] = __ballot_sync(0xffffffffu, win);
+                wtot += __popc(bal[j]);
             }
-            // warp-level slot allocation inside the tile (order within a tile is irrelevant)
-            uint32_t inc = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t nn = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += nn;
-            }
-            const uint32_t wtot = __shfl_sync(0xffffffffu, inc, 31);
             uint32_t wbase = 0;
             if (lane == 0 && wtot) wbase = atomicAdd(&s_cursor[par], wtot);
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            if (mine) {
+            {
                 const uint32_t pos0 = s_chunk_pos, nxt0 = s_next_base;
                 const uint32_t room = s_chunk_end - pos0;  // slots left in the current chunk
-                uint32_t o = wbase + inc - mine;
+                const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-                for (int j = 0; j < kSlotsPer; j++) {
-                    if (v[j] != kEmpty) {
-                        const uint32_t cell = v[j] >> kLogTile, li = v[j] & (kTile - 1);
+                for (int j = 0; j < kPer; j++) {
+                    if (cand[j]) {
+                        const uint32_t o = wbase + __popc(bal[j] & lt);
                         const uint32_t p = o < room ? pos0 + o : nxt0 + (o - room);
-                        a.keys[p] = tb * kp.cells + cell;
-                        a.first[p] = base + li + a.first_offset;
-                        a.xy[p] = tile[li].x;
-                        o++;
+                        a.keys[p] = tb * kp.cells + (cv[j] >> kLogTile);
+                        a.first[p] = base + (cv[j] & (kTile - 1)) + a.first_offset;
+                        a.xy[p] = cxy[j];
                     }
+                    wbase += __popc(bal[j]);
                 }
             }
             __syncthreads();  // S2: bitmap marked, table reset, tile and chunk state consumed
@@ -289,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
                     s_next_base = pend_chunk * kChunk;
                     pend_chunk = kNoChunk;
                 }
-                const uint32_t c = s_new[par];
+                const uint32_t c = s_cursor[par];  // voxels this tile emitted
                 const uint32_t room = s_chunk_end - s_chunk_pos;
                 if (c >= room) {  // spilled into the next chunk: make it current, request another
                     const uint32_t nb0 = s_next_base;
@@ -300,13 +295,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
                 } else {
                     s_chunk_pos += c;
                 }
-                s_new[par] = 0;
                 s_cursor[par] = 0;
             }
         }
         if (COUNT_REP) {
             uint32_t r = 0;
-            for (uint32_t i = tid; i < a.words; i += kThreads) r += __popc(s_rep[i]);
+            for (uint32_t i = tid; i < a.words; i += kThreads) r += __popc(s_map[i] >> 16);
             r = __reduce_add_sync(0xffffffffu, r);
             if (lane == 0 && r) atomicAdd(&cnt->n_repeated, (unsigned long long)r);
         }
@@ -416,9 +410,12 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-size_t slab_smem_bytes(uint32_t words, bool count_rep) {
+uint32_t map_words(uint64_t cells, bool count_rep) {
+    return (uint32_t)(count_rep ? (cells + 15) / 16 : (cells + 31) / 32);
+}
+size_t slab_smem_bytes(uint64_t cells, bool count_rep) {
     return (size_t)kStages * kTile * 16 + (size_t)kHash * 4 +
-           (size_t)words * (count_rep ? 2 : 1) * 4;
+           (size_t)map_words(cells, count_rep) * 4;
 }
 constexpr size_t kSmemLimit = 220 * 1024;
 
@@ -432,8 +429,7 @@ bool evk_slab_supported(const evk_handle* h, const KeyParams& kp) {
     if (kp.keyfn != EVK_KEY_VOXEL || kp.vt <= 0 || h->n_events == 0) return false;
     if (kp.cells >= (1ull << (32 - kLogTile))) return false;  // packed (cell, index) word
     if (2 * h->sm_count > kMaxList) return false;
-    const uint32_t words = (uint32_t)((kp.cells + 31) / 32);
-    return slab_smem_bytes(words, true) <= kSmemLimit;
+    return slab_smem_bytes(kp.cells, true) <= kSmemLimit;
 }
 
 int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, bool* ok,
@@ -452,11 +448,11 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
     FixPlan* plan = reinterpret_cast<FixPlan*>(h->d_slab_scratch);
     a.chunk_list = reinterpret_cast<uint32_t*>(plan + 1);
     a.first_offset = (uint32_t)h->shard_first;
-    a.words = (uint32_t)((kp.cells + 31) / 32);
+    a.words = map_words(kp.cells, count_repeated != 0);
     a.max_bins = (uint32_t)h->max_bins;
     // a single CTA walks a bin sequentially: with few bins and many events the table is faster
     a.min_bins = h->n_events > (1u << 22) ? 32 : 1;
-    const size_t smem = slab_smem_bytes(a.words, count_repeated != 0);
+    const size_t smem = slab_smem_bytes(kp.cells, count_repeated != 0);
     if (count_repeated)
         EVK_CUDA(h, cudaFuncSetAttribute(k_slab_main<true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
