@@ -1,25 +1,585 @@
-// evk_comm.cu — multi-GPU (one process per GPU) entry points.  Placeholder until the sharded
-// path lands: every call reports EVK_ERR_COMM.
+// evk_comm.cu — multi-GPU path: one process per GPU, NCCL over NVLink 5 / NVSwitch.
+//
+// The reference is single-device (one clCreateContext / one in-order queue per program:
+// ACCEL/store.cpp:237,277; KM/assign_to_centers2.c:171,207); this file is the build's addition
+// (SURVEY.md 8e).  Events are sharded by contiguous index range.  Two exchange schemes:
+//
+//  EVK_OWNER_TIME_RANGE (default; time-ordered streams).  Ownership of a voxel key is decided by
+//    its time bin: rank r owns every bin that starts inside its index shard.  Only the bin that
+//    straddles a shard boundary has events on two GPUs, so rank r+1 sends the head of its shard
+//    (a fixed block of `halo` events, one ncclSend/ncclRecv pair per neighbour) and rank r keeps
+//    the received events that belong to its last bin; rank r+1 skips them.  After that every bin
+//    is wholly on one GPU, the unchanged single-GPU kernels run, and no voxel has to move.  The
+//    slab kernel's partition check doubles as the check that the stream really is time-ordered;
+//    ranks agree on the outcome with one allreduce and otherwise fall through to
+//  EVK_OWNER_MIX64 (general).  owner = mix64(key) % G.  Local downsample, bucket the voxels by
+//    owner, exchange counts (allgather), NCCL all-to-all of (key, first index, xy, representative)
+//    with grouped send/recv, then the owner merges what it received in its hash-owned table
+//    (lowest global first index wins).
+//
+// K-means: each rank accumulates exact integer partial sums over its voxel shard; one
+// ncclAllReduce of K x 5 u64 per iteration; every rank finalises identical centroids.
+//
+// NCCL is bound at run time (dlopen "libnccl.so.2"): inside a PyTorch process this resolves to the
+// copy torch already loaded, so both share one NCCL.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+
 #include "evk_internal.cuh"
 
-extern "C" {
-int evk_comm_unique_id(uint8_t*) { return EVK_ERR_COMM; }
-int evk_comm_init(evk_handle* h, int, int, const uint8_t*) {
-    return evk_fail(h, EVK_ERR_COMM, "sharded path not built");
+namespace {
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+
+bool load_nccl() {
+    if (g_nccl.ok) return true;
+    void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) return false;
+    g_nccl.lib = lib;
+#define SYM(field, name)                                                    \
+    *reinterpret_cast<void**>(&g_nccl.field) = dlsym(lib, name);            \
+    if (!g_nccl.field) return false
+    SYM(GetUniqueId, "ncclGetUniqueId");
+    SYM(CommInitRank, "ncclCommInitRank");
+    SYM(CommDestroy, "ncclCommDestroy");
+    SYM(AllReduce, "ncclAllReduce");
+    SYM(AllGather, "ncclAllGather");
+    SYM(Broadcast, "ncclBroadcast");
+    SYM(Send, "ncclSend");
+    SYM(Recv, "ncclRecv");
+    SYM(GroupStart, "ncclGroupStart");
+    SYM(GroupEnd, "ncclGroupEnd");
+    SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+    g_nccl.ok = true;
+    return true;
 }
-int evk_comm_destroy(evk_handle*) { return EVK_OK; }
+
+constexpr int kMaxWorld = 64;
+constexpr int kBlock = 256;
+
+}  // namespace
+
+struct CommState {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1;
+    uint32_t halo = 1u << 18;              // events sent to the previous rank (4 MB)
+    unsigned long long* d_stats = nullptr;  // [8 + kMaxWorld * (kMaxWorld + 2)]
+    unsigned long long* h_stats = nullptr;  // pinned mirror
+    // general-mode staging (lazy): voxels bucketed by owner / received from peers
+    uint64_t *sk = nullptr, *rk = nullptr;
+    uint32_t *sf = nullptr, *rf = nullptr, *sx = nullptr, *rx = nullptr;
+    evk_event *sr = nullptr, *rr = nullptr;
+    size_t stage_cap = 0;
+    int last_mode = -1;
+};
+
+#define EVK_NCCL(h, expr)                                                                  \
+    do {                                                                                   \
+        ncclResult_t _r = (expr);                                                          \
+        if (_r != ncclSuccess)                                                             \
+            return evk_fail((h), EVK_ERR_COMM, "%s:%d %s: %s", __FILE__, __LINE__, #expr,  \
+                            g_nccl.GetErrorString(_r));                                    \
+    } while (0)
+
+namespace {
+
+// stats layout
+enum { ST_FLAG = 0, ST_U = 1, ST_R = 2, ST_SKIP = 3, ST_KEEP = 4, ST_HIST = 8 };
+
+// time-range halo: how many of my leading events belong to my first bin (they go to the previous
+// rank) and how many of the received events belong to the sender's first bin (I keep them)
+__global__ void k_halo_range(KeyParams kp, const evk_event* ev, uint32_t n_own, uint32_t halo,
+                             int rank, int world, unsigned long long* stats) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    unsigned long long flag = 0, skip = 0, keep = 0;
+    auto bin_of = [&](uint32_t i, bool& ok) -> uint64_t {
+        const int64_t t = ev[i].t;
+        ok = t >= kp.t0;
+        return ok ? evk_tbin(kp, t) : 0;
+    };
+    auto run_len = [&](uint32_t start, uint32_t len) -> uint32_t {  // events sharing ev[start]'s bin
+        bool ok;
+        const uint64_t b0 = bin_of(start, ok);
+        if (!ok) {
+            flag = 1;
+            return 0;
+        }
+        uint32_t lo = 0, hi = len;  // first offset whose bin differs (assumes time order; the slab
+        while (lo < hi) {           // kernel verifies the resulting partition)
+            const uint32_t mid = (lo + hi) >> 1;
+            bool ok2;
+            const uint64_t b = bin_of(start + mid, ok2);
+            if (ok2 && b == b0) lo = mid + 1;
+            else hi = mid;
+        }
+        return lo;
+    };
+    if (n_own < halo) flag = 1;  // my block for the previous rank is not all real events
+    if (!flag && rank > 0) {
+        skip = run_len(0, halo);
+        if (skip >= halo || skip >= n_own) flag = 1;  // first bin does not end inside the block
+    }
+    if (!flag && rank < world - 1) {
+        keep = run_len(n_own, halo);
+        if (keep >= halo) flag = 1;
+    }
+    stats[ST_FLAG] = flag;
+    stats[ST_SKIP] = skip;
+    stats[ST_KEEP] = keep;
+}
+
+__device__ __forceinline__ int owner_of(uint64_t key, int world) {
+    return (int)(evk_mix64(key ^ 0x9E3779B97F4A7C15ull) % (uint64_t)world);
+}
+
+__global__ void __launch_bounds__(kBlock)
+    k_owner_hist(const uint64_t* __restrict__ keys, size_t n, int world, unsigned long long* hist) {
+    __shared__ unsigned int s_h[kMaxWorld];
+    for (int i = threadIdx.x; i < world; i += kBlock) s_h[i] = 0;
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        atomicAdd(&s_h[owner_of(keys[i], world)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < world; i += kBlock)
+        if (s_h[i]) atomicAdd(&hist[i], (unsigned long long)s_h[i]);
+}
+
+__global__ void __launch_bounds__(kBlock)
+    k_owner_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ first,
+                    const uint32_t* __restrict__ xy, const evk_event* __restrict__ ev0, size_t n,
+                    int world, const unsigned long long* __restrict__ send_off,
+                    unsigned long long* cursor, uint64_t* sk, uint32_t* sf, uint32_t* sx,
+                    evk_event* sr) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t k = keys[i];
+        const int o = owner_of(k, world);
+        const size_t p = (size_t)send_off[o] + (size_t)atomicAdd(&cursor[o], 1ull);
+        const uint32_t f = first[i];
+        sk[p] = k;
+        sf[p] = f;
+        sx[p] = xy[i];
+        sr[p] = ev0[f];  // ev0 is indexable by global index
+    }
+}
+
+__device__ __forceinline__ uint64_t ld_relaxed_u64(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+
+// owner-side merge, pass 1: key -> lowest global first index
+__global__ void __launch_bounds__(kBlock)
+    k_merge_insert(const uint64_t* __restrict__ rk, const uint32_t* __restrict__ rf, size_t m,
+                   uint64_t* tkeys, uint32_t* tfirst, uint64_t mask) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        const uint64_t key = rk[i];
+        uint64_t slot = evk_mix64(key) & mask;
+        for (;;) {
+            uint64_t cur = ld_relaxed_u64(tkeys + slot);
+            if (cur == EVK_EMPTY_KEY)
+                cur = atomicCAS((unsigned long long*)(tkeys + slot), EVK_EMPTY_KEY, key);
+            if (cur == EVK_EMPTY_KEY || cur == key) {
+                atomicMin(tfirst + slot, rf[i]);
+                break;
+            }
+            slot = (slot + 1) & mask;
+        }
+    }
+}
+
+// pass 2: the record whose first index survived in the table is the voxel; compact the winners
+__global__ void __launch_bounds__(kBlock)
+    k_merge_emit(const uint64_t* __restrict__ rk, const uint32_t* __restrict__ rf,
+                 const uint32_t* __restrict__ rx, const evk_event* __restrict__ rr, size_t m,
+                 const uint64_t* __restrict__ tkeys, const uint32_t* __restrict__ tfirst,
+                 uint64_t mask, uint64_t* keys, uint32_t* first, uint32_t* xy, evk_event* reps,
+                 uint32_t* slot_out, DsCounters* cnt) {
+    const int lane = threadIdx.x & 31;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t m_pad = (m + 31) & ~(size_t)31;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m_pad; i += stride) {
+        bool win = false;
+        uint64_t key = 0;
+        uint32_t f = 0;
+        if (i < m) {
+            key = rk[i];
+            f = rf[i];
+            uint64_t slot = evk_mix64(key) & mask;
+            while (tkeys[slot] != key) slot = (slot + 1) & mask;
+            win = tfirst[slot] == f;
+            slot_out[i] = (uint32_t)slot;  // pass 3 resets exactly this slot
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, win);
+        unsigned long long base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&cnt->n_unique, (unsigned long long)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (win) {
+            const size_t o = (size_t)base + __popc(bal & ((1u << lane) - 1u));
+            keys[o] = key;
+            first[o] = f;
+            xy[o] = rx[i];
+            reps[o] = rr[i];
+        }
+    }
+}
+
+// pass 3: leave the table clean
+__global__ void __launch_bounds__(kBlock)
+    k_merge_reset(const uint32_t* __restrict__ slots, size_t m, uint64_t* tkeys, uint32_t* tfirst) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        const uint32_t slot = slots[i];  // records of one key write the same values: benign
+        tkeys[slot] = EVK_EMPTY_KEY;
+        tfirst[slot] = EVK_EMPTY_IDX;
+    }
+}
+
+int grid_for(size_t n, int sm) {
+    size_t need = (n + kBlock - 1) / kBlock;
+    size_t cap = (size_t)sm * 8;
+    return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+int stage_alloc(evk_handle* h, CommState* c) {
+    if (c->sk) return EVK_OK;
+    const size_t m = h->max_events;
+    EVK_CUDA(h, cudaMalloc(&c->sk, m * 8));
+    EVK_CUDA(h, cudaMalloc(&c->rk, m * 8));
+    EVK_CUDA(h, cudaMalloc(&c->sf, m * 4));
+    EVK_CUDA(h, cudaMalloc(&c->rf, m * 4));
+    EVK_CUDA(h, cudaMalloc(&c->sx, m * 4));
+    EVK_CUDA(h, cudaMalloc(&c->rx, m * 4));
+    EVK_CUDA(h, cudaMalloc(&c->sr, m * 16));
+    EVK_CUDA(h, cudaMalloc(&c->rr, m * 16));
+    if (!h->d_reps) EVK_CUDA(h, cudaMalloc(&h->d_reps, h->out_cap * 16));
+    c->stage_cap = m;
+    return EVK_OK;
+}
+
+// allreduce (sum) of the first `n` stats words, result mirrored to the host
+int stats_allreduce(evk_handle* h, CommState* c, int n) {
+    EVK_NCCL(h, g_nccl.AllReduce(c->d_stats, c->d_stats, n, ncclUint64, ncclSum, c->comm,
+                                 h->stream));
+    EVK_CUDA(h, cudaMemcpyAsync(c->h_stats, c->d_stats, n * 8, cudaMemcpyDeviceToHost, h->stream));
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EVK_OK;
+}
+
+int sharded_time_range(evk_handle* h, const evk_ds_params* p, bool* ok) {
+    CommState* c = h->comm;
+    *ok = false;
+    KeyParams kp;
+    EVK_TRY(evk_make_key_params(h, p, &kp));
+    const size_t n_own = h->n_events;
+    const uint32_t halo = c->halo;
+    if (n_own + halo > h->max_events)
+        return evk_fail(h, EVK_ERR_CAPACITY,
+                        "sharded downsample needs max_events >= n_events + %u (halo)", halo);
+    unsigned long long local_flag = evk_slab_supported(h, kp) ? 0 : 1;
+    // 1. boundary block: my head goes to the previous rank, the next rank's head arrives behind
+    //    my own events (contiguous in the global index space)
+    EVK_NCCL(h, g_nccl.GroupStart());
+    if (c->rank > 0)
+        EVK_NCCL(h, g_nccl.Send(h->d_events, (size_t)halo * 16, ncclUint8, c->rank - 1, c->comm,
+                                h->stream));
+    if (c->rank < c->world - 1)
+        EVK_NCCL(h, g_nccl.Recv(h->d_events + n_own, (size_t)halo * 16, ncclUint8, c->rank + 1,
+                                c->comm, h->stream));
+    EVK_NCCL(h, g_nccl.GroupEnd());
+    // 2. who keeps what
+    k_halo_range<<<1, 32, 0, h->stream>>>(kp, h->d_events, (uint32_t)n_own, halo, c->rank,
+                                          c->world, c->d_stats);
+    EVK_CUDA(h, cudaGetLastError());
+    EVK_CUDA(h, cudaMemcpyAsync(c->h_stats, c->d_stats, 8 * 8, cudaMemcpyDeviceToHost, h->stream));
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    local_flag |= c->h_stats[ST_FLAG];
+    const size_t skip = local_flag ? 0 : (size_t)c->h_stats[ST_SKIP];
+    const size_t keep = local_flag ? 0 : (size_t)c->h_stats[ST_KEEP];
+    // 3. the single-GPU path on my bins: events [skip, n_own + keep)
+    evk_event* ev_saved = h->d_events;
+    const uint64_t first_saved = h->shard_first;
+    int st = EVK_OK;
+    if (!local_flag) {
+        h->d_events = ev_saved + skip;
+        h->n_events = n_own - skip + keep;
+        h->shard_first = first_saved + skip;
+        evk_ds_params q = *p;
+        q.algo = EVK_ALGO_SLAB;
+        st = evk_downsample_local(h, &q);
+        if (st == EVK_OK && h->times.ds_algo_used != EVK_ALGO_SLAB) local_flag = 1;  // unordered
+        h->d_events = ev_saved;
+        h->n_events = n_own;
+        h->shard_first = first_saved;
+    }
+    if (st != EVK_OK) local_flag = 1;
+    // 4. all ranks agree
+    c->h_stats[ST_FLAG] = local_flag;
+    c->h_stats[ST_U] = local_flag ? 0 : h->n_unique;
+    c->h_stats[ST_R] = local_flag ? 0 : h->n_repeated;
+    EVK_CUDA(h, cudaMemcpyAsync(c->d_stats, c->h_stats, 3 * 8, cudaMemcpyHostToDevice, h->stream));
+    EVK_TRY(stats_allreduce(h, c, 3));
+    if (st != EVK_OK && c->h_stats[ST_FLAG] == 0) return st;
+    *ok = c->h_stats[ST_FLAG] == 0;
+    return EVK_OK;
+}
+
+int sharded_mix64(evk_handle* h, const evk_ds_params* p) {
+    CommState* c = h->comm;
+    const int G = c->world;
+    if (h->table_cap > (1ull << 32))
+        return evk_fail(h, EVK_ERR_CAPACITY, "hash-owned exchange supports max_events < 2^31");
+    EVK_TRY(stage_alloc(h, c));
+    evk_ds_params q = *p;
+    if (q.algo == EVK_ALGO_SLAB) q.algo = EVK_ALGO_AUTO;
+    EVK_TRY(evk_downsample_local(h, &q));  // local voxels, global first indices
+    const size_t U = h->n_unique;
+    unsigned long long* d_hist = c->d_stats + ST_HIST;          // [G] mine
+    unsigned long long* d_all = d_hist + kMaxWorld;             // [G][G] everyone's
+    unsigned long long* d_off = d_all + kMaxWorld * kMaxWorld;  // [G] send offsets
+    unsigned long long* d_cur = d_off + kMaxWorld;              // [G] cursors
+    EVK_CUDA(h, cudaMemsetAsync(d_hist, 0, kMaxWorld * 8, h->stream));
+    EVK_CUDA(h, cudaMemsetAsync(d_cur, 0, kMaxWorld * 8, h->stream));
+    if (U) k_owner_hist<<<grid_for(U, h->sm_count), kBlock, 0, h->stream>>>(h->d_keys, U, G, d_hist);
+    EVK_CUDA(h, cudaGetLastError());
+    EVK_NCCL(h, g_nccl.AllGather(d_hist, d_all, G, ncclUint64, c->comm, h->stream));
+    unsigned long long* hs = c->h_stats + ST_HIST;
+    EVK_CUDA(h, cudaMemcpyAsync(hs, d_all, (size_t)G * G * 8, cudaMemcpyDeviceToHost, h->stream));
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    // counts[src][dst] = hs[src * G + dst]
+    std::vector<unsigned long long> soff(G + 1, 0), roff(G + 1, 0);
+    for (int d = 0; d < G; d++) soff[d + 1] = soff[d] + hs[c->rank * G + d];
+    for (int s = 0; s < G; s++) roff[s + 1] = roff[s] + hs[s * G + c->rank];
+    const size_t M = (size_t)roff[G];
+    if (M > c->stage_cap || M > h->max_events)
+        return evk_fail(h, EVK_ERR_CAPACITY, "rank %d would own %zu voxels (capacity %zu)", c->rank,
+                        M, h->max_events);
+    EVK_CUDA(h, cudaMemcpyAsync(d_off, soff.data(), G * 8, cudaMemcpyHostToDevice, h->stream));
+    const evk_event* ev0 = h->d_events - h->shard_first;
+    if (U)
+        k_owner_scatter<<<grid_for(U, h->sm_count), kBlock, 0, h->stream>>>(
+            h->d_keys, h->d_first, h->d_xy, ev0, U, G, d_off, d_cur, c->sk, c->sf, c->sx, c->sr);
+    EVK_CUDA(h, cudaGetLastError());
+    // all-to-all of the voxel records (one grouped exchange; own bucket is a device copy)
+    EVK_NCCL(h, g_nccl.GroupStart());
+    for (int peer = 0; peer < G; peer++) {
+        const size_t sn = (size_t)(soff[peer + 1] - soff[peer]), so = (size_t)soff[peer];
+        const size_t rn = (size_t)(roff[peer + 1] - roff[peer]), ro = (size_t)roff[peer];
+        if (peer == c->rank) continue;
+        if (sn) {
+            EVK_NCCL(h, g_nccl.Send(c->sk + so, sn * 8, ncclUint8, peer, c->comm, h->stream));
+            EVK_NCCL(h, g_nccl.Send(c->sf + so, sn * 4, ncclUint8, peer, c->comm, h->stream));
+            EVK_NCCL(h, g_nccl.Send(c->sx + so, sn * 4, ncclUint8, peer, c->comm, h->stream));
+            EVK_NCCL(h, g_nccl.Send(c->sr + so, sn * 16, ncclUint8, peer, c->comm, h->stream));
+        }
+        if (rn) {
+            EVK_NCCL(h, g_nccl.Recv(c->rk + ro, rn * 8, ncclUint8, peer, c->comm, h->stream));
+            EVK_NCCL(h, g_nccl.Recv(c->rf + ro, rn * 4, ncclUint8, peer, c->comm, h->stream));
+            EVK_NCCL(h, g_nccl.Recv(c->rx + ro, rn * 4, ncclUint8, peer, c->comm, h->stream));
+            EVK_NCCL(h, g_nccl.Recv(c->rr + ro, rn * 16, ncclUint8, peer, c->comm, h->stream));
+        }
+    }
+    EVK_NCCL(h, g_nccl.GroupEnd());
+    {
+        const size_t sn = (size_t)(soff[c->rank + 1] - soff[c->rank]), so = (size_t)soff[c->rank];
+        const size_t ro = (size_t)roff[c->rank];
+        if (sn) {
+            EVK_CUDA(h, cudaMemcpyAsync(c->rk + ro, c->sk + so, sn * 8, cudaMemcpyDeviceToDevice, h->stream));
+            EVK_CUDA(h, cudaMemcpyAsync(c->rf + ro, c->sf + so, sn * 4, cudaMemcpyDeviceToDevice, h->stream));
+            EVK_CUDA(h, cudaMemcpyAsync(c->rx + ro, c->sx + so, sn * 4, cudaMemcpyDeviceToDevice, h->stream));
+            EVK_CUDA(h, cudaMemcpyAsync(c->rr + ro, c->sr + so, sn * 16, cudaMemcpyDeviceToDevice, h->stream));
+        }
+    }
+    // owner-side merge in the hash-owned table
+    EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
+    if (M) {
+        const uint64_t mask = (uint64_t)h->table_cap - 1;
+        const int grid = grid_for(M, h->sm_count);
+        k_merge_insert<<<grid, kBlock, 0, h->stream>>>(c->rk, c->rf, M, h->d_tkeys, h->d_tfirst, mask);
+        k_merge_emit<<<grid, kBlock, 0, h->stream>>>(c->rk, c->rf, c->rx, c->rr, M, h->d_tkeys,
+                                                     h->d_tfirst, mask, h->d_keys, h->d_first,
+                                                     h->d_xy, h->d_reps, c->sx, h->d_cnt);
+        k_merge_reset<<<grid, kBlock, 0, h->stream>>>(c->sx, M, h->d_tkeys, h->d_tfirst);
+        EVK_CUDA(h, cudaGetLastError());
+    }
+    EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost, h->stream));
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->n_unique = (size_t)h->h_cnt->n_unique;
+    h->n_repeated = 0;  // per-key hit counts are not exchanged in this mode
+    h->perm_valid = false;
+    h->reps_valid = true;
+    h->have_voxels = true;
+    c->h_stats[ST_FLAG] = 0;
+    c->h_stats[ST_U] = h->n_unique;
+    c->h_stats[ST_R] = 0;
+    EVK_CUDA(h, cudaMemcpyAsync(c->d_stats, c->h_stats, 3 * 8, cudaMemcpyHostToDevice, h->stream));
+    EVK_TRY(stats_allreduce(h, c, 3));
+    return EVK_OK;
+}
+
+int allreduce_acc(evk_handle* h, int K, int D) {
+    (void)D;
+    CommState* c = h->comm;
+    EVK_NCCL(h, g_nccl.AllReduce(h->d_acc, h->d_acc, (size_t)K * 5, ncclUint64, ncclSum, c->comm,
+                                 h->stream));
+    return EVK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int evk_comm_unique_id(uint8_t* id128) {
+    if (!id128 || !load_nccl()) return EVK_ERR_COMM;
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return EVK_ERR_COMM;
+    memcpy(id128, &id, 128);
+    return EVK_OK;
+}
+
+int evk_comm_init(evk_handle* h, int rank, int world, const uint8_t* id128) {
+    if (!h) return EVK_ERR_INVALID;
+    if (!id128 || world < 1 || world > kMaxWorld || rank < 0 || rank >= world)
+        return evk_fail(h, EVK_ERR_INVALID, "bad communicator shape rank=%d world=%d", rank, world);
+    if (!load_nccl()) return evk_fail(h, EVK_ERR_COMM, "libnccl.so.2 not found: %s", dlerror());
+    if (h->comm) evk_comm_destroy(h);
+    EVK_CUDA(h, cudaSetDevice(h->device));
+    CommState* c = new CommState();
+    c->rank = rank;
+    c->world = world;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    ncclResult_t r = g_nccl.CommInitRank(&c->comm, world, id, rank);
+    if (r != ncclSuccess) {
+        delete c;
+        return evk_fail(h, EVK_ERR_COMM, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+    }
+    const size_t words = ST_HIST + (size_t)kMaxWorld * (kMaxWorld + 3);
+    if (cudaMalloc(&c->d_stats, words * 8) != cudaSuccess ||
+        cudaMallocHost(&c->h_stats, words * 8) != cudaSuccess) {
+        delete c;
+        return evk_fail(h, EVK_ERR_NOMEM, "communicator scratch");
+    }
+    if ((size_t)c->halo * 4 > h->max_events) c->halo = (uint32_t)(h->max_events / 4);
+    h->comm = c;
+    return EVK_OK;
+}
+
+int evk_comm_destroy(evk_handle* h) {
+    if (!h || !h->comm) return EVK_OK;
+    CommState* c = h->comm;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
+    void* ptrs[] = {c->d_stats, c->sk, c->rk, c->sf, c->rf, c->sx, c->rx, c->sr, c->rr};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (c->h_stats) cudaFreeHost(c->h_stats);
+    delete c;
+    h->comm = nullptr;
+    return EVK_OK;
+}
+
 int evk_set_shard(evk_handle* h, uint64_t first_global_index) {
     if (!h) return EVK_ERR_INVALID;
+    if (first_global_index + h->max_events >= 0xFF000000ull)
+        return evk_fail(h, EVK_ERR_INVALID, "global indices must stay below 2^32");
     h->shard_first = first_global_index;
     return EVK_OK;
 }
-int evk_downsample_sharded(evk_handle* h, const evk_ds_params*, int, size_t*, size_t*) {
-    return evk_fail(h, EVK_ERR_COMM, "sharded path not built");
+
+int evk_downsample_sharded(evk_handle* h, const evk_ds_params* p, int owner_mode,
+                           size_t* n_unique_local, size_t* n_unique_global) {
+    if (!h) return EVK_ERR_INVALID;
+    if (!h->comm) return evk_fail(h, EVK_ERR_COMM, "evk_comm_init has not been called");
+    if (!p) return evk_fail(h, EVK_ERR_INVALID, "ds params are NULL");
+    CommState* c = h->comm;
+    EVK_CUDA(h, cudaSetDevice(h->device));
+    bool done = false;
+    if (owner_mode == EVK_OWNER_TIME_RANGE) {
+        EVK_TRY(sharded_time_range(h, p, &done));
+        if (done) c->last_mode = EVK_OWNER_TIME_RANGE;
+    } else if (owner_mode != EVK_OWNER_MIX64) {
+        return evk_fail(h, EVK_ERR_INVALID, "unknown owner mode %d", owner_mode);
+    }
+    if (!done) {
+        EVK_TRY(sharded_mix64(h, p));
+        c->last_mode = EVK_OWNER_MIX64;
+    }
+    if (n_unique_local) *n_unique_local = h->n_unique;
+    if (n_unique_global) *n_unique_global = (size_t)c->h_stats[ST_U];
+    return EVK_OK;
 }
-int evk_kmeans_sharded(evk_handle* h, const evk_km_params*, int*) {
-    return evk_fail(h, EVK_ERR_COMM, "sharded path not built");
+
+int evk_kmeans_sharded(evk_handle* h, const evk_km_params* p, int* iters_done) {
+    if (!h) return EVK_ERR_INVALID;
+    if (!h->comm) return evk_fail(h, EVK_ERR_COMM, "evk_comm_init has not been called");
+    if (p && p->on_events) return evk_fail(h, EVK_ERR_INVALID, "sharded k-means clusters voxels");
+    return evk_kmeans_run(h, p, iters_done, allreduce_acc);
 }
-int evk_init_centroids_first_k_sharded(evk_handle* h, const evk_km_params*) {
-    return evk_fail(h, EVK_ERR_COMM, "sharded path not built");
+
+int evk_init_centroids_first_k_sharded(evk_handle* h, const evk_km_params* p) {
+    if (!h) return EVK_ERR_INVALID;
+    if (!h->comm) return evk_fail(h, EVK_ERR_COMM, "evk_comm_init has not been called");
+    if (!p || p->K < 1 || p->K > EVK_MAX_K || p->D < 2 || p->D > EVK_MAX_D)
+        return evk_fail(h, EVK_ERR_INVALID, "bad k-means params");
+    if (!h->have_ds) return evk_fail(h, EVK_ERR_STATE, "evk_downsample_sharded has not run");
+    CommState* c = h->comm;
+    EVK_CUDA(h, cudaSetDevice(h->device));
+    // the K globally lowest first indices are the first K distinct keys of rank 0's shard
+    unsigned long long* d_found = c->d_stats + 5;
+    EVK_CUDA(h, cudaMemsetAsync(d_found, 0, 8, h->stream));
+    if (c->rank == 0) {
+        KmLaunch kl;
+        kl.K = p->K;
+        kl.D = p->D;
+        kl.best2 = 0.f;
+        kl.t_scale = p->t_scale;
+        kl.p_scale = p->p_scale;
+        kl.t0 = h->ds.t0_us;
+        kl.write_labels = 0;
+        const size_t n_scan = h->n_events < (1u << 20) ? h->n_events : (1u << 20);
+        if (n_scan)
+            EVK_CUDA(h, evk_launch_init_first_k_walk(h->kp, kl, h->d_events, n_scan, h->d_cent,
+                                                     d_found, h->stream));
+    }
+    EVK_NCCL(h, g_nccl.Broadcast(h->d_cent, h->d_cent, (size_t)p->K * p->D, ncclFloat, 0, c->comm,
+                                 h->stream));
+    EVK_NCCL(h, g_nccl.Broadcast(d_found, d_found, 1, ncclUint64, 0, c->comm, h->stream));
+    EVK_CUDA(h, cudaMemcpyAsync(c->h_stats + 5, d_found, 8, cudaMemcpyDeviceToHost, h->stream));
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (c->h_stats[5] != (unsigned long long)p->K)
+        return evk_fail(h, EVK_ERR_CAPACITY, "rank 0 holds only %llu distinct voxels in its first "
+                        "2^20 events (K=%d)", c->h_stats[5], p->K);
+    h->K = p->K;
+    h->D = p->D;
+    h->have_centroids = true;
+    return EVK_OK;
 }
-}
+
+}  // extern "C"
