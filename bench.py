@@ -205,7 +205,8 @@ def main():
             "slab": evk.ALGO_SLAB}[args.algo]
     ds = evk.ds_params(W, H, VOX[0], VOX[1], VOX[2], 0, VOX[3], algo=algo)
     km = evk.km_params(K, D, iters=1)
-    h = evk.Evk(n, device=local_rank)
+    # sharded runs receive the next rank's boundary block behind their own events
+    h = evk.Evk(n + (1 << 19) if world > 1 else n, device=local_rank)
     h.synth(evk.synth_params(SEED, n, W, H, RATE, N_BLOBS, first_index=rank * n))
     h.sync()
     if world > 1:
