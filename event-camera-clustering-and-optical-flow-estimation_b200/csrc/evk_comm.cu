@@ -172,16 +172,35 @@ __global__ void __launch_bounds__(kBlock)
                     int world, const unsigned long long* __restrict__ send_off,
                     unsigned long long* cursor, uint64_t* sk, uint32_t* sf, uint32_t* sx,
                     evk_event* sr) {
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint64_t k = keys[i];
-        const int o = owner_of(k, world);
-        const size_t p = (size_t)send_off[o] + (size_t)atomicAdd(&cursor[o], 1ull);
-        const uint32_t f = first[i];
-        sk[p] = k;
-        sf[p] = f;
-        sx[p] = xy[i];
-        sr[p] = ev0[f];  // ev0 is indexable by global index
+    // block-aggregated bucket cursors: one global atomic per (block tile, owner)
+    __shared__ unsigned int s_cnt[kMaxWorld];
+    __shared__ unsigned long long s_base[kMaxWorld];
+    const size_t n_pad = (n + kBlock - 1) / kBlock * kBlock;
+    for (size_t i0 = (size_t)blockIdx.x * kBlock; i0 < n_pad; i0 += (size_t)gridDim.x * kBlock) {
+        const size_t i = i0 + threadIdx.x;
+        for (int o = threadIdx.x; o < world; o += kBlock) s_cnt[o] = 0;
+        __syncthreads();
+        uint64_t k = 0;
+        int o = 0;
+        unsigned int local = 0;
+        if (i < n) {
+            k = keys[i];
+            o = owner_of(k, world);
+            local = atomicAdd(&s_cnt[o], 1u);
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < world; q += kBlock)
+            s_base[q] = s_cnt[q] ? atomicAdd(&cursor[q], (unsigned long long)s_cnt[q]) : 0ull;
+        __syncthreads();
+        if (i < n) {
+            const size_t p = (size_t)send_off[o] + (size_t)s_base[o] + local;
+            const uint32_t f = first[i];
+            sk[p] = k;
+            sf[p] = f;
+            sx[p] = xy[i];
+            sr[p] = ev0[f];  // ev0 is indexable by global index
+        }
+        __syncthreads();
     }
 }
 
