@@ -6,17 +6,15 @@
 //   s_map    2 bits per spatial cell: "seen" and "hit at least twice" (the kernel's
 //            repeated_count semantics, ACCEL/build/coordinate_processor.cl:73-75), 16 cells per
 //            word so one load answers both (115 KB for Gen4 2x2 px + polarity)
-//   s_hash   two 4096-slot tile tables (alternating) of packed (cell << 11 | index-in-tile) words:
-//            a 32-bit atomicCAS claims, a 32-bit atomicMin keeps the LOWEST stream index (SURVEY
-//            8a); after the tile's barrier each candidate re-reads its slot: the survivor commits
-//            with an atomicOr on s_map whose return value says whether the cell really is new
+//   s_hash   an 8192-slot tile table of packed (cell << 11 | index-in-tile) words: a 32-bit
+//            atomicCAS claims, a 32-bit atomicMin keeps the LOWEST stream index;
+//            after the barrier each candidate re-reads its slot: the survivor is the new voxel
 //   s_ev     a 2-stage ring of 2048-event tiles (32 KB each) filled by TMA bulk copies
-//            (cp.async.bulk + mbarrier complete_tx) issued two tiles ahead by an elected thread
-// Per tile there is ONE block barrier and no global atomic: commit of tile i overlaps with the
-// classification of tile i+1; output slots come from CTA-private chunks of the output arrays
-// (claimed from a global counter three tiles before they are needed, so the round trip is never
-// waited for); a tiny fix-up pass moves the tail of the last chunks into the holes so the voxel
-// shard is dense.  HBM sees each event read once and each voxel written once
+//            (cp.async.bulk + mbarrier complete_tx) issued one tile ahead by an elected thread
+// Per tile there are two block barriers and no global atomic: output slots come from a CTA-private
+// chunk of the output arrays (chunks are claimed from a global counter one chunk ahead, so the
+// round trip is never waited for); a tiny fix-up pass moves the tail of the last chunks into the
+// holes so the voxel shard is dense.  HBM sees each event read once and each voxel written once
 // (16 B SoA); no table lives in HBM.
 //
 // This is the "perfect-hash" specialisation of the mandated open-addressing table
@@ -31,14 +29,13 @@ constexpr int kThreads = 1024;
 constexpr int kLogTile = 11;
 constexpr int kTile = 1 << kLogTile;    // events per tile
 constexpr int kPer = kTile / kThreads;  // events per thread per tile
-constexpr int kLogHash = kLogTile + 1;
-constexpr int kHash = 1 << kLogHash;    // slots per tile table (two tables, load <= 0.5)
-constexpr int kListPerCta = 3;          // chunks a CTA can leave partly filled / untouched
+constexpr int kLogHash = kLogTile + 2;
+constexpr int kHash = 1 << kLogHash;    // tile table slots (load <= 0.25)
 constexpr int kStages = 2;
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kChunk = EVK_SLAB_CHUNK;  // output slots per CTA-private chunk (>= 2 tiles)
 constexpr uint32_t kNoChunk = 0xFFFFFFFFu;
-static_assert(kChunk >= 4 * kTile, "chunks are requested three tiles ahead");
+static_assert(kChunk >= 2 * kTile, "a fresh chunk must absorb a whole tile");
 
 struct SlabArgs {
     KeyParams kp;
@@ -133,18 +130,20 @@ __device__ __forceinline__ uint32_t hash_slot(uint32_t cell) {
     return (cell * 0x9E3779B1u) >> (32 - kLogHash);
 }
 
+constexpr int kTmaThread = kThreads - 32;  // lane 0 of the last warp issues the bulk copies;
+                                           // thread 0 keeps the output-chunk bookkeeping
 template <bool COUNT_REP, bool POW2>
 __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint4* s_ev = reinterpret_cast<uint4*>(smem_raw);                        // [2][kTile]
-    uint32_t* s_hash = reinterpret_cast<uint32_t*>(s_ev + kStages * kTile);  // [2][kHash]
+    uint4* s_ev = reinterpret_cast<uint4*>(smem_raw);                        // [kStages][kTile]
+    uint32_t* s_hash = reinterpret_cast<uint32_t*>(s_ev + kStages * kTile);  // [kHash]
     // bin bitmap.  COUNT_REP: 16 cells per word, bit c = "seen", bit 16 + c = "hit at least twice"
     // (one load answers both questions); else 32 cells per word, "seen" only.
-    uint32_t* s_map = s_hash + 2 * kHash;  // [words]
+    uint32_t* s_map = s_hash + kHash;  // [words]
     __shared__ __align__(8) uint64_t s_bar[kStages];
     __shared__ uint32_t s_bin;
-    __shared__ uint32_t s_total;          // voxels emitted by this CTA so far (never reset)
-    __shared__ uint32_t s_chunk_base[4];  // ring: output base of the CTA's q-th chunk at [q & 3]
+    __shared__ uint32_t s_cursor[2];  // voxels emitted by the current tile (by tile parity)
+    __shared__ uint32_t s_chunk_pos, s_chunk_end, s_next_base;
 
     DsCounters* cnt = a.cnt;
     if (cnt->slab_violation) return;
@@ -152,20 +151,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
     const uint32_t nb = (uint32_t)cnt->scratch[0];
     const uint64_t tb0 = cnt->scratch[2];
     const int tid = threadIdx.x, lane = tid & 31;
-    const uint32_t lt = (1u << lane) - 1u;
 
-    for (int i = tid; i < 2 * kHash; i += kThreads) s_hash[i] = kEmpty;
-    uint32_t claimed = 2;            // thread 0: chunks this CTA owns
-    uint32_t pend_chunk = kNoChunk;  // thread 0: chunk requested, not yet published
+    for (int i = tid; i < kHash; i += kThreads) s_hash[i] = kEmpty;
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) mbar_init(&s_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_total = 0;
+        s_cursor[0] = s_cursor[1] = 0;
+        // two chunks up front: the current one and the one after it
         const uint32_t c0 = (uint32_t)atomicAdd(&cnt->scratch[3], 2ull);
-        s_chunk_base[0] = c0 * kChunk;
-        s_chunk_base[1] = (c0 + 1) * kChunk;
+        s_chunk_pos = c0 * kChunk;
+        s_chunk_end = s_chunk_pos + kChunk;
+        s_next_base = (c0 + 1) * kChunk;
     }
-    uint32_t tile_seq = 0;  // tiles consumed by this CTA: stage = seq & 1, mbarrier parity = seq >> 1
+    uint32_t pend_chunk = kNoChunk;  // thread 0: chunk index requested but not yet published
+    uint32_t tile_seq = 0;           // tiles consumed by this CTA (stage = seq % kStages)
 
     for (;;) {
         __syncthreads();
@@ -182,39 +181,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
         const uint64_t tb = tb0 + b;
         const int64_t t_lo = kp.t0 + (int64_t)(tb * (uint64_t)kp.vt);
         const uint64_t key_base = tb * kp.cells;
-        const uint32_t n_tiles = (hi - lo + kTile - 1) >> kLogTile;
-        if (tid == 0) {  // the first two tiles of the bin
-            for (uint32_t q = 0; q < 2 && q < n_tiles; q++) {
-                const uint32_t st = (tile_seq + q) & 1, from = lo + q * kTile;
-                const uint32_t bytes = min((uint32_t)kTile, hi - from) * 16u;
-                mbar_expect_tx(&s_bar[st], bytes);
-                tma_load_1d(s_ev + st * kTile, a.ev + from, bytes, &s_bar[st]);
-            }
+        if (tid == kTmaThread) {  // first tile of the bin
+            const uint32_t cntev = min((uint32_t)kTile, hi - lo);
+            uint64_t* bar = &s_bar[tile_seq % kStages];
+            mbar_expect_tx(bar, cntev * 16u);
+            tma_load_1d(s_ev + (tile_seq % kStages) * kTile, a.ev + lo, cntev * 16u, bar);
         }
         for (uint32_t i = tid; i < a.words; i += kThreads) s_map[i] = 0;
         __syncthreads();
 
-        for (uint32_t ti = 0; ti < n_tiles; ti++, tile_seq++) {
-            const uint32_t base = lo + ti * kTile;
-            const uint32_t p = tile_seq & 1;
-            const uint4* tile = s_ev + p * kTile;
-            uint32_t* hash = s_hash + p * kHash;
-            mbar_wait(&s_bar[p], (tile_seq >> 1) & 1);
-            // ---- phase A: bitmap hint, candidates into this tile's table
-            uint32_t cv[kPer], cslot[kPer], cxy[kPer];  // candidate word, its slot, its x|y<<16
-            bool cand[kPer];
+        for (uint32_t base = lo; base < hi; base += kTile, tile_seq++) {
+            const uint32_t stage = tile_seq % kStages, par = tile_seq & 1;
+            const uint4* tile = s_ev + stage * kTile;
+            // the next tile goes into the other stage, which every thread left before the barrier
+            // that ended the previous tile
+            if (tid == kTmaThread && base + kTile < hi) {
+                const uint32_t nxt = base + kTile;
+                const uint32_t cntev = min((uint32_t)kTile, hi - nxt);
+                uint64_t* bar = &s_bar[(tile_seq + 1) % kStages];
+                mbar_expect_tx(bar, cntev * 16u);
+                tma_load_1d(s_ev + ((tile_seq + 1) % kStages) * kTile, a.ev + nxt, cntev * 16u,
+                            bar);
+            }
+            mbar_wait(&s_bar[stage], (tile_seq / kStages) & 1);
+            // ---- phase A: classify against the bin bitmap, insert candidates in the tile table
+            // cv: candidate word (cell << 11 | index in tile) or kEmpty; its slot; its x|y<<16
+            uint32_t cv[kPer], cslot[kPer], cxy[kPer];
 #pragma unroll
-            for (int j = 0; j < kPer; j++) {
-                cand[j] = false;
+            for (int j = 0; j < kPer; j++) {  // classification: independent per event (ILP)
                 const uint32_t li = j * kThreads + tid;
                 const uint4 ev = tile[li];
                 const uint32_t x = ev.x & 0xFFFFu, y = ev.x >> 16;
-                const bool inb = (base + li < hi) & (x < (uint32_t)kp.width) & (y < (uint32_t)kp.height);
-                if (!inb) continue;
-                if ((uint64_t)(ev_t(ev) - t_lo) >= (uint64_t)kp.vt) {  // not an event of this bin
-                    atomicOr(&cnt->slab_violation, 1u);
-                    continue;
-                }
+                bool ok = (base + li < hi) & (x < (uint32_t)kp.width) & (y < (uint32_t)kp.height);
+                const bool inbin = (uint64_t)(ev_t(ev) - t_lo) < (uint64_t)kp.vt;
+                if (ok & !inbin) atomicOr(&cnt->slab_violation, 1u);  // not an event of this bin
+                ok &= inbin;
                 uint32_t cell;
                 if (POW2) cell = (y >> kp.sy) * kp.NX + (x >> kp.sx);
                 else cell = (kp.sy >= 0 ? y >> kp.sy : __umulhi(y, kp.my)) * kp.NX +
@@ -222,83 +223,87 @@ __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
                 if (kp.use_p) cell = cell * 2u + ev_pbit(ev);
                 const uint32_t w = COUNT_REP ? cell >> 4 : cell >> 5;
                 const uint32_t sbit = 1u << (cell & (COUNT_REP ? 15u : 31u));
-                const uint32_t wv = s_map[w];
-                if (wv & sbit) {  // emitted earlier in this bin: duplicate
-                    if (COUNT_REP && !(wv & (sbit << 16))) atomicOr(&s_map[w], sbit << 16);
-                    continue;
-                }
-                const uint32_t v = (cell << kLogTile) | li;
-                uint32_t s = hash_slot(cell);
+                const uint32_t wv = ok ? s_map[w] : 0xFFFFFFFFu;  // gated events: nothing to do
+                if (COUNT_REP && (wv & sbit) && !(wv & (sbit << 16)))
+                    atomicOr(&s_map[w], sbit << 16);  // duplicate of an earlier tile's voxel
+                cv[j] = (wv & sbit) ? kEmpty : ((cell << kLogTile) | li);
+                cxy[j] = ev.x;
+                cslot[j] = hash_slot(cell);
+            }
+#pragma unroll
+            for (int j = 0; j < kPer; j++) {  // insertion into the tile table
+                if (cv[j] == kEmpty) continue;
+                const uint32_t cell = cv[j] >> kLogTile;
+                uint32_t s = cslot[j];
                 for (;;) {
-                    const uint32_t old = atomicCAS(&hash[s], kEmpty, v);
+                    const uint32_t old = atomicCAS(&s_hash[s], kEmpty, cv[j]);
                     if (old == kEmpty) break;
                     if ((old >> kLogTile) == cell) {  // same cell inside this tile: keep the lowest
-                        atomicMin(&hash[s], v);
-                        if (COUNT_REP && !(wv & (sbit << 16))) atomicOr(&s_map[w], sbit << 16);
+                        atomicMin(&s_hash[s], cv[j]);
+                        if (COUNT_REP) atomicOr(&s_map[cell >> 4], 1u << (16 + (cell & 15)));
                         break;
                     }
                     s = (s + 1) & (kHash - 1);
                 }
-                cand[j] = true;
-                cv[j] = v;
                 cslot[j] = s;
-                cxy[j] = ev.x;
             }
-            __syncthreads();  // the only barrier of the tile: table complete, stage p consumed
-            if (tid == 0) {
-                if (ti + 2 < n_tiles) {  // stage p is free again: tile ti + 2
-                    const uint32_t from = base + 2 * kTile;
-                    const uint32_t bytes = min((uint32_t)kTile, hi - from) * 16u;
-                    mbar_expect_tx(&s_bar[p], bytes);
-                    tma_load_1d(s_ev + p * kTile, a.ev + from, bytes, &s_bar[p]);
-                }
-                // chunk ring: publish the chunk requested one tile ago; request the next one three
-                // tiles before the cursor can reach it (nobody waits for the round trip)
-                if (pend_chunk != kNoChunk) {
-                    s_chunk_base[claimed & 3] = pend_chunk * kChunk;
-                    claimed++;
-                    pend_chunk = kNoChunk;
-                } else if (*(volatile uint32_t*)&s_total + 3u * kTile >= claimed * kChunk) {
-                    pend_chunk = (uint32_t)atomicAdd(&cnt->scratch[3], 1ull);
-                }
-            }
-            // ---- phase B: a candidate whose word survived in its slot is the lowest index of its
-            // cell in this tile; the atomicOr on the bin bitmap decides whether the cell is new
+            __syncthreads();  // S1: tile table complete
+            // ---- phase B: a candidate whose word survived in its slot is a new voxel (lowest
+            // index of its cell in this tile, and no earlier tile had the cell)
             uint32_t bal[kPer], wtot = 0;
+            bool cand[kPer];
 #pragma unroll
             for (int j = 0; j < kPer; j++) {
-                bool win = cand[j] && hash[cslot[j]] == cv[j];
+                const bool win = cv[j] != kEmpty && s_hash[cslot[j]] == cv[j];
                 if (win) {
-                    hash[cslot[j]] = kEmpty;
+                    s_hash[cslot[j]] = kEmpty;
                     const uint32_t cell = cv[j] >> kLogTile;
-                    const uint32_t w = COUNT_REP ? cell >> 4 : cell >> 5;
-                    const uint32_t sbit = 1u << (cell & (COUNT_REP ? 15u : 31u));
-                    const uint32_t old = atomicOr(&s_map[w], sbit);
-                    if (old & sbit) {  // an earlier tile emitted it while this one was in flight
-                        win = false;
-                        if (COUNT_REP && !(old & (sbit << 16))) atomicOr(&s_map[w], sbit << 16);
-                    }
+                    if (COUNT_REP) atomicOr(&s_map[cell >> 4], 1u << (cell & 15));
+                    else atomicOr(&s_map[cell >> 5], 1u << (cell & 31));
                 }
                 cand[j] = win;
                 bal[j] = __ballot_sync(0xffffffffu, win);
                 wtot += __popc(bal[j]);
             }
             uint32_t wbase = 0;
-            if (lane == 0 && wtot) wbase = atomicAdd(&s_total, wtot);
+            if (lane == 0 && wtot) wbase = atomicAdd(&s_cursor[par], wtot);
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
+            {
+                const uint32_t pos0 = s_chunk_pos, nxt0 = s_next_base;
+                const uint32_t room = s_chunk_end - pos0;  // slots left in the current chunk
+                const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
-            for (int j = 0; j < kPer; j++) {
-                if (cand[j]) {
-                    const uint32_t L = wbase + __popc(bal[j] & lt);
-                    const uint32_t pos = s_chunk_base[(L / kChunk) & 3] + (L & (kChunk - 1));
-                    a.keys[pos] = key_base + (cv[j] >> kLogTile);
-                    a.first[pos] = base + (cv[j] & (kTile - 1)) + a.first_offset;
-                    a.xy[pos] = cxy[j];
+                for (int j = 0; j < kPer; j++) {
+                    if (cand[j]) {
+                        const uint32_t o = wbase + __popc(bal[j] & lt);
+                        const uint32_t p = o < room ? pos0 + o : nxt0 + (o - room);
+                        a.keys[p] = key_base + (cv[j] >> kLogTile);
+                        a.first[p] = base + (cv[j] & (kTile - 1)) + a.first_offset;
+                        a.xy[p] = cxy[j];
+                    }
+                    wbase += __popc(bal[j]);
                 }
-                wbase += __popc(bal[j]);
+            }
+            __syncthreads();  // S2: bitmap marked, table reset, tile and chunk state consumed
+            if (tid == 0) {
+                if (pend_chunk != kNoChunk) {  // requested one tile ago: has arrived by now
+                    s_next_base = pend_chunk * kChunk;
+                    pend_chunk = kNoChunk;
+                }
+                const uint32_t c = s_cursor[par];  // voxels this tile emitted
+                const uint32_t room = s_chunk_end - s_chunk_pos;
+                if (c >= room) {  // spilled into the next chunk: make it current, request another
+                    const uint32_t nb0 = s_next_base;
+                    s_chunk_pos = nb0 + (c - room);
+                    s_chunk_end = nb0 + kChunk;
+                    s_next_base = kNoChunk;
+                    pend_chunk = (uint32_t)atomicAdd(&cnt->scratch[3], 1ull);
+                } else {
+                    s_chunk_pos += c;
+                }
+                s_cursor[par] = 0;
             }
         }
-        __syncthreads();  // every warp has committed the last tile: the bitmap is final
         if (COUNT_REP) {
             uint32_t r = 0;
             for (uint32_t i = tid; i < a.words; i += kThreads) r += __popc(s_map[i] >> 16);
@@ -306,25 +311,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
             if (lane == 0 && r) atomicAdd(&cnt->n_repeated, (unsigned long long)r);
         }
     }
-    if (tid == 0) {  // publish the chunks this CTA leaves partly filled or untouched
-        if (pend_chunk != kNoChunk) {
-            s_chunk_base[claimed & 3] = pend_chunk * kChunk;
-            claimed++;
-        }
-        const uint32_t total = s_total;
-        const uint32_t q_cur = total / kChunk;
-        uint32_t* cl = a.chunk_list + 2 * kListPerCta * blockIdx.x;
-        for (uint32_t e = 0; e < kListPerCta; e++) {
-            const uint32_t q = q_cur + e;
-            if (q < claimed) {
-                cl[2 * e] = s_chunk_base[q & 3];
-                cl[2 * e + 1] = e == 0 ? total - q_cur * kChunk : 0u;
-            } else {
-                cl[2 * e] = kNoChunk;
-                cl[2 * e + 1] = kChunk;
-            }
-        }
-        if (claimed > q_cur + kListPerCta) atomicOr(&cnt->overflow, 1u);
+    if (tid == 0) {  // publish the two chunks this CTA leaves partly filled
+        if (pend_chunk != kNoChunk) s_next_base = pend_chunk * kChunk;
+        uint32_t* cl = a.chunk_list + 4 * blockIdx.x;
+        cl[0] = s_chunk_end - kChunk;
+        cl[1] = kChunk - (s_chunk_end - s_chunk_pos);
+        cl[2] = s_next_base;
+        cl[3] = 0;
     }
 }
 
@@ -350,7 +343,7 @@ __global__ void __launch_bounds__(kMaxList)
     __syncthreads();
     if (i < n_list) {
         s_base[i] = chunk_list[2 * i];
-        s_fill[i] = s_base[i] == kNoChunk ? kChunk : chunk_list[2 * i + 1];  // unused list entry
+        s_fill[i] = chunk_list[2 * i + 1];
         atomicAdd(&s_holes, (unsigned long long)(kChunk - s_fill[i]));
     }
     __syncthreads();
@@ -427,7 +420,7 @@ uint32_t map_words(uint64_t cells, bool count_rep) {
     return (uint32_t)(count_rep ? (cells + 15) / 16 : (cells + 31) / 32);
 }
 size_t slab_smem_bytes(uint64_t cells, bool count_rep) {
-    return (size_t)kStages * kTile * 16 + (size_t)2 * kHash * 4 +
+    return (size_t)kStages * kTile * 16 + (size_t)kHash * 4 +
            (size_t)map_words(cells, count_rep) * 4;
 }
 constexpr size_t kSmemLimit = 220 * 1024;
@@ -435,13 +428,13 @@ constexpr size_t kSmemLimit = 220 * 1024;
 }  // namespace
 
 size_t evk_slab_scratch_bytes(int sm_count) {
-    return sizeof(FixPlan) + (size_t)sm_count * 2 * kListPerCta * sizeof(uint32_t);
+    return sizeof(FixPlan) + (size_t)sm_count * 4 * sizeof(uint32_t);
 }
 
 bool evk_slab_supported(const evk_handle* h, const KeyParams& kp) {
     if (kp.keyfn != EVK_KEY_VOXEL || kp.vt <= 0 || h->n_events == 0) return false;
     if (kp.cells >= (1ull << (32 - kLogTile))) return false;  // packed (cell, index) word
-    if (kListPerCta * h->sm_count > kMaxList) return false;
+    if (2 * h->sm_count > kMaxList) return false;
     return slab_smem_bytes(kp.cells, true) <= kSmemLimit;
 }
 
@@ -478,7 +471,7 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
     kern<<<grid, kThreads, smem, h->stream>>>(a);
     EVK_CUDA(h, cudaGetLastError());
     if (h->profiling) cudaEventRecord(h->ev[6], h->stream);
-    k_slab_fix_plan<<<1, kMaxList, 0, h->stream>>>(a.chunk_list, kListPerCta * grid, h->d_cnt, plan);
+    k_slab_fix_plan<<<1, kMaxList, 0, h->stream>>>(a.chunk_list, 2 * grid, h->d_cnt, plan);
     k_slab_fix_move<<<grid, 256, 0, h->stream>>>(plan, h->d_cnt, h->d_keys, h->d_first, h->d_xy);
     EVK_CUDA(h, cudaGetLastError());
     *launches += 4;
