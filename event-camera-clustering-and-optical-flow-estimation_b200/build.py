@@ -20,7 +20,8 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std
 
 
 def _deps():
-    out = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    out = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if not f.endswith(".o")]
+    out += [os.path.join(HERE, "host", f) for f in os.listdir(os.path.join(HERE, "host"))]
     inc = os.path.join(os.path.dirname(HERE), "include")
     out += [os.path.join(inc, f) for f in os.listdir(inc)]
     return out
@@ -47,6 +48,14 @@ def build(force=False, verbose=False):
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)
         raise RuntimeError("link failed")
+    # C++ host demo over the C-ABI (the reference's store sample without the SDK)
+    demo = os.path.join(HERE, "store_replay")
+    cmd = ["/usr/bin/g++", "-std=c++17", "-O2", os.path.join(HERE, "host", "store_replay.cpp"),
+           "-L" + HERE, "-levk", "-Wl,-rpath,$ORIGIN", "-o", demo]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError("host demo build failed")
     with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

@@ -1,0 +1,163 @@
+// evk.hpp — C++17 RAII view of the C-ABI (include/evk.h) with the reference's call shape.
+//
+// The reference wires everything inside main(): an SDK callback packs events
+// (ACCEL/store.cpp:570-611), a reslicer fires on_new_slice every 50 ms (:349-352,370), which
+// uploads, launches process_coordinates, waits, reads back (:389-430) and hands the unique
+// coordinates to the consumer (:435-445).  `evk::Pipeline` keeps that order:
+//   add_events(begin,end)  <->  cam.cd().add_callback / reslicer.process_events  (:614-615)
+//   on_new_slice(fn)       <->  reslicer.set_on_new_slice_callback               (:370)
+// with the slice body running on the GPU through libevk.so.  Errors are exceptions carrying the
+// evk_status (the reference calls exit(1)).
+#pragma once
+
+#include <cstdint>
+#include <functional>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/evk.h"
+
+namespace evk {
+
+struct Error : std::runtime_error {
+    int status;
+    Error(int st, const std::string& what) : std::runtime_error(what), status(st) {}
+};
+
+class Handle {
+  public:
+    explicit Handle(std::size_t max_events, int device = 0) {
+        int st = evk_create(&h_, device, max_events);
+        if (st != EVK_OK) throw Error(st, "evk_create failed (no CUDA device? there is no CPU path)");
+    }
+    ~Handle() { evk_destroy(h_); }
+    Handle(const Handle&) = delete;
+    Handle& operator=(const Handle&) = delete;
+    evk_handle* get() const { return h_; }
+
+    void check(int st) const {
+        if (st != EVK_OK) throw Error(st, evk_last_error(h_));
+    }
+    // load events
+    void load_events(const evk_event* b, const evk_event* e) { check(evk_load_events(h_, b, e)); }
+    void append_events(const evk_event* b, const evk_event* e) { check(evk_append_events(h_, b, e)); }
+    void load_csv(const std::string& path) { check(evk_load_csv(h_, path.c_str())); }
+    void synth(const evk_synth_params& sp) { check(evk_synth(h_, &sp)); }
+    // downsample
+    struct Counts {
+        std::size_t unique = 0, repeated = 0;
+    };
+    Counts downsample(const evk_ds_params& p) {
+        Counts c;
+        check(evk_downsample(h_, &p, &c.unique, &c.repeated));
+        n_unique_ = c.unique;
+        return c;
+    }
+    void voxels(std::vector<uint64_t>* keys, std::vector<evk_event>* reps,
+                std::vector<uint32_t>* first) {
+        if (keys) keys->resize(n_unique_);
+        if (reps) reps->resize(n_unique_);
+        if (first) first->resize(n_unique_);
+        check(evk_get_voxels(h_, keys ? keys->data() : nullptr, reps ? reps->data() : nullptr,
+                             first ? first->data() : nullptr, n_unique_));
+    }
+    // cluster
+    void set_centroids(const std::vector<float>& c, int K, int D) {
+        check(evk_set_centroids(h_, c.data(), K, D));
+    }
+    void init_centroids_first_k(const evk_km_params& p) { check(evk_init_centroids_first_k(h_, &p)); }
+    int kmeans(const evk_km_params& p) {
+        int it = 0;
+        check(evk_kmeans(h_, &p, &it));
+        km_ = p;
+        return it;
+    }
+    // labels and centroids
+    std::vector<int32_t> labels() {
+        std::size_t n = n_unique_;
+        if (km_.on_events) check(evk_num_events(h_, &n));
+        std::vector<int32_t> l(n);
+        check(evk_get_labels(h_, l.data(), n));
+        return l;
+    }
+    void centroids(std::vector<float>* c, std::vector<uint64_t>* counts) {
+        c->resize(static_cast<std::size_t>(km_.K) * km_.D);
+        counts->resize(km_.K);
+        check(evk_get_centroids(h_, c->data(), counts->data()));
+    }
+    std::size_t n_unique() const { return n_unique_; }
+
+  private:
+    evk_handle* h_ = nullptr;
+    std::size_t n_unique_ = 0;
+    evk_km_params km_{};
+};
+
+// One slice result, what the reference's on_new_slice body has in hand at ACCEL/store.cpp:430-460
+struct Slice {
+    int64_t t_begin_us = 0;
+    std::size_t n_events = 0, n_unique = 0, n_repeated = 0;
+    std::vector<float> centroids;   // K x D
+    std::vector<uint64_t> counts;   // K
+};
+
+// Replays the reference's streaming structure: events arrive in arbitrary chunks, a slice is
+// closed every `slice_us` of event time, the slice callback sees the clustered result.
+class Pipeline {
+  public:
+    Pipeline(std::size_t max_events_per_slice, const evk_ds_params& ds, const evk_km_params& km,
+             int64_t slice_us = 50000, int device = 0)
+        : h_(max_events_per_slice, device), ds_(ds), km_(km), slice_us_(slice_us) {}
+
+    void on_new_slice(std::function<void(const Slice&)> fn) { cb_ = std::move(fn); }
+
+    // the event callback: a borrowed range, valid only during the call
+    void add_events(const evk_event* begin, const evk_event* end) {
+        for (const evk_event* e = begin; e != end; ++e) {
+            if (!started_) {
+                started_ = true;
+                t0_ = e->t - (e->t % slice_us_);
+            }
+            while (e->t >= t0_ + slice_us_) close_slice();
+            buf_.push_back(*e);
+        }
+    }
+    void flush() {
+        if (!buf_.empty()) close_slice();
+    }
+    Handle& handle() { return h_; }
+
+  private:
+    void close_slice() {
+        if (!buf_.empty()) {
+            Slice s;
+            s.t_begin_us = t0_;
+            s.n_events = buf_.size();
+            h_.load_events(buf_.data(), buf_.data() + buf_.size());
+            evk_ds_params ds = ds_;
+            ds.t0_us = t0_;
+            auto c = h_.downsample(ds);
+            s.n_unique = c.unique;
+            s.n_repeated = c.repeated;
+            if (c.unique >= static_cast<std::size_t>(km_.K)) {
+                if (!warm_) h_.init_centroids_first_k(km_);  // later slices start warm
+                warm_ = true;
+                h_.kmeans(km_);
+                h_.centroids(&s.centroids, &s.counts);
+            }
+            if (cb_) cb_(s);
+            buf_.clear();
+        }
+        t0_ += slice_us_;
+    }
+    Handle h_;
+    evk_ds_params ds_;
+    evk_km_params km_;
+    int64_t slice_us_, t0_ = 0;
+    bool started_ = false, warm_ = false;
+    std::vector<evk_event> buf_;
+    std::function<void(const Slice&)> cb_;
+};
+
+}  // namespace evk

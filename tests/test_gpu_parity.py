@@ -370,3 +370,19 @@ def test_full_size_properties(evk, orc):
         Up, Rp = h.downsample(evk.ds_params(W, H, 2, 2, 500, 0, 1))
         keys, _, first = h.get_voxels(reps=False)
         assert (Up, Rp) == (len(ok), orr) and (keys == ok).all() and (first == of).all()
+
+
+def test_cpp_host_replay(evk, orc):
+    """the C++ host layer (host/evk.hpp + store_replay.cpp) replays 50 ms slices through the C-ABI"""
+    import subprocess
+    exe = os.path.join(evk_loader.PKG_DIR, "store_replay")
+    assert os.path.exists(exe), "host demo not built"
+    r = subprocess.run([exe, "synth:1500000", "8"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith("slice ")]
+    assert len(lines) == 3 and r.stdout.strip().endswith("3 slices")  # 0.15 s at 10 Mev/s
+    # slice 0 against the oracle: same stream, same 50 ms window
+    ev = orc.synth(orc.synth_params(0xE7CA0005, 1_500_000, 1280, 720, 10_000_000, 8))
+    e0 = ev[ev["t"] < 50_000]
+    ok, of, orr = orc.downsample(e0, orc.ds_params(1280, 720, 4, 4, 1000, 0, 1))
+    assert f"events={len(e0)} unique={len(ok)} repeated={orr}" in lines[0]
