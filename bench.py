@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--owner", default="time", choices=["time", "mix64"])
+    ap.add_argument("--no-repeated", action="store_true", help="do not count repeated keys")
     ap.add_argument("--algo", default="auto", choices=["auto", "table", "sort", "slab"])
     return ap.parse_args()
 
@@ -203,7 +204,8 @@ def main():
     n = args.events
     algo = {"auto": evk.ALGO_AUTO, "table": evk.ALGO_TABLE, "sort": evk.ALGO_SORT,
             "slab": evk.ALGO_SLAB}[args.algo]
-    ds = evk.ds_params(W, H, VOX[0], VOX[1], VOX[2], 0, VOX[3], algo=algo)
+    ds = evk.ds_params(W, H, VOX[0], VOX[1], VOX[2], 0, VOX[3], algo=algo,
+                       count_repeated=0 if args.no_repeated else 1)
     km = evk.km_params(K, D, iters=1)
     # sharded runs receive the next rank's boundary block behind their own events
     h = evk.Evk(n + (1 << 19) if world > 1 else n, device=local_rank)

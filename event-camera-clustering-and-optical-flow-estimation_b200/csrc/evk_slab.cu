@@ -25,8 +25,15 @@
 
 namespace {
 
-constexpr int kThreads = 1024;
-constexpr int kLogTile = 11;
+#ifndef EVK_SLAB_THREADS
+#define EVK_SLAB_THREADS 1024
+#endif
+#ifndef EVK_SLAB_LOGTILE
+#define EVK_SLAB_LOGTILE 11
+#endif
+constexpr int kThreads = EVK_SLAB_THREADS;
+constexpr int kCtasPerSm = kThreads <= 512 ? 2 : 1;
+constexpr int kLogTile = EVK_SLAB_LOGTILE;
 constexpr int kTile = 1 << kLogTile;    // events per tile
 constexpr int kPer = kTile / kThreads;  // events per thread per tile
 constexpr int kLogHash = kLogTile + 2;
@@ -133,7 +140,7 @@ __device__ __forceinline__ uint32_t hash_slot(uint32_t cell) {
 constexpr int kTmaThread = kThreads - 32;  // lane 0 of the last warp issues the bulk copies;
                                            // thread 0 keeps the output-chunk bookkeeping
 template <bool COUNT_REP, bool POW2>
-__global__ void __launch_bounds__(kThreads, 1) k_slab_main(SlabArgs a) {
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* s_ev = reinterpret_cast<uint4*>(smem_raw);                        // [kStages][kTile]
     uint32_t* s_hash = reinterpret_cast<uint32_t*>(s_ev + kStages * kTile);  // [kHash]
@@ -428,20 +435,20 @@ constexpr size_t kSmemLimit = 220 * 1024;
 }  // namespace
 
 size_t evk_slab_scratch_bytes(int sm_count) {
-    return sizeof(FixPlan) + (size_t)sm_count * 4 * sizeof(uint32_t);
+    return sizeof(FixPlan) + (size_t)sm_count * kCtasPerSm * 4 * sizeof(uint32_t);
 }
 
 bool evk_slab_supported(const evk_handle* h, const KeyParams& kp) {
     if (kp.keyfn != EVK_KEY_VOXEL || kp.vt <= 0 || h->n_events == 0) return false;
     if (kp.cells >= (1ull << (32 - kLogTile))) return false;  // packed (cell, index) word
-    if (2 * h->sm_count > kMaxList) return false;
+    if (2 * kCtasPerSm * h->sm_count > kMaxList) return false;
     return slab_smem_bytes(kp.cells, true) <= kSmemLimit;
 }
 
 int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, bool* ok,
                         int* launches) {
     *ok = false;
-    const int grid = h->sm_count;
+    const int grid = h->sm_count * kCtasPerSm;
     SlabArgs a;
     a.kp = kp;
     a.ev = h->d_events;
