@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--owner", default="time", choices=["time", "mix64"])
     ap.add_argument("--no-repeated", action="store_true", help="do not count repeated keys")
+    ap.add_argument("--unfused", action="store_true",
+                    help="three separate calls (downsample, init, k-means) instead of the fused step")
     ap.add_argument("--algo", default="auto", choices=["auto", "table", "sort", "slab"])
     return ap.parse_args()
 
@@ -226,10 +228,14 @@ def main():
             h.init_centroids_first_k_sharded(km)
             h.kmeans_sharded(km)
             state["U_local"], state["U"] = ul, ug
-        else:
+        elif args.unfused:
             u, r = h.downsample(ds)
             h.init_centroids_first_k(km)
             h.kmeans(km)
+            state["U_local"] = state["U"] = u
+            state["R"] = r
+        else:
+            u, r, _ = h.downsample_kmeans(ds, km, True)
             state["U_local"] = state["U"] = u
             state["R"] = r
 
@@ -247,7 +253,7 @@ def main():
         step()
         t = h.stage_times()
         ds_main += t.ds_main_ms; ds_total += t.ds_total_ms; km_total += t.km_total_ms
-        launches += t.ds_launches + t.km_launches + 2
+        launches += t.ds_launches + t.km_launches + (2 if (args.unfused or world > 1) else 0)
     total_ms = h.timer_stop()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -291,7 +297,10 @@ def main():
         names = {evk.ALGO_SLAB: "k_slab_main", evk.ALGO_TABLE: "k_table_insert",
                  evk.ALGO_SORT: "sort+unique"}
         traffic = ncu_traffic()
-        if ds_ms >= km_ms:
+        fused = world == 1 and not args.unfused and algo_used == evk.ALGO_SLAB
+        if fused:  # one kernel reads the events, writes the voxels, assigns and accumulates them
+            kern, a_bytes, a_ms = "k_slab_main<fused>", 16.0 * n + 36.0 * U, ds_ms
+        elif ds_ms >= km_ms:
             kern, a_bytes, a_ms = names.get(algo_used, "?"), ds_bytes, ds_ms
         else:
             kern, a_bytes, a_ms = "k_km_assign", km_bytes, km_ms
@@ -311,7 +320,7 @@ def main():
                          "algorithmic_bytes_per_launch": a_bytes, "kernel_ms": a_ms,
                          "traffic": traffic.get(kern)},
             "stage_ms": {"downsample_dominant_kernel": ds_ms, "downsample_total": ds_total / args.steps,
-                         "kmeans_iteration": km_ms},
+                         "kmeans_iteration": km_ms, "fused": fused},
             "step_roofline": {"algorithmic_bytes": step_bytes,
                               "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                               "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,

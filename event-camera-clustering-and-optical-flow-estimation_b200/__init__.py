@@ -69,7 +69,7 @@ SYMBOLS = [
     "evk_create", "evk_destroy", "evk_last_error", "evk_version", "evk_load_events",
     "evk_append_events", "evk_load_events_soa", "evk_load_coords_i32", "evk_load_csv", "evk_synth",
     "evk_num_events", "evk_get_events", "evk_downsample", "evk_get_voxels", "evk_set_centroids",
-    "evk_init_centroids_first_k", "evk_kmeans", "evk_get_labels", "evk_get_centroids",
+    "evk_init_centroids_first_k", "evk_kmeans", "evk_downsample_kmeans", "evk_get_labels", "evk_get_centroids",
     "evk_window_config", "evk_window_push", "evk_window_flush", "evk_set_profiling",
     "evk_get_stage_times", "evk_timer_start", "evk_timer_stop", "evk_sync", "evk_flush_l2",
     "evk_comm_unique_id", "evk_comm_init", "evk_comm_destroy", "evk_set_shard",
@@ -106,6 +106,8 @@ def lib():
         "evk_set_centroids": [vp, vp, i32, i32],
         "evk_init_centroids_first_k": [vp, C.POINTER(KmParams)],
         "evk_kmeans": [vp, C.POINTER(KmParams), C.POINTER(i32)],
+        "evk_downsample_kmeans": [vp, C.POINTER(DsParams), C.POINTER(KmParams), i32, psz, psz,
+                                  C.POINTER(i32)],
         "evk_get_labels": [vp, vp, sz],
         "evk_get_centroids": [vp, vp, vp],
         "evk_window_config": [vp, C.POINTER(DsParams), C.POINTER(KmParams), C.c_int64],
@@ -266,6 +268,16 @@ class Evk:
         self._ck(self._L.evk_kmeans(self._h, C.byref(km), C.byref(it)))
         self._km = km
         return it.value
+
+    def downsample_kmeans(self, ds, km, init_first_k=True):
+        """Fused step (evk_downsample_kmeans). Returns (n_unique, n_repeated, iters_done)."""
+        u, r, it = C.c_size_t(0), C.c_size_t(0), C.c_int(0)
+        self._ck(self._L.evk_downsample_kmeans(self._h, C.byref(ds), C.byref(km),
+                                               1 if init_first_k else 0, C.byref(u), C.byref(r),
+                                               C.byref(it)))
+        self.n_unique = u.value
+        self._km = km
+        return u.value, r.value, it.value
 
     def get_labels(self, n=None):
         if n is None:

@@ -70,6 +70,23 @@ int km_validate(evk_handle* h, const evk_km_params* p) {
     return EVK_OK;
 }
 
+// label map of the current frame size (lazy; frames beyond 64 Mpixel use the per-point scan)
+uint8_t* ensure_label_map(evk_handle* h, int width, int height) {
+    const size_t need = (size_t)width * (size_t)height;
+    if (need > (64ull << 20)) return nullptr;
+    if (h->label_map_bytes < need) {
+        if (h->d_label_map) cudaFree(h->d_label_map);
+        h->d_label_map = nullptr;
+        h->label_map_bytes = 0;
+        if (cudaMalloc((void**)&h->d_label_map, need) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        h->label_map_bytes = need;
+    }
+    return h->d_label_map;
+}
+
 KmLaunch km_launch_params(const evk_handle* h, const evk_km_params* p) {
     KmLaunch kl;
     kl.K = p->K;
@@ -183,7 +200,7 @@ int evk_create(evk_handle** out, int device, size_t max_events) {
     ALLOC(h->d_first, h->out_cap * sizeof(uint32_t));
     ALLOC(h->d_xy, h->out_cap * sizeof(uint32_t));
     ALLOC(h->d_slab_scratch, evk_slab_scratch_bytes(h->sm_count));
-    ALLOC(h->d_labels, m * sizeof(int32_t));
+    ALLOC(h->d_labels, h->out_cap * sizeof(int32_t));  // the fused step labels un-compacted slots
     ALLOC(h->d_bin_start, (h->max_bins + 2) * sizeof(uint32_t));
     ALLOC(h->d_cnt, sizeof(DsCounters));
     ALLOC(h->d_cent, EVK_MAX_K * EVK_MAX_D * sizeof(float));
@@ -220,7 +237,7 @@ int evk_destroy(evk_handle* h) {
                     h->d_reps,   h->d_labels, h->d_perm,   h->d_sort_tmp, h->d_sort_a, h->d_sort_b,
                     h->d_sort_c, h->d_sk_in,  h->d_sk_out, h->d_si_in,  h->d_si_out, h->d_sv_tmp,
                     h->d_bin_start, h->d_slab_scratch, h->d_cnt, h->d_cent,   h->d_acc,    h->d_counts, h->d_shift,
-                    h->d_cand,   h->d_flush, h->d_prune_lists};
+                    h->d_cand,   h->d_flush, h->d_prune_lists, h->d_label_map};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
@@ -536,7 +553,11 @@ int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_done,
     while (it < p->iters) {
         kl.write_labels = (p->tol >= 0.f || it == p->iters - 1) ? 1 : 0;
         cudaError_t ce = cudaErrorNotSupported;
-        if (xy && h->have_ds)  // voxels are gated to the frame: exact candidate pruning applies
+        if (xy && h->have_ds && p->D == 2 && p->K <= 254)  // integer pixels: label map + gather
+            ce = evk_launch_km_assign_map(kl, h->ds.width, h->ds.height, h->d_prune_lists,
+                                          ensure_label_map(h, h->ds.width, h->ds.height), xy, n,
+                                          h->d_cent, h->d_acc, h->d_labels, h->sm_count, h->stream);
+        if (ce == cudaErrorNotSupported && xy && h->have_ds)  // exact candidate pruning per point
             ce = evk_launch_km_assign_pruned(kl, h->ds.width, h->ds.height, h->d_prune_lists, xy, n,
                                              h->d_cent, h->d_acc, h->d_labels, h->sm_count,
                                              h->stream);
@@ -547,7 +568,7 @@ int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_done,
         if (reduce) EVK_TRY(reduce(h, p->K, p->D));
         EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
                                            h->stream));
-        launches += n ? 2 : 1;
+        launches += n ? (p->D == 2 && xy ? 4 : 2) : 1;
         it++;
         if (p->tol >= 0.f) {
             EVK_CUDA(h, cudaMemcpyAsync(h->h_shift, h->d_shift, sizeof(float),
@@ -574,6 +595,132 @@ int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_done,
 int evk_kmeans(evk_handle* h, const evk_km_params* p, int* iters_done) {
     EVK_TRY(check_handle(h));
     return evk_kmeans_run(h, p, iters_done, nullptr);
+}
+
+// ---- fused step -----------------------------------------------------------------------------
+// One submission, one host synchronisation: bins -> (first-K walk) -> candidate lists -> slab
+// kernel whose consumer warps assign + accumulate every voxel it emits -> fix-up -> finalise.
+// Shapes the fused kernel does not take (unordered stream, D > 2, K > 254, raw-event clustering,
+// key space too large for shared memory) run the three separate calls: same results either way.
+static int step_unfused(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
+                        int init_first_k, int* iters_done) {
+    EVK_TRY(evk_downsample_local(h, ds));
+    if (init_first_k) EVK_TRY(evk_init_centroids_first_k(h, km));
+    return evk_kmeans_run(h, km, iters_done, nullptr);
+}
+
+int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
+                          int init_first_k, size_t* n_unique, size_t* n_repeated,
+                          int* iters_done) {
+    EVK_TRY(check_handle(h));
+    EVK_TRY(km_validate(h, km));
+    KeyParams kp;
+    EVK_TRY(evk_make_key_params(h, ds, &kp));
+    h->shard_first = h->comm ? h->shard_first : 0;
+    if (!init_first_k && (!h->have_centroids || h->K != km->K || h->D != km->D))
+        return evk_fail(h, EVK_ERR_STATE, "centroids for K=%d, D=%d have not been set", km->K, km->D);
+    const bool fusable = km->D == 2 && !km->on_events &&
+                         (ds->algo == EVK_ALGO_AUTO || ds->algo == EVK_ALGO_SLAB) &&
+                         evk_slab_fuse_supported(h, kp, ds->count_repeated, km->K);
+    int st = EVK_OK;
+    bool done = false;
+    uint8_t* map = nullptr;
+    if (fusable) {
+        DeviceGuard g(h->device);
+        map = ensure_label_map(h, ds->width, ds->height);
+    }
+    if (fusable && map) {
+        DeviceGuard g(h->device);
+        invalidate_results(h);
+        h->ds = *ds;
+        h->kp = kp;
+        h->have_ds = true;
+        KmLaunch kl = km_launch_params(h, km);
+        kl.write_labels = (km->iters == 1 || km->tol >= 0.f) ? 1 : 0;
+        int launches = 0;
+        EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
+        prof_rec(h, 0);
+        if (init_first_k) {
+            const size_t n_scan = h->n_events < (1u << 20) ? h->n_events : (1u << 20);
+            EVK_CUDA(h, evk_launch_init_first_k_walk(kp, kl, h->d_events, n_scan, h->d_cent,
+                                                     &h->d_cnt->scratch[4], h->stream));
+            launches++;
+        }
+        else  // warm start: keep a copy in case the stream check sends us to the general path
+            EVK_CUDA(h, cudaMemcpyAsync(h->d_cent + EVK_MAX_K * 2, h->d_cent,
+                                        (size_t)km->K * 2 * sizeof(float), cudaMemcpyDeviceToDevice,
+                                        h->stream));
+        SlabFuse fu;
+        fu.kl = kl;
+        fu.pg = evk_make_prune_grid(ds->width, ds->height);
+        fu.map = map;
+        fu.acc = h->d_acc;
+        fu.labels = h->d_labels;
+        EVK_CUDA(h, evk_launch_km_candidates(kl, fu.pg, h->d_cent, h->d_prune_lists, h->stream));
+        EVK_CUDA(h, evk_launch_km_label_map(kl, fu.pg, h->d_prune_lists, h->d_cent, map, h->stream));
+        launches += 2;
+        bool ok = false;
+        EVK_TRY(evk_downsample_slab(h, kp, ds->count_repeated, &ok, &launches, &fu, false));
+        prof_rec(h, 2);
+        prof_rec(h, 3);
+        EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
+                                           h->stream));
+        prof_rec(h, 4);
+        EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,
+                                    h->stream));
+        EVK_CUDA(h, cudaMemcpyAsync(h->h_shift, h->d_shift, sizeof(float), cudaMemcpyDeviceToHost,
+                                    h->stream));
+        EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+        ok = h->h_cnt->slab_violation == 0 && h->h_cnt->overflow == 0 &&
+             (!init_first_k || h->h_cnt->scratch[4] == (unsigned long long)km->K);
+        if (ok) {
+            h->n_unique = (size_t)h->h_cnt->n_unique;
+            h->n_repeated = ds->count_repeated ? (size_t)h->h_cnt->n_repeated : 0;
+            h->have_voxels = true;
+            h->K = km->K;
+            h->D = km->D;
+            h->have_centroids = true;
+            h->n_labels = h->n_unique;
+            h->labels_on_events = false;
+            h->km_last = *km;
+            h->times.ds_algo_used = EVK_ALGO_SLAB;
+            h->times.ds_launches = launches + 1;
+            h->times.km_launches = 1;
+            h->times.km_iters = 1;
+            h->times.ds_compact_ms = 0.f;
+            if (h->profiling) {
+                h->times.ds_total_ms = prof_ms(h, 0, 2);
+                h->times.ds_main_ms = prof_ms(h, 5, 6);  // downsample AND assign: one kernel
+                h->times.km_total_ms = h->times.km_assign_ms = prof_ms(h, 3, 4);
+            }
+            int it = 1;
+            const bool converged = km->tol >= 0.f && *h->h_shift <= km->tol;
+            if (km->iters > 1 && !converged) {
+                evk_km_params rest = *km;
+                rest.iters = km->iters - 1;
+                int more = 0;
+                st = evk_kmeans_run(h, &rest, &more, nullptr);
+                it += more;
+                h->km_last = *km;
+                h->times.km_iters = it;
+            }
+            if (iters_done) *iters_done = it;
+            done = true;
+        } else {
+            // the accumulators may hold partial sums of the abandoned pass
+            EVK_CUDA(h, cudaMemsetAsync(h->d_acc, 0, EVK_MAX_K * 5 * sizeof(unsigned long long),
+                                        h->stream));
+            if (!init_first_k)  // finalise has overwritten the caller's centroids: put them back
+                EVK_CUDA(h, cudaMemcpyAsync(h->d_cent, h->d_cent + EVK_MAX_K * 2,
+                                            (size_t)km->K * 2 * sizeof(float),
+                                            cudaMemcpyDeviceToDevice, h->stream));
+        }
+    }
+    if (!done && st == EVK_OK) st = step_unfused(h, ds, km, init_first_k, iters_done);
+    if (st != EVK_OK) return st;
+    if (n_unique) *n_unique = h->n_unique;
+    if (n_repeated) *n_repeated = h->n_repeated;
+    return EVK_OK;
 }
 
 int evk_get_labels(evk_handle* h, int32_t* labels, size_t cap) {
@@ -631,17 +778,18 @@ int evk_window_config(evk_handle* h, const evk_ds_params* ds, const evk_km_param
 }
 
 static int window_run(evk_handle* h) {
-    // one slice: the body of on_new_slice (ACCEL/store.cpp:370-568) minus consumer and drawing
+    // one slice: the body of on_new_slice (ACCEL/store.cpp:370-568) minus consumer and drawing,
+    // as ONE fused submission (downsample + warm-started k-means) with one host synchronisation
     const evk_event* b = h->win_buf.data();
     EVK_TRY(evk_load_events(h, b, b + h->win_buf.size()));
     evk_ds_params ds = h->win_ds;
     ds.t0_us = h->win_start;  // time bins restart with every window
-    size_t U = 0;
-    EVK_TRY(evk_downsample(h, &ds, &U, nullptr));
-    if (U >= (size_t)h->win_km.K) {
-        if (!h->have_centroids) EVK_TRY(evk_init_centroids_first_k(h, &h->win_km));  // else warm start
-        EVK_TRY(evk_kmeans(h, &h->win_km, nullptr));
-    }
+    const bool seeded = h->have_centroids && h->K == h->win_km.K && h->D == h->win_km.D;
+    int st = evk_downsample_kmeans(h, &ds, &h->win_km, seeded ? 0 : 1, nullptr, nullptr, nullptr);
+    // fewer voxels than clusters in the first windows: downsampled only, seeding waits
+    if (st == EVK_ERR_INVALID && !seeded && h->have_voxels && h->n_unique < (size_t)h->win_km.K)
+        st = EVK_OK;
+    EVK_TRY(st);
     h->win_count++;
     return EVK_OK;
 }

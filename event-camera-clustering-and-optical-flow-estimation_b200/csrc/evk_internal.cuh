@@ -154,6 +154,8 @@ struct evk_handle {
     unsigned long long* d_acc = nullptr;     // [EVK_MAX_K * (EVK_MAX_D + 1)]
     unsigned long long* d_counts = nullptr;  // [EVK_MAX_K] counts of the last iteration
     void* d_prune_lists = nullptr;           // [EVK_PRUNE_TILES] uint4 candidate lists
+    uint8_t* d_label_map = nullptr;          // [height * width] label of every pixel (lazy, D == 2)
+    size_t label_map_bytes = 0;
     float* d_shift = nullptr;                // [1]
     float* h_shift = nullptr;                // pinned
     size_t n_labels = 0;
@@ -222,9 +224,14 @@ cudaError_t evk_launch_table_compact(const evk_event* ev, uint64_t* tkeys, uint3
                                      cudaStream_t s);
 // downsample: sort + unique
 int evk_downsample_sort(evk_handle* h, const KeyParams& kp, int* launches);
-// downsample: time-slab kernel
+// downsample: time-slab kernel.  fuse != nullptr: the kernel's consumer warps also run the pruned
+// k-means assign + accumulate on every voxel it emits (labels follow the records through the
+// fix-up).  sync = false: everything is only enqueued (counters are copied to h->h_cnt); the caller
+// synchronises and reads slab_violation / overflow itself.
+struct SlabFuse;
 int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, bool* ok,
-                        int* launches);
+                        int* launches, const SlabFuse* fuse = nullptr, bool sync = true);
+bool evk_slab_fuse_supported(const evk_handle* h, const KeyParams& kp, int count_repeated, int K);
 bool evk_slab_supported(const evk_handle* h, const KeyParams& kp);
 size_t evk_slab_scratch_bytes(int sm_count);
 // canonical order
@@ -234,6 +241,8 @@ cudaError_t evk_launch_gather_voxels(const evk_handle* h, uint64_t* keys, evk_ev
 cudaError_t evk_launch_gather_labels(const int32_t* labels, const uint32_t* perm, int32_t* out,
                                      size_t n, cudaStream_t s);
 // k-means
+// accumulator slots per cluster in global memory (d_acc)
+enum { ACC_CNT = 0, ACC_X = 1, ACC_Y = 2, ACC_T = 3, ACC_P = 4, ACC_STRIDE = 5 };
 struct KmLaunch {
     int K, D;
     float best2;  // gate on the squared distance (+inf: none)
@@ -246,10 +255,32 @@ cudaError_t evk_launch_km_assign(const KmLaunch& kl, const uint32_t* xy, const e
                                  unsigned long long* acc, int32_t* labels, int sm_count,
                                  cudaStream_t s);
 #define EVK_PRUNE_TILES 4096
+// exact candidate pruning (evk_kmeans.cu): the frame is cut into (1 << shift)-pixel square tiles,
+// tx * ty <= EVK_PRUNE_TILES; lists[tile] = up to 16 ascending centroid indices (0xFF = end,
+// first byte 0xFE = scan all K)
+struct PruneGrid {
+    int32_t width, height, shift, tx, ty;
+};
+PruneGrid evk_make_prune_grid(int width, int height);
+cudaError_t evk_launch_km_candidates(const KmLaunch& kl, const PruneGrid& pg, const float* cent,
+                                     void* lists, cudaStream_t s);
+struct SlabFuse {
+    KmLaunch kl;
+    PruneGrid pg;
+    const uint8_t* map;       // [height * width] label map built from the current centroids
+    unsigned long long* acc;  // [K * 5] exact partial sums (ACC_* layout of evk_kmeans.cu)
+    int32_t* labels;          // indexed like the voxel shard
+};
 cudaError_t evk_launch_km_assign_pruned(const KmLaunch& kl, int width, int height, void* lists,
                                         const uint32_t* xy, size_t n, const float* cent,
                                         unsigned long long* acc, int32_t* labels, int sm_count,
                                         cudaStream_t s);
+cudaError_t evk_launch_km_label_map(const KmLaunch& kl, const PruneGrid& pg, const void* lists,
+                                    const float* cent, uint8_t* map, cudaStream_t s);
+cudaError_t evk_launch_km_assign_map(const KmLaunch& kl, int width, int height, void* lists,
+                                     uint8_t* map, const uint32_t* xy, size_t n, const float* cent,
+                                     unsigned long long* acc, int32_t* labels, int sm_count,
+                                     cudaStream_t s);
 cudaError_t evk_launch_km_finalise(const KmLaunch& kl, float* cent, unsigned long long* acc,
                                    unsigned long long* counts, float* shift, cudaStream_t s);
 cudaError_t evk_launch_collect_below(const uint32_t* first, size_t n, uint32_t bound,

@@ -18,9 +18,6 @@ constexpr int kBlock = 256;
 constexpr int kPPT = 4;                        // points per thread per pass
 constexpr int kChunk = kBlock * kPPT * 32;     // 32768 points between flushes: sums fit u32
 
-// accumulator slots per cluster in global memory
-enum { ACC_CNT = 0, ACC_X = 1, ACC_Y = 2, ACC_T = 3, ACC_P = 4, ACC_STRIDE = 5 };
-
 // SRC: 0 = packed xy[i] (voxels, D == 2), 1 = raw events ev[i], 2 = gather ev[first[i]]
 template <int D, int SRC>
 __global__ void __launch_bounds__(kBlock)
@@ -251,9 +248,6 @@ __global__ void __launch_bounds__(1024)
 // slack far above fp32 rounding, so the labels are bit-identical to the full scan; tiles with
 // more than 16 candidates are marked and scanned in full.
 constexpr int kListLen = 16;
-struct PruneGrid {
-    int32_t width, height, shift, tx, ty;
-};
 
 __global__ void __launch_bounds__(128)
     k_km_candidates(KmLaunch kl, PruneGrid pg, const float* __restrict__ cent, uint4* lists) {
@@ -401,6 +395,130 @@ __global__ void __launch_bounds__(kBlock)
     }
 }
 
+// ---- label map (D == 2, voxels) ---------------------------------------------------------------
+// Voxel representatives have integer pixel coordinates, so with D == 2 the label of a point is a
+// pure function of its pixel: one pass evaluates the contract arithmetic once per PIXEL (through
+// the candidate lists: a handful of distances each) into a W x H byte image that stays in L2
+// (0.9 MB for Gen4), and the per-point work of an iteration collapses to a 1-byte gather, the
+// label store and three shared-memory atomics.  Bit-identical to the per-point scan by
+// construction: same operands, same operations, same order.  0xFF = unassigned (gate).
+__global__ void __launch_bounds__(256)
+    k_km_label_map(KmLaunch kl, PruneGrid pg, const uint4* __restrict__ lists,
+                   const float* __restrict__ cent, uint8_t* __restrict__ map) {
+    extern __shared__ float2 s_cc[];
+    for (int i = threadIdx.x; i < kl.K; i += blockDim.x)
+        s_cc[i] = reinterpret_cast<const float2*>(cent)[i];
+    __syncthreads();
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= pg.width) return;
+    const uint4 l4 = __ldg(lists + (y >> pg.shift) * pg.tx + (x >> pg.shift));
+    const float px = (float)x, py = (float)y;
+    float best = kl.best2;
+    int lab = 0xFF;
+    if ((l4.x & 0xFFu) == 0xFEu) {
+        for (int k = 0; k < kl.K; k++) {
+            const float2 cc = s_cc[k];
+            const float dx = __fsub_rn(cc.x, px), dy = __fsub_rn(cc.y, py);
+            const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+            if (d2 < best) {
+                best = d2;
+                lab = k;
+            }
+        }
+    } else {
+        const uint32_t lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+        for (int s = 0; s < kListLen; s++) {
+            const uint32_t k = (lw[s >> 2] >> (8 * (s & 3))) & 0xFFu;
+            if (k == 0xFFu) break;
+            const float2 cc = s_cc[k];
+            const float dx = __fsub_rn(cc.x, px), dy = __fsub_rn(cc.y, py);
+            const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+            if (d2 < best) {
+                best = d2;
+                lab = (int)k;
+            }
+        }
+    }
+    map[(size_t)y * pg.width + x] = (uint8_t)lab;
+}
+
+constexpr int kMapPPT = 4;  // points per thread: one 16-B load of xy, one 16-B store of labels
+__global__ void __launch_bounds__(kBlock)
+    k_km_assign_map(KmLaunch kl, int width, const uint8_t* __restrict__ map,
+                    const uint32_t* __restrict__ xy, size_t n,
+                    unsigned long long* __restrict__ acc, int32_t* __restrict__ labels) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = kl.K;
+    uint32_t* s_acc = reinterpret_cast<uint32_t*>(smem_raw);  // [kRep][3][K]
+    for (int i = threadIdx.x; i < kRep * 3 * K; i += kBlock) s_acc[i] = 0;
+    __syncthreads();
+    uint32_t* my_acc = s_acc + (threadIdx.x & (kRep - 1)) * 3 * K;
+    const size_t n_chunks = (n + kChunk - 1) / kChunk;
+    for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const size_t cbase = c * (size_t)kChunk;
+#pragma unroll 2
+        for (int r = 0; r < kChunk / (kBlock * kMapPPT); r++) {
+            const size_t i0 = cbase + ((size_t)r * kBlock + threadIdx.x) * kMapPPT;
+            if (i0 >= n) break;
+            uint32_t w[kMapPPT];
+            if (i0 + kMapPPT <= n) {
+                const uint4 v = __ldcs(reinterpret_cast<const uint4*>(xy + i0));
+                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < kMapPPT; q++) w[q] = i0 + q < n ? xy[i0 + q] : 0u;
+            }
+            uint32_t lab[kMapPPT];
+#pragma unroll
+            for (int q = 0; q < kMapPPT; q++)
+                lab[q] = __ldg(map + (size_t)(w[q] >> 16) * width + (w[q] & 0xFFFFu));
+            if (kl.write_labels) {
+                int4 o;
+                o.x = lab[0] == 0xFFu ? -1 : (int)lab[0];
+                o.y = lab[1] == 0xFFu ? -1 : (int)lab[1];
+                o.z = lab[2] == 0xFFu ? -1 : (int)lab[2];
+                o.w = lab[3] == 0xFFu ? -1 : (int)lab[3];
+                if (i0 + kMapPPT <= n) {
+                    __stcs(reinterpret_cast<int4*>(labels + i0), o);
+                } else {
+                    const int ov[4] = {o.x, o.y, o.z, o.w};
+                    for (int q = 0; q < kMapPPT; q++)
+                        if (i0 + q < n) labels[i0 + q] = ov[q];
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kMapPPT; q++) {
+                if (i0 + q < n && lab[q] != 0xFFu) {
+                    atomicAdd(&my_acc[lab[q]], 1u);
+                    atomicAdd(&my_acc[K + lab[q]], w[q] & 0xFFFFu);
+                    atomicAdd(&my_acc[2 * K + lab[q]], w[q] >> 16);
+                }
+            }
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += kBlock) {
+            unsigned long long sc = 0, sx = 0, sy = 0;
+#pragma unroll
+            for (int rr = 0; rr < kRep; rr++) {
+                uint32_t* a = s_acc + rr * 3 * K;
+                sc += a[k];
+                sx += a[K + k];
+                sy += a[2 * K + k];
+                a[k] = 0;
+                a[K + k] = 0;
+                a[2 * K + k] = 0;
+            }
+            if (sc) {
+                atomicAdd(&acc[k * ACC_STRIDE + ACC_CNT], sc);
+                atomicAdd(&acc[k * ACC_STRIDE + ACC_X], sx);
+                atomicAdd(&acc[k * ACC_STRIDE + ACC_Y], sy);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // "first K voxel representatives in canonical order" == the first K distinct keys met when the
 // stream is walked in order.  One warp walks the head of the stream: lane l holds event base+l,
 // the 32 events are committed one after the other, the list of keys found so far is compared
@@ -496,6 +614,19 @@ cudaError_t evk_launch_km_assign_pruned(const KmLaunch& kl, int width, int heigh
                                         unsigned long long* acc, int32_t* labels, int sm_count,
                                         cudaStream_t s) {
     if (kl.D != 2 || kl.K <= 16 || kl.K > 254) return cudaErrorNotSupported;
+    const PruneGrid pg = evk_make_prune_grid(width, height);
+    if (n == 0) return cudaSuccess;
+    evk_launch_km_candidates(kl, pg, cent, lists, s);
+    size_t chunks = (n + kChunk - 1) / kChunk;
+    size_t cap = (size_t)sm_count * 8;
+    int grid = (int)(chunks < cap ? chunks : cap);
+    size_t smem = (size_t)kl.K * sizeof(float2) + (size_t)kRep * 3 * kl.K * sizeof(uint32_t);
+    k_km_assign_pruned<<<grid, kBlock, smem, s>>>(kl, pg, reinterpret_cast<const uint4*>(lists),
+                                                  xy, n, cent, acc, labels);
+    return cudaGetLastError();
+}
+
+PruneGrid evk_make_prune_grid(int width, int height) {
     PruneGrid pg;
     pg.width = width;
     pg.height = height;
@@ -506,16 +637,40 @@ cudaError_t evk_launch_km_assign_pruned(const KmLaunch& kl, int width, int heigh
         if ((long long)pg.tx * pg.ty <= EVK_PRUNE_TILES) break;
         pg.shift++;
     }
-    if (n == 0) return cudaSuccess;
+    return pg;
+}
+
+cudaError_t evk_launch_km_candidates(const KmLaunch& kl, const PruneGrid& pg, const float* cent,
+                                     void* lists, cudaStream_t s) {
     const int tiles = pg.tx * pg.ty;
     k_km_candidates<<<(tiles + 127) / 128, 128, kl.K * sizeof(float2), s>>>(
         kl, pg, cent, reinterpret_cast<uint4*>(lists));
+    return cudaGetLastError();
+}
+
+cudaError_t evk_launch_km_label_map(const KmLaunch& kl, const PruneGrid& pg, const void* lists,
+                                    const float* cent, uint8_t* map, cudaStream_t s) {
+    dim3 grid((pg.width + 255) / 256, pg.height);
+    k_km_label_map<<<grid, 256, kl.K * sizeof(float2), s>>>(
+        kl, pg, reinterpret_cast<const uint4*>(lists), cent, map);
+    return cudaGetLastError();
+}
+
+// D == 2 on the voxel shard, K <= 254: candidate lists -> label map -> per-point gather.
+cudaError_t evk_launch_km_assign_map(const KmLaunch& kl, int width, int height, void* lists,
+                                     uint8_t* map, const uint32_t* xy, size_t n, const float* cent,
+                                     unsigned long long* acc, int32_t* labels, int sm_count,
+                                     cudaStream_t s) {
+    if (kl.D != 2 || kl.K > 254 || !map) return cudaErrorNotSupported;
+    if (n == 0) return cudaSuccess;
+    const PruneGrid pg = evk_make_prune_grid(width, height);
+    evk_launch_km_candidates(kl, pg, cent, lists, s);
+    evk_launch_km_label_map(kl, pg, lists, cent, map, s);
     size_t chunks = (n + kChunk - 1) / kChunk;
     size_t cap = (size_t)sm_count * 8;
     int grid = (int)(chunks < cap ? chunks : cap);
-    size_t smem = (size_t)kl.K * sizeof(float2) + (size_t)kRep * 3 * kl.K * sizeof(uint32_t);
-    k_km_assign_pruned<<<grid, kBlock, smem, s>>>(kl, pg, reinterpret_cast<const uint4*>(lists),
-                                                  xy, n, cent, acc, labels);
+    k_km_assign_map<<<grid, kBlock, (size_t)kRep * 3 * kl.K * sizeof(uint32_t), s>>>(
+        kl, width, map, xy, n, acc, labels);
     return cudaGetLastError();
 }
 

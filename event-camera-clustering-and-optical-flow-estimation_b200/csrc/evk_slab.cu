@@ -31,11 +31,11 @@ namespace {
 #ifndef EVK_SLAB_LOGTILE
 #define EVK_SLAB_LOGTILE 11
 #endif
-constexpr int kThreads = EVK_SLAB_THREADS;
+constexpr int kThreads = EVK_SLAB_THREADS;  // CTA size (the hardware maximum by default)
 constexpr int kCtasPerSm = kThreads <= 512 ? 2 : 1;
-constexpr int kLogTile = EVK_SLAB_LOGTILE;
-constexpr int kTile = 1 << kLogTile;    // events per tile
-constexpr int kPer = kTile / kThreads;  // events per thread per tile
+constexpr int kLogTile = EVK_SLAB_LOGTILE;  // bits of the index-in-tile field of a table word
+constexpr int kTile = 1 << kLogTile;        // events per tile (stage buffers hold this many)
+constexpr int kPer = kTile / kThreads;      // events per thread per tile
 constexpr int kLogHash = kLogTile + 2;
 constexpr int kHash = 1 << kLogHash;    // tile table slots (load <= 0.25)
 constexpr int kStages = 2;
@@ -43,6 +43,7 @@ constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kChunk = EVK_SLAB_CHUNK;  // output slots per CTA-private chunk (>= 2 tiles)
 constexpr uint32_t kNoChunk = 0xFFFFFFFFu;
 static_assert(kChunk >= 2 * kTile, "a fresh chunk must absorb a whole tile");
+static_assert(kThreads * kPer == kTile, "tile = events per thread x CTA size");
 
 struct SlabArgs {
     KeyParams kp;
@@ -137,17 +138,134 @@ __device__ __forceinline__ uint32_t hash_slot(uint32_t cell) {
     return (cell * 0x9E3779B1u) >> (32 - kLogHash);
 }
 
-constexpr int kTmaThread = kThreads - 32;  // lane 0 of the last warp issues the bulk copies;
-                                           // thread 0 keeps the output-chunk bookkeeping
-template <bool COUNT_REP, bool POW2>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) {
+// lane 0 of the last producer warp issues the bulk copies; thread 0 keeps the output-chunk
+// bookkeeping
+
+// ---- fused k-means consumer ------------------------------------------------------------------
+// FUSED: kConsWarps of the CTA's 32 warps are consumers (a CTA cannot exceed 1024 threads, so the
+// producers work on tiles of (1024 - kCons) * kPer events).  After every tile the producers publish a
+// descriptor (where the tile's voxels went and how many) through a small mbarrier ring; the
+// consumer warps read the packed coordinates the producers have just written (L2 hits), look the
+// label up in the per-pixel label map of evk_kmeans.cu (exact: same arithmetic, same lowest-k tie
+// rule, evaluated once per pixel), store it next to the record and accumulate exact integer sums
+// in shared memory.  They run in the issue slots the producers leave idle around their barriers.
+#ifndef EVK_SLAB_CONS_WARPS
+#define EVK_SLAB_CONS_WARPS 4
+#endif
+#ifndef EVK_SLAB_CONS_PPT
+#define EVK_SLAB_CONS_PPT 4
+#endif
+constexpr int kConsWarps = EVK_SLAB_CONS_WARPS;
+constexpr int kCons = 32 * kConsWarps;
+constexpr int kConsPPT = EVK_SLAB_CONS_PPT;  // voxels per consumer thread per pass
+constexpr int kRing = 4;                      // descriptor ring depth
+constexpr uint32_t kEndOfStream = 0xFFFFFFFFu;
+constexpr uint32_t kFlushEvery = 32768;       // u32 sums: 32768 * 65535 < 2^32
+
+struct FuseDev {
+    int K, rep;
+    int32_t width;
+    int write_labels;
+    const uint8_t* map;  // label of every pixel for the current centroids (evk_kmeans.cu)
+    unsigned long long* acc;
+    int32_t* labels;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+template <int NT>
+__device__ __forceinline__ void prod_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
+}
+__device__ __forceinline__ void cons_sync() {
+    asm volatile("bar.sync 2, %0;" ::"n"(kCons) : "memory");
+}
+
+__device__ __forceinline__ void cons_flush(const FuseDev& f, uint32_t* s_acc, int ctid) {
+    cons_sync();
+    for (int k = ctid; k < f.K; k += kCons) {
+        unsigned long long sc = 0, sx = 0, sy = 0;
+        for (int r = 0; r < f.rep; r++) {
+            uint32_t* a = s_acc + r * 3 * f.K;
+            sc += a[k];
+            sx += a[f.K + k];
+            sy += a[2 * f.K + k];
+            a[k] = 0;
+            a[f.K + k] = 0;
+            a[2 * f.K + k] = 0;
+        }
+        if (sc) {
+            atomicAdd(&f.acc[k * ACC_STRIDE + ACC_CNT], sc);
+            atomicAdd(&f.acc[k * ACC_STRIDE + ACC_X], sx);
+            atomicAdd(&f.acc[k * ACC_STRIDE + ACC_Y], sy);
+        }
+    }
+    cons_sync();
+}
+
+__device__ __forceinline__ void consumer_loop(const FuseDev& f, const uint32_t* xy,
+                                              uint32_t* s_acc, uint64_t* s_full,
+                                              uint64_t* s_empty, const uint4* s_desc, int ctid) {
+    const int lane = ctid & 31;
+    const int K = f.K;
+    uint32_t* my_acc = s_acc + (ctid & (f.rep - 1)) * 3 * K;
+    uint32_t since_flush = 0;
+    for (uint32_t seq = 0;; seq++) {
+        const uint32_t slot = seq % kRing;
+        mbar_wait(&s_full[slot], (seq / kRing) & 1);
+        const uint4 d = s_desc[slot];  // room, pos0, next chunk base, voxel count
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[slot]);  // descriptor is in registers: slot is free
+        if (d.w == kEndOfStream) break;
+        for (uint32_t o0 = 0; o0 < d.w; o0 += kCons * kConsPPT) {
+            uint32_t w[kConsPPT], pos[kConsPPT], lab[kConsPPT];
+#pragma unroll
+            for (int q = 0; q < kConsPPT; q++) {
+                const uint32_t o = o0 + q * kCons + ctid;
+                pos[q] = o < d.x ? d.y + o : d.z + (o - d.x);
+                // L1 may hold a stale copy of a line that an earlier tile's read pulled in
+                w[q] = o < d.w ? __ldcg(xy + pos[q]) : 0u;
+                if (o >= d.w) pos[q] = kEndOfStream;
+            }
+#pragma unroll
+            for (int q = 0; q < kConsPPT; q++)
+                lab[q] = __ldg(f.map + (size_t)(w[q] >> 16) * f.width + (w[q] & 0xFFFFu));
+#pragma unroll
+            for (int q = 0; q < kConsPPT; q++) {
+                if (pos[q] == kEndOfStream) continue;
+                if (f.write_labels) f.labels[pos[q]] = lab[q] == 0xFFu ? -1 : (int)lab[q];
+                if (lab[q] != 0xFFu) {
+                    atomicAdd(&my_acc[lab[q]], 1u);
+                    atomicAdd(&my_acc[K + lab[q]], w[q] & 0xFFFFu);
+                    atomicAdd(&my_acc[2 * K + lab[q]], w[q] >> 16);
+                }
+            }
+        }
+        since_flush += d.w;
+        if (since_flush >= kFlushEvery) {
+            cons_flush(f, s_acc, ctid);
+            since_flush = 0;
+        }
+    }
+    cons_flush(f, s_acc, ctid);
+}
+
+template <bool COUNT_REP, bool POW2, bool FUSED>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a, FuseDev f) {
+    constexpr int NT = FUSED ? kThreads - kCons : kThreads;  // producer threads
+    constexpr int TILE = NT * kPer;                          // events per tile
+    constexpr int kTmaThread = NT - 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* s_ev = reinterpret_cast<uint4*>(smem_raw);                        // [kStages][kTile]
     uint32_t* s_hash = reinterpret_cast<uint32_t*>(s_ev + kStages * kTile);  // [kHash]
     // bin bitmap.  COUNT_REP: 16 cells per word, bit c = "seen", bit 16 + c = "hit at least twice"
     // (one load answers both questions); else 32 cells per word, "seen" only.
     uint32_t* s_map = s_hash + kHash;  // [words]
+    uint32_t* s_acc = s_map + ((a.words + 3) & ~3u);  // [rep][3][K]  (FUSED)
     __shared__ __align__(8) uint64_t s_bar[kStages];
+    __shared__ __align__(8) uint64_t s_full[kRing], s_empty[kRing];
+    __shared__ __align__(16) uint4 s_desc[kRing];
     __shared__ uint32_t s_bin;
     __shared__ uint32_t s_cursor[2];  // voxels emitted by the current tile (by tile parity)
     __shared__ uint32_t s_chunk_pos, s_chunk_end, s_next_base;
@@ -159,9 +277,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
     const uint64_t tb0 = cnt->scratch[2];
     const int tid = threadIdx.x, lane = tid & 31;
 
-    for (int i = tid; i < kHash; i += kThreads) s_hash[i] = kEmpty;
+    for (int i = tid; i < kHash; i += blockDim.x) s_hash[i] = kEmpty;
+    if (FUSED)
+        for (int i = tid; i < f.rep * 3 * f.K; i += blockDim.x) s_acc[i] = 0;
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) mbar_init(&s_bar[s], 1);
+        for (int s = 0; s < kRing; s++) {
+            mbar_init(&s_full[s], 1);
+            mbar_init(&s_empty[s], kConsWarps);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_cursor[0] = s_cursor[1] = 0;
         // two chunks up front: the current one and the one after it
@@ -170,13 +294,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
         s_chunk_end = s_chunk_pos + kChunk;
         s_next_base = (c0 + 1) * kChunk;
     }
+    __syncthreads();
+    if (FUSED && tid >= NT) {
+        consumer_loop(f, a.xy, s_acc, s_full, s_empty, s_desc, tid - NT);
+        return;
+    }
     uint32_t pend_chunk = kNoChunk;  // thread 0: chunk index requested but not yet published
     uint32_t tile_seq = 0;           // tiles consumed by this CTA (stage = seq % kStages)
+    uint32_t pub_seq = 0;            // thread 0: descriptors published to the consumer warps
 
     for (;;) {
-        __syncthreads();
+        prod_sync<NT>();
         if (tid == 0) s_bin = (uint32_t)atomicAdd(&cnt->scratch[1], 1ull);
-        __syncthreads();
+        prod_sync<NT>();
         const uint32_t b = s_bin;
         if (b >= nb) break;
         const uint32_t lo = a.bin_start[b], hi = a.bin_start[b + 1];
@@ -189,22 +319,22 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
         const int64_t t_lo = kp.t0 + (int64_t)(tb * (uint64_t)kp.vt);
         const uint64_t key_base = tb * kp.cells;
         if (tid == kTmaThread) {  // first tile of the bin
-            const uint32_t cntev = min((uint32_t)kTile, hi - lo);
+            const uint32_t cntev = min((uint32_t)TILE, hi - lo);
             uint64_t* bar = &s_bar[tile_seq % kStages];
             mbar_expect_tx(bar, cntev * 16u);
             tma_load_1d(s_ev + (tile_seq % kStages) * kTile, a.ev + lo, cntev * 16u, bar);
         }
-        for (uint32_t i = tid; i < a.words; i += kThreads) s_map[i] = 0;
-        __syncthreads();
+        for (uint32_t i = tid; i < a.words; i += NT) s_map[i] = 0;
+        prod_sync<NT>();
 
-        for (uint32_t base = lo; base < hi; base += kTile, tile_seq++) {
+        for (uint32_t base = lo; base < hi; base += TILE, tile_seq++) {
             const uint32_t stage = tile_seq % kStages, par = tile_seq & 1;
             const uint4* tile = s_ev + stage * kTile;
             // the next tile goes into the other stage, which every thread left before the barrier
             // that ended the previous tile
-            if (tid == kTmaThread && base + kTile < hi) {
-                const uint32_t nxt = base + kTile;
-                const uint32_t cntev = min((uint32_t)kTile, hi - nxt);
+            if (tid == kTmaThread && base + TILE < hi) {
+                const uint32_t nxt = base + TILE;
+                const uint32_t cntev = min((uint32_t)TILE, hi - nxt);
                 uint64_t* bar = &s_bar[(tile_seq + 1) % kStages];
                 mbar_expect_tx(bar, cntev * 16u);
                 tma_load_1d(s_ev + ((tile_seq + 1) % kStages) * kTile, a.ev + nxt, cntev * 16u,
@@ -216,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
             uint32_t cv[kPer], cslot[kPer], cxy[kPer];
 #pragma unroll
             for (int j = 0; j < kPer; j++) {  // classification: independent per event (ILP)
-                const uint32_t li = j * kThreads + tid;
+                const uint32_t li = j * NT + tid;
                 const uint4 ev = tile[li];
                 const uint32_t x = ev.x & 0xFFFFu, y = ev.x >> 16;
                 bool ok = (base + li < hi) & (x < (uint32_t)kp.width) & (y < (uint32_t)kp.height);
@@ -254,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 }
                 cslot[j] = s;
             }
-            __syncthreads();  // S1: tile table complete
+            prod_sync<NT>();  // S1: tile table complete
             // ---- phase B: a candidate whose word survived in its slot is a new voxel (lowest
             // index of its cell in this tile, and no earlier tile had the cell)
             uint32_t bal[kPer], wtot = 0;
@@ -291,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                     wbase += __popc(bal[j]);
                 }
             }
-            __syncthreads();  // S2: bitmap marked, table reset, tile and chunk state consumed
+            prod_sync<NT>();  // S2: bitmap marked, table reset, tile and chunk state consumed
             if (tid == 0) {
                 if (pend_chunk != kNoChunk) {  // requested one tile ago: has arrived by now
                     s_next_base = pend_chunk * kChunk;
@@ -299,6 +429,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 }
                 const uint32_t c = s_cursor[par];  // voxels this tile emitted
                 const uint32_t room = s_chunk_end - s_chunk_pos;
+                if (FUSED && c) {  // hand the tile's voxels to the consumer warps
+                    const uint32_t slot = pub_seq % kRing;
+                    mbar_wait(&s_empty[slot], ((pub_seq / kRing) & 1) ^ 1);
+                    s_desc[slot] = make_uint4(room, s_chunk_pos, s_next_base, c);
+                    mbar_arrive(&s_full[slot]);
+                    pub_seq++;
+                }
                 if (c >= room) {  // spilled into the next chunk: make it current, request another
                     const uint32_t nb0 = s_next_base;
                     s_chunk_pos = nb0 + (c - room);
@@ -313,12 +450,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
         }
         if (COUNT_REP) {
             uint32_t r = 0;
-            for (uint32_t i = tid; i < a.words; i += kThreads) r += __popc(s_map[i] >> 16);
+            for (uint32_t i = tid; i < a.words; i += NT) r += __popc(s_map[i] >> 16);
             r = __reduce_add_sync(0xffffffffu, r);
             if (lane == 0 && r) atomicAdd(&cnt->n_repeated, (unsigned long long)r);
         }
     }
     if (tid == 0) {  // publish the two chunks this CTA leaves partly filled
+        if (FUSED) {
+            const uint32_t slot = pub_seq % kRing;
+            mbar_wait(&s_empty[slot], ((pub_seq / kRing) & 1) ^ 1);
+            s_desc[slot] = make_uint4(0, 0, 0, kEndOfStream);
+            mbar_arrive(&s_full[slot]);
+        }
         if (pend_chunk != kNoChunk) s_next_base = pend_chunk * kChunk;
         uint32_t* cl = a.chunk_list + 4 * blockIdx.x;
         cl[0] = s_chunk_end - kChunk;
@@ -410,7 +553,7 @@ __device__ __forceinline__ uint32_t plan_locate(const uint32_t* start, const uin
 
 __global__ void __launch_bounds__(256)
     k_slab_fix_move(const FixPlan* plan, const DsCounters* cnt, uint64_t* keys, uint32_t* first,
-                    uint32_t* xy) {
+                    uint32_t* xy, int32_t* labels) {
     if (cnt->slab_violation) return;
     const uint32_t total = plan->total;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total;
@@ -420,6 +563,7 @@ __global__ void __launch_bounds__(256)
         keys[d] = keys[s];
         first[d] = first[s];
         xy[d] = xy[s];
+        if (labels) labels[d] = labels[s];  // fused k-means: the label travels with its record
     }
 }
 
@@ -428,9 +572,10 @@ uint32_t map_words(uint64_t cells, bool count_rep) {
 }
 size_t slab_smem_bytes(uint64_t cells, bool count_rep) {
     return (size_t)kStages * kTile * 16 + (size_t)kHash * 4 +
-           (size_t)map_words(cells, count_rep) * 4;
+           (size_t)((map_words(cells, count_rep) + 3) & ~3u) * 4;
 }
-constexpr size_t kSmemLimit = 220 * 1024;
+size_t fuse_smem_bytes(int K, int rep) { return (size_t)rep * 3 * K * 4; }
+constexpr size_t kSmemLimit = 232448 - 1024;  // 227 KB opt-in maximum minus the static part
 
 }  // namespace
 
@@ -445,8 +590,19 @@ bool evk_slab_supported(const evk_handle* h, const KeyParams& kp) {
     return slab_smem_bytes(kp.cells, true) <= kSmemLimit;
 }
 
+bool evk_slab_fuse_supported(const evk_handle* h, const KeyParams& kp, int count_repeated, int K) {
+    if (kCtasPerSm != 1 || K < 1 || K > 254 || !evk_slab_supported(h, kp)) return false;
+    return slab_smem_bytes(kp.cells, count_repeated != 0) + fuse_smem_bytes(K, 1) <= kSmemLimit;
+}
+
+template <bool FUSED>
+static void (*pick_kernel(bool count_rep, bool pow2))(SlabArgs, FuseDev) {
+    return count_rep ? (pow2 ? k_slab_main<true, true, FUSED> : k_slab_main<true, false, FUSED>)
+                     : (pow2 ? k_slab_main<false, true, FUSED> : k_slab_main<false, false, FUSED>);
+}
+
 int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, bool* ok,
-                        int* launches) {
+                        int* launches, const SlabFuse* fuse, bool sync) {
     *ok = false;
     const int grid = h->sm_count * kCtasPerSm;
     SlabArgs a;
@@ -465,23 +621,38 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
     a.max_bins = (uint32_t)h->max_bins;
     // a single CTA walks a bin sequentially: with few bins and many events the table is faster
     a.min_bins = h->n_events > (1u << 22) ? 32 : 1;
-    const size_t smem = slab_smem_bytes(kp.cells, count_repeated != 0);
+    size_t smem = slab_smem_bytes(kp.cells, count_repeated != 0);
     const bool pow2 = kp.sx >= 0 && kp.sy >= 0;
-    void (*kern)(SlabArgs) =
-        count_repeated ? (pow2 ? k_slab_main<true, true> : k_slab_main<true, false>)
-                       : (pow2 ? k_slab_main<false, true> : k_slab_main<false, false>);
+    FuseDev f{};
+    f.K = 0;
+    f.rep = 1;
+    if (fuse) {
+        f.K = fuse->kl.K;
+        f.rep = 8;
+        while (f.rep > 1 && smem + fuse_smem_bytes(f.K, f.rep) > kSmemLimit) f.rep >>= 1;
+        smem += fuse_smem_bytes(f.K, f.rep);
+        f.width = fuse->pg.width;
+        f.write_labels = fuse->kl.write_labels;
+        f.map = fuse->map;
+        f.acc = fuse->acc;
+        f.labels = fuse->labels;
+    }
+    void (*kern)(SlabArgs, FuseDev) =
+        fuse ? pick_kernel<true>(count_repeated != 0, pow2) : pick_kernel<false>(count_repeated != 0, pow2);
     EVK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kSmemLimit));
     k_slab_bins<<<grid, 256, 0, h->stream>>>(a);
     EVK_CUDA(h, cudaGetLastError());
     if (h->profiling) cudaEventRecord(h->ev[5], h->stream);
-    kern<<<grid, kThreads, smem, h->stream>>>(a);
+    kern<<<grid, kThreads, smem, h->stream>>>(a, f);
     EVK_CUDA(h, cudaGetLastError());
     if (h->profiling) cudaEventRecord(h->ev[6], h->stream);
     k_slab_fix_plan<<<1, kMaxList, 0, h->stream>>>(a.chunk_list, 2 * grid, h->d_cnt, plan);
-    k_slab_fix_move<<<grid, 256, 0, h->stream>>>(plan, h->d_cnt, h->d_keys, h->d_first, h->d_xy);
+    k_slab_fix_move<<<grid, 256, 0, h->stream>>>(plan, h->d_cnt, h->d_keys, h->d_first, h->d_xy,
+                                                 fuse && fuse->kl.write_labels ? fuse->labels : nullptr);
     EVK_CUDA(h, cudaGetLastError());
     *launches += 4;
+    if (!sync) return EVK_OK;
     // the verification flag decides whether the result stands
     EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,
                                 h->stream));

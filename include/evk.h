@@ -186,6 +186,16 @@ EVK_API int evk_init_centroids_first_k(evk_handle* h, const evk_km_params* p);
  * KM/assign_to_centers.cl:1-140) by a fused assign+accumulate kernel and a finalise kernel. */
 EVK_API int evk_kmeans(evk_handle* h, const evk_km_params* p, int* iters_done);
 
+/* Fused step: the same results as evk_downsample, then (init_first_k != 0) evk_init_centroids_first_k
+ * or (== 0) the centroids already held by the handle (warm start), then evk_kmeans -- submitted as
+ * one pass with a single host synchronisation.  On time-ordered streams with D = 2 the first Lloyd
+ * iteration runs inside the downsample kernel (every voxel is assigned and accumulated as it is
+ * emitted); other shapes run the three calls one after the other.  Replaces the per-slice sequence
+ * launch -> clFinish -> read -> consumer of ACCEL/store.cpp:397-445 when the consumer is k-means. */
+EVK_API int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
+                                  int init_first_k, size_t* n_unique, size_t* n_repeated,
+                                  int* iters_done);
+
 /* ---- return labels and centroids ----------------------------------------------------------- */
 /* Replaces clEnqueueReadBuffer(assign_buffer) (KM/assign_to_centers2.c:259-265).  labels[i] in
  * [0,K) or -1 (unassigned; the reference writes 2k or 255, assign_to_centers.cl:12,22,26), in the
