@@ -253,7 +253,7 @@ def main():
         step()
         t = h.stage_times()
         ds_main += t.ds_main_ms; ds_total += t.ds_total_ms; km_total += t.km_total_ms
-        launches += t.ds_launches + t.km_launches + (2 if (args.unfused or world > 1) else 0)
+        launches += t.ds_launches + t.km_launches + (1 if (args.unfused or world > 1) else 0)
     total_ms = h.timer_stop()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -298,9 +298,7 @@ def main():
                  evk.ALGO_SORT: "sort+unique"}
         traffic = ncu_traffic()
         fused = world == 1 and not args.unfused and algo_used == evk.ALGO_SLAB
-        if fused:  # one kernel reads the events, writes the voxels, assigns and accumulates them
-            kern, a_bytes, a_ms = "k_slab_main<fused>", 16.0 * n + 36.0 * U, ds_ms
-        elif ds_ms >= km_ms:
+        if ds_ms >= km_ms:
             kern, a_bytes, a_ms = names.get(algo_used, "?"), ds_bytes, ds_ms
         else:
             kern, a_bytes, a_ms = "k_km_assign", km_bytes, km_ms

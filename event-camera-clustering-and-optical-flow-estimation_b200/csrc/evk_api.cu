@@ -60,6 +60,7 @@ void invalidate_results(evk_handle* h) {
     h->reps_valid = false;
     h->n_unique = h->n_repeated = 0;
     h->n_labels = 0;
+    h->pix_valid = false;
 }
 
 int km_validate(evk_handle* h, const evk_km_params* p) {
@@ -70,21 +71,25 @@ int km_validate(evk_handle* h, const evk_km_params* p) {
     return EVK_OK;
 }
 
-// label map of the current frame size (lazy; frames beyond 64 Mpixel use the per-point scan)
-uint8_t* ensure_label_map(evk_handle* h, int width, int height) {
+// pixel images of the current frame size (lazy; frames beyond 64 Mpixel use the per-point scan)
+bool ensure_images(evk_handle* h, int width, int height) {
     const size_t need = (size_t)width * (size_t)height;
-    if (need > (64ull << 20)) return nullptr;
-    if (h->label_map_bytes < need) {
+    if (need > (64ull << 20)) return false;
+    if (h->image_pixels < need) {
         if (h->d_label_map) cudaFree(h->d_label_map);
+        if (h->d_pixcnt) cudaFree(h->d_pixcnt);
         h->d_label_map = nullptr;
-        h->label_map_bytes = 0;
-        if (cudaMalloc((void**)&h->d_label_map, need) != cudaSuccess) {
+        h->d_pixcnt = nullptr;
+        h->image_pixels = 0;
+        h->pix_valid = false;
+        if (cudaMalloc((void**)&h->d_label_map, need) != cudaSuccess ||
+            cudaMalloc((void**)&h->d_pixcnt, need * sizeof(uint32_t)) != cudaSuccess) {
             cudaGetLastError();
-            return nullptr;
+            return false;
         }
-        h->label_map_bytes = need;
+        h->image_pixels = need;
     }
-    return h->d_label_map;
+    return true;
 }
 
 KmLaunch km_launch_params(const evk_handle* h, const evk_km_params* p) {
@@ -182,7 +187,10 @@ int evk_create(evk_handle** out, int device, size_t max_events) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(EVK_ERR_CUDA);
     h->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess)
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess)
         return bail(EVK_ERR_CUDA);
     const size_t m = max_events;
     h->table_cap = next_pow2(2 * m + 2);
@@ -208,6 +216,7 @@ int evk_create(evk_handle** out, int device, size_t max_events) {
     ALLOC(h->d_counts, EVK_MAX_K * sizeof(unsigned long long));
     ALLOC(h->d_shift, sizeof(float));
     ALLOC(h->d_prune_lists, EVK_PRUNE_TILES * 16);
+    ALLOC(h->d_quads, EVK_MAX_QUADS);
     ALLOC(h->d_cand, 2 * h->cand_cap * sizeof(uint32_t));
     ALLOC(h->d_flush, h->flush_bytes);
 #undef ALLOC
@@ -237,7 +246,7 @@ int evk_destroy(evk_handle* h) {
                     h->d_reps,   h->d_labels, h->d_perm,   h->d_sort_tmp, h->d_sort_a, h->d_sort_b,
                     h->d_sort_c, h->d_sk_in,  h->d_sk_out, h->d_si_in,  h->d_si_out, h->d_sv_tmp,
                     h->d_bin_start, h->d_slab_scratch, h->d_cnt, h->d_cent,   h->d_acc,    h->d_counts, h->d_shift,
-                    h->d_cand,   h->d_flush, h->d_prune_lists, h->d_label_map};
+                    h->d_cand,   h->d_flush, h->d_prune_lists, h->d_label_map, h->d_pixcnt, h->d_quads};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
@@ -246,6 +255,9 @@ int evk_destroy(evk_handle* h) {
         if (e) cudaEventDestroy(e);
     for (auto& e : h->ev_timer)
         if (e) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side) cudaStreamDestroy(h->side);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return EVK_OK;
@@ -550,25 +562,46 @@ int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_done,
     h->times.km_total_ms = h->times.km_assign_ms = 0.f;
     int it = 0, launches = 0;
     prof_rec(h, 3);
+    // D == 2 on voxels: integer pixels, so labels come from a per-pixel label map (exact).  With
+    // three or more iterations (or a tolerance stop) the iterations run on the W x H histogram of
+    // the representatives and the voxel list is touched twice in total (histogram, final labels);
+    // else every iteration is one two-level pass over the voxel list.
+    const bool image = xy && h->have_ds && p->D == 2 && p->K <= 254 &&
+                       ensure_images(h, h->ds.width, h->ds.height);
+    const bool on_hist = image && (p->iters >= 3 || p->tol >= 0.f);
+    if (on_hist && !h->pix_valid) {
+        EVK_CUDA(h, evk_launch_pix_hist(xy, n, h->ds.width, h->ds.height, h->d_pixcnt, h->sm_count,
+                                        h->stream));
+        h->pix_valid = true;
+        launches++;
+    }
     while (it < p->iters) {
         kl.write_labels = (p->tol >= 0.f || it == p->iters - 1) ? 1 : 0;
         cudaError_t ce = cudaErrorNotSupported;
-        if (xy && h->have_ds && p->D == 2 && p->K <= 254)  // integer pixels: label map + gather
-            ce = evk_launch_km_assign_map(kl, h->ds.width, h->ds.height, h->d_prune_lists,
-                                          ensure_label_map(h, h->ds.width, h->ds.height), xy, n,
-                                          h->d_cent, h->d_acc, h->d_labels, h->sm_count, h->stream);
-        if (ce == cudaErrorNotSupported && xy && h->have_ds)  // exact candidate pruning per point
-            ce = evk_launch_km_assign_pruned(kl, h->ds.width, h->ds.height, h->d_prune_lists, xy, n,
-                                             h->d_cent, h->d_acc, h->d_labels, h->sm_count,
-                                             h->stream);
-        if (ce == cudaErrorNotSupported)
-            ce = evk_launch_km_assign(kl, xy, ev, h->d_first, n, h->d_cent, h->d_acc, h->d_labels,
-                                      h->sm_count, h->stream);
+        if (image) {
+            const bool last = it == p->iters - 1;  // quads: only where a per-voxel pass follows
+            ce = evk_launch_km_image(kl, h->ds.width, h->ds.height, h->d_prune_lists, h->d_cent,
+                                     on_hist ? h->d_pixcnt : nullptr, h->d_label_map,
+                                     (!on_hist || last || p->tol >= 0.f) ? h->d_quads : nullptr,
+                                     h->d_acc, h->stream);
+            if (ce == cudaSuccess && !on_hist)
+                ce = evk_launch_km_assign_tiles(kl, h->ds.width, h->ds.height, h->d_quads,
+                                                h->d_label_map, xy, n, nullptr, true, h->d_acc,
+                                                h->d_labels, h->sm_count, h->stream);
+        } else {
+            if (xy && h->have_ds)  // voxels are gated to the frame: exact candidate pruning applies
+                ce = evk_launch_km_assign_pruned(kl, h->ds.width, h->ds.height, h->d_prune_lists,
+                                                 xy, n, h->d_cent, h->d_acc, h->d_labels,
+                                                 h->sm_count, h->stream);
+            if (ce == cudaErrorNotSupported)
+                ce = evk_launch_km_assign(kl, xy, ev, h->d_first, n, h->d_cent, h->d_acc,
+                                          h->d_labels, h->sm_count, h->stream);
+        }
         EVK_CUDA(h, ce);
         if (reduce) EVK_TRY(reduce(h, p->K, p->D));
         EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
                                            h->stream));
-        launches += n ? (p->D == 2 && xy ? 4 : 2) : 1;
+        launches += image ? (on_hist ? 3 : 5) : (n ? 2 : 1);
         it++;
         if (p->tol >= 0.f) {
             EVK_CUDA(h, cudaMemcpyAsync(h->h_shift, h->d_shift, sizeof(float),
@@ -576,6 +609,12 @@ int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_done,
             EVK_CUDA(h, cudaStreamSynchronize(h->stream));
             if (*h->h_shift <= p->tol) break;
         }
+    }
+    if (on_hist) {  // the label map holds the assignment of the last iteration
+        EVK_CUDA(h, evk_launch_km_assign_tiles(kl, h->ds.width, h->ds.height, h->d_quads,
+                                               h->d_label_map, xy, n, nullptr, false, h->d_acc,
+                                               h->d_labels, h->sm_count, h->stream));
+        launches++;
     }
     prof_rec(h, 4);
     h->n_labels = n;
@@ -619,56 +658,53 @@ int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const evk_km_p
     h->shard_first = h->comm ? h->shard_first : 0;
     if (!init_first_k && (!h->have_centroids || h->K != km->K || h->D != km->D))
         return evk_fail(h, EVK_ERR_STATE, "centroids for K=%d, D=%d have not been set", km->K, km->D);
-    const bool fusable = km->D == 2 && !km->on_events &&
+    const bool fusable = km->D == 2 && !km->on_events && km->K <= 254 && h->n_events &&
+                         km->iters == 1 && km->tol < 0.f &&
                          (ds->algo == EVK_ALGO_AUTO || ds->algo == EVK_ALGO_SLAB) &&
-                         evk_slab_fuse_supported(h, kp, ds->count_repeated, km->K);
+                         evk_slab_supported(h, kp) && ensure_images(h, ds->width, ds->height);
     int st = EVK_OK;
     bool done = false;
-    uint8_t* map = nullptr;
     if (fusable) {
-        DeviceGuard g(h->device);
-        map = ensure_label_map(h, ds->width, ds->height);
-    }
-    if (fusable && map) {
         DeviceGuard g(h->device);
         invalidate_results(h);
         h->ds = *ds;
         h->kp = kp;
         h->have_ds = true;
         KmLaunch kl = km_launch_params(h, km);
-        kl.write_labels = (km->iters == 1 || km->tol >= 0.f) ? 1 : 0;
         int launches = 0;
         EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
         prof_rec(h, 0);
+        // side stream: everything that depends on the centroids only (first-K walk over the head
+        // of the stream, candidate lists, label map, quads) runs beside the downsample
+        EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+        EVK_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
         if (init_first_k) {
             const size_t n_scan = h->n_events < (1u << 20) ? h->n_events : (1u << 20);
             EVK_CUDA(h, evk_launch_init_first_k_walk(kp, kl, h->d_events, n_scan, h->d_cent,
-                                                     &h->d_cnt->scratch[4], h->stream));
+                                                     &h->d_cnt->scratch[4], h->side));
             launches++;
-        }
-        else  // warm start: keep a copy in case the stream check sends us to the general path
+        } else {  // warm start: keep a copy in case the stream check sends us to the general path
             EVK_CUDA(h, cudaMemcpyAsync(h->d_cent + EVK_MAX_K * 2, h->d_cent,
                                         (size_t)km->K * 2 * sizeof(float), cudaMemcpyDeviceToDevice,
-                                        h->stream));
-        SlabFuse fu;
-        fu.kl = kl;
-        fu.pg = evk_make_prune_grid(ds->width, ds->height);
-        fu.map = map;
-        fu.acc = h->d_acc;
-        fu.labels = h->d_labels;
-        EVK_CUDA(h, evk_launch_km_candidates(kl, fu.pg, h->d_cent, h->d_prune_lists, h->stream));
-        EVK_CUDA(h, evk_launch_km_label_map(kl, fu.pg, h->d_prune_lists, h->d_cent, map, h->stream));
-        launches += 2;
+                                        h->side));
+        }
+        EVK_CUDA(h, evk_launch_km_image(kl, ds->width, ds->height, h->d_prune_lists, h->d_cent,
+                                        nullptr, h->d_label_map, h->d_quads, h->d_acc, h->side));
+        EVK_CUDA(h, cudaEventRecord(h->ev_join, h->side));
         bool ok = false;
-        EVK_TRY(evk_downsample_slab(h, kp, ds->count_repeated, &ok, &launches, &fu, false));
+        EVK_TRY(evk_downsample_slab(h, kp, ds->count_repeated, &ok, &launches, false));
+        EVK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         prof_rec(h, 2);
         prof_rec(h, 3);
+        EVK_CUDA(h, evk_launch_km_assign_tiles(kl, ds->width, ds->height, h->d_quads,
+                                               h->d_label_map, h->d_xy, h->n_events,
+                                               &h->d_cnt->n_unique, true, h->d_acc, h->d_labels,
+                                               h->sm_count, h->stream));
         EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
                                            h->stream));
         prof_rec(h, 4);
+        launches += 5;
         EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,
-                                    h->stream));
-        EVK_CUDA(h, cudaMemcpyAsync(h->h_shift, h->d_shift, sizeof(float), cudaMemcpyDeviceToHost,
                                     h->stream));
         EVK_CUDA(h, cudaStreamSynchronize(h->stream));
         ok = h->h_cnt->slab_violation == 0 && h->h_cnt->overflow == 0 &&
@@ -684,36 +720,21 @@ int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const evk_km_p
             h->labels_on_events = false;
             h->km_last = *km;
             h->times.ds_algo_used = EVK_ALGO_SLAB;
-            h->times.ds_launches = launches + 1;
-            h->times.km_launches = 1;
+            h->times.ds_launches = launches - 5;
+            h->times.km_launches = 5;
             h->times.km_iters = 1;
             h->times.ds_compact_ms = 0.f;
             if (h->profiling) {
                 h->times.ds_total_ms = prof_ms(h, 0, 2);
-                h->times.ds_main_ms = prof_ms(h, 5, 6);  // downsample AND assign: one kernel
+                h->times.ds_main_ms = prof_ms(h, 5, 6);
                 h->times.km_total_ms = h->times.km_assign_ms = prof_ms(h, 3, 4);
             }
-            int it = 1;
-            const bool converged = km->tol >= 0.f && *h->h_shift <= km->tol;
-            if (km->iters > 1 && !converged) {
-                evk_km_params rest = *km;
-                rest.iters = km->iters - 1;
-                int more = 0;
-                st = evk_kmeans_run(h, &rest, &more, nullptr);
-                it += more;
-                h->km_last = *km;
-                h->times.km_iters = it;
-            }
-            if (iters_done) *iters_done = it;
+            if (iters_done) *iters_done = 1;
             done = true;
-        } else {
-            // the accumulators may hold partial sums of the abandoned pass
-            EVK_CUDA(h, cudaMemsetAsync(h->d_acc, 0, EVK_MAX_K * 5 * sizeof(unsigned long long),
-                                        h->stream));
-            if (!init_first_k)  // finalise has overwritten the caller's centroids: put them back
-                EVK_CUDA(h, cudaMemcpyAsync(h->d_cent, h->d_cent + EVK_MAX_K * 2,
-                                            (size_t)km->K * 2 * sizeof(float),
-                                            cudaMemcpyDeviceToDevice, h->stream));
+        } else if (!init_first_k) {  // finalise has overwritten the caller's centroids
+            EVK_CUDA(h, cudaMemcpyAsync(h->d_cent, h->d_cent + EVK_MAX_K * 2,
+                                        (size_t)km->K * 2 * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, h->stream));
         }
     }
     if (!done && st == EVK_OK) st = step_unfused(h, ds, km, init_first_k, iters_done);

@@ -154,8 +154,14 @@ struct evk_handle {
     unsigned long long* d_acc = nullptr;     // [EVK_MAX_K * (EVK_MAX_D + 1)]
     unsigned long long* d_counts = nullptr;  // [EVK_MAX_K] counts of the last iteration
     void* d_prune_lists = nullptr;           // [EVK_PRUNE_TILES] uint4 candidate lists
-    uint8_t* d_label_map = nullptr;          // [height * width] label of every pixel (lazy, D == 2)
-    size_t label_map_bytes = 0;
+    // pixel-image k-means (lazy, D == 2): label of every pixel, voxel representatives per pixel
+    uint8_t* d_label_map = nullptr;          // [height * width]
+    uint32_t* d_pixcnt = nullptr;            // [height * width]
+    uint8_t* d_quads = nullptr;              // [EVK_MAX_QUADS] label of uniformly labelled squares
+    cudaStream_t side = nullptr;             // centroid-only kernels run beside the downsample
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    size_t image_pixels = 0;                 // capacity of both
+    bool pix_valid = false;                  // d_pixcnt matches the current voxel shard
     float* d_shift = nullptr;                // [1]
     float* h_shift = nullptr;                // pinned
     size_t n_labels = 0;
@@ -224,14 +230,10 @@ cudaError_t evk_launch_table_compact(const evk_event* ev, uint64_t* tkeys, uint3
                                      cudaStream_t s);
 // downsample: sort + unique
 int evk_downsample_sort(evk_handle* h, const KeyParams& kp, int* launches);
-// downsample: time-slab kernel.  fuse != nullptr: the kernel's consumer warps also run the pruned
-// k-means assign + accumulate on every voxel it emits (labels follow the records through the
-// fix-up).  sync = false: everything is only enqueued (counters are copied to h->h_cnt); the caller
-// synchronises and reads slab_violation / overflow itself.
-struct SlabFuse;
+// downsample: time-slab kernel.  sync = false: everything is only enqueued; the caller copies the
+// counters, synchronises and reads slab_violation / overflow itself.
 int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, bool* ok,
-                        int* launches, const SlabFuse* fuse = nullptr, bool sync = true);
-bool evk_slab_fuse_supported(const evk_handle* h, const KeyParams& kp, int count_repeated, int K);
+                        int* launches, bool sync = true);
 bool evk_slab_supported(const evk_handle* h, const KeyParams& kp);
 size_t evk_slab_scratch_bytes(int sm_count);
 // canonical order
@@ -264,23 +266,27 @@ struct PruneGrid {
 PruneGrid evk_make_prune_grid(int width, int height);
 cudaError_t evk_launch_km_candidates(const KmLaunch& kl, const PruneGrid& pg, const float* cent,
                                      void* lists, cudaStream_t s);
-struct SlabFuse {
-    KmLaunch kl;
-    PruneGrid pg;
-    const uint8_t* map;       // [height * width] label map built from the current centroids
-    unsigned long long* acc;  // [K * 5] exact partial sums (ACC_* layout of evk_kmeans.cu)
-    int32_t* labels;          // indexed like the voxel shard
-};
 cudaError_t evk_launch_km_assign_pruned(const KmLaunch& kl, int width, int height, void* lists,
                                         const uint32_t* xy, size_t n, const float* cent,
                                         unsigned long long* acc, int32_t* labels, int sm_count,
                                         cudaStream_t s);
-cudaError_t evk_launch_km_label_map(const KmLaunch& kl, const PruneGrid& pg, const void* lists,
-                                    const float* cent, uint8_t* map, cudaStream_t s);
-cudaError_t evk_launch_km_assign_map(const KmLaunch& kl, int width, int height, void* lists,
-                                     uint8_t* map, const uint32_t* xy, size_t n, const float* cent,
-                                     unsigned long long* acc, int32_t* labels, int sm_count,
-                                     cudaStream_t s);
+// pixel-image k-means (D == 2, K <= 254; evk_kmeans.cu)
+cudaError_t evk_launch_pix_hist(const uint32_t* xy, size_t n, int width, int height,
+                                uint32_t* pixcnt, int sm_count, cudaStream_t s);
+#define EVK_MAX_QUADS 16384
+struct QuadGrid {  // squares of (1 << shift) pixels, tx * ty <= EVK_MAX_QUADS
+    int32_t width, shift, tx, ty;
+};
+QuadGrid evk_make_quad_grid(int width, int height);
+cudaError_t evk_launch_km_image(const KmLaunch& kl, int width, int height, void* lists,
+                                const float* cent, const uint32_t* pixcnt, uint8_t* map,
+                                uint8_t* quads, unsigned long long* acc, cudaStream_t s);
+cudaError_t evk_launch_km_assign_tiles(const KmLaunch& kl, int width, int height,
+                                       const uint8_t* quads, const uint8_t* map,
+                                       const uint32_t* xy, size_t n,
+                                       const unsigned long long* n_dev, bool accumulate,
+                                       unsigned long long* acc, int32_t* labels, int sm_count,
+                                       cudaStream_t s);
 cudaError_t evk_launch_km_finalise(const KmLaunch& kl, float* cent, unsigned long long* acc,
                                    unsigned long long* counts, float* shift, cudaStream_t s);
 cudaError_t evk_launch_collect_below(const uint32_t* first, size_t n, uint32_t bound,

@@ -395,127 +395,217 @@ __global__ void __launch_bounds__(kBlock)
     }
 }
 
-// ---- label map (D == 2, voxels) ---------------------------------------------------------------
-// Voxel representatives have integer pixel coordinates, so with D == 2 the label of a point is a
-// pure function of its pixel: one pass evaluates the contract arithmetic once per PIXEL (through
-// the candidate lists: a handful of distances each) into a W x H byte image that stays in L2
-// (0.9 MB for Gen4), and the per-point work of an iteration collapses to a 1-byte gather, the
-// label store and three shared-memory atomics.  Bit-identical to the per-point scan by
-// construction: same operands, same operations, same order.  0xFF = unassigned (gate).
+// ---- pixel-image k-means (D == 2, voxels, K <= 254) -------------------------------------------
+// Voxel representatives have integer pixel coordinates, so with D == 2 everything an iteration
+// needs from the voxel list is the histogram pixcnt[y][x] = number of representatives at that pixel
+// (built once per downsample: by the slab kernel itself in the fused step, else by k_pix_hist).
+//   assign      : label[y][x] = argmin over the tile's candidate list, the contract arithmetic
+//                 evaluated once per PIXEL (same operands, operations and order as the per-point
+//                 scan, so labels are bit-identical); 0xFF = unassigned (gate)
+//   accumulate  : sum_k += pixcnt * (1, x, y) -- exact integers, same sums as adding point by point
+// A Lloyd iteration therefore costs O(W * H) (0.9 M pixels for Gen4, L2-resident) instead of
+// O(U) (55 M voxels); the per-voxel labels are one 1-byte gather at the end.
 __global__ void __launch_bounds__(256)
-    k_km_label_map(KmLaunch kl, PruneGrid pg, const uint4* __restrict__ lists,
-                   const float* __restrict__ cent, uint8_t* __restrict__ map) {
-    extern __shared__ float2 s_cc[];
-    for (int i = threadIdx.x; i < kl.K; i += blockDim.x)
-        s_cc[i] = reinterpret_cast<const float2*>(cent)[i];
-    __syncthreads();
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-    if (x >= pg.width) return;
-    const uint4 l4 = __ldg(lists + (y >> pg.shift) * pg.tx + (x >> pg.shift));
-    const float px = (float)x, py = (float)y;
-    float best = kl.best2;
-    int lab = 0xFF;
-    if ((l4.x & 0xFFu) == 0xFEu) {
-        for (int k = 0; k < kl.K; k++) {
-            const float2 cc = s_cc[k];
-            const float dx = __fsub_rn(cc.x, px), dy = __fsub_rn(cc.y, py);
-            const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
-            if (d2 < best) {
-                best = d2;
-                lab = k;
-            }
+    k_pix_hist(const uint32_t* __restrict__ xy, size_t n, uint32_t width, uint32_t* pixcnt) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+    for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < n; i0 += stride) {
+        uint32_t w[4];
+        int m = 4;
+        if (i0 + 4 <= n) {
+            const uint4 v = __ldcs(reinterpret_cast<const uint4*>(xy + i0));
+            w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+        } else {
+            m = (int)(n - i0);
+            for (int q = 0; q < m; q++) w[q] = xy[i0 + q];
         }
-    } else {
-        const uint32_t lw[4] = {l4.x, l4.y, l4.z, l4.w};
-#pragma unroll
-        for (int s = 0; s < kListLen; s++) {
-            const uint32_t k = (lw[s >> 2] >> (8 * (s & 3))) & 0xFFu;
-            if (k == 0xFFu) break;
-            const float2 cc = s_cc[k];
-            const float dx = __fsub_rn(cc.x, px), dy = __fsub_rn(cc.y, py);
-            const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
-            if (d2 < best) {
-                best = d2;
-                lab = (int)k;
-            }
-        }
+        for (int q = 0; q < m; q++) atomicAdd(pixcnt + (size_t)(w[q] >> 16) * width + (w[q] & 0xFFFFu), 1u);
     }
-    map[(size_t)y * pg.width + x] = (uint8_t)lab;
 }
 
-constexpr int kMapPPT = 4;  // points per thread: one 16-B load of xy, one 16-B store of labels
-__global__ void __launch_bounds__(kBlock)
-    k_km_assign_map(KmLaunch kl, int width, const uint8_t* __restrict__ map,
-                    const uint32_t* __restrict__ xy, size_t n,
-                    unsigned long long* __restrict__ acc, int32_t* __restrict__ labels) {
+// one thread per pixel: label into `map`, pixcnt-weighted sums into acc (warp-aggregated: a warp's
+// 32 neighbouring pixels nearly always share one label)
+__global__ void __launch_bounds__(256)
+    k_km_image(KmLaunch kl, PruneGrid pg, const uint4* __restrict__ lists,
+               const float* __restrict__ cent, const uint32_t* __restrict__ pixcnt,
+               uint8_t* __restrict__ map, unsigned long long* __restrict__ acc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int K = kl.K;
-    uint32_t* s_acc = reinterpret_cast<uint32_t*>(smem_raw);  // [kRep][3][K]
-    for (int i = threadIdx.x; i < kRep * 3 * K; i += kBlock) s_acc[i] = 0;
+    float2* s_cc = reinterpret_cast<float2*>(smem_raw);                                // [K]
+    unsigned long long* s_acc = reinterpret_cast<unsigned long long*>(s_cc + kl.K);    // [K][3]
+    for (int i = threadIdx.x; i < kl.K; i += blockDim.x)
+        s_cc[i] = reinterpret_cast<const float2*>(cent)[i];
+    for (int i = threadIdx.x; i < 3 * kl.K; i += blockDim.x) s_acc[i] = 0;
     __syncthreads();
-    uint32_t* my_acc = s_acc + (threadIdx.x & (kRep - 1)) * 3 * K;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const bool in = x < pg.width;
+    uint32_t lab = 0xFFu, c = 0;
+    if (in) {
+        const uint4 l4 = __ldg(lists + (y >> pg.shift) * pg.tx + (x >> pg.shift));
+        c = pixcnt ? pixcnt[(size_t)y * pg.width + x] : 0u;
+        const float px = (float)x, py = (float)y;
+        float best = kl.best2;
+        if ((l4.x & 0xFFu) == 0xFEu) {  // more than 16 candidates: scan all K
+            for (int k = 0; k < kl.K; k++) {
+                const float2 cc = s_cc[k];
+                const float dx = __fsub_rn(cc.x, px), dy = __fsub_rn(cc.y, py);
+                const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+                if (d2 < best) {
+                    best = d2;
+                    lab = (uint32_t)k;
+                }
+            }
+        } else {
+            const uint32_t lw[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+            for (int s = 0; s < kListLen; s++) {
+                const uint32_t k = (lw[s >> 2] >> (8 * (s & 3))) & 0xFFu;
+                if (k == 0xFFu) break;
+                const float2 cc = s_cc[k];
+                const float dx = __fsub_rn(cc.x, px), dy = __fsub_rn(cc.y, py);
+                const float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+                if (d2 < best) {
+                    best = d2;
+                    lab = k;
+                }
+            }
+        }
+        map[(size_t)y * pg.width + x] = (uint8_t)lab;
+    }
+    // warp-aggregated accumulation: one leader per distinct label in the warp
+    const int lane = threadIdx.x & 31;
+    uint32_t todo = __ballot_sync(0xffffffffu, in && c != 0 && lab != 0xFFu);
+    const uint64_t vx = (uint64_t)c * (uint32_t)x, vy = (uint64_t)c * (uint32_t)y;  // < 2^48
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const uint32_t l0 = __shfl_sync(0xffffffffu, lab, leader);
+        const uint32_t grp = __ballot_sync(0xffffffffu, lab == l0) & todo;
+        const bool mine = (grp >> lane) & 1u;
+        // 24-bit limbs: a warp's sum of 32 limbs fits 32 bits
+        const uint32_t c0 = __reduce_add_sync(0xffffffffu, mine ? (c & 0xFFFFFFu) : 0u);
+        const uint32_t c1 = __reduce_add_sync(0xffffffffu, mine ? (c >> 24) : 0u);
+        const uint32_t x0 = __reduce_add_sync(0xffffffffu, mine ? (uint32_t)(vx & 0xFFFFFFu) : 0u);
+        const uint32_t x1 = __reduce_add_sync(0xffffffffu, mine ? (uint32_t)(vx >> 24) : 0u);
+        const uint32_t y0 = __reduce_add_sync(0xffffffffu, mine ? (uint32_t)(vy & 0xFFFFFFu) : 0u);
+        const uint32_t y1 = __reduce_add_sync(0xffffffffu, mine ? (uint32_t)(vy >> 24) : 0u);
+        if (lane == leader) {
+            atomicAdd(&s_acc[l0 * 3 + 0], (unsigned long long)c0 + ((unsigned long long)c1 << 24));
+            atomicAdd(&s_acc[l0 * 3 + 1], (unsigned long long)x0 + ((unsigned long long)x1 << 24));
+            atomicAdd(&s_acc[l0 * 3 + 2], (unsigned long long)y0 + ((unsigned long long)y1 << 24));
+        }
+        todo &= ~grp;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < kl.K; k += blockDim.x) {
+        if (s_acc[k * 3]) {
+            atomicAdd(&acc[k * ACC_STRIDE + ACC_CNT], s_acc[k * 3 + 0]);
+            atomicAdd(&acc[k * ACC_STRIDE + ACC_X], s_acc[k * 3 + 1]);
+            atomicAdd(&acc[k * ACC_STRIDE + ACC_Y], s_acc[k * 3 + 2]);
+        }
+    }
+}
+
+// quads[t] = the label shared by every pixel of the (1 << shift)-pixel square t, or 0xFE (mixed)
+__global__ void __launch_bounds__(128)
+    k_km_quads(const uint8_t* __restrict__ map, int width, int height, int shift, int qx, int qy,
+               uint8_t* __restrict__ quads) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= qx * qy) return;
+    const int ty = t / qx, tx = t - ty * qx;
+    const int x0 = tx << shift, y0 = ty << shift;
+    const int x1 = min(width, x0 + (1 << shift)), y1 = min(height, y0 + (1 << shift));
+    const uint8_t first = map[(size_t)y0 * width + x0];
+    bool uniform = true;
+    for (int y = y0; y < y1; y++)
+        for (int x = x0; x < x1; x++) uniform &= map[(size_t)y * width + x] == first;
+    quads[t] = uniform ? first : (uint8_t)0xFE;
+}
+
+// Per-voxel pass, two levels: the label map is piecewise constant (Voronoi cells), so most small
+// squares ("quads", 8 x 8 px for Gen4) carry ONE label -- a byte from a <= 16 KB table in shared
+// memory; only points in mixed quads (0xFE) gather their label from the pixel map (L2; a random
+// L2 access per point costs an SM about a cycle per lane, so it pays to keep them rare).
+// ACC: also accumulate the exact sums (single-iteration path); else labels only (gather at the end
+// of the image iterations).  Accumulators: one private column per lane (bank == lane: no conflicts)
+// shared by the CTA's warps through 32-bit shared atomics, flushed with 64-bit global atomics.
+constexpr int kTlMax = EVK_MAX_QUADS;
+template <bool ACC>
+__global__ void __launch_bounds__(kBlock)
+    k_km_assign_tiles(KmLaunch kl, QuadGrid pg, const uint8_t* __restrict__ quads,
+                      const uint8_t* __restrict__ map, const uint32_t* __restrict__ xy, size_t n,
+                      const unsigned long long* __restrict__ n_dev, int copies,
+                      unsigned long long* __restrict__ acc, int32_t* __restrict__ labels) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint8_t* s_tl = smem_raw;                                         // [kTlMax]
+    uint32_t* s_acc = reinterpret_cast<uint32_t*>(smem_raw + kTlMax);  // [3][K][copies]
+    const int K = kl.K;
+    if (n_dev) n = (size_t)*n_dev;  // voxel count still on the device (fused step)
+    for (int t = threadIdx.x; t < (pg.tx * pg.ty + 3) / 4; t += kBlock)  // table is padded to 4
+        reinterpret_cast<uint32_t*>(s_tl)[t] = __ldg(reinterpret_cast<const uint32_t*>(quads) + t);
+    if (ACC)
+        for (int i = threadIdx.x; i < 3 * K * copies; i += kBlock) s_acc[i] = 0;
+    __syncthreads();
+    const uint32_t col = threadIdx.x & (copies - 1);
     const size_t n_chunks = (n + kChunk - 1) / kChunk;
     for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
         const size_t cbase = c * (size_t)kChunk;
 #pragma unroll 2
-        for (int r = 0; r < kChunk / (kBlock * kMapPPT); r++) {
-            const size_t i0 = cbase + ((size_t)r * kBlock + threadIdx.x) * kMapPPT;
+        for (int r = 0; r < kChunk / (kBlock * 4); r++) {
+            const size_t i0 = cbase + ((size_t)r * kBlock + threadIdx.x) * 4;
             if (i0 >= n) break;
-            uint32_t w[kMapPPT];
-            if (i0 + kMapPPT <= n) {
+            uint32_t w[4], lab[4];
+            const bool full = i0 + 4 <= n;
+            if (full) {
                 const uint4 v = __ldcs(reinterpret_cast<const uint4*>(xy + i0));
                 w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
             } else {
 #pragma unroll
-                for (int q = 0; q < kMapPPT; q++) w[q] = i0 + q < n ? xy[i0 + q] : 0u;
+                for (int q = 0; q < 4; q++) w[q] = i0 + q < n ? xy[i0 + q] : 0u;
             }
-            uint32_t lab[kMapPPT];
 #pragma unroll
-            for (int q = 0; q < kMapPPT; q++)
-                lab[q] = __ldg(map + (size_t)(w[q] >> 16) * width + (w[q] & 0xFFFFu));
-            if (kl.write_labels) {
+            for (int q = 0; q < 4; q++) {
+                const uint32_t px = w[q] & 0xFFFFu, py = w[q] >> 16;
+                lab[q] = s_tl[(py >> pg.shift) * pg.tx + (px >> pg.shift)];  // quad
+                if (lab[q] == 0xFEu) lab[q] = __ldg(map + (size_t)py * pg.width + px);
+            }
+            if (!ACC || kl.write_labels) {
                 int4 o;
                 o.x = lab[0] == 0xFFu ? -1 : (int)lab[0];
                 o.y = lab[1] == 0xFFu ? -1 : (int)lab[1];
                 o.z = lab[2] == 0xFFu ? -1 : (int)lab[2];
                 o.w = lab[3] == 0xFFu ? -1 : (int)lab[3];
-                if (i0 + kMapPPT <= n) {
+                if (full) {
                     __stcs(reinterpret_cast<int4*>(labels + i0), o);
                 } else {
                     const int ov[4] = {o.x, o.y, o.z, o.w};
-                    for (int q = 0; q < kMapPPT; q++)
+                    for (int q = 0; q < 4; q++)
                         if (i0 + q < n) labels[i0 + q] = ov[q];
                 }
             }
+            if (ACC) {
 #pragma unroll
-            for (int q = 0; q < kMapPPT; q++) {
-                if (i0 + q < n && lab[q] != 0xFFu) {
-                    atomicAdd(&my_acc[lab[q]], 1u);
-                    atomicAdd(&my_acc[K + lab[q]], w[q] & 0xFFFFu);
-                    atomicAdd(&my_acc[2 * K + lab[q]], w[q] >> 16);
+                for (int q = 0; q < 4; q++) {
+                    if (i0 + q < n && lab[q] != 0xFFu) {
+                        uint32_t* a = s_acc + lab[q] * copies + col;
+                        atomicAdd(a, 1u);
+                        atomicAdd(a + K * copies, w[q] & 0xFFFFu);
+                        atomicAdd(a + 2 * K * copies, w[q] >> 16);
+                    }
                 }
             }
         }
-        __syncthreads();
-        for (int k = threadIdx.x; k < K; k += kBlock) {
-            unsigned long long sc = 0, sx = 0, sy = 0;
-#pragma unroll
-            for (int rr = 0; rr < kRep; rr++) {
-                uint32_t* a = s_acc + rr * 3 * K;
-                sc += a[k];
-                sx += a[K + k];
-                sy += a[2 * K + k];
-                a[k] = 0;
-                a[K + k] = 0;
-                a[2 * K + k] = 0;
+        if (ACC) {  // u32 cannot overflow within one chunk: 32768 * 65535 < 2^32
+            __syncthreads();
+            for (int j = threadIdx.x; j < 3 * K; j += kBlock) {
+                unsigned long long sum = 0;
+                for (int cc = 0; cc < copies; cc++) {
+                    const int idx = j * copies + ((cc + threadIdx.x) & (copies - 1));  // skewed
+                    sum += s_acc[idx];
+                    s_acc[idx] = 0;
+                }
+                const int which = j / K, k = j - which * K;  // 0: count, 1: sum x, 2: sum y
+                if (sum) atomicAdd(&acc[k * ACC_STRIDE + (which == 0 ? ACC_CNT : which == 1 ? ACC_X : ACC_Y)], sum);
             }
-            if (sc) {
-                atomicAdd(&acc[k * ACC_STRIDE + ACC_CNT], sc);
-                atomicAdd(&acc[k * ACC_STRIDE + ACC_X], sx);
-                atomicAdd(&acc[k * ACC_STRIDE + ACC_Y], sy);
-            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
@@ -648,29 +738,80 @@ cudaError_t evk_launch_km_candidates(const KmLaunch& kl, const PruneGrid& pg, co
     return cudaGetLastError();
 }
 
-cudaError_t evk_launch_km_label_map(const KmLaunch& kl, const PruneGrid& pg, const void* lists,
-                                    const float* cent, uint8_t* map, cudaStream_t s) {
-    dim3 grid((pg.width + 255) / 256, pg.height);
-    k_km_label_map<<<grid, 256, kl.K * sizeof(float2), s>>>(
-        kl, pg, reinterpret_cast<const uint4*>(lists), cent, map);
+cudaError_t evk_launch_pix_hist(const uint32_t* xy, size_t n, int width, int height,
+                                uint32_t* pixcnt, int sm_count, cudaStream_t s) {
+    cudaError_t e = cudaMemsetAsync(pixcnt, 0, (size_t)width * height * sizeof(uint32_t), s);
+    if (e != cudaSuccess || n == 0) return e;
+    const size_t need = (n + 1023) / 1024;
+    const size_t cap = (size_t)sm_count * 16;
+    k_pix_hist<<<(int)(need < cap ? need : cap), 256, 0, s>>>(xy, n, (uint32_t)width, pixcnt);
     return cudaGetLastError();
 }
 
-// D == 2 on the voxel shard, K <= 254: candidate lists -> label map -> per-point gather.
-cudaError_t evk_launch_km_assign_map(const KmLaunch& kl, int width, int height, void* lists,
-                                     uint8_t* map, const uint32_t* xy, size_t n, const float* cent,
-                                     unsigned long long* acc, int32_t* labels, int sm_count,
-                                     cudaStream_t s) {
+// one Lloyd assign + accumulate over the pixel image: candidate lists -> labels + weighted sums
+QuadGrid evk_make_quad_grid(int width, int height) {
+    QuadGrid qg;
+    qg.width = width;
+    qg.shift = 1;
+    for (;;) {
+        qg.tx = (width + (1 << qg.shift) - 1) >> qg.shift;
+        qg.ty = (height + (1 << qg.shift) - 1) >> qg.shift;
+        if ((long long)qg.tx * qg.ty <= EVK_MAX_QUADS) break;
+        qg.shift++;
+    }
+    return qg;
+}
+
+// quads != nullptr: also the table of uniformly labelled squares for evk_launch_km_assign_tiles
+cudaError_t evk_launch_km_image(const KmLaunch& kl, int width, int height, void* lists,
+                                const float* cent, const uint32_t* pixcnt, uint8_t* map,
+                                uint8_t* quads, unsigned long long* acc, cudaStream_t s) {
     if (kl.D != 2 || kl.K > 254 || !map) return cudaErrorNotSupported;
-    if (n == 0) return cudaSuccess;
     const PruneGrid pg = evk_make_prune_grid(width, height);
     evk_launch_km_candidates(kl, pg, cent, lists, s);
-    evk_launch_km_label_map(kl, pg, lists, cent, map, s);
-    size_t chunks = (n + kChunk - 1) / kChunk;
-    size_t cap = (size_t)sm_count * 8;
-    int grid = (int)(chunks < cap ? chunks : cap);
-    k_km_assign_map<<<grid, kBlock, (size_t)kRep * 3 * kl.K * sizeof(uint32_t), s>>>(
-        kl, width, map, xy, n, acc, labels);
+    dim3 grid((width + 255) / 256, height);
+    const size_t smem = (size_t)kl.K * (sizeof(float2) + 3 * sizeof(unsigned long long));
+    k_km_image<<<grid, 256, smem, s>>>(kl, pg, reinterpret_cast<const uint4*>(lists), cent, pixcnt,
+                                       map, acc);
+    if (quads) {
+        const QuadGrid qg = evk_make_quad_grid(width, height);
+        k_km_quads<<<(qg.tx * qg.ty + 127) / 128, 128, 0, s>>>(map, width, height, qg.shift, qg.tx,
+                                                              qg.ty, quads);
+    }
+    return cudaGetLastError();
+}
+
+// Per-voxel pass over the voxel shard with the two-level label lookup.  accumulate: also the exact
+// sums (one Lloyd assign + accumulate); the candidate lists and the pixel map must already have
+// been built from the current centroids (evk_launch_km_image with or without a histogram).
+// n_dev != nullptr: the voxel count is read on the device, n is only an upper bound for the grid.
+cudaError_t evk_launch_km_assign_tiles(const KmLaunch& kl, int width, int height,
+                                       const uint8_t* quads, const uint8_t* map,
+                                       const uint32_t* xy, size_t n,
+                                       const unsigned long long* n_dev, bool accumulate,
+                                       unsigned long long* acc, int32_t* labels, int sm_count,
+                                       cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const QuadGrid pg = evk_make_quad_grid(width, height);
+    int copies = 32;
+    while (copies > 1 && (size_t)3 * kl.K * copies * 4 > 48 * 1024) copies >>= 1;
+    const size_t smem = kTlMax + (accumulate ? (size_t)3 * kl.K * copies * 4 : 0);
+    const size_t chunks = (n + kChunk - 1) / kChunk;
+    const size_t cap = (size_t)sm_count * 8;
+    const int grid = (int)(chunks < cap ? chunks : cap);
+    if (accumulate) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(k_km_assign_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 64 * 1024);
+            attr_done = true;
+        }
+        k_km_assign_tiles<true><<<grid, kBlock, smem, s>>>(kl, pg, quads, map, xy, n, n_dev, copies,
+                                                           acc, labels);
+    } else {
+        k_km_assign_tiles<false><<<grid, kBlock, smem, s>>>(kl, pg, quads, map, xy, n, n_dev,
+                                                            copies, acc, labels);
+    }
     return cudaGetLastError();
 }
 

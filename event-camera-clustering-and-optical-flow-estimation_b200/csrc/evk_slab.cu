@@ -141,120 +141,15 @@ __device__ __forceinline__ uint32_t hash_slot(uint32_t cell) {
 // lane 0 of the last producer warp issues the bulk copies; thread 0 keeps the output-chunk
 // bookkeeping
 
-// ---- fused k-means consumer ------------------------------------------------------------------
-// FUSED: kConsWarps of the CTA's 32 warps are consumers (a CTA cannot exceed 1024 threads, so the
-// producers work on tiles of (1024 - kCons) * kPer events).  After every tile the producers publish a
-// descriptor (where the tile's voxels went and how many) through a small mbarrier ring; the
-// consumer warps read the packed coordinates the producers have just written (L2 hits), look the
-// label up in the per-pixel label map of evk_kmeans.cu (exact: same arithmetic, same lowest-k tie
-// rule, evaluated once per pixel), store it next to the record and accumulate exact integer sums
-// in shared memory.  They run in the issue slots the producers leave idle around their barriers.
-#ifndef EVK_SLAB_CONS_WARPS
-#define EVK_SLAB_CONS_WARPS 4
-#endif
-#ifndef EVK_SLAB_CONS_PPT
-#define EVK_SLAB_CONS_PPT 4
-#endif
-constexpr int kConsWarps = EVK_SLAB_CONS_WARPS;
-constexpr int kCons = 32 * kConsWarps;
-constexpr int kConsPPT = EVK_SLAB_CONS_PPT;  // voxels per consumer thread per pass
-constexpr int kRing = 4;                      // descriptor ring depth
-constexpr uint32_t kEndOfStream = 0xFFFFFFFFu;
-constexpr uint32_t kFlushEvery = 32768;       // u32 sums: 32768 * 65535 < 2^32
-
-struct FuseDev {
-    int K, rep;
-    int32_t width;
-    int write_labels;
-    const uint8_t* map;  // label of every pixel for the current centroids (evk_kmeans.cu)
-    unsigned long long* acc;
-    int32_t* labels;
-};
-
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 template <int NT>
 __device__ __forceinline__ void prod_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
 }
-__device__ __forceinline__ void cons_sync() {
-    asm volatile("bar.sync 2, %0;" ::"n"(kCons) : "memory");
-}
 
-__device__ __forceinline__ void cons_flush(const FuseDev& f, uint32_t* s_acc, int ctid) {
-    cons_sync();
-    for (int k = ctid; k < f.K; k += kCons) {
-        unsigned long long sc = 0, sx = 0, sy = 0;
-        for (int r = 0; r < f.rep; r++) {
-            uint32_t* a = s_acc + r * 3 * f.K;
-            sc += a[k];
-            sx += a[f.K + k];
-            sy += a[2 * f.K + k];
-            a[k] = 0;
-            a[f.K + k] = 0;
-            a[2 * f.K + k] = 0;
-        }
-        if (sc) {
-            atomicAdd(&f.acc[k * ACC_STRIDE + ACC_CNT], sc);
-            atomicAdd(&f.acc[k * ACC_STRIDE + ACC_X], sx);
-            atomicAdd(&f.acc[k * ACC_STRIDE + ACC_Y], sy);
-        }
-    }
-    cons_sync();
-}
-
-__device__ __forceinline__ void consumer_loop(const FuseDev& f, const uint32_t* xy,
-                                              uint32_t* s_acc, uint64_t* s_full,
-                                              uint64_t* s_empty, const uint4* s_desc, int ctid) {
-    const int lane = ctid & 31;
-    const int K = f.K;
-    uint32_t* my_acc = s_acc + (ctid & (f.rep - 1)) * 3 * K;
-    uint32_t since_flush = 0;
-    for (uint32_t seq = 0;; seq++) {
-        const uint32_t slot = seq % kRing;
-        mbar_wait(&s_full[slot], (seq / kRing) & 1);
-        const uint4 d = s_desc[slot];  // room, pos0, next chunk base, voxel count
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[slot]);  // descriptor is in registers: slot is free
-        if (d.w == kEndOfStream) break;
-        for (uint32_t o0 = 0; o0 < d.w; o0 += kCons * kConsPPT) {
-            uint32_t w[kConsPPT], pos[kConsPPT], lab[kConsPPT];
-#pragma unroll
-            for (int q = 0; q < kConsPPT; q++) {
-                const uint32_t o = o0 + q * kCons + ctid;
-                pos[q] = o < d.x ? d.y + o : d.z + (o - d.x);
-                // L1 may hold a stale copy of a line that an earlier tile's read pulled in
-                w[q] = o < d.w ? __ldcg(xy + pos[q]) : 0u;
-                if (o >= d.w) pos[q] = kEndOfStream;
-            }
-#pragma unroll
-            for (int q = 0; q < kConsPPT; q++)
-                lab[q] = __ldg(f.map + (size_t)(w[q] >> 16) * f.width + (w[q] & 0xFFFFu));
-#pragma unroll
-            for (int q = 0; q < kConsPPT; q++) {
-                if (pos[q] == kEndOfStream) continue;
-                if (f.write_labels) f.labels[pos[q]] = lab[q] == 0xFFu ? -1 : (int)lab[q];
-                if (lab[q] != 0xFFu) {
-                    atomicAdd(&my_acc[lab[q]], 1u);
-                    atomicAdd(&my_acc[K + lab[q]], w[q] & 0xFFFFu);
-                    atomicAdd(&my_acc[2 * K + lab[q]], w[q] >> 16);
-                }
-            }
-        }
-        since_flush += d.w;
-        if (since_flush >= kFlushEvery) {
-            cons_flush(f, s_acc, ctid);
-            since_flush = 0;
-        }
-    }
-    cons_flush(f, s_acc, ctid);
-}
-
-template <bool COUNT_REP, bool POW2, bool FUSED>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a, FuseDev f) {
-    constexpr int NT = FUSED ? kThreads - kCons : kThreads;  // producer threads
-    constexpr int TILE = NT * kPer;                          // events per tile
+template <bool COUNT_REP, bool POW2>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) {
+    constexpr int NT = kThreads;
+    constexpr int TILE = NT * kPer;  // events per tile
     constexpr int kTmaThread = NT - 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* s_ev = reinterpret_cast<uint4*>(smem_raw);                        // [kStages][kTile]
@@ -262,10 +157,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a, 
     // bin bitmap.  COUNT_REP: 16 cells per word, bit c = "seen", bit 16 + c = "hit at least twice"
     // (one load answers both questions); else 32 cells per word, "seen" only.
     uint32_t* s_map = s_hash + kHash;  // [words]
-    uint32_t* s_acc = s_map + ((a.words + 3) & ~3u);  // [rep][3][K]  (FUSED)
     __shared__ __align__(8) uint64_t s_bar[kStages];
-    __shared__ __align__(8) uint64_t s_full[kRing], s_empty[kRing];
-    __shared__ __align__(16) uint4 s_desc[kRing];
     __shared__ uint32_t s_bin;
     __shared__ uint32_t s_cursor[2];  // voxels emitted by the current tile (by tile parity)
     __shared__ uint32_t s_chunk_pos, s_chunk_end, s_next_base;
@@ -278,14 +170,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a, 
     const int tid = threadIdx.x, lane = tid & 31;
 
     for (int i = tid; i < kHash; i += blockDim.x) s_hash[i] = kEmpty;
-    if (FUSED)
-        for (int i = tid; i < f.rep * 3 * f.K; i += blockDim.x) s_acc[i] = 0;
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) mbar_init(&s_bar[s], 1);
-        for (int s = 0; s < kRing; s++) {
-            mbar_init(&s_full[s], 1);
-            mbar_init(&s_empty[s], kConsWarps);
-        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_cursor[0] = s_cursor[1] = 0;
         // two chunks up front: the current one and the one after it
@@ -295,13 +181,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a, 
         s_next_base = (c0 + 1) * kChunk;
     }
     __syncthreads();
-    if (FUSED && tid >= NT) {
-        consumer_loop(f, a.xy, s_acc, s_full, s_empty, s_desc, tid - NT);
-        return;
-    }
     uint32_t pend_chunk = kNoChunk;  // thread 0: chunk index requested but not yet published
     uint32_t tile_seq = 0;           // tiles consumed by this CTA (stage = seq % kStages)
-    uint32_t pub_seq = 0;            // thread 0: descriptors published to the consumer warps
 
     for (;;) {
         prod_sync<NT>();
@@ -429,13 +310,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a, 
                 }
                 const uint32_t c = s_cursor[par];  // voxels this tile emitted
                 const uint32_t room = s_chunk_end - s_chunk_pos;
-                if (FUSED && c) {  // hand the tile's voxels to the consumer warps
-                    const uint32_t slot = pub_seq % kRing;
-                    mbar_wait(&s_empty[slot], ((pub_seq / kRing) & 1) ^ 1);
-                    s_desc[slot] = make_uint4(room, s_chunk_pos, s_next_base, c);
-                    mbar_arrive(&s_full[slot]);
-                    pub_seq++;
-                }
                 if (c >= room) {  // spilled into the next chunk: make it current, request another
                     const uint32_t nb0 = s_next_base;
                     s_chunk_pos = nb0 + (c - room);
@@ -456,12 +330,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a, 
         }
     }
     if (tid == 0) {  // publish the two chunks this CTA leaves partly filled
-        if (FUSED) {
-            const uint32_t slot = pub_seq % kRing;
-            mbar_wait(&s_empty[slot], ((pub_seq / kRing) & 1) ^ 1);
-            s_desc[slot] = make_uint4(0, 0, 0, kEndOfStream);
-            mbar_arrive(&s_full[slot]);
-        }
         if (pend_chunk != kNoChunk) s_next_base = pend_chunk * kChunk;
         uint32_t* cl = a.chunk_list + 4 * blockIdx.x;
         cl[0] = s_chunk_end - kChunk;
@@ -473,71 +341,36 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a, 
 
 // ---- fix-up: make the voxel shard dense -------------------------------------------------------
 // Chunks not listed are full.  U = total filled.  Every live slot at a position >= U is moved into
-// a hole (unfilled slot of a listed chunk) below U; the counts match by construction.
+// a hole (unfilled slot of a listed chunk) below U; the counts match by construction.  One launch:
+// every CTA rebuilds the (tiny) plan in shared memory from the chunk list, then moves its share.
 constexpr int kMaxList = 1024;
-struct FixPlan {
-    uint32_t n_src, n_dst, total, pad;
-    uint32_t src_start[kMaxList + 2], src_prefix[kMaxList + 2];
-    uint32_t dst_start[kMaxList + 2], dst_prefix[kMaxList + 2];
-};
+constexpr int kFixThreads = 1024;
 
-__global__ void __launch_bounds__(kMaxList)
-    k_slab_fix_plan(const uint32_t* chunk_list, uint32_t n_list, DsCounters* cnt, FixPlan* plan) {
-    __shared__ uint32_t s_base[kMaxList], s_fill[kMaxList];
-    __shared__ uint32_t s_len[2][kMaxList + 2];
-    __shared__ unsigned long long s_holes;
-    if (cnt->slab_violation) return;
-    const uint32_t M = (uint32_t)cnt->scratch[3];  // chunks handed out
-    const uint32_t i = threadIdx.x;
-    if (i == 0) s_holes = 0;
-    __syncthreads();
-    if (i < n_list) {
-        s_base[i] = chunk_list[2 * i];
-        s_fill[i] = chunk_list[2 * i + 1];
-        atomicAdd(&s_holes, (unsigned long long)(kChunk - s_fill[i]));
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp,
+                                                         uint32_t* total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
     }
+    if (lane == 31) s_warp[wid] = inc;
     __syncthreads();
-    const uint64_t U = (uint64_t)M * kChunk - s_holes;
-    const uint32_t m0 = (uint32_t)(U / kChunk);  // first chunk that may hold slots >= U
-    const uint32_t n_src = M - m0;               // <= n_list + 1 by construction
-    // destination segments: the part of each listed chunk's hole that lies below U
-    if (i < n_list) {
-        const uint64_t h0 = (uint64_t)s_base[i] + s_fill[i], h1 = (uint64_t)s_base[i] + kChunk;
-        const uint64_t e = h1 < U ? h1 : U;
-        plan->dst_start[i] = (uint32_t)h0;
-        s_len[1][i] = h0 < e ? (uint32_t)(e - h0) : 0;
-    }
-    // source segments: live slots at positions >= U, chunk by chunk
-    if (i < n_src && i <= kMaxList) {
-        const uint32_t m = m0 + i;
-        uint32_t fill = kChunk;
-        for (uint32_t q = 0; q < n_list; q++)
-            if (s_base[q] == m * kChunk) fill = s_fill[q];
-        const uint64_t l0 = (uint64_t)m * kChunk, l1 = l0 + fill;
-        const uint64_t s = l0 > U ? l0 : U;
-        plan->src_start[i] = (uint32_t)s;
-        s_len[0][i] = s < l1 ? (uint32_t)(l1 - s) : 0;
-    }
-    __syncthreads();
-    if (i == 0) {
-        cnt->n_unique = U;
-        uint32_t sp = 0, dp = 0;
-        const uint32_t ns = n_src <= kMaxList ? n_src : kMaxList;
-        for (uint32_t q = 0; q < ns; q++) {
-            plan->src_prefix[q] = sp;
-            sp += s_len[0][q];
+    if (wid == 0) {
+        uint32_t w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
         }
-        plan->src_prefix[ns] = sp;
-        for (uint32_t q = 0; q < n_list; q++) {
-            plan->dst_prefix[q] = dp;
-            dp += s_len[1][q];
-        }
-        plan->dst_prefix[n_list] = dp;
-        plan->n_src = ns;
-        plan->n_dst = n_list;
-        plan->total = sp < dp ? sp : dp;
-        if (sp != dp || n_src > kMaxList) cnt->overflow = 1;  // cannot happen; checked by host
+        s_warp[lane] = w;  // inclusive over warps
     }
+    __syncthreads();
+    const uint32_t base = wid ? s_warp[wid - 1] : 0u;
+    *total = s_warp[31];
+    __syncthreads();
+    return base + inc - v;
 }
 
 __device__ __forceinline__ uint32_t plan_locate(const uint32_t* start, const uint32_t* prefix,
@@ -551,19 +384,66 @@ __device__ __forceinline__ uint32_t plan_locate(const uint32_t* start, const uin
     return start[lo] + (j - prefix[lo]);
 }
 
-__global__ void __launch_bounds__(256)
-    k_slab_fix_move(const FixPlan* plan, const DsCounters* cnt, uint64_t* keys, uint32_t* first,
-                    uint32_t* xy, int32_t* labels) {
+__global__ void __launch_bounds__(kFixThreads)
+    k_slab_fix(const uint32_t* chunk_list, uint32_t n_list, DsCounters* cnt, uint64_t* keys,
+               uint32_t* first, uint32_t* xy) {
+    __shared__ uint32_t s_base[kMaxList], s_fill[kMaxList];
+    __shared__ uint32_t s_src_start[kMaxList + 1], s_src_prefix[kMaxList + 1];
+    __shared__ uint32_t s_dst_start[kMaxList], s_dst_prefix[kMaxList];
+    __shared__ uint32_t s_warp[32];
     if (cnt->slab_violation) return;
-    const uint32_t total = plan->total;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total;
-         j += gridDim.x * blockDim.x) {
-        const uint32_t s = plan_locate(plan->src_start, plan->src_prefix, plan->n_src, j);
-        const uint32_t d = plan_locate(plan->dst_start, plan->dst_prefix, plan->n_dst, j);
+    const uint32_t M = (uint32_t)cnt->scratch[3];  // chunks handed out
+    const uint32_t i = threadIdx.x;
+    uint32_t hole = 0;
+    if (i < n_list) {
+        s_base[i] = chunk_list[2 * i];
+        s_fill[i] = chunk_list[2 * i + 1];
+        hole = kChunk - s_fill[i];
+    }
+    uint32_t holes;
+    block_exclusive_scan(hole, s_warp, &holes);
+    const uint64_t U = (uint64_t)M * kChunk - holes;
+    const uint32_t m0 = (uint32_t)(U / kChunk);  // first chunk that may hold slots >= U
+    const uint32_t n_src = min(M - m0, (uint32_t)kMaxList);  // <= n_list + 1 by construction
+    // destination segments: the part of each listed chunk's hole that lies below U
+    uint32_t dlen = 0;
+    if (i < n_list) {
+        const uint64_t h0 = (uint64_t)s_base[i] + s_fill[i], h1 = (uint64_t)s_base[i] + kChunk;
+        const uint64_t e = h1 < U ? h1 : U;
+        s_dst_start[i] = (uint32_t)h0;
+        dlen = h0 < e ? (uint32_t)(e - h0) : 0;
+    }
+    uint32_t dtot;
+    const uint32_t dpre = block_exclusive_scan(dlen, s_warp, &dtot);
+    if (i < n_list) s_dst_prefix[i] = dpre;
+    // source segments: live slots at positions >= U, chunk by chunk
+    uint32_t slen = 0;
+    if (i < n_src) {
+        const uint32_t m = m0 + i;
+        uint32_t fill = kChunk;
+        for (uint32_t q = 0; q < n_list; q++)
+            if (s_base[q] == m * kChunk) fill = s_fill[q];
+        const uint64_t l0 = (uint64_t)m * kChunk, l1 = l0 + fill;
+        const uint64_t s = l0 > U ? l0 : U;
+        s_src_start[i] = (uint32_t)s;
+        slen = s < l1 ? (uint32_t)(l1 - s) : 0;
+    }
+    uint32_t stot;
+    const uint32_t spre = block_exclusive_scan(slen, s_warp, &stot);
+    if (i < n_src) s_src_prefix[i] = spre;
+    __syncthreads();
+    if (blockIdx.x == 0 && i == 0) {
+        cnt->n_unique = U;
+        if (stot != dtot || M - m0 > (uint32_t)kMaxList) cnt->overflow = 1;  // cannot happen
+    }
+    const uint32_t total = stot < dtot ? stot : dtot;
+    if (n_src == 0 || n_list == 0) return;
+    for (uint32_t j = blockIdx.x * blockDim.x + i; j < total; j += gridDim.x * blockDim.x) {
+        const uint32_t s = plan_locate(s_src_start, s_src_prefix, n_src, j);
+        const uint32_t d = plan_locate(s_dst_start, s_dst_prefix, n_list, j);
         keys[d] = keys[s];
         first[d] = first[s];
         xy[d] = xy[s];
-        if (labels) labels[d] = labels[s];  // fused k-means: the label travels with its record
     }
 }
 
@@ -574,13 +454,12 @@ size_t slab_smem_bytes(uint64_t cells, bool count_rep) {
     return (size_t)kStages * kTile * 16 + (size_t)kHash * 4 +
            (size_t)((map_words(cells, count_rep) + 3) & ~3u) * 4;
 }
-size_t fuse_smem_bytes(int K, int rep) { return (size_t)rep * 3 * K * 4; }
 constexpr size_t kSmemLimit = 232448 - 1024;  // 227 KB opt-in maximum minus the static part
 
 }  // namespace
 
 size_t evk_slab_scratch_bytes(int sm_count) {
-    return sizeof(FixPlan) + (size_t)sm_count * kCtasPerSm * 4 * sizeof(uint32_t);
+    return (size_t)sm_count * kCtasPerSm * 4 * sizeof(uint32_t);
 }
 
 bool evk_slab_supported(const evk_handle* h, const KeyParams& kp) {
@@ -590,19 +469,8 @@ bool evk_slab_supported(const evk_handle* h, const KeyParams& kp) {
     return slab_smem_bytes(kp.cells, true) <= kSmemLimit;
 }
 
-bool evk_slab_fuse_supported(const evk_handle* h, const KeyParams& kp, int count_repeated, int K) {
-    if (kCtasPerSm != 1 || K < 1 || K > 254 || !evk_slab_supported(h, kp)) return false;
-    return slab_smem_bytes(kp.cells, count_repeated != 0) + fuse_smem_bytes(K, 1) <= kSmemLimit;
-}
-
-template <bool FUSED>
-static void (*pick_kernel(bool count_rep, bool pow2))(SlabArgs, FuseDev) {
-    return count_rep ? (pow2 ? k_slab_main<true, true, FUSED> : k_slab_main<true, false, FUSED>)
-                     : (pow2 ? k_slab_main<false, true, FUSED> : k_slab_main<false, false, FUSED>);
-}
-
 int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, bool* ok,
-                        int* launches, const SlabFuse* fuse, bool sync) {
+                        int* launches, bool sync) {
     *ok = false;
     const int grid = h->sm_count * kCtasPerSm;
     SlabArgs a;
@@ -614,44 +482,29 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
     a.first = h->d_first;
     a.xy = h->d_xy;
     a.cnt = h->d_cnt;
-    FixPlan* plan = reinterpret_cast<FixPlan*>(h->d_slab_scratch);
-    a.chunk_list = reinterpret_cast<uint32_t*>(plan + 1);
+    a.chunk_list = reinterpret_cast<uint32_t*>(h->d_slab_scratch);
     a.first_offset = (uint32_t)h->shard_first;
     a.words = map_words(kp.cells, count_repeated != 0);
     a.max_bins = (uint32_t)h->max_bins;
     // a single CTA walks a bin sequentially: with few bins and many events the table is faster
     a.min_bins = h->n_events > (1u << 22) ? 32 : 1;
-    size_t smem = slab_smem_bytes(kp.cells, count_repeated != 0);
+    const size_t smem = slab_smem_bytes(kp.cells, count_repeated != 0);
     const bool pow2 = kp.sx >= 0 && kp.sy >= 0;
-    FuseDev f{};
-    f.K = 0;
-    f.rep = 1;
-    if (fuse) {
-        f.K = fuse->kl.K;
-        f.rep = 8;
-        while (f.rep > 1 && smem + fuse_smem_bytes(f.K, f.rep) > kSmemLimit) f.rep >>= 1;
-        smem += fuse_smem_bytes(f.K, f.rep);
-        f.width = fuse->pg.width;
-        f.write_labels = fuse->kl.write_labels;
-        f.map = fuse->map;
-        f.acc = fuse->acc;
-        f.labels = fuse->labels;
-    }
-    void (*kern)(SlabArgs, FuseDev) =
-        fuse ? pick_kernel<true>(count_repeated != 0, pow2) : pick_kernel<false>(count_repeated != 0, pow2);
+    void (*kern)(SlabArgs) =
+        count_repeated ? (pow2 ? k_slab_main<true, true> : k_slab_main<true, false>)
+                       : (pow2 ? k_slab_main<false, true> : k_slab_main<false, false>);
     EVK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kSmemLimit));
     k_slab_bins<<<grid, 256, 0, h->stream>>>(a);
     EVK_CUDA(h, cudaGetLastError());
     if (h->profiling) cudaEventRecord(h->ev[5], h->stream);
-    kern<<<grid, kThreads, smem, h->stream>>>(a, f);
+    kern<<<grid, kThreads, smem, h->stream>>>(a);
     EVK_CUDA(h, cudaGetLastError());
     if (h->profiling) cudaEventRecord(h->ev[6], h->stream);
-    k_slab_fix_plan<<<1, kMaxList, 0, h->stream>>>(a.chunk_list, 2 * grid, h->d_cnt, plan);
-    k_slab_fix_move<<<grid, 256, 0, h->stream>>>(plan, h->d_cnt, h->d_keys, h->d_first, h->d_xy,
-                                                 fuse && fuse->kl.write_labels ? fuse->labels : nullptr);
+    k_slab_fix<<<grid, kFixThreads, 0, h->stream>>>(a.chunk_list, 2 * grid, h->d_cnt, h->d_keys,
+                                                   h->d_first, h->d_xy);
     EVK_CUDA(h, cudaGetLastError());
-    *launches += 4;
+    *launches += 3;
     if (!sync) return EVK_OK;
     // the verification flag decides whether the result stands
     EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,
