@@ -674,9 +674,13 @@ int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const evk_km_p
         int launches = 0;
         EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
         prof_rec(h, 0);
+        EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+        // main stream first, so the GPU starts on the downsample while the rest is still being
+        // enqueued
+        bool ok = false;
+        EVK_TRY(evk_downsample_slab(h, kp, ds->count_repeated, &ok, &launches, false));
         // side stream: everything that depends on the centroids only (first-K walk over the head
         // of the stream, candidate lists, label map, quads) runs beside the downsample
-        EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
         EVK_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
         if (init_first_k) {
             const size_t n_scan = h->n_events < (1u << 20) ? h->n_events : (1u << 20);
@@ -691,8 +695,6 @@ int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const evk_km_p
         EVK_CUDA(h, evk_launch_km_image(kl, ds->width, ds->height, h->d_prune_lists, h->d_cent,
                                         nullptr, h->d_label_map, h->d_quads, h->d_acc, h->side));
         EVK_CUDA(h, cudaEventRecord(h->ev_join, h->side));
-        bool ok = false;
-        EVK_TRY(evk_downsample_slab(h, kp, ds->count_repeated, &ok, &launches, false));
         EVK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         prof_rec(h, 2);
         prof_rec(h, 3);

@@ -527,6 +527,26 @@ __global__ void __launch_bounds__(128)
 // of the image iterations).  Accumulators: one private column per lane (bank == lane: no conflicts)
 // shared by the CTA's warps through 32-bit shared atomics, flushed with 64-bit global atomics.
 constexpr int kTlMax = EVK_MAX_QUADS;
+constexpr int kUnit = kBlock * 8;  // points per work unit
+constexpr int kFlushUnits = 64;
+
+__device__ __forceinline__ void tiles_flush(uint32_t* s_acc, int K, int copies,
+                                            unsigned long long* acc) {
+    __syncthreads();
+    for (int j = threadIdx.x; j < 3 * K; j += kBlock) {
+        unsigned long long sum = 0;
+        for (int cc = 0; cc < copies; cc++) {
+            const int idx = j * copies + ((cc + threadIdx.x) & (copies - 1));  // skewed: no conflicts
+            sum += s_acc[idx];
+            s_acc[idx] = 0;
+        }
+        const int which = j / K, k = j - which * K;  // 0: count, 1: sum x, 2: sum y
+        if (sum)
+            atomicAdd(&acc[k * ACC_STRIDE + (which == 0 ? ACC_CNT : which == 1 ? ACC_X : ACC_Y)], sum);
+    }
+    __syncthreads();
+}
+
 template <bool ACC>
 __global__ void __launch_bounds__(kBlock)
     k_km_assign_tiles(KmLaunch kl, QuadGrid pg, const uint8_t* __restrict__ quads,
@@ -544,69 +564,71 @@ __global__ void __launch_bounds__(kBlock)
         for (int i = threadIdx.x; i < 3 * K * copies; i += kBlock) s_acc[i] = 0;
     __syncthreads();
     const uint32_t col = threadIdx.x & (copies - 1);
-    const size_t n_chunks = (n + kChunk - 1) / kChunk;
-    for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
-        const size_t cbase = c * (size_t)kChunk;
-#pragma unroll 2
-        for (int r = 0; r < kChunk / (kBlock * 4); r++) {
-            const size_t i0 = cbase + ((size_t)r * kBlock + threadIdx.x) * 4;
-            if (i0 >= n) break;
-            uint32_t w[4], lab[4];
-            const bool full = i0 + 4 <= n;
-            if (full) {
-                const uint4 v = __ldcs(reinterpret_cast<const uint4*>(xy + i0));
-                w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+    // work unit: kUnit points = two 16-B loads per thread, units dealt round-robin to the CTAs
+    const size_t n_units = (n + kUnit - 1) / kUnit;
+    int since_flush = 0;
+    for (size_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const size_t ubase = u * (size_t)kUnit;
+        uint32_t w[8], lab[8];
+        size_t i0[2];
+        bool full[2];
+#pragma unroll
+        for (int hlf = 0; hlf < 2; hlf++) {
+            i0[hlf] = ubase + (size_t)hlf * (kUnit / 2) + (size_t)threadIdx.x * 4;
+            full[hlf] = i0[hlf] + 4 <= n;
+            if (full[hlf]) {
+                const uint4 v = __ldcs(reinterpret_cast<const uint4*>(xy + i0[hlf]));
+                w[4 * hlf + 0] = v.x; w[4 * hlf + 1] = v.y; w[4 * hlf + 2] = v.z; w[4 * hlf + 3] = v.w;
             } else {
 #pragma unroll
-                for (int q = 0; q < 4; q++) w[q] = i0 + q < n ? xy[i0 + q] : 0u;
+                for (int q = 0; q < 4; q++) w[4 * hlf + q] = i0[hlf] + q < n ? xy[i0[hlf] + q] : 0u;
             }
+        }
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint32_t px = w[q] & 0xFFFFu, py = w[q] >> 16;
-                lab[q] = s_tl[(py >> pg.shift) * pg.tx + (px >> pg.shift)];  // quad
-                if (lab[q] == 0xFEu) lab[q] = __ldg(map + (size_t)py * pg.width + px);
-            }
-            if (!ACC || kl.write_labels) {
+        for (int q = 0; q < 8; q++) {
+            const uint32_t px = w[q] & 0xFFFFu, py = w[q] >> 16;
+            lab[q] = s_tl[(py >> pg.shift) * pg.tx + (px >> pg.shift)];  // quad
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+            if (lab[q] == 0xFEu)
+                lab[q] = __ldg(map + (size_t)(w[q] >> 16) * pg.width + (w[q] & 0xFFFFu));
+        if (!ACC || kl.write_labels) {
+#pragma unroll
+            for (int hlf = 0; hlf < 2; hlf++) {
                 int4 o;
-                o.x = lab[0] == 0xFFu ? -1 : (int)lab[0];
-                o.y = lab[1] == 0xFFu ? -1 : (int)lab[1];
-                o.z = lab[2] == 0xFFu ? -1 : (int)lab[2];
-                o.w = lab[3] == 0xFFu ? -1 : (int)lab[3];
-                if (full) {
-                    __stcs(reinterpret_cast<int4*>(labels + i0), o);
+                o.x = lab[4 * hlf + 0] == 0xFFu ? -1 : (int)lab[4 * hlf + 0];
+                o.y = lab[4 * hlf + 1] == 0xFFu ? -1 : (int)lab[4 * hlf + 1];
+                o.z = lab[4 * hlf + 2] == 0xFFu ? -1 : (int)lab[4 * hlf + 2];
+                o.w = lab[4 * hlf + 3] == 0xFFu ? -1 : (int)lab[4 * hlf + 3];
+                if (full[hlf]) {
+                    __stcs(reinterpret_cast<int4*>(labels + i0[hlf]), o);
                 } else {
                     const int ov[4] = {o.x, o.y, o.z, o.w};
                     for (int q = 0; q < 4; q++)
-                        if (i0 + q < n) labels[i0 + q] = ov[q];
-                }
-            }
-            if (ACC) {
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    if (i0 + q < n && lab[q] != 0xFFu) {
-                        uint32_t* a = s_acc + lab[q] * copies + col;
-                        atomicAdd(a, 1u);
-                        atomicAdd(a + K * copies, w[q] & 0xFFFFu);
-                        atomicAdd(a + 2 * K * copies, w[q] >> 16);
-                    }
+                        if (i0[hlf] + q < n) labels[i0[hlf] + q] = ov[q];
                 }
             }
         }
-        if (ACC) {  // u32 cannot overflow within one chunk: 32768 * 65535 < 2^32
-            __syncthreads();
-            for (int j = threadIdx.x; j < 3 * K; j += kBlock) {
-                unsigned long long sum = 0;
-                for (int cc = 0; cc < copies; cc++) {
-                    const int idx = j * copies + ((cc + threadIdx.x) & (copies - 1));  // skewed
-                    sum += s_acc[idx];
-                    s_acc[idx] = 0;
+        if (ACC) {
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                if (i0[q >> 2] + (q & 3) < n && lab[q] != 0xFFu) {
+                    uint32_t* a = s_acc + lab[q] * copies + col;
+                    atomicAdd(a, 1u);
+                    atomicAdd(a + K * copies, w[q] & 0xFFFFu);
+                    atomicAdd(a + 2 * K * copies, w[q] >> 16);
                 }
-                const int which = j / K, k = j - which * K;  // 0: count, 1: sum x, 2: sum y
-                if (sum) atomicAdd(&acc[k * ACC_STRIDE + (which == 0 ? ACC_CNT : which == 1 ? ACC_X : ACC_Y)], sum);
             }
-            __syncthreads();
+            // a column receives at most 8 * (kBlock / 32) * 8 = 512 points per unit:
+            // 512 * kFlushUnits * 65535 < 2^32
+            if (++since_flush == kFlushUnits) {
+                since_flush = 0;
+                tiles_flush(s_acc, K, copies, acc);
+            }
         }
     }
+    if (ACC) tiles_flush(s_acc, K, copies, acc);
 }
 
 // "first K voxel representatives in canonical order" == the first K distinct keys met when the
@@ -796,16 +818,20 @@ cudaError_t evk_launch_km_assign_tiles(const KmLaunch& kl, int width, int height
     int copies = 32;
     while (copies > 1 && (size_t)3 * kl.K * copies * 4 > 48 * 1024) copies >>= 1;
     const size_t smem = kTlMax + (accumulate ? (size_t)3 * kl.K * copies * 4 : 0);
-    const size_t chunks = (n + kChunk - 1) / kChunk;
-    const size_t cap = (size_t)sm_count * 8;
-    const int grid = (int)(chunks < cap ? chunks : cap);
+    if (accumulate)
+        cudaFuncSetAttribute(k_km_assign_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             64 * 1024);
+    // one wave: as many CTAs as are resident at once, units dealt round-robin
+    int per_sm = 1;
+    if (accumulate)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_km_assign_tiles<true>, kBlock, smem);
+    else
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_km_assign_tiles<false>, kBlock, smem);
+    if (per_sm < 1) per_sm = 1;
+    const size_t units = (n + kUnit - 1) / kUnit;
+    const size_t cap = (size_t)sm_count * per_sm;
+    const int grid = (int)(units < cap ? units : cap);
     if (accumulate) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(k_km_assign_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 64 * 1024);
-            attr_done = true;
-        }
         k_km_assign_tiles<true><<<grid, kBlock, smem, s>>>(kl, pg, quads, map, xy, n, n_dev, copies,
                                                            acc, labels);
     } else {

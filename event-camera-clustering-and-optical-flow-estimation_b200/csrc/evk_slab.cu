@@ -96,6 +96,8 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 }
 
 // scratch[0] = n_bins, scratch[1] = bin work counter, scratch[2] = tb0, scratch[3] = chunk counter
+// bin_start[b] = first index whose time bin is >= tb0 + b.  One warp per bin, 32-way search: six
+// rounds of 32 parallel probes instead of 27 dependent loads.
 __global__ void __launch_bounds__(256) k_slab_bins(SlabArgs a) {
     DsCounters* cnt = a.cnt;
     const KeyParams& kp = a.kp;
@@ -117,20 +119,29 @@ __global__ void __launch_bounds__(256) k_slab_bins(SlabArgs a) {
         cnt->scratch[0] = nb;
         cnt->scratch[2] = tb0;
     }
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b <= nb; b += stride) {
-        size_t lo = 0, hi = a.n;  // lower_bound: first i with tbin(ev[i]) >= tb0 + b
+    const int lane = threadIdx.x & 31;
+    const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+    for (size_t b = warp; b <= nb; b += n_warps) {
+        size_t lo = 0, hi = a.n;  // invariant: pred(lo - 1) false, pred(hi) true (pred(n) = true)
         if (b == 0) hi = 0;
         else if (b == nb) lo = a.n;
         while (lo < hi) {
-            size_t mid = (lo + hi) >> 1;
+            const size_t span = hi - lo;
+            // 32 probes spread over [lo, hi): lo + span * (l + 1) / 33 (span < 2^33: no overflow)
+            const size_t p = lo + span * (size_t)(lane + 1) / 33u;
             const int64_t t = *reinterpret_cast<const int64_t*>(
-                reinterpret_cast<const char*>(a.ev + mid) + 8);
-            bool ge = t >= kp.t0 && evk_tbin(kp, t) >= tb0 + b;
-            if (ge) hi = mid;
-            else lo = mid + 1;
+                reinterpret_cast<const char*>(a.ev + p) + 8);
+            const bool ge = t >= kp.t0 && evk_tbin(kp, t) >= tb0 + b;
+            const uint32_t m = __ballot_sync(0xffffffffu, ge);
+            // first lane whose probe satisfies the predicate bounds hi; the lane before it bounds lo
+            const int f = m ? __ffs(m) - 1 : 32;
+            const size_t p_f = __shfl_sync(0xffffffffu, p, f < 32 ? f : 0);
+            const size_t p_b = __shfl_sync(0xffffffffu, p, f > 0 ? f - 1 : 0);
+            if (f < 32) hi = p_f;
+            if (f > 0) lo = p_b + 1;
         }
-        a.bin_start[b] = (uint32_t)lo;
+        if (lane == 0) a.bin_start[b] = (uint32_t)lo;
     }
 }
 
@@ -495,7 +506,7 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
                        : (pow2 ? k_slab_main<false, true> : k_slab_main<false, false>);
     EVK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kSmemLimit));
-    k_slab_bins<<<grid, 256, 0, h->stream>>>(a);
+    k_slab_bins<<<2 * grid, 256, 0, h->stream>>>(a);
     EVK_CUDA(h, cudaGetLastError());
     if (h->profiling) cudaEventRecord(h->ev[5], h->stream);
     kern<<<grid, kThreads, smem, h->stream>>>(a);
