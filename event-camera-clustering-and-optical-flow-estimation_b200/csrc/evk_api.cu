@@ -203,7 +203,7 @@ int evk_create(evk_handle** out, int device, size_t max_events) {
     ALLOC(h->d_tkeys, h->table_cap * sizeof(uint64_t));
     ALLOC(h->d_tfirst, h->table_cap * sizeof(uint32_t));
     // the slab kernel hands out output slots in CTA-private chunks: room for the unfilled tails
-    h->out_cap = m + (size_t)EVK_SLAB_CHUNK * (2 * (size_t)h->sm_count + 4);
+    h->out_cap = m + (size_t)EVK_SLAB_CHUNK * (3 * (size_t)h->sm_count + 4);
     ALLOC(h->d_keys, h->out_cap * sizeof(uint64_t));
     ALLOC(h->d_first, h->out_cap * sizeof(uint32_t));
     ALLOC(h->d_xy, h->out_cap * sizeof(uint32_t));

@@ -6,16 +6,24 @@
 //   s_map    2 bits per spatial cell: "seen" and "hit at least twice" (the kernel's
 //            repeated_count semantics, ACCEL/build/coordinate_processor.cl:73-75), 16 cells per
 //            word so one load answers both (115 KB for Gen4 2x2 px + polarity)
-//   s_hash   an 8192-slot tile table of packed (cell << 11 | index-in-tile) words: a 32-bit
-//            atomicCAS claims, a 32-bit atomicMin keeps the LOWEST stream index;
-//            after the barrier each candidate re-reads its slot: the survivor is the new voxel
 //   s_ev     a 2-stage ring of 2048-event tiles (32 KB each) filled by TMA bulk copies
 //            (cp.async.bulk + mbarrier complete_tx) issued one tile ahead by an elected thread
-// Per tile there are two block barriers and no global atomic: output slots come from a CTA-private
-// chunk of the output arrays (chunks are claimed from a global counter one chunk ahead, so the
-// round trip is never waited for); a tiny fix-up pass moves the tail of the last chunks into the
-// holes so the voxel shard is dense.  HBM sees each event read once and each voxel written once
-// (16 B SoA); no table lives in HBM.
+//   s_late   two small tables (one per tile parity) for the rare events that lose a claim race
+// Per tile:  classify  one bitmap load per event: seen -> duplicate of an earlier tile
+//            -- barrier: every read of the tile precedes every claim of the tile --
+//            claim     each unseen event does ONE returning atomicOr on the bitmap: bit was clear
+//                      -> it owns the cell ("claimant"); bit was set -> a peer of the SAME tile got
+//                      there first ("late peer"): its packed (cell, index) word goes into s_late,
+//                      where a 32-bit atomicMin keeps the lowest index of the cell
+//            -- barrier --
+//            resolve   a claimant probes s_late once: a late peer with a lower index replaces it
+//                      as representative (lowest stream index wins); then warp ballot
+//                      + one shared atomic per warp claim output slots and the 16-B record goes
+//                      to HBM from registers
+// Two block barriers per tile and no global atomic: output slots come from a CTA-private chunk of
+// the output arrays (claimed from a global counter one chunk ahead); a small fix-up pass moves
+// the tail of the last chunks into the holes so the voxel shard is dense.  HBM sees each event
+// read once and each voxel written once (16 B SoA); no table lives in HBM.
 //
 // This is the "perfect-hash" specialisation of the mandated open-addressing table
 // (evk_downsample.cu), which remains the general path: the kernel verifies on the fly that
@@ -36,8 +44,9 @@ constexpr int kCtasPerSm = kThreads <= 512 ? 2 : 1;
 constexpr int kLogTile = EVK_SLAB_LOGTILE;  // bits of the index-in-tile field of a table word
 constexpr int kTile = 1 << kLogTile;        // events per tile (stage buffers hold this many)
 constexpr int kPer = kTile / kThreads;      // events per thread per tile
-constexpr int kLogHash = kLogTile + 2;
-constexpr int kHash = 1 << kLogHash;    // tile table slots (load <= 0.25)
+constexpr int kLogHash = kLogTile;
+constexpr int kHash = 1 << kLogHash;    // late-peer table slots per parity (load <= 0.5: a late
+                                        // cell has at least two events in the tile)
 constexpr int kStages = 2;
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kChunk = EVK_SLAB_CHUNK;  // output slots per CTA-private chunk (>= 2 tiles)
@@ -164,10 +173,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
     constexpr int kTmaThread = NT - 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4* s_ev = reinterpret_cast<uint4*>(smem_raw);                        // [kStages][kTile]
-    uint32_t* s_hash = reinterpret_cast<uint32_t*>(s_ev + kStages * kTile);  // [kHash]
+    uint32_t* s_late = reinterpret_cast<uint32_t*>(s_ev + kStages * kTile);  // [2][kHash]
     // bin bitmap.  COUNT_REP: 16 cells per word, bit c = "seen", bit 16 + c = "hit at least twice"
     // (one load answers both questions); else 32 cells per word, "seen" only.
-    uint32_t* s_map = s_hash + kHash;  // [words]
+    uint32_t* s_map = s_late + 2 * kHash;  // [words]
     __shared__ __align__(8) uint64_t s_bar[kStages];
     __shared__ uint32_t s_bin;
     __shared__ uint32_t s_cursor[2];  // voxels emitted by the current tile (by tile parity)
@@ -180,7 +189,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
     const uint64_t tb0 = cnt->scratch[2];
     const int tid = threadIdx.x, lane = tid & 31;
 
-    for (int i = tid; i < kHash; i += blockDim.x) s_hash[i] = kEmpty;
+    for (int i = tid; i < 2 * kHash; i += NT) s_late[i] = kEmpty;
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) mbar_init(&s_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -193,17 +202,44 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
     }
     __syncthreads();
     uint32_t pend_chunk = kNoChunk;  // thread 0: chunk index requested but not yet published
+    uint32_t book_par = 2;           // thread 0: parity of the tile whose output is not yet booked
     uint32_t tile_seq = 0;           // tiles consumed by this CTA (stage = seq % kStages)
+    uint32_t viol = 0;
+
+    // thread 0, once every warp has claimed its output slots of a tile: advance the chunk state
+    auto book = [&]() {
+        if (book_par > 1) return;
+        if (pend_chunk != kNoChunk) {  // requested one tile ago: has arrived by now
+            s_next_base = pend_chunk * kChunk;
+            pend_chunk = kNoChunk;
+        }
+        const uint32_t c = s_cursor[book_par];  // voxels that tile emitted
+        const uint32_t room = s_chunk_end - s_chunk_pos;
+        if (c >= room) {  // spilled into the next chunk: make it current, request another
+            const uint32_t nb0 = s_next_base;
+            s_chunk_pos = nb0 + (c - room);
+            s_chunk_end = nb0 + kChunk;
+            s_next_base = kNoChunk;
+            pend_chunk = (uint32_t)atomicAdd(&cnt->scratch[3], 1ull);
+        } else {
+            s_chunk_pos += c;
+        }
+        s_cursor[book_par] = 0;
+        book_par = 2;
+    };
 
     for (;;) {
-        prod_sync<NT>();
-        if (tid == 0) s_bin = (uint32_t)atomicAdd(&cnt->scratch[1], 1ull);
+        prod_sync<NT>();  // every thread has left the previous bin (bitmap, ring, cursor)
+        if (tid == 0) {
+            book();
+            s_bin = (uint32_t)atomicAdd(&cnt->scratch[1], 1ull);
+        }
         prod_sync<NT>();
         const uint32_t b = s_bin;
         if (b >= nb) break;
         const uint32_t lo = a.bin_start[b], hi = a.bin_start[b + 1];
         if (hi < lo) {  // ranges do not partition the stream: not time-ordered
-            if (tid == 0) atomicOr(&cnt->slab_violation, 1u);
+            viol = 1;
             continue;
         }
         if (hi == lo) continue;
@@ -222,28 +258,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
         for (uint32_t base = lo; base < hi; base += TILE, tile_seq++) {
             const uint32_t stage = tile_seq % kStages, par = tile_seq & 1;
             const uint4* tile = s_ev + stage * kTile;
-            // the next tile goes into the other stage, which every thread left before the barrier
-            // that ended the previous tile
-            if (tid == kTmaThread && base + TILE < hi) {
-                const uint32_t nxt = base + TILE;
-                const uint32_t cntev = min((uint32_t)TILE, hi - nxt);
-                uint64_t* bar = &s_bar[(tile_seq + 1) % kStages];
-                mbar_expect_tx(bar, cntev * 16u);
-                tma_load_1d(s_ev + ((tile_seq + 1) % kStages) * kTile, a.ev + nxt, cntev * 16u,
-                            bar);
-            }
+            uint32_t* late_tbl = s_late + par * kHash;
             mbar_wait(&s_bar[stage], (tile_seq / kStages) & 1);
-            // ---- phase A: classify against the bin bitmap, insert candidates in the tile table
-            // cv: candidate word (cell << 11 | index in tile) or kEmpty; its slot; its x|y<<16
-            uint32_t cv[kPer], cslot[kPer], cxy[kPer];
+            // ---- classify: cv = candidate word (cell << kLogTile | index in tile) or kEmpty
+            uint32_t cv[kPer], cxy[kPer];
 #pragma unroll
-            for (int j = 0; j < kPer; j++) {  // classification: independent per event (ILP)
+            for (int j = 0; j < kPer; j++) {
                 const uint32_t li = j * NT + tid;
                 const uint4 ev = tile[li];
                 const uint32_t x = ev.x & 0xFFFFu, y = ev.x >> 16;
                 bool ok = (base + li < hi) & (x < (uint32_t)kp.width) & (y < (uint32_t)kp.height);
                 const bool inbin = (uint64_t)(ev_t(ev) - t_lo) < (uint64_t)kp.vt;
-                if (ok & !inbin) atomicOr(&cnt->slab_violation, 1u);  // not an event of this bin
+                if (ok & !inbin) viol = 1;  // not an event of this bin
                 ok &= inbin;
                 uint32_t cell;
                 if (POW2) cell = (y >> kp.sy) * kp.NX + (x >> kp.sx);
@@ -257,43 +283,74 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                     atomicOr(&s_map[w], sbit << 16);  // duplicate of an earlier tile's voxel
                 cv[j] = (wv & sbit) ? kEmpty : ((cell << kLogTile) | li);
                 cxy[j] = ev.x;
-                cslot[j] = hash_slot(cell);
             }
+            prod_sync<NT>();  // B0: every bitmap read of this tile precedes every claim below
+            // the other ring slot and the previous tile's output claims are no longer in use
+            if (tid == kTmaThread && base + TILE < hi) {
+                const uint32_t nxt = base + TILE;
+                const uint32_t cntev = min((uint32_t)TILE, hi - nxt);
+                uint64_t* bar = &s_bar[(tile_seq + 1) % kStages];
+                mbar_expect_tx(bar, cntev * 16u);
+                tma_load_1d(s_ev + ((tile_seq + 1) % kStages) * kTile, a.ev + nxt, cntev * 16u,
+                            bar);
+            }
+            if (tid == 0) book();
+            // ---- claim: one returning atomic per unseen event
+            bool late[kPer];
 #pragma unroll
-            for (int j = 0; j < kPer; j++) {  // insertion into the tile table
+            for (int j = 0; j < kPer; j++) {
+                late[j] = false;
                 if (cv[j] == kEmpty) continue;
                 const uint32_t cell = cv[j] >> kLogTile;
-                uint32_t s = cslot[j];
+                uint32_t* wp = COUNT_REP ? &s_map[cell >> 4] : &s_map[cell >> 5];
+                const uint32_t sbit = 1u << (cell & (COUNT_REP ? 15u : 31u));
+                const uint32_t old = atomicOr(wp, sbit);
+                late[j] = (old & sbit) != 0;
+            }
+#pragma unroll
+            for (int j = 0; j < kPer; j++) {  // a peer of this tile claimed the cell first (rare)
+                if (!late[j]) continue;
+                const uint32_t cell = cv[j] >> kLogTile;
+                if (COUNT_REP) atomicOr(&s_map[cell >> 4], 1u << (16 + (cell & 15)));
+                uint32_t s = hash_slot(cell);
                 for (;;) {
-                    const uint32_t old = atomicCAS(&s_hash[s], kEmpty, cv[j]);
+                    const uint32_t old = atomicCAS(&late_tbl[s], kEmpty, cv[j]);
                     if (old == kEmpty) break;
-                    if ((old >> kLogTile) == cell) {  // same cell inside this tile: keep the lowest
-                        atomicMin(&s_hash[s], cv[j]);
-                        if (COUNT_REP) atomicOr(&s_map[cell >> 4], 1u << (16 + (cell & 15)));
+                    if ((old >> kLogTile) == cell) {  // keep the lowest index of the cell
+                        atomicMin(&late_tbl[s], cv[j]);
                         break;
                     }
                     s = (s + 1) & (kHash - 1);
                 }
-                cslot[j] = s;
+                cv[j] = kEmpty;
             }
-            prod_sync<NT>();  // S1: tile table complete
-            // ---- phase B: a candidate whose word survived in its slot is a new voxel (lowest
-            // index of its cell in this tile, and no earlier tile had the cell)
+            prod_sync<NT>();  // S1: every claim of the tile is in the bitmap, s_late is complete
+            // ---- resolve: the claimant is the new voxel unless a late peer has a lower index
             uint32_t bal[kPer], wtot = 0;
-            bool cand[kPer];
 #pragma unroll
             for (int j = 0; j < kPer; j++) {
-                const bool win = cv[j] != kEmpty && s_hash[cslot[j]] == cv[j];
+                const bool win = cv[j] != kEmpty;
                 if (win) {
-                    s_hash[cslot[j]] = kEmpty;
                     const uint32_t cell = cv[j] >> kLogTile;
-                    if (COUNT_REP) atomicOr(&s_map[cell >> 4], 1u << (cell & 15));
-                    else atomicOr(&s_map[cell >> 5], 1u << (cell & 31));
+                    uint32_t s = hash_slot(cell);
+                    for (;;) {
+                        const uint32_t w = late_tbl[s];
+                        if (w == kEmpty) break;
+                        if ((w >> kLogTile) == cell) {
+                            if (w < cv[j]) {  // lower index: that event is the representative
+                                cv[j] = w;
+                                cxy[j] = tile[w & (kTile - 1)].x;
+                            }
+                            break;
+                        }
+                        s = (s + 1) & (kHash - 1);
+                    }
                 }
-                cand[j] = win;
                 bal[j] = __ballot_sync(0xffffffffu, win);
                 wtot += __popc(bal[j]);
             }
+            // the other parity's table was last read one tile ago: clean it for the next tile
+            for (int i = tid; i < kHash; i += NT) s_late[(par ^ 1) * kHash + i] = kEmpty;
             uint32_t wbase = 0;
             if (lane == 0 && wtot) wbase = atomicAdd(&s_cursor[par], wtot);
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
@@ -303,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
                 for (int j = 0; j < kPer; j++) {
-                    if (cand[j]) {
+                    if (cv[j] != kEmpty) {
                         const uint32_t o = wbase + __popc(bal[j] & lt);
                         const uint32_t p = o < room ? pos0 + o : nxt0 + (o - room);
                         a.keys[p] = key_base + (cv[j] >> kLogTile);
@@ -313,25 +370,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                     wbase += __popc(bal[j]);
                 }
             }
-            prod_sync<NT>();  // S2: bitmap marked, table reset, tile and chunk state consumed
-            if (tid == 0) {
-                if (pend_chunk != kNoChunk) {  // requested one tile ago: has arrived by now
-                    s_next_base = pend_chunk * kChunk;
-                    pend_chunk = kNoChunk;
-                }
-                const uint32_t c = s_cursor[par];  // voxels this tile emitted
-                const uint32_t room = s_chunk_end - s_chunk_pos;
-                if (c >= room) {  // spilled into the next chunk: make it current, request another
-                    const uint32_t nb0 = s_next_base;
-                    s_chunk_pos = nb0 + (c - room);
-                    s_chunk_end = nb0 + kChunk;
-                    s_next_base = kNoChunk;
-                    pend_chunk = (uint32_t)atomicAdd(&cnt->scratch[3], 1ull);
-                } else {
-                    s_chunk_pos += c;
-                }
-                s_cursor[par] = 0;
-            }
+            if (tid == 0) book_par = par;
         }
         if (COUNT_REP) {
             uint32_t r = 0;
@@ -340,6 +379,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
             if (lane == 0 && r) atomicAdd(&cnt->n_repeated, (unsigned long long)r);
         }
     }
+    if (viol) atomicOr(&cnt->slab_violation, 1u);
     if (tid == 0) {  // publish the two chunks this CTA leaves partly filled
         if (pend_chunk != kNoChunk) s_next_base = pend_chunk * kChunk;
         uint32_t* cl = a.chunk_list + 4 * blockIdx.x;
@@ -462,7 +502,7 @@ uint32_t map_words(uint64_t cells, bool count_rep) {
     return (uint32_t)(count_rep ? (cells + 15) / 16 : (cells + 31) / 32);
 }
 size_t slab_smem_bytes(uint64_t cells, bool count_rep) {
-    return (size_t)kStages * kTile * 16 + (size_t)kHash * 4 +
+    return (size_t)kStages * kTile * 16 + (size_t)2 * kHash * 4 +
            (size_t)((map_words(cells, count_rep) + 3) & ~3u) * 4;
 }
 constexpr size_t kSmemLimit = 232448 - 1024;  // 227 KB opt-in maximum minus the static part
