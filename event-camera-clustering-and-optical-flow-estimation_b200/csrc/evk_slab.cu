@@ -6,8 +6,9 @@
 //   s_map    2 bits per spatial cell: "seen" and "hit at least twice" (the kernel's
 //            repeated_count semantics, ACCEL/build/coordinate_processor.cl:73-75), 16 cells per
 //            word so one load answers both (115 KB for Gen4 2x2 px + polarity)
-//   s_ev     a 2-stage ring of 2048-event tiles (32 KB each) filled by TMA bulk copies
-//            (cp.async.bulk + mbarrier complete_tx) issued one tile ahead by an elected thread
+//   s_ev     a 3-stage ring of 2048-event tiles (32 KB each) filled by TMA bulk copies
+//            (cp.async.bulk + mbarrier complete_tx) issued two tiles ahead by an elected thread,
+//            across bin boundaries (bins are dealt round-robin, so the order is known)
 //   s_late   two small tables (one per tile parity) for the rare events that lose a claim race
 // Per tile:  classify  one bitmap load per event: seen -> duplicate of an earlier tile
 //            -- barrier: every read of the tile precedes every claim of the tile --
@@ -47,7 +48,7 @@ constexpr int kPer = kTile / kThreads;      // events per thread per tile
 constexpr int kLogHash = kLogTile;
 constexpr int kHash = 1 << kLogHash;    // late-peer table slots per parity (load <= 0.5: a late
                                         // cell has at least two events in the tile)
-constexpr int kStages = 2;
+constexpr int kStages = 3;
 constexpr uint32_t kEmpty = 0xFFFFFFFFu;
 constexpr uint32_t kChunk = EVK_SLAB_CHUNK;  // output slots per CTA-private chunk (>= 2 tiles)
 constexpr uint32_t kNoChunk = 0xFFFFFFFFu;
@@ -166,6 +167,23 @@ __device__ __forceinline__ void prod_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
 }
 
+// the CTA's tile stream: bins blockIdx.x, blockIdx.x + gridDim.x, ...; TILE-event tiles in each
+struct TileIt {
+    uint32_t b, hi, base;  // tile [base, min(base + TILE, hi)) of bin b; b >= nb: end of stream
+};
+// first tile of the first non-empty bin at or after it.b
+__device__ __forceinline__ void it_enter(TileIt& it, const uint32_t* bin_start, uint32_t nb) {
+    while (it.b < nb) {
+        const uint32_t lo = bin_start[it.b], hi = bin_start[it.b + 1];
+        if (hi > lo) {  // (hi < lo: the stream is not time-ordered; the consumer side reports it)
+            it.base = lo;
+            it.hi = hi;
+            return;
+        }
+        it.b += gridDim.x;
+    }
+}
+
 template <bool COUNT_REP, bool POW2>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) {
     constexpr int NT = kThreads;
@@ -178,7 +196,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
     // (one load answers both questions); else 32 cells per word, "seen" only.
     uint32_t* s_map = s_late + 2 * kHash;  // [words]
     __shared__ __align__(8) uint64_t s_bar[kStages];
-    __shared__ uint32_t s_bin;
     __shared__ uint32_t s_cursor[2];  // voxels emitted by the current tile (by tile parity)
     __shared__ uint32_t s_chunk_pos, s_chunk_end, s_next_base;
 
@@ -190,6 +207,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
     const int tid = threadIdx.x, lane = tid & 31;
 
     for (int i = tid; i < 2 * kHash; i += NT) s_late[i] = kEmpty;
+    for (uint32_t i = tid; i < a.words; i += NT) s_map[i] = 0;
     if (tid == 0) {
         for (int s = 0; s < kStages; s++) mbar_init(&s_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -228,31 +246,50 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
         book_par = 2;
     };
 
-    for (;;) {
-        prod_sync<NT>();  // every thread has left the previous bin (bitmap, ring, cursor)
-        if (tid == 0) {
-            book();
-            s_bin = (uint32_t)atomicAdd(&cnt->scratch[1], 1ull);
+    // the TMA thread runs two tiles ahead of the consumers through the same tile stream
+    TileIt tma;
+    tma.b = blockIdx.x;
+    tma.hi = tma.base = 0;
+    uint32_t tma_seq = 0;
+    auto fetch = [&]() {  // issue the next tile of the stream, if any
+        if (tma.b >= nb) return;
+        const uint32_t cntev = min((uint32_t)TILE, tma.hi - tma.base);
+        uint64_t* bar = &s_bar[tma_seq % kStages];
+        mbar_expect_tx(bar, cntev * 16u);
+        tma_load_1d(s_ev + (tma_seq % kStages) * kTile, a.ev + tma.base, cntev * 16u, bar);
+        tma_seq++;
+        tma.base += TILE;
+        if (tma.base >= tma.hi) {
+            tma.b += gridDim.x;
+            it_enter(tma, a.bin_start, nb);
         }
-        prod_sync<NT>();
-        const uint32_t b = s_bin;
-        if (b >= nb) break;
+    };
+    if (tid == kTmaThread) {
+        it_enter(tma, a.bin_start, nb);
+        fetch();
+        fetch();
+    }
+
+    for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
         const uint32_t lo = a.bin_start[b], hi = a.bin_start[b + 1];
-        if (hi < lo) {  // ranges do not partition the stream: not time-ordered
-            viol = 1;
-            continue;
-        }
-        if (hi == lo) continue;
+        if (hi < lo) viol = 1;  // ranges do not partition the stream: not time-ordered
+        if (hi <= lo) continue;
         const uint64_t tb = tb0 + b;
         const int64_t t_lo = kp.t0 + (int64_t)(tb * (uint64_t)kp.vt);
         const uint64_t key_base = tb * kp.cells;
-        if (tid == kTmaThread) {  // first tile of the bin
-            const uint32_t cntev = min((uint32_t)TILE, hi - lo);
-            uint64_t* bar = &s_bar[tile_seq % kStages];
-            mbar_expect_tx(bar, cntev * 16u);
-            tma_load_1d(s_ev + (tile_seq % kStages) * kTile, a.ev + lo, cntev * 16u, bar);
+        prod_sync<NT>();  // every thread has left the previous bin (bitmap, cursor)
+        if (tid == 0) book();
+        {  // count the previous bin's repeated cells and clear the bitmap in one pass
+            uint32_t r = 0;
+            for (uint32_t i = tid; i < a.words; i += NT) {
+                if (COUNT_REP) r += __popc(s_map[i] >> 16);
+                s_map[i] = 0;
+            }
+            if (COUNT_REP) {
+                r = __reduce_add_sync(0xffffffffu, r);
+                if (lane == 0 && r) atomicAdd(&cnt->n_repeated, (unsigned long long)r);
+            }
         }
-        for (uint32_t i = tid; i < a.words; i += NT) s_map[i] = 0;
         prod_sync<NT>();
 
         for (uint32_t base = lo; base < hi; base += TILE, tile_seq++) {
@@ -285,15 +322,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 cxy[j] = ev.x;
             }
             prod_sync<NT>();  // B0: every bitmap read of this tile precedes every claim below
-            // the other ring slot and the previous tile's output claims are no longer in use
-            if (tid == kTmaThread && base + TILE < hi) {
-                const uint32_t nxt = base + TILE;
-                const uint32_t cntev = min((uint32_t)TILE, hi - nxt);
-                uint64_t* bar = &s_bar[(tile_seq + 1) % kStages];
-                mbar_expect_tx(bar, cntev * 16u);
-                tma_load_1d(s_ev + ((tile_seq + 1) % kStages) * kTile, a.ev + nxt, cntev * 16u,
-                            bar);
-            }
+            // the ring slot of the previous tile and its output claims are no longer in use
+            if (tid == kTmaThread) fetch();  // tile + 2 of the stream
             if (tid == 0) book();
             // ---- claim: one returning atomic per unseen event
             bool late[kPer];
@@ -372,12 +402,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
             }
             if (tid == 0) book_par = par;
         }
-        if (COUNT_REP) {
-            uint32_t r = 0;
-            for (uint32_t i = tid; i < a.words; i += NT) r += __popc(s_map[i] >> 16);
-            r = __reduce_add_sync(0xffffffffu, r);
-            if (lane == 0 && r) atomicAdd(&cnt->n_repeated, (unsigned long long)r);
-        }
+    }
+    prod_sync<NT>();
+    if (tid == 0) book();
+    if (COUNT_REP) {  // the last bin's repeated cells
+        uint32_t r = 0;
+        for (uint32_t i = tid; i < a.words; i += NT) r += __popc(s_map[i] >> 16);
+        r = __reduce_add_sync(0xffffffffu, r);
+        if (lane == 0 && r) atomicAdd(&cnt->n_repeated, (unsigned long long)r);
     }
     if (viol) atomicOr(&cnt->slab_violation, 1u);
     if (tid == 0) {  // publish the two chunks this CTA leaves partly filled

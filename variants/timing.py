@@ -13,5 +13,5 @@ for it in range(3):
     L.evk_debug_slab_timing(out)
     v = list(out)
     tot = sum(v)
-    names = ["prologue/bookkeeping", "tma wait", "classify", "insert", "S1 wait", "phase B", "S2 wait", "epilogue"]
+    names = ["bin prologue+top", "tma wait", "classify", "B0 wait+tma issue", "claim", "S1 wait", "resolve", "epilogue"]
     print(it, {nm: f"{100*x/tot:.1f}%" for nm, x in zip(names, v)}, "cycles/warp", tot / (148 * 32))
