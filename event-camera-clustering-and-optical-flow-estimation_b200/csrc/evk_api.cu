@@ -12,6 +12,17 @@
 
 #include "evk_internal.cuh"
 
+// stage timestamps; inside a stream capture the record becomes an event-record NODE of the graph
+// (cudaEventRecordExternal), so the stage times stay measurable when the fused step is replayed
+void evk_prof_rec(evk_handle* h, int i) {
+    if (!h->profiling) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(h->stream, &cs);
+    cudaEventRecordWithFlags(h->ev[i], h->stream,
+                             cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal
+                                                                 : cudaEventRecordDefault);
+}
+
 int evk_fail(evk_handle* h, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
@@ -43,12 +54,13 @@ struct DeviceGuard {
     }
 };
 
-void prof_rec(evk_handle* h, int i) {
-    if (h->profiling) cudaEventRecord(h->ev[i], h->stream);
-}
+void prof_rec(evk_handle* h, int i) { evk_prof_rec(h, i); }
 float prof_ms(evk_handle* h, int a, int b) {
     float ms = 0.f;
-    if (h->profiling) cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]);
+    if (h->profiling && cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]) != cudaSuccess) {
+        cudaGetLastError();
+        ms = 0.f;
+    }
     return ms;
 }
 
@@ -255,6 +267,7 @@ int evk_destroy(evk_handle* h) {
         if (e) cudaEventDestroy(e);
     for (auto& e : h->ev_timer)
         if (e) cudaEventDestroy(e);
+    if (h->fused_exec) cudaGraphExecDestroy(h->fused_exec);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side) cudaStreamDestroy(h->side);
@@ -648,6 +661,47 @@ static int step_unfused(evk_handle* h, const evk_ds_params* ds, const evk_km_par
     return evk_kmeans_run(h, km, iters_done, nullptr);
 }
 
+// everything the fused step submits, on h->stream and h->side (captured into a graph by the caller)
+static int enqueue_fused(evk_handle* h, const KeyParams& kp, const evk_ds_params* ds,
+                         const evk_km_params* km, int init_first_k, int* launches) {
+    KmLaunch kl = km_launch_params(h, km);
+    EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
+    prof_rec(h, 0);
+    EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+    bool ok = false;
+    EVK_TRY(evk_downsample_slab(h, kp, ds->count_repeated, &ok, launches, false));
+    // side stream: everything that depends on the centroids only (first-K walk over the head
+    // of the stream, candidate lists, label map, quads) runs beside the downsample
+    EVK_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    if (init_first_k) {
+        const size_t n_scan = h->n_events < (1u << 20) ? h->n_events : (1u << 20);
+        EVK_CUDA(h, evk_launch_init_first_k_walk(kp, kl, h->d_events, n_scan, h->d_cent,
+                                                 &h->d_cnt->scratch[4], h->side));
+        (*launches)++;
+    } else {  // warm start: keep a copy in case the stream check sends us to the general path
+        EVK_CUDA(h, cudaMemcpyAsync(h->d_cent + EVK_MAX_K * 2, h->d_cent,
+                                    (size_t)km->K * 2 * sizeof(float), cudaMemcpyDeviceToDevice,
+                                    h->side));
+    }
+    EVK_CUDA(h, evk_launch_km_image(kl, ds->width, ds->height, h->d_prune_lists, h->d_cent,
+                                    nullptr, h->d_label_map, h->d_quads, h->d_acc, h->side));
+    EVK_CUDA(h, cudaEventRecord(h->ev_join, h->side));
+    EVK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    prof_rec(h, 2);
+    prof_rec(h, 3);
+    // one pass over the new voxels, whose count never leaves the device
+    EVK_CUDA(h, evk_launch_km_assign_tiles(kl, ds->width, ds->height, h->d_quads, h->d_label_map,
+                                           h->d_xy, h->n_events, &h->d_cnt->n_unique, true,
+                                           h->d_acc, h->d_labels, h->sm_count, h->stream));
+    EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
+                                       h->stream));
+    prof_rec(h, 4);
+    *launches += 5;
+    EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,
+                                h->stream));
+    return EVK_OK;
+}
+
 int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
                           int init_first_k, size_t* n_unique, size_t* n_repeated,
                           int* iters_done) {
@@ -670,45 +724,41 @@ int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const evk_km_p
         h->ds = *ds;
         h->kp = kp;
         h->have_ds = true;
-        KmLaunch kl = km_launch_params(h, km);
+        // The whole pass is one CUDA graph, re-instantiated only when the shape of the call changes
+        // (event count, parameters, profiling): a replay costs one launch instead of a dozen.
+        FusedKey key;
+        memset(&key, 0, sizeof key);
+        key.n = h->n_events;
+        key.ds = *ds;
+        key.km = *km;
+        key.init = init_first_k ? 1 : 0;
+        key.profiling = h->profiling ? 1 : 0;
+        key.shard_first = h->shard_first;
         int launches = 0;
-        EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
-        prof_rec(h, 0);
-        EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
-        // main stream first, so the GPU starts on the downsample while the rest is still being
-        // enqueued
-        bool ok = false;
-        EVK_TRY(evk_downsample_slab(h, kp, ds->count_repeated, &ok, &launches, false));
-        // side stream: everything that depends on the centroids only (first-K walk over the head
-        // of the stream, candidate lists, label map, quads) runs beside the downsample
-        EVK_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-        if (init_first_k) {
-            const size_t n_scan = h->n_events < (1u << 20) ? h->n_events : (1u << 20);
-            EVK_CUDA(h, evk_launch_init_first_k_walk(kp, kl, h->d_events, n_scan, h->d_cent,
-                                                     &h->d_cnt->scratch[4], h->side));
-            launches++;
-        } else {  // warm start: keep a copy in case the stream check sends us to the general path
-            EVK_CUDA(h, cudaMemcpyAsync(h->d_cent + EVK_MAX_K * 2, h->d_cent,
-                                        (size_t)km->K * 2 * sizeof(float), cudaMemcpyDeviceToDevice,
-                                        h->side));
+        if (h->fused_exec && memcmp(&key, &h->fused_key, sizeof key) == 0) {
+            launches = h->fused_launches;
+        } else {
+            if (h->fused_exec) cudaGraphExecDestroy(h->fused_exec);
+            h->fused_exec = nullptr;
+            cudaGraph_t graph = nullptr;
+            EVK_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            int st_enq = enqueue_fused(h, kp, ds, km, init_first_k, &launches);
+            cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+            if (st_enq != EVK_OK) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                return st_enq;
+            }
+            EVK_CUDA(h, ce);
+            ce = cudaGraphInstantiate(&h->fused_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            EVK_CUDA(h, ce);
+            h->fused_key = key;
+            h->fused_launches = launches;
         }
-        EVK_CUDA(h, evk_launch_km_image(kl, ds->width, ds->height, h->d_prune_lists, h->d_cent,
-                                        nullptr, h->d_label_map, h->d_quads, h->d_acc, h->side));
-        EVK_CUDA(h, cudaEventRecord(h->ev_join, h->side));
-        EVK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-        prof_rec(h, 2);
-        prof_rec(h, 3);
-        EVK_CUDA(h, evk_launch_km_assign_tiles(kl, ds->width, ds->height, h->d_quads,
-                                               h->d_label_map, h->d_xy, h->n_events,
-                                               &h->d_cnt->n_unique, true, h->d_acc, h->d_labels,
-                                               h->sm_count, h->stream));
-        EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
-                                           h->stream));
-        prof_rec(h, 4);
-        launches += 5;
-        EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,
-                                    h->stream));
+        EVK_CUDA(h, cudaGraphLaunch(h->fused_exec, h->stream));
         EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+        bool ok;
         ok = h->h_cnt->slab_violation == 0 && h->h_cnt->overflow == 0 &&
              (!init_first_k || h->h_cnt->scratch[4] == (unsigned long long)km->K);
         if (ok) {

@@ -106,6 +106,14 @@ struct DsCounters {  // device-side counters, mirrored into pinned host memory a
 
 struct CommState;
 
+struct FusedKey {  // what the captured fused-step graph depends on
+    size_t n;
+    evk_ds_params ds;
+    evk_km_params km;
+    int init, profiling;
+    uint64_t shard_first;
+};
+
 struct evk_handle {
     int device = 0;
     int sm_count = 148;
@@ -160,6 +168,9 @@ struct evk_handle {
     uint8_t* d_quads = nullptr;              // [EVK_MAX_QUADS] label of uniformly labelled squares
     cudaStream_t side = nullptr;             // centroid-only kernels run beside the downsample
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaGraphExec_t fused_exec = nullptr;    // the fused step as one graph (evk_downsample_kmeans)
+    FusedKey fused_key{};
+    int fused_launches = 0;
     size_t image_pixels = 0;                 // capacity of both
     bool pix_valid = false;                  // d_pixcnt matches the current voxel shard
     float* d_shift = nullptr;                // [1]
@@ -194,6 +205,7 @@ struct evk_handle {
 
 // ---- error handling -------------------------------------------------------------------------
 int evk_fail(evk_handle* h, int code, const char* fmt, ...);
+void evk_prof_rec(evk_handle* h, int i);  // cudaEventRecord(h->ev[i]) when profiling is on
 #define EVK_CUDA(h, expr)                                                                    \
     do {                                                                                     \
         cudaError_t _e = (expr);                                                             \

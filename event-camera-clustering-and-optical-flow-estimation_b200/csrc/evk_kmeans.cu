@@ -567,22 +567,34 @@ __global__ void __launch_bounds__(kBlock)
     // work unit: kUnit points = two 16-B loads per thread, units dealt round-robin to the CTAs
     const size_t n_units = (n + kUnit - 1) / kUnit;
     int since_flush = 0;
+    // the next unit's coordinates are requested before the current unit is processed
+    auto fetch = [&](size_t u, uint32_t (&w)[8]) {
+#pragma unroll
+        for (int hlf = 0; hlf < 2; hlf++) {
+            const size_t i0 = u * (size_t)kUnit + (size_t)hlf * (kUnit / 2) + (size_t)threadIdx.x * 4;
+            if (i0 + 4 <= n) {
+                const uint4 v = __ldcs(reinterpret_cast<const uint4*>(xy + i0));
+                w[4 * hlf + 0] = v.x; w[4 * hlf + 1] = v.y; w[4 * hlf + 2] = v.z; w[4 * hlf + 3] = v.w;
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; q++) w[4 * hlf + q] = i0 + q < n ? xy[i0 + q] : 0u;
+            }
+        }
+    };
+    uint32_t wn[8];
+    if (blockIdx.x < n_units) fetch(blockIdx.x, wn);
     for (size_t u = blockIdx.x; u < n_units; u += gridDim.x) {
         const size_t ubase = u * (size_t)kUnit;
         uint32_t w[8], lab[8];
         size_t i0[2];
         bool full[2];
 #pragma unroll
+        for (int q = 0; q < 8; q++) w[q] = wn[q];
+        if (u + gridDim.x < n_units) fetch(u + gridDim.x, wn);
+#pragma unroll
         for (int hlf = 0; hlf < 2; hlf++) {
             i0[hlf] = ubase + (size_t)hlf * (kUnit / 2) + (size_t)threadIdx.x * 4;
             full[hlf] = i0[hlf] + 4 <= n;
-            if (full[hlf]) {
-                const uint4 v = __ldcs(reinterpret_cast<const uint4*>(xy + i0[hlf]));
-                w[4 * hlf + 0] = v.x; w[4 * hlf + 1] = v.y; w[4 * hlf + 2] = v.z; w[4 * hlf + 3] = v.w;
-            } else {
-#pragma unroll
-                for (int q = 0; q < 4; q++) w[4 * hlf + q] = i0[hlf] + q < n ? xy[i0[hlf] + q] : 0u;
-            }
         }
 #pragma unroll
         for (int q = 0; q < 8; q++) {

@@ -580,10 +580,10 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
                                      (int)kSmemLimit));
     k_slab_bins<<<2 * grid, 256, 0, h->stream>>>(a);
     EVK_CUDA(h, cudaGetLastError());
-    if (h->profiling) cudaEventRecord(h->ev[5], h->stream);
+    evk_prof_rec(h, 5);
     kern<<<grid, kThreads, smem, h->stream>>>(a);
     EVK_CUDA(h, cudaGetLastError());
-    if (h->profiling) cudaEventRecord(h->ev[6], h->stream);
+    evk_prof_rec(h, 6);
     k_slab_fix<<<grid, kFixThreads, 0, h->stream>>>(a.chunk_list, 2 * grid, h->d_cnt, h->d_keys,
                                                    h->d_first, h->d_xy);
     EVK_CUDA(h, cudaGetLastError());
