@@ -693,6 +693,7 @@ static int enqueue_fused(evk_handle* h, const KeyParams& kp, const evk_ds_params
     EVK_CUDA(h, evk_launch_km_assign_tiles(kl, ds->width, ds->height, h->d_quads, h->d_label_map,
                                            h->d_xy, h->n_events, &h->d_cnt->n_unique, true,
                                            h->d_acc, h->d_labels, h->sm_count, h->stream));
+    // (finalising in the last CTA of the assign kernel was measured slower than this launch)
     EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
                                        h->stream));
     prof_rec(h, 4);

@@ -521,12 +521,31 @@ __global__ void __launch_bounds__(kFixThreads)
     }
     const uint32_t total = stot < dtot ? stot : dtot;
     if (n_src == 0 || n_list == 0) return;
-    for (uint32_t j = blockIdx.x * blockDim.x + i; j < total; j += gridDim.x * blockDim.x) {
-        const uint32_t s = plan_locate(s_src_start, s_src_prefix, n_src, j);
-        const uint32_t d = plan_locate(s_dst_start, s_dst_prefix, n_list, j);
-        keys[d] = keys[s];
-        first[d] = first[s];
-        xy[d] = xy[s];
+    // four independent moves per thread and pass: the searches and the loads overlap
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t j0 = blockIdx.x * blockDim.x + i; j0 < total; j0 += 4 * stride) {
+        uint32_t sp[4], dp[4], f[4], x[4];
+        uint64_t k[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint32_t j = j0 + q * stride;
+            sp[q] = j < total ? plan_locate(s_src_start, s_src_prefix, n_src, j) : 0xFFFFFFFFu;
+            dp[q] = j < total ? plan_locate(s_dst_start, s_dst_prefix, n_list, j) : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (sp[q] == 0xFFFFFFFFu) continue;
+            k[q] = keys[sp[q]];
+            f[q] = first[sp[q]];
+            x[q] = xy[sp[q]];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            if (sp[q] == 0xFFFFFFFFu) continue;
+            keys[dp[q]] = k[q];
+            first[dp[q]] = f[q];
+            xy[dp[q]] = x[q];
+        }
     }
 }
 
