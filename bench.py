@@ -145,7 +145,7 @@ def cpu_port(n_sample, steps, threads):
     return n_sample / best / 1e6, threads, U, best
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, out):
     if rank != 0:
         return
     n_sample = min(args.cpu_sample, args.events)
@@ -166,7 +166,7 @@ def run_reference(args, rank):
         "note": "reference's OpenCL/Metavision code cannot be built here; this is the CPU oracle "
                 "port of its semantics on all host threads",
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
 
 
 def workload_config(args, world):
@@ -180,11 +180,22 @@ def workload_config(args, world):
 
 def main():
     args = parse()
+    # the JSON line is the only thing on stdout: libraries (NCCL banner, warnings) go to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = sys.stderr
+    try:
+        _main(args, real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(args, real_stdout):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, real_stdout)
         return
     import numpy as np
     import torch
@@ -223,10 +234,13 @@ def main():
     state = {}
 
     def step():
-        if world > 1:
+        if world > 1 and args.unfused:
             ul, ug = h.downsample_sharded(ds, owner)
             h.init_centroids_first_k_sharded(km)
             h.kmeans_sharded(km)
+            state["U_local"], state["U"] = ul, ug
+        elif world > 1:
+            ul, ug, _ = h.downsample_kmeans_sharded(ds, km, True, owner)
             state["U_local"], state["U"] = ul, ug
         elif args.unfused:
             u, r = h.downsample(ds)
@@ -253,7 +267,7 @@ def main():
         step()
         t = h.stage_times()
         ds_main += t.ds_main_ms; ds_total += t.ds_total_ms; km_total += t.km_total_ms
-        launches += t.ds_launches + t.km_launches + (1 if (args.unfused or world > 1) else 0)
+        launches += t.ds_launches + t.km_launches + (1 if args.unfused else 0)
     total_ms = h.timer_stop()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -297,7 +311,7 @@ def main():
         names = {evk.ALGO_SLAB: "k_slab_main", evk.ALGO_TABLE: "k_table_insert",
                  evk.ALGO_SORT: "sort+unique"}
         traffic = ncu_traffic()
-        fused = world == 1 and not args.unfused and algo_used == evk.ALGO_SLAB
+        fused = not args.unfused and algo_used == evk.ALGO_SLAB
         if ds_ms >= km_ms:
             kern, a_bytes, a_ms = names.get(algo_used, "?"), ds_bytes, ds_ms
         else:
@@ -336,7 +350,7 @@ def main():
                 "value": mev, "unit": "Mevents/s", "cores": threads, "kind": "port",
                 "sample": f"first {n_sample} events of the workload stream (U={Us}), best of 2 "
                           f"passes ({best:.2f} s each), generation excluded"}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=real_stdout, flush=True)
     h.close()
     if world > 1:
         dist.destroy_process_group()

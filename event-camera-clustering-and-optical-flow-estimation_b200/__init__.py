@@ -74,6 +74,7 @@ SYMBOLS = [
     "evk_get_stage_times", "evk_timer_start", "evk_timer_stop", "evk_sync", "evk_flush_l2",
     "evk_comm_unique_id", "evk_comm_init", "evk_comm_destroy", "evk_set_shard",
     "evk_downsample_sharded", "evk_kmeans_sharded", "evk_init_centroids_first_k_sharded",
+    "evk_downsample_kmeans_sharded",
 ]
 
 _lib = None
@@ -126,6 +127,8 @@ def lib():
         "evk_downsample_sharded": [vp, C.POINTER(DsParams), i32, psz, psz],
         "evk_kmeans_sharded": [vp, C.POINTER(KmParams), C.POINTER(i32)],
         "evk_init_centroids_first_k_sharded": [vp, C.POINTER(KmParams)],
+        "evk_downsample_kmeans_sharded": [vp, C.POINTER(DsParams), C.POINTER(KmParams), i32, i32,
+                                          psz, psz, C.POINTER(i32)],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -357,6 +360,16 @@ class Evk:
 
     def init_centroids_first_k_sharded(self, km):
         self._ck(self._L.evk_init_centroids_first_k_sharded(self._h, C.byref(km)))
+
+    def downsample_kmeans_sharded(self, ds, km, init_first_k=True, owner_mode=0):
+        """Fused sharded step. Returns (n_unique_local, n_unique_global, iters_done)."""
+        ul, ug, it = C.c_size_t(0), C.c_size_t(0), C.c_int(0)
+        self._ck(self._L.evk_downsample_kmeans_sharded(self._h, C.byref(ds), C.byref(km),
+                                                       1 if init_first_k else 0, owner_mode,
+                                                       C.byref(ul), C.byref(ug), C.byref(it)))
+        self.n_unique = ul.value
+        self._km = km
+        return ul.value, ug.value, it.value
 
     def kmeans_sharded(self, km):
         it = C.c_int(0)

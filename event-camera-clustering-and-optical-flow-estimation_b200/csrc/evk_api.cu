@@ -118,6 +118,15 @@ KmLaunch km_launch_params(const evk_handle* h, const evk_km_params* p) {
 
 }  // namespace
 
+int evk_km_validate(evk_handle* h, const evk_km_params* p) { return km_validate(h, p); }
+KmLaunch evk_km_launch_params(const evk_handle* h, const evk_km_params* p) {
+    return km_launch_params(h, p);
+}
+bool evk_ensure_images(evk_handle* h, int width, int height) {
+    return ensure_images(h, width, height);
+}
+void evk_invalidate_results(evk_handle* h) { invalidate_results(h); }
+
 int evk_make_key_params(evk_handle* h, const evk_ds_params* p, KeyParams* kp) {
     if (!p) return evk_fail(h, EVK_ERR_INVALID, "ds params are NULL");
     if (p->width < 1 || p->height < 1 || p->width > 65536 || p->height > 65536)

@@ -108,10 +108,13 @@ namespace {
 enum { ST_FLAG = 0, ST_U = 1, ST_R = 2, ST_SKIP = 3, ST_KEEP = 4, ST_HIST = 8 };
 
 // time-range halo: how many of my leading events belong to my first bin (they go to the previous
-// rank) and how many of the received events belong to the sender's first bin (I keep them)
-__global__ void k_halo_range(KeyParams kp, const evk_event* ev, uint32_t n_own, uint32_t halo,
-                             int rank, int world, unsigned long long* stats) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+// rank) and how many of the received events belong to the sender's first bin (I keep them).
+// One warp; run lengths by 32-way search (assumes time order; the slab kernel verifies the
+// resulting partition).
+__global__ void __launch_bounds__(32)
+    k_halo_range(KeyParams kp, const evk_event* ev, uint32_t n_own, uint32_t halo, int rank,
+                 int world, unsigned long long* stats) {
+    const int lane = threadIdx.x;
     unsigned long long flag = 0, skip = 0, keep = 0;
     auto bin_of = [&](uint32_t i, bool& ok) -> uint64_t {
         const int64_t t = ev[i].t;
@@ -125,13 +128,19 @@ __global__ void k_halo_range(KeyParams kp, const evk_event* ev, uint32_t n_own, 
             flag = 1;
             return 0;
         }
-        uint32_t lo = 0, hi = len;  // first offset whose bin differs (assumes time order; the slab
-        while (lo < hi) {           // kernel verifies the resulting partition)
-            const uint32_t mid = (lo + hi) >> 1;
+        uint32_t lo = 0, hi = len;  // first offset whose bin differs
+        while (lo < hi) {
+            const uint32_t span = hi - lo;
+            const uint32_t p = lo + (uint32_t)((uint64_t)span * (uint32_t)(lane + 1) / 33u);
             bool ok2;
-            const uint64_t b = bin_of(start + mid, ok2);
-            if (ok2 && b == b0) lo = mid + 1;
-            else hi = mid;
+            const uint64_t b = bin_of(start + p, ok2);
+            const bool differs = !(ok2 && b == b0);
+            const uint32_t m = __ballot_sync(0xffffffffu, differs);
+            const int f = m ? __ffs(m) - 1 : 32;
+            const uint32_t p_f = __shfl_sync(0xffffffffu, p, f < 32 ? f : 0);
+            const uint32_t p_b = __shfl_sync(0xffffffffu, p, f > 0 ? f - 1 : 0);
+            if (f < 32) hi = p_f;
+            if (f > 0) lo = p_b + 1;
         }
         return lo;
     };
@@ -144,9 +153,22 @@ __global__ void k_halo_range(KeyParams kp, const evk_event* ev, uint32_t n_own, 
         keep = run_len(n_own, halo);
         if (keep >= halo) flag = 1;
     }
-    stats[ST_FLAG] = flag;
-    stats[ST_SKIP] = skip;
-    stats[ST_KEEP] = keep;
+    if (lane == 0) {
+        stats[ST_FLAG] = flag;
+        stats[ST_SKIP] = skip;
+        stats[ST_KEEP] = keep;
+    }
+}
+
+// fused sharded step: [K * 5 + 0] = any reason to abandon the pass, [+1] = voxels, [+2] = repeated
+__global__ void k_pack_step_stats(const DsCounters* cnt, const unsigned long long* range,
+                                  unsigned long long found_want, int check_found,
+                                  unsigned long long* tail) {
+    unsigned long long flag = cnt->slab_violation | cnt->overflow | range[ST_FLAG];
+    if (check_found && cnt->scratch[4] != found_want) flag |= 1;
+    tail[0] = flag ? 1 : 0;
+    tail[1] = cnt->n_unique;
+    tail[2] = cnt->n_repeated;
 }
 
 __device__ __forceinline__ int owner_of(uint64_t key, int world) {
@@ -560,6 +582,149 @@ int evk_kmeans_sharded(evk_handle* h, const evk_km_params* p, int* iters_done) {
     if (!h->comm) return evk_fail(h, EVK_ERR_COMM, "evk_comm_init has not been called");
     if (p && p->on_events) return evk_fail(h, EVK_ERR_INVALID, "sharded k-means clusters voxels");
     return evk_kmeans_run(h, p, iters_done, allreduce_acc);
+}
+
+// Fused sharded step (time-range ownership): halo exchange, downsample, centroid broadcast, one
+// assign + accumulate pass and ONE allreduce (partial sums + voxel counters + give-up flag), all
+// stream-ordered with a single host synchronisation at the end.  The event range a rank works on
+// (after giving its first partial bin to the previous rank and keeping the next rank's) stays on
+// the device.  Anything the fused pass does not take -- other ownership mode, D > 2, several
+// iterations, an unordered stream on any rank -- runs the separate sharded calls.
+int evk_downsample_kmeans_sharded(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
+                                  int init_first_k, int owner_mode, size_t* n_unique_local,
+                                  size_t* n_unique_global, int* iters_done) {
+    if (!h) return EVK_ERR_INVALID;
+    if (!h->comm) return evk_fail(h, EVK_ERR_COMM, "evk_comm_init has not been called");
+    EVK_TRY(evk_km_validate(h, km));
+    KeyParams kp;
+    EVK_TRY(evk_make_key_params(h, ds, &kp));
+    CommState* c = h->comm;
+    EVK_CUDA(h, cudaSetDevice(h->device));
+    if (!init_first_k && (!h->have_centroids || h->K != km->K || h->D != km->D))
+        return evk_fail(h, EVK_ERR_STATE, "centroids for K=%d, D=%d have not been set", km->K, km->D);
+    const size_t n_own = h->n_events;
+    const uint32_t halo = c->halo;
+    // rank-independent conditions only: every rank must take the same branch
+    bool fusable = owner_mode == EVK_OWNER_TIME_RANGE && km->D == 2 && !km->on_events &&
+                   km->K <= 254 && km->iters == 1 && km->tol < 0.f &&
+                   (ds->algo == EVK_ALGO_AUTO || ds->algo == EVK_ALGO_SLAB) &&
+                   ds->keyfn == EVK_KEY_VOXEL && kp.vt > 0 && (uint64_t)ds->width * ds->height <= (64ull << 20);
+    if (fusable) {
+        evk_handle probe_shape = evk_handle();  // slab shape check without the rank's event count
+        probe_shape.n_events = 1;
+        probe_shape.sm_count = h->sm_count;
+        fusable = evk_slab_supported(&probe_shape, kp);
+    }
+    bool done = false;
+    if (fusable) {
+        if (n_own + halo > h->max_events)
+            return evk_fail(h, EVK_ERR_CAPACITY,
+                            "sharded downsample needs max_events >= n_events + %u (halo)", halo);
+        if (!evk_ensure_images(h, ds->width, ds->height))
+            return evk_fail(h, EVK_ERR_NOMEM, "pixel images");
+        evk_invalidate_results(h);
+        h->ds = *ds;
+        h->kp = kp;
+        h->have_ds = true;
+        const KmLaunch kl = evk_km_launch_params(h, km);
+        int launches = 0;
+        unsigned long long* tail = h->d_acc + (size_t)km->K * 5;
+        EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
+        evk_prof_rec(h, 0);
+        // main stream: rank 0 walks the head of the global stream for the initial centroids; ONE
+        // NCCL group carries the boundary blocks and the centroid broadcast (collectives cannot
+        // start beside the downsample: its CTAs leave no shared memory on any SM)
+        if (init_first_k && c->rank == 0) {
+            const size_t n_scan = n_own < (1u << 20) ? n_own : (1u << 20);
+            if (n_scan)
+                EVK_CUDA(h, evk_launch_init_first_k_walk(kp, kl, h->d_events, n_scan, h->d_cent,
+                                                         &h->d_cnt->scratch[4], h->stream));
+        }
+        if (!init_first_k)  // warm start: keep a copy in case the pass is abandoned
+            EVK_CUDA(h, cudaMemcpyAsync(h->d_cent + EVK_MAX_K * 2, h->d_cent,
+                                        (size_t)km->K * 2 * sizeof(float), cudaMemcpyDeviceToDevice,
+                                        h->stream));
+        EVK_NCCL(h, g_nccl.GroupStart());
+        if (c->rank > 0)
+            EVK_NCCL(h, g_nccl.Send(h->d_events, (size_t)halo * 16, ncclUint8, c->rank - 1, c->comm,
+                                    h->stream));
+        if (c->rank < c->world - 1)
+            EVK_NCCL(h, g_nccl.Recv(h->d_events + n_own, (size_t)halo * 16, ncclUint8, c->rank + 1,
+                                    c->comm, h->stream));
+        if (init_first_k)
+            EVK_NCCL(h, g_nccl.Broadcast(h->d_cent, h->d_cent, (size_t)km->K * 2, ncclFloat, 0,
+                                         c->comm, h->stream));
+        EVK_NCCL(h, g_nccl.GroupEnd());
+        EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+        // who keeps what (on the device), then the downsample on that range
+        k_halo_range<<<1, 32, 0, h->stream>>>(kp, h->d_events, (uint32_t)n_own, halo, c->rank,
+                                              c->world, c->d_stats);
+        EVK_CUDA(h, cudaGetLastError());
+        bool ok = false;
+        EVK_TRY(evk_downsample_slab(h, kp, ds->count_repeated, &ok, &launches, false, c->d_stats));
+        // side stream, beside the downsample: candidate lists, label map, quads
+        EVK_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        EVK_CUDA(h, evk_launch_km_image(kl, ds->width, ds->height, h->d_prune_lists, h->d_cent,
+                                        nullptr, h->d_label_map, h->d_quads, h->d_acc, h->side));
+        EVK_CUDA(h, cudaEventRecord(h->ev_join, h->side));
+        EVK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        evk_prof_rec(h, 2);
+        evk_prof_rec(h, 3);
+        EVK_CUDA(h, evk_launch_km_assign_tiles(kl, ds->width, ds->height, h->d_quads, h->d_label_map,
+                                               h->d_xy, n_own + halo, &h->d_cnt->n_unique, true,
+                                               h->d_acc, h->d_labels, h->sm_count, h->stream));
+        k_pack_step_stats<<<1, 1, 0, h->stream>>>(h->d_cnt, c->d_stats, (unsigned long long)km->K,
+                                                  init_first_k && c->rank == 0, tail);
+        EVK_CUDA(h, cudaGetLastError());
+        EVK_NCCL(h, g_nccl.AllReduce(h->d_acc, h->d_acc, (size_t)km->K * 5 + 3, ncclUint64, ncclSum,
+                                     c->comm, h->stream));
+        EVK_CUDA(h, cudaMemcpyAsync(c->h_stats, tail, 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+        EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
+                                           h->stream));
+        evk_prof_rec(h, 4);
+        EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,
+                                    h->stream));
+        EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (c->h_stats[0] == 0) {
+            h->n_unique = (size_t)h->h_cnt->n_unique;
+            h->n_repeated = ds->count_repeated ? (size_t)h->h_cnt->n_repeated : 0;
+            c->h_stats[ST_U] = c->h_stats[1];
+            h->have_voxels = true;
+            h->K = km->K;
+            h->D = km->D;
+            h->have_centroids = true;
+            h->n_labels = h->n_unique;
+            h->labels_on_events = false;
+            h->km_last = *km;
+            c->last_mode = EVK_OWNER_TIME_RANGE;
+            h->times.ds_algo_used = EVK_ALGO_SLAB;
+            h->times.ds_launches = launches + 2;
+            h->times.km_launches = 6;
+            h->times.km_iters = 1;
+            if (h->profiling) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, h->ev[0], h->ev[2]) == cudaSuccess) h->times.ds_total_ms = ms;
+                if (cudaEventElapsedTime(&ms, h->ev[5], h->ev[6]) == cudaSuccess) h->times.ds_main_ms = ms;
+                if (cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]) == cudaSuccess)
+                    h->times.km_total_ms = h->times.km_assign_ms = ms;
+                cudaGetLastError();
+            }
+            if (iters_done) *iters_done = 1;
+            done = true;
+        } else if (!init_first_k) {  // finalise has overwritten the caller's centroids
+            EVK_CUDA(h, cudaMemcpyAsync(h->d_cent, h->d_cent + EVK_MAX_K * 2,
+                                        (size_t)km->K * 2 * sizeof(float),
+                                        cudaMemcpyDeviceToDevice, h->stream));
+        }
+    }
+    if (!done) {
+        EVK_TRY(evk_downsample_sharded(h, ds, fusable ? EVK_OWNER_MIX64 : owner_mode, nullptr, nullptr));
+        if (init_first_k) EVK_TRY(evk_init_centroids_first_k_sharded(h, km));
+        EVK_TRY(evk_kmeans_sharded(h, km, iters_done));
+    }
+    if (n_unique_local) *n_unique_local = h->n_unique;
+    if (n_unique_global) *n_unique_global = (size_t)c->h_stats[ST_U];
+    return EVK_OK;
 }
 
 int evk_init_centroids_first_k_sharded(evk_handle* h, const evk_km_params* p) {

@@ -224,6 +224,12 @@ extern "C" int evk_downsample_local(evk_handle* h, const evk_ds_params* p);
 extern "C" int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_done,
                               int (*reduce)(evk_handle*, int K, int D));
 
+// host helpers of evk_api.cu used by the sharded step (evk_comm.cu)
+struct KmLaunch;
+int evk_km_validate(evk_handle* h, const evk_km_params* p);
+bool evk_ensure_images(evk_handle* h, int width, int height);
+void evk_invalidate_results(evk_handle* h);
+
 // ---- kernel launchers (implemented in the .cu files) ----------------------------------------
 int evk_make_key_params(evk_handle* h, const evk_ds_params* p, KeyParams* kp);
 // synth
@@ -244,8 +250,10 @@ cudaError_t evk_launch_table_compact(const evk_event* ev, uint64_t* tkeys, uint3
 int evk_downsample_sort(evk_handle* h, const KeyParams& kp, int* launches);
 // downsample: time-slab kernel.  sync = false: everything is only enqueued; the caller copies the
 // counters, synchronises and reads slab_violation / overflow itself.
+// range (device, sharded runs): [0] give-up flag, [3] events to skip, [4] events to keep behind n.
 int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, bool* ok,
-                        int* launches, bool sync = true);
+                        int* launches, bool sync = true,
+                        const unsigned long long* range = nullptr);
 bool evk_slab_supported(const evk_handle* h, const KeyParams& kp);
 size_t evk_slab_scratch_bytes(int sm_count);
 // canonical order
@@ -264,6 +272,7 @@ struct KmLaunch {
     int64_t t0;
     int write_labels;
 };
+KmLaunch evk_km_launch_params(const evk_handle* h, const evk_km_params* p);
 cudaError_t evk_launch_km_assign(const KmLaunch& kl, const uint32_t* xy, const evk_event* ev,
                                  const uint32_t* first, size_t n, const float* cent,
                                  unsigned long long* acc, int32_t* labels, int sm_count,

@@ -69,7 +69,36 @@ struct SlabArgs {
     uint32_t words;         // bitmap words per bin
     uint32_t max_bins;
     uint32_t min_bins;
+    // sharded runs: [0] != 0 -> give up; [3] = leading events that belong to the previous rank's
+    // last bin; [4] = events received behind my own that belong to my last bin.  Read on the device
+    // so that the halo exchange and the downsample need no host round trip in between.
+    const unsigned long long* range;
 };
+
+// the event range the kernels work on
+struct SlabRange {
+    const evk_event* ev;
+    size_t n;
+    uint32_t first_offset;
+    bool bad;
+};
+__device__ __forceinline__ SlabRange slab_range(const SlabArgs& a) {
+    SlabRange r;
+    r.ev = a.ev;
+    r.n = a.n;
+    r.first_offset = a.first_offset;
+    r.bad = false;
+    if (a.range) {
+        const size_t skip = (size_t)a.range[3], keep = (size_t)a.range[4];
+        r.bad = a.range[0] != 0 || skip > a.n;
+        if (!r.bad) {
+            r.ev = a.ev + skip;
+            r.n = a.n - skip + keep;
+            r.first_offset = a.first_offset + (uint32_t)skip;
+        }
+    }
+    return r;
+}
 
 // ---- PTX helpers: mbarrier + 1-D TMA bulk copy ------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -111,8 +140,15 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
 __global__ void __launch_bounds__(256) k_slab_bins(SlabArgs a) {
     DsCounters* cnt = a.cnt;
     const KeyParams& kp = a.kp;
-    const uint4 e0 = ld_event(a.ev);
-    const uint4 e1 = ld_event(a.ev + (a.n - 1));
+    const SlabRange rg = slab_range(a);
+    if (rg.bad || rg.n == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) cnt->slab_violation = 2;
+        return;
+    }
+    const evk_event* ev = rg.ev;
+    const size_t n = rg.n;
+    const uint4 e0 = ld_event(ev);
+    const uint4 e1 = ld_event(ev + (n - 1));
     const int64_t t_first = ev_t(e0), t_last = ev_t(e1);
     bool bad = t_first < kp.t0 || t_last < t_first;
     uint64_t tb0 = 0, nb = 0;
@@ -133,15 +169,15 @@ __global__ void __launch_bounds__(256) k_slab_bins(SlabArgs a) {
     const size_t warp = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
     for (size_t b = warp; b <= nb; b += n_warps) {
-        size_t lo = 0, hi = a.n;  // invariant: pred(lo - 1) false, pred(hi) true (pred(n) = true)
+        size_t lo = 0, hi = n;  // invariant: pred(lo - 1) false, pred(hi) true (pred(n) = true)
         if (b == 0) hi = 0;
-        else if (b == nb) lo = a.n;
+        else if (b == nb) lo = n;
         while (lo < hi) {
             const size_t span = hi - lo;
             // 32 probes spread over [lo, hi): lo + span * (l + 1) / 33 (span < 2^33: no overflow)
             const size_t p = lo + span * (size_t)(lane + 1) / 33u;
             const int64_t t = *reinterpret_cast<const int64_t*>(
-                reinterpret_cast<const char*>(a.ev + p) + 8);
+                reinterpret_cast<const char*>(ev + p) + 8);
             const bool ge = t >= kp.t0 && evk_tbin(kp, t) >= tb0 + b;
             const uint32_t m = __ballot_sync(0xffffffffu, ge);
             // first lane whose probe satisfies the predicate bounds hi; the lane before it bounds lo
@@ -205,6 +241,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
     const uint32_t nb = (uint32_t)cnt->scratch[0];
     const uint64_t tb0 = cnt->scratch[2];
     const int tid = threadIdx.x, lane = tid & 31;
+    const SlabRange rg = slab_range(a);
+    const evk_event* const evs = rg.ev;
+    const uint32_t first_offset = rg.first_offset;
 
     for (int i = tid; i < 2 * kHash; i += NT) s_late[i] = kEmpty;
     for (uint32_t i = tid; i < a.words; i += NT) s_map[i] = 0;
@@ -256,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
         const uint32_t cntev = min((uint32_t)TILE, tma.hi - tma.base);
         uint64_t* bar = &s_bar[tma_seq % kStages];
         mbar_expect_tx(bar, cntev * 16u);
-        tma_load_1d(s_ev + (tma_seq % kStages) * kTile, a.ev + tma.base, cntev * 16u, bar);
+        tma_load_1d(s_ev + (tma_seq % kStages) * kTile, evs + tma.base, cntev * 16u, bar);
         tma_seq++;
         tma.base += TILE;
         if (tma.base >= tma.hi) {
@@ -394,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                         const uint32_t o = wbase + __popc(bal[j] & lt);
                         const uint32_t p = o < room ? pos0 + o : nxt0 + (o - room);
                         a.keys[p] = key_base + (cv[j] >> kLogTile);
-                        a.first[p] = base + (cv[j] & (kTile - 1)) + a.first_offset;
+                        a.first[p] = base + (cv[j] & (kTile - 1)) + first_offset;
                         a.xy[p] = cxy[j];
                     }
                     wbase += __popc(bal[j]);
@@ -572,7 +611,7 @@ bool evk_slab_supported(const evk_handle* h, const KeyParams& kp) {
 }
 
 int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, bool* ok,
-                        int* launches, bool sync) {
+                        int* launches, bool sync, const unsigned long long* range) {
     *ok = false;
     const int grid = h->sm_count * kCtasPerSm;
     SlabArgs a;
@@ -590,6 +629,7 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
     a.max_bins = (uint32_t)h->max_bins;
     // a single CTA walks a bin sequentially: with few bins and many events the table is faster
     a.min_bins = h->n_events > (1u << 22) ? 32 : 1;
+    a.range = range;
     const size_t smem = slab_smem_bytes(kp.cells, count_repeated != 0);
     const bool pow2 = kp.sx >= 0 && kp.sy >= 0;
     void (*kern)(SlabArgs) =

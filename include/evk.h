@@ -238,6 +238,15 @@ EVK_API int evk_downsample_sharded(evk_handle* h, const evk_ds_params* p, int ow
                                    size_t* n_unique_local, size_t* n_unique_global);
 /* k-means on the local voxel shard with an allreduce of the K*(D+1) exact partial sums */
 EVK_API int evk_kmeans_sharded(evk_handle* h, const evk_km_params* p, int* iters_done);
+/* Fused sharded step: evk_downsample_sharded + (init_first_k != 0) evk_init_centroids_first_k_sharded
+ * + evk_kmeans_sharded as one stream-ordered pass with a single host synchronisation: boundary
+ * block exchange, downsample on a device-side event range, centroid broadcast beside it, one
+ * assign + accumulate pass, ONE allreduce of the K x 5 partial sums together with the voxel
+ * counters.  Shapes it does not take run the three calls; same results either way. */
+EVK_API int evk_downsample_kmeans_sharded(evk_handle* h, const evk_ds_params* ds,
+                                          const evk_km_params* km, int init_first_k,
+                                          int owner_mode, size_t* n_unique_local,
+                                          size_t* n_unique_global, int* iters_done);
 /* broadcast-free deterministic init: the K globally lowest first indices */
 EVK_API int evk_init_centroids_first_k_sharded(evk_handle* h, const evk_km_params* p);
 

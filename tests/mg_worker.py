@@ -81,6 +81,27 @@ def main():
                     assert abs(d[lab[i]] - d[ol[pos[i]]]) <= 1e-6 * d.max()
             if rank == 0:
                 print(f"mg ok: {name} {mode_name} world={world} U={ug}", flush=True)
+        # fused sharded step (one iteration): same voxel set, centroids and counts as the oracle
+        km1 = evk.km_params(K, 2, iters=1)
+        oc1, ol1, ocnt1, _ = orc.kmeans(pts, pts[:K], iters=1, threads=4)
+        for rep in range(2):
+            h.synth(evk.synth_params(seed, n, W, H, rate, blobs, first_index=rank * n))
+            ul, ug, it = h.downsample_kmeans_sharded(ds, km1, True, evk.OWNER_TIME_RANGE)
+            assert (ug, it) == (len(ok), 1), (name, rank, ug, len(ok))
+            assert h.stage_times().km_launches == 6, "fused sharded pass did not run"
+            keys, reps, first = h.get_voxels()
+            assert len(keys) == ul and reps.tobytes() == ev_all[first].tobytes()
+            all_keys = np.concatenate(gather_arrays(keys, rank, world))
+            all_first = np.concatenate(gather_arrays(first, rank, world))
+            order = np.argsort(all_first, kind="stable")
+            assert len(all_keys) == len(ok)
+            assert (all_keys[order] == ok).all() and (all_first[order] == of).all()
+            cent, counts = h.get_centroids(K, 2)
+            assert (counts == ocnt1).all() and np.allclose(cent, oc1, rtol=1e-5, atol=0)
+            lab = h.get_labels()
+            assert (lab == ol1[np.searchsorted(of, first)]).all()
+        if rank == 0:
+            print(f"mg ok: {name} fused sharded step world={world} U={ug}", flush=True)
         # unordered stream: the time-range scheme must detect it on every rank and fall back
         rng = np.random.default_rng(5)
         perm = rng.permutation(total)
@@ -93,6 +114,18 @@ def main():
         all_first = np.concatenate(gather_arrays(first, rank, world))
         order = np.argsort(all_first, kind="stable")
         assert ug == len(ok2) and (all_keys[order] == ok2).all() and (all_first[order] == of2).all()
+        # ... and so must the fused step (general path, same answer)
+        h.load_events(ev_shuf[rank * n:(rank + 1) * n])
+        ul, ug, it = h.downsample_kmeans_sharded(ds, km1, True, evk.OWNER_TIME_RANGE)
+        keys, _, first = h.get_voxels(reps=False)
+        all_keys = np.concatenate(gather_arrays(keys, rank, world))
+        all_first = np.concatenate(gather_arrays(first, rank, world))
+        order = np.argsort(all_first, kind="stable")
+        assert ug == len(ok2) and (all_keys[order] == ok2).all() and (all_first[order] == of2).all()
+        pts2 = orc.points(ev_shuf, of2, 2)
+        oc2, _, ocnt2, _ = orc.kmeans(pts2, pts2[:K], iters=1, threads=4)
+        cent, counts = h.get_centroids(K, 2)
+        assert (counts == ocnt2).all() and np.allclose(cent, oc2, rtol=1e-5, atol=0)
         if rank == 0:
             print(f"mg ok: {name} unordered fallback world={world} U={ug}", flush=True)
         h.close()
