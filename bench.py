@@ -5,10 +5,13 @@
 
 Workload at N=1 (BASELINE.json configs[2], the config the metric is quoted on): 100 M synthetic
 Prophesee Gen4 (1280x720) events at 100 Mev/s, 2x2 px x 500 us voxels (+ polarity), k-means K=64,
-D=2.  A step = downsample -> first-K centroid initialisation -> one fused assign+accumulate
-iteration (+ finalise).  N>1: weak scaling, each rank owns a contiguous 100 M-event index shard of
-an N x 100 M-event stream (configs[3]); voxels are exchanged by ownership with an NCCL all-to-all
-and the K x (D+1) partial sums are allreduced.
+D=2.  A step = ONE call of the fused entry point evk_downsample_kmeans (downsample -> first-K
+centroid initialisation -> one assign + accumulate iteration -> finalise; a replayed CUDA graph,
+one host synchronisation).  --unfused runs the three separate calls instead (same results).
+N>1: weak scaling, each rank owns a contiguous 100 M-event index shard of an N x 100 M-event stream
+(configs[3]); evk_downsample_kmeans_sharded: boundary blocks move between neighbours (time-range
+ownership; --owner mix64 = hash ownership with an NCCL all-to-all of voxels) and the K x (D+1)
+partial sums are allreduced.
 
 `value`  : events resident in HBM, timed with CUDA events on the library's stream.
 `e2e`    : the same step through the C-ABI from pinned HOST memory: H2D of the events and D2H of
@@ -315,7 +318,7 @@ def _main(args, real_stdout):
         if ds_ms >= km_ms:
             kern, a_bytes, a_ms = names.get(algo_used, "?"), ds_bytes, ds_ms
         else:
-            kern, a_bytes, a_ms = "k_km_assign", km_bytes, km_ms
+            kern, a_bytes, a_ms = "k_km_assign_tiles", km_bytes, km_ms
         achieved = a_bytes / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0
         step_bytes = 16.0 * n + 36.0 * U
         line = {

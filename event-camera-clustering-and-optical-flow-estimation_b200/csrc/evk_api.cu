@@ -267,7 +267,8 @@ int evk_destroy(evk_handle* h) {
                     h->d_reps,   h->d_labels, h->d_perm,   h->d_sort_tmp, h->d_sort_a, h->d_sort_b,
                     h->d_sort_c, h->d_sk_in,  h->d_sk_out, h->d_si_in,  h->d_si_out, h->d_sv_tmp,
                     h->d_bin_start, h->d_slab_scratch, h->d_cnt, h->d_cent,   h->d_acc,    h->d_counts, h->d_shift,
-                    h->d_cand,   h->d_flush, h->d_prune_lists, h->d_label_map, h->d_pixcnt, h->d_quads};
+                    h->d_cand,   h->d_flush, h->d_prune_lists, h->d_label_map, h->d_pixcnt, h->d_quads,
+                    h->d_win_stage};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->h_cnt) cudaFreeHost(h->h_cnt);
@@ -854,7 +855,7 @@ int evk_window_config(evk_handle* h, const evk_ds_params* ds, const evk_km_param
     h->win_us = window_us;
     h->win_cfg = true;
     h->win_started = false;
-    h->win_buf.clear();
+    h->win_pending = 0;
     h->win_count = 0;
     h->have_centroids = false;
     return EVK_OK;
@@ -862,9 +863,16 @@ int evk_window_config(evk_handle* h, const evk_ds_params* ds, const evk_km_param
 
 static int window_run(evk_handle* h) {
     // one slice: the body of on_new_slice (ACCEL/store.cpp:370-568) minus consumer and drawing,
-    // as ONE fused submission (downsample + warm-started k-means) with one host synchronisation
-    const evk_event* b = h->win_buf.data();
-    EVK_TRY(evk_load_events(h, b, b + h->win_buf.size()));
+    // as ONE fused submission (downsample + warm-started k-means) with one host synchronisation.
+    // The slice's events are already on the device (staged as they arrived); they replace the
+    // previous slice's only now, so that slice's results stay readable until this point.
+    {
+        DeviceGuard g(h->device);
+        EVK_CUDA(h, cudaMemcpyAsync(h->d_events, h->d_win_stage, h->win_pending * sizeof(evk_event),
+                                    cudaMemcpyDeviceToDevice, h->stream));
+        h->n_events = h->win_pending;
+        invalidate_results(h);
+    }
     evk_ds_params ds = h->win_ds;
     ds.t0_us = h->win_start;  // time bins restart with every window
     const bool seeded = h->have_centroids && h->K == h->win_km.K && h->D == h->win_km.D;
@@ -874,30 +882,52 @@ static int window_run(evk_handle* h) {
         st = EVK_OK;
     EVK_TRY(st);
     h->win_count++;
+    h->win_pending = 0;
     return EVK_OK;
 }
 
+// Events of a push are time-ordered (the SDK delivers them so, ACCEL/store.cpp:614-615): the end of
+// the current window inside the range is found by binary search and whole sub-ranges go to the
+// device with one copy each -- no per-event host work, no host-side staging buffer.
 int evk_window_push(evk_handle* h, const evk_event* begin, const evk_event* end, int* windows_done) {
     EVK_TRY(check_handle(h));
     if (!h->win_cfg) return evk_fail(h, EVK_ERR_STATE, "evk_window_config has not been called");
     if ((!begin && end != begin) || end < begin) return evk_fail(h, EVK_ERR_INVALID, "bad event range");
     int done = 0;
-    for (const evk_event* e = begin; e != end; ++e) {
+    const evk_event* p = begin;
+    while (p != end) {
         if (!h->win_started) {
             h->win_started = true;
-            h->win_start = e->t - (e->t % h->win_us);
+            h->win_start = p->t - (p->t % h->win_us);
         }
-        while (e->t >= h->win_start + h->win_us) {  // window complete (possibly an empty one)
-            if (!h->win_buf.empty()) {
+        const int64_t win_end = h->win_start + h->win_us;
+        const evk_event* q =
+            std::partition_point(p, end, [win_end](const evk_event& e) { return e.t < win_end; });
+        if (q != p) {
+            const size_t m = (size_t)(q - p);
+            if (h->win_pending + m > h->max_events)
+                return evk_fail(h, EVK_ERR_CAPACITY, "window exceeds the handle capacity");
+            DeviceGuard g(h->device);
+            if (!h->d_win_stage)
+                EVK_CUDA(h, cudaMalloc((void**)&h->d_win_stage, h->max_events * sizeof(evk_event)));
+            EVK_CUDA(h, cudaMemcpyAsync(h->d_win_stage + h->win_pending, p, m * sizeof(evk_event),
+                                        cudaMemcpyHostToDevice, h->stream));
+            h->win_pending += m;
+        }
+        if (q != end) {  // an event of a later window has arrived: this one is complete
+            if (h->win_pending) {
                 EVK_TRY(window_run(h));
                 done++;
-                h->win_buf.clear();
             }
             h->win_start += h->win_us;
+            while (q->t >= h->win_start + h->win_us) h->win_start += h->win_us;  // empty windows
         }
-        if (h->win_buf.size() >= h->max_events)
-            return evk_fail(h, EVK_ERR_CAPACITY, "window exceeds the handle capacity");
-        h->win_buf.push_back(*e);
+        p = q;
+    }
+    // the ranges are borrowed: their copies must have left host memory before we return
+    {
+        DeviceGuard g(h->device);
+        EVK_CUDA(h, cudaStreamSynchronize(h->stream));
     }
     if (windows_done) *windows_done = done;
     return EVK_OK;
@@ -907,10 +937,9 @@ int evk_window_flush(evk_handle* h, int* windows_done) {
     EVK_TRY(check_handle(h));
     if (!h->win_cfg) return evk_fail(h, EVK_ERR_STATE, "evk_window_config has not been called");
     int done = 0;
-    if (!h->win_buf.empty()) {
+    if (h->win_pending) {
         EVK_TRY(window_run(h));
         done = 1;
-        h->win_buf.clear();
         h->win_start += h->win_us;
     }
     if (windows_done) *windows_done = done;

@@ -92,6 +92,9 @@ struct CommState {
     evk_event *sr = nullptr, *rr = nullptr;
     size_t stage_cap = 0;
     int last_mode = -1;
+    cudaGraphExec_t step_exec = nullptr;  // the fused sharded step as one graph
+    FusedKey step_key{};
+    int step_launches = 0;
 };
 
 #define EVK_NCCL(h, expr)                                                                  \
@@ -536,6 +539,7 @@ int evk_comm_destroy(evk_handle* h) {
     CommState* c = h->comm;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (c->step_exec) cudaGraphExecDestroy(c->step_exec);
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
     void* ptrs[] = {c->d_stats, c->sk, c->rk, c->sf, c->rf, c->sx, c->rx, c->sr, c->rr};
     for (void* p : ptrs)
@@ -584,6 +588,72 @@ int evk_kmeans_sharded(evk_handle* h, const evk_km_params* p, int* iters_done) {
     return evk_kmeans_run(h, p, iters_done, allreduce_acc);
 }
 
+// everything the fused sharded step submits (captured into a graph by the caller)
+static int enqueue_fused_sharded(evk_handle* h, const KeyParams& kp, const evk_ds_params* ds,
+                                 const evk_km_params* km, int init_first_k, int* launches) {
+    CommState* c = h->comm;
+    const size_t n_own = h->n_events;
+    const uint32_t halo = c->halo;
+    const KmLaunch kl = evk_km_launch_params(h, km);
+    unsigned long long* tail = h->d_acc + (size_t)km->K * 5;
+    EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
+    evk_prof_rec(h, 0);
+    // main stream: rank 0 walks the head of the global stream for the initial centroids; ONE
+    // NCCL group carries the boundary blocks and the centroid broadcast (collectives cannot
+    // start beside the downsample: its CTAs leave no shared memory on any SM)
+    if (init_first_k && c->rank == 0) {
+        const size_t n_scan = n_own < (1u << 20) ? n_own : (1u << 20);
+        if (n_scan)
+            EVK_CUDA(h, evk_launch_init_first_k_walk(kp, kl, h->d_events, n_scan, h->d_cent,
+                                                     &h->d_cnt->scratch[4], h->stream));
+    }
+    if (!init_first_k)  // warm start: keep a copy in case the pass is abandoned
+        EVK_CUDA(h, cudaMemcpyAsync(h->d_cent + EVK_MAX_K * 2, h->d_cent,
+                                    (size_t)km->K * 2 * sizeof(float), cudaMemcpyDeviceToDevice,
+                                    h->stream));
+    EVK_NCCL(h, g_nccl.GroupStart());
+    if (c->rank > 0)
+        EVK_NCCL(h, g_nccl.Send(h->d_events, (size_t)halo * 16, ncclUint8, c->rank - 1, c->comm,
+                                h->stream));
+    if (c->rank < c->world - 1)
+        EVK_NCCL(h, g_nccl.Recv(h->d_events + n_own, (size_t)halo * 16, ncclUint8, c->rank + 1,
+                                c->comm, h->stream));
+    if (init_first_k)
+        EVK_NCCL(h, g_nccl.Broadcast(h->d_cent, h->d_cent, (size_t)km->K * 2, ncclFloat, 0,
+                                     c->comm, h->stream));
+    EVK_NCCL(h, g_nccl.GroupEnd());
+    EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+    // who keeps what (on the device), then the downsample on that range
+    k_halo_range<<<1, 32, 0, h->stream>>>(kp, h->d_events, (uint32_t)n_own, halo, c->rank,
+                                          c->world, c->d_stats);
+    EVK_CUDA(h, cudaGetLastError());
+    bool ok = false;
+    EVK_TRY(evk_downsample_slab(h, kp, ds->count_repeated, &ok, launches, false, c->d_stats));
+    // side stream, beside the downsample: candidate lists, label map, quads
+    EVK_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    EVK_CUDA(h, evk_launch_km_image(kl, ds->width, ds->height, h->d_prune_lists, h->d_cent,
+                                    nullptr, h->d_label_map, h->d_quads, h->d_acc, h->side));
+    EVK_CUDA(h, cudaEventRecord(h->ev_join, h->side));
+    EVK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+    evk_prof_rec(h, 2);
+    evk_prof_rec(h, 3);
+    EVK_CUDA(h, evk_launch_km_assign_tiles(kl, ds->width, ds->height, h->d_quads, h->d_label_map,
+                                           h->d_xy, n_own + halo, &h->d_cnt->n_unique, true,
+                                           h->d_acc, h->d_labels, h->sm_count, h->stream));
+    k_pack_step_stats<<<1, 1, 0, h->stream>>>(h->d_cnt, c->d_stats, (unsigned long long)km->K,
+                                              init_first_k && c->rank == 0, tail);
+    EVK_CUDA(h, cudaGetLastError());
+    EVK_NCCL(h, g_nccl.AllReduce(h->d_acc, h->d_acc, (size_t)km->K * 5 + 3, ncclUint64, ncclSum,
+                                 c->comm, h->stream));
+    EVK_CUDA(h, cudaMemcpyAsync(c->h_stats, tail, 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+    EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
+                                       h->stream));
+    evk_prof_rec(h, 4);
+    EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,
+                                h->stream));
+    return EVK_OK;
+}
+
 // Fused sharded step (time-range ownership): halo exchange, downsample, centroid broadcast, one
 // assign + accumulate pass and ONE allreduce (partial sums + voxel counters + give-up flag), all
 // stream-ordered with a single host synchronisation at the end.  The event range a rank works on
@@ -626,64 +696,38 @@ int evk_downsample_kmeans_sharded(evk_handle* h, const evk_ds_params* ds, const 
         h->ds = *ds;
         h->kp = kp;
         h->have_ds = true;
-        const KmLaunch kl = evk_km_launch_params(h, km);
+        // one CUDA graph (NCCL operations included), re-captured only when the call's shape changes
+        FusedKey key;
+        memset(&key, 0, sizeof key);
+        key.n = n_own;
+        key.ds = *ds;
+        key.km = *km;
+        key.init = init_first_k ? 1 : 0;
+        key.profiling = h->profiling ? 1 : 0;
+        key.shard_first = h->shard_first;
         int launches = 0;
-        unsigned long long* tail = h->d_acc + (size_t)km->K * 5;
-        EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
-        evk_prof_rec(h, 0);
-        // main stream: rank 0 walks the head of the global stream for the initial centroids; ONE
-        // NCCL group carries the boundary blocks and the centroid broadcast (collectives cannot
-        // start beside the downsample: its CTAs leave no shared memory on any SM)
-        if (init_first_k && c->rank == 0) {
-            const size_t n_scan = n_own < (1u << 20) ? n_own : (1u << 20);
-            if (n_scan)
-                EVK_CUDA(h, evk_launch_init_first_k_walk(kp, kl, h->d_events, n_scan, h->d_cent,
-                                                         &h->d_cnt->scratch[4], h->stream));
+        if (c->step_exec && memcmp(&key, &c->step_key, sizeof key) == 0) {
+            launches = c->step_launches;
+        } else {
+            if (c->step_exec) cudaGraphExecDestroy(c->step_exec);
+            c->step_exec = nullptr;
+            cudaGraph_t graph = nullptr;
+            EVK_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            const int st_enq = enqueue_fused_sharded(h, kp, ds, km, init_first_k, &launches);
+            cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+            if (st_enq != EVK_OK) {
+                if (graph) cudaGraphDestroy(graph);
+                cudaGetLastError();
+                return st_enq;
+            }
+            EVK_CUDA(h, ce);
+            ce = cudaGraphInstantiate(&c->step_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            EVK_CUDA(h, ce);
+            c->step_key = key;
+            c->step_launches = launches;
         }
-        if (!init_first_k)  // warm start: keep a copy in case the pass is abandoned
-            EVK_CUDA(h, cudaMemcpyAsync(h->d_cent + EVK_MAX_K * 2, h->d_cent,
-                                        (size_t)km->K * 2 * sizeof(float), cudaMemcpyDeviceToDevice,
-                                        h->stream));
-        EVK_NCCL(h, g_nccl.GroupStart());
-        if (c->rank > 0)
-            EVK_NCCL(h, g_nccl.Send(h->d_events, (size_t)halo * 16, ncclUint8, c->rank - 1, c->comm,
-                                    h->stream));
-        if (c->rank < c->world - 1)
-            EVK_NCCL(h, g_nccl.Recv(h->d_events + n_own, (size_t)halo * 16, ncclUint8, c->rank + 1,
-                                    c->comm, h->stream));
-        if (init_first_k)
-            EVK_NCCL(h, g_nccl.Broadcast(h->d_cent, h->d_cent, (size_t)km->K * 2, ncclFloat, 0,
-                                         c->comm, h->stream));
-        EVK_NCCL(h, g_nccl.GroupEnd());
-        EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
-        // who keeps what (on the device), then the downsample on that range
-        k_halo_range<<<1, 32, 0, h->stream>>>(kp, h->d_events, (uint32_t)n_own, halo, c->rank,
-                                              c->world, c->d_stats);
-        EVK_CUDA(h, cudaGetLastError());
-        bool ok = false;
-        EVK_TRY(evk_downsample_slab(h, kp, ds->count_repeated, &ok, &launches, false, c->d_stats));
-        // side stream, beside the downsample: candidate lists, label map, quads
-        EVK_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
-        EVK_CUDA(h, evk_launch_km_image(kl, ds->width, ds->height, h->d_prune_lists, h->d_cent,
-                                        nullptr, h->d_label_map, h->d_quads, h->d_acc, h->side));
-        EVK_CUDA(h, cudaEventRecord(h->ev_join, h->side));
-        EVK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
-        evk_prof_rec(h, 2);
-        evk_prof_rec(h, 3);
-        EVK_CUDA(h, evk_launch_km_assign_tiles(kl, ds->width, ds->height, h->d_quads, h->d_label_map,
-                                               h->d_xy, n_own + halo, &h->d_cnt->n_unique, true,
-                                               h->d_acc, h->d_labels, h->sm_count, h->stream));
-        k_pack_step_stats<<<1, 1, 0, h->stream>>>(h->d_cnt, c->d_stats, (unsigned long long)km->K,
-                                                  init_first_k && c->rank == 0, tail);
-        EVK_CUDA(h, cudaGetLastError());
-        EVK_NCCL(h, g_nccl.AllReduce(h->d_acc, h->d_acc, (size_t)km->K * 5 + 3, ncclUint64, ncclSum,
-                                     c->comm, h->stream));
-        EVK_CUDA(h, cudaMemcpyAsync(c->h_stats, tail, 3 * 8, cudaMemcpyDeviceToHost, h->stream));
-        EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
-                                           h->stream));
-        evk_prof_rec(h, 4);
-        EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,
-                                    h->stream));
+        EVK_CUDA(h, cudaGraphLaunch(c->step_exec, h->stream));
         EVK_CUDA(h, cudaStreamSynchronize(h->stream));
         if (c->h_stats[0] == 0) {
             h->n_unique = (size_t)h->h_cnt->n_unique;

@@ -195,7 +195,8 @@ struct evk_handle {
     evk_km_params win_km{};
     int64_t win_us = 0, win_start = 0;
     bool win_started = false;
-    std::vector<evk_event> win_buf;
+    size_t win_pending = 0;  // events of the open window already on the device (d_win_stage)
+    evk_event* d_win_stage = nullptr;  // [max_events], lazy
     size_t win_count = 0;
     // multi-GPU
     CommState* comm = nullptr;

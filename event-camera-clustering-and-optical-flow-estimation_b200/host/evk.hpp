@@ -73,6 +73,17 @@ class Handle {
         km_ = p;
         return it;
     }
+    // fused step: downsample + (first-K init | warm start) + k-means in one submission
+    Counts downsample_kmeans(const evk_ds_params& ds, const evk_km_params& km, bool init_first_k,
+                             int* iters = nullptr) {
+        Counts c;
+        int it = 0;
+        check(evk_downsample_kmeans(h_, &ds, &km, init_first_k ? 1 : 0, &c.unique, &c.repeated, &it));
+        n_unique_ = c.unique;
+        km_ = km;
+        if (iters) *iters = it;
+        return c;
+    }
     // labels and centroids
     std::vector<int32_t> labels() {
         std::size_t n = n_unique_;
@@ -137,15 +148,19 @@ class Pipeline {
             h_.load_events(buf_.data(), buf_.data() + buf_.size());
             evk_ds_params ds = ds_;
             ds.t0_us = t0_;
-            auto c = h_.downsample(ds);
+            // one fused submission per slice; later slices start warm.  A first slice with fewer
+            // voxels than clusters is only downsampled (seeding waits for the next one).
+            Handle::Counts c;
+            try {
+                c = h_.downsample_kmeans(ds, km_, !warm_);
+                warm_ = true;
+                h_.centroids(&s.centroids, &s.counts);
+            } catch (const Error& e) {
+                if (warm_ || e.status != EVK_ERR_INVALID) throw;
+                c = h_.downsample(ds);
+            }
             s.n_unique = c.unique;
             s.n_repeated = c.repeated;
-            if (c.unique >= static_cast<std::size_t>(km_.K)) {
-                if (!warm_) h_.init_centroids_first_k(km_);  // later slices start warm
-                warm_ = true;
-                h_.kmeans(km_);
-                h_.centroids(&s.centroids, &s.counts);
-            }
             if (cb_) cb_(s);
             buf_.clear();
         }
