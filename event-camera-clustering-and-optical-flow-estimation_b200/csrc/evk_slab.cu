@@ -54,6 +54,7 @@ constexpr uint32_t kChunk = EVK_SLAB_CHUNK;  // output slots per CTA-private chu
 constexpr uint32_t kNoChunk = 0xFFFFFFFFu;
 static_assert(kChunk >= 2 * kTile, "a fresh chunk must absorb a whole tile");
 static_assert(kThreads * kPer == kTile, "tile = events per thread x CTA size");
+static_assert(kThreads >= (1 << kLogTile) / 4, "one 16-B store per thread clears a late-peer table");
 
 struct SlabArgs {
     KeyParams kp;
@@ -198,6 +199,13 @@ __device__ __forceinline__ uint32_t hash_slot(uint32_t cell) {
 // lane 0 of the last producer warp issues the bulk copies; thread 0 keeps the output-chunk
 // bookkeeping
 
+// predicated shared-memory reduction: no branch, no return value
+__device__ __forceinline__ void sred_or_if(uint32_t* addr, uint32_t v, uint32_t pred) {
+    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q red.shared.or.b32 [%0], %1; }" ::"r"(
+                     smem_u32(addr)),
+                 "r"(v), "r"(pred)
+                 : "memory");
+}
 template <int NT>
 __device__ __forceinline__ void prod_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
@@ -355,8 +363,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 const uint32_t w = COUNT_REP ? cell >> 4 : cell >> 5;
                 const uint32_t sbit = 1u << (cell & (COUNT_REP ? 15u : 31u));
                 const uint32_t wv = ok ? s_map[w] : 0xFFFFFFFFu;  // gated events: nothing to do
-                if (COUNT_REP && (wv & sbit) && !(wv & (sbit << 16)))
-                    atomicOr(&s_map[w], sbit << 16);  // duplicate of an earlier tile's voxel
+                if (COUNT_REP) {  // duplicate of an earlier tile's voxel: mark it "hit twice"
+                    // (a predicated reduction: the branch the compiler builds around an atomicOr
+                    // here costs 2 % of the kernel)
+                    const uint32_t need = (wv & sbit) && !(wv & (sbit << 16)) && ok;
+                    sred_or_if(&s_map[w], sbit << 16, need);
+                }
                 cv[j] = (wv & sbit) ? kEmpty : ((cell << kLogTile) | li);
                 cxy[j] = ev.x;
             }
@@ -395,16 +407,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
             }
             prod_sync<NT>();  // S1: every claim of the tile is in the bitmap, s_late is complete
             // ---- resolve: the claimant is the new voxel unless a late peer has a lower index
-            uint32_t bal[kPer], wtot = 0;
+            uint32_t bal[kPer], wtot = 0, w0[kPer];
+#pragma unroll
+            for (int j = 0; j < kPer; j++)  // first probe: nearly always an empty slot
+                w0[j] = cv[j] != kEmpty ? late_tbl[hash_slot(cv[j] >> kLogTile)] : kEmpty;
 #pragma unroll
             for (int j = 0; j < kPer; j++) {
-                const bool win = cv[j] != kEmpty;
-                if (win) {
+                if (w0[j] != kEmpty) {
                     const uint32_t cell = cv[j] >> kLogTile;
-                    uint32_t s = hash_slot(cell);
+                    uint32_t s = hash_slot(cell), w = w0[j];
                     for (;;) {
-                        const uint32_t w = late_tbl[s];
-                        if (w == kEmpty) break;
                         if ((w >> kLogTile) == cell) {
                             if (w < cv[j]) {  // lower index: that event is the representative
                                 cv[j] = w;
@@ -413,13 +425,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                             break;
                         }
                         s = (s + 1) & (kHash - 1);
+                        w = late_tbl[s];
+                        if (w == kEmpty) break;
                     }
                 }
-                bal[j] = __ballot_sync(0xffffffffu, win);
+                bal[j] = __ballot_sync(0xffffffffu, cv[j] != kEmpty);
                 wtot += __popc(bal[j]);
             }
             // the other parity's table was last read one tile ago: clean it for the next tile
-            for (int i = tid; i < kHash; i += NT) s_late[(par ^ 1) * kHash + i] = kEmpty;
+            if (tid < kHash / 4)
+                reinterpret_cast<uint4*>(s_late + (par ^ 1) * kHash)[tid] =
+                    make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
             uint32_t wbase = 0;
             if (lane == 0 && wtot) wbase = atomicAdd(&s_cursor[par], wtot);
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
