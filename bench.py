@@ -225,13 +225,21 @@ def _main(args, real_stdout):
     km = evk.km_params(K, D, iters=1)
     # sharded runs receive the next rank's boundary block behind their own events
     h = evk.Evk(n + (1 << 19) if world > 1 else n, device=local_rank)
-    h.synth(evk.synth_params(SEED, n, W, H, RATE, N_BLOBS, first_index=rank * n))
+    # index sharding of the N x n-event stream (the rule is stated in <package>/sharding.py)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "evk_sharding", os.path.join(evk_loader.PKG_DIR, "sharding.py"))
+    sharding = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sharding)
+    shard_lo, shard_hi = sharding.shard_range(n * world, rank, world)
+    assert shard_hi - shard_lo == n
+    h.synth(evk.synth_params(SEED, n, W, H, RATE, N_BLOBS, first_index=shard_lo))
     h.sync()
     if world > 1:
         uid = [evk.Evk.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         h.comm_init(rank, world, uid[0])
-        h.set_shard(rank * n)
+        h.set_shard(shard_lo)
     owner = evk.OWNER_TIME_RANGE if args.owner == "time" else evk.OWNER_MIX64
 
     state = {}
