@@ -168,6 +168,14 @@ struct evk_handle {
     uint8_t* d_quads = nullptr;              // [EVK_MAX_QUADS] label of uniformly labelled squares
     cudaStream_t side = nullptr;             // centroid-only kernels run beside the downsample
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // fixed-count Lloyd loops on the pixel histogram as one graph (evk_kmeans, iters >= 3, tol < 0)
+    cudaGraphExec_t loop_exec = nullptr;
+    struct LoopKey {
+        int width, height, K, iters, need_hist, profiling;
+        float max_dist;
+        size_t cap;
+    } loop_key{};
+    unsigned long long* d_n_points = nullptr;  // point count read by the loop graph's kernels
     cudaGraphExec_t fused_exec = nullptr;    // the fused step as one graph (evk_downsample_kmeans)
     FusedKey fused_key{};
     int fused_launches = 0;
@@ -294,7 +302,9 @@ cudaError_t evk_launch_km_assign_pruned(const KmLaunch& kl, int width, int heigh
                                         cudaStream_t s);
 // pixel-image k-means (D == 2, K <= 254; evk_kmeans.cu)
 cudaError_t evk_launch_pix_hist(const uint32_t* xy, size_t n, int width, int height,
-                                uint32_t* pixcnt, int sm_count, cudaStream_t s);
+                                uint32_t* pixcnt, int sm_count, cudaStream_t s,
+                                const unsigned long long* n_dev = nullptr);
+cudaError_t evk_launch_set_u64(unsigned long long* dst, unsigned long long v, cudaStream_t s);
 #define EVK_MAX_QUADS 16384
 struct QuadGrid {  // squares of (1 << shift) pixels, tx * ty <= EVK_MAX_QUADS
     int32_t width, shift, tx, ty;

@@ -406,7 +406,9 @@ __global__ void __launch_bounds__(kBlock)
 // A Lloyd iteration therefore costs O(W * H) (0.9 M pixels for Gen4, L2-resident) instead of
 // O(U) (55 M voxels); the per-voxel labels are one 1-byte gather at the end.
 __global__ void __launch_bounds__(256)
-    k_pix_hist(const uint32_t* __restrict__ xy, size_t n, uint32_t width, uint32_t* pixcnt) {
+    k_pix_hist(const uint32_t* __restrict__ xy, size_t n, const unsigned long long* n_dev,
+               uint32_t width, uint32_t* pixcnt) {
+    if (n_dev) n = (size_t)*n_dev;  // point count kept on the device (graph replay)
     const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
     for (size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i0 < n; i0 += stride) {
         uint32_t w[4];
@@ -773,12 +775,13 @@ cudaError_t evk_launch_km_candidates(const KmLaunch& kl, const PruneGrid& pg, co
 }
 
 cudaError_t evk_launch_pix_hist(const uint32_t* xy, size_t n, int width, int height,
-                                uint32_t* pixcnt, int sm_count, cudaStream_t s) {
+                                uint32_t* pixcnt, int sm_count, cudaStream_t s,
+                                const unsigned long long* n_dev) {
     cudaError_t e = cudaMemsetAsync(pixcnt, 0, (size_t)width * height * sizeof(uint32_t), s);
     if (e != cudaSuccess || n == 0) return e;
     const size_t need = (n + 1023) / 1024;
     const size_t cap = (size_t)sm_count * 16;
-    k_pix_hist<<<(int)(need < cap ? need : cap), 256, 0, s>>>(xy, n, (uint32_t)width, pixcnt);
+    k_pix_hist<<<(int)(need < cap ? need : cap), 256, 0, s>>>(xy, n, n_dev, (uint32_t)width, pixcnt);
     return cudaGetLastError();
 }
 
@@ -850,6 +853,12 @@ cudaError_t evk_launch_km_assign_tiles(const KmLaunch& kl, int width, int height
         k_km_assign_tiles<false><<<grid, kBlock, smem, s>>>(kl, pg, quads, map, xy, n, n_dev,
                                                             copies, acc, labels);
     }
+    return cudaGetLastError();
+}
+
+__global__ void k_set_u64(unsigned long long* dst, unsigned long long v) { *dst = v; }
+cudaError_t evk_launch_set_u64(unsigned long long* dst, unsigned long long v, cudaStream_t s) {
+    k_set_u64<<<1, 1, 0, s>>>(dst, v);
     return cudaGetLastError();
 }
 
