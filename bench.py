@@ -314,6 +314,32 @@ def _main(args, real_stdout):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_val = n * world / float(te.item()) / 1e6
 
+    # ---- end to end from the sensor's RAW EVT 2.0 words (4 B per event over PCIe) --------------
+    e2e_raw = None
+    if world == 1:
+        from oracle import orc as _orc  # the encoder only produces the input file format
+        words_np = _orc.evt2_encode(host_np)
+        raw = torch.empty(len(words_np), dtype=torch.int32, pin_memory=True)
+        raw.numpy().view(np.uint32)[:] = words_np
+        n_words = len(words_np)
+
+        def raw_step():
+            assert h.load_evt2_ptr(raw.data_ptr(), n_words) == n
+            step()
+            return h.get_centroids(K, D)[0]
+
+        cent_raw = raw_step()
+        assert (cent_raw == cent).all(), "RAW ingest changed the result"
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            raw_step()
+        torch.cuda.synchronize()
+        raw_s = (time.perf_counter() - t0) / e2e_steps
+        e2e_raw = {"value": n / raw_s / 1e6, "unit": "Mevents/s", "ms_per_step": raw_s * 1e3,
+                   "h2d_bytes_per_step": 4 * n_words, "d2h_bytes_per_step": K * D * 4 + K * 8 + 64,
+                   "input": "RAW EVT 2.0 words (evk_load_evt2), decoded on the device"}
+
     if rank == 0:
         peak, peak_src = peaks()
         U = state["U_local"]
@@ -354,6 +380,8 @@ def _main(args, real_stdout):
                     "result_read": "centroids + counts (+ voxel counters)"},
             "gpu_launches": launches, "clocks": clocks,
         }
+        if e2e_raw:
+            line["e2e_raw_evt2"] = e2e_raw
         if world == 1 and not args.no_cpu_baseline:
             n_sample = min(args.cpu_sample, n)
             mev, threads, Us, best = cpu_port(n_sample, 2, 0)

@@ -4,6 +4,7 @@
 // KM/assign_to_centers2.c:105-568.  There is no CPU path: every entry point needs the device.
 #include <math.h>
 #include <stdarg.h>
+#include <ctype.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -281,7 +282,7 @@ int evk_destroy(evk_handle* h) {
                     h->d_sort_c, h->d_sk_in,  h->d_sk_out, h->d_si_in,  h->d_si_out, h->d_sv_tmp,
                     h->d_bin_start, h->d_slab_scratch, h->d_cnt, h->d_cent,   h->d_acc,    h->d_counts, h->d_shift,
                     h->d_cand,   h->d_flush, h->d_prune_lists, h->d_label_map, h->d_pixcnt, h->d_quads,
-                    h->d_win_stage, h->d_n_points};
+                    h->d_win_stage, h->d_n_points, h->d_raw, h->d_raw_blk};
     for (void* p : ptrs)
         if (p) chk(cudaFree(p), "free");
     if (h->h_cnt) chk(cudaFreeHost(h->h_cnt), "free host");
@@ -384,6 +385,96 @@ int evk_load_csv(evk_handle* h, const char* path) {
     int st = evk_load_events(h, ev.data(), ev.data() + ev.size());
     if (st == EVK_OK) cudaStreamSynchronize(h->stream);  // ev goes out of scope
     return st;
+}
+
+// RAW EVT 2.0 words: uploaded as they are (4 B per event), decoded on the device (evk_evt2.cu)
+int evk_load_evt2(evk_handle* h, const uint32_t* words, size_t n_words, size_t* n_events) {
+    EVK_TRY(check_handle(h));
+    if (n_words && !words) return evk_fail(h, EVK_ERR_INVALID, "words is NULL");
+    DeviceGuard g(h->device);
+    invalidate_results(h);
+    h->n_events = 0;
+    if (n_events) *n_events = 0;
+    if (!n_words) return EVK_OK;
+    if (h->raw_cap_words < n_words) {
+        if (h->d_raw) cudaFree(h->d_raw);
+        h->d_raw = nullptr;
+        h->raw_cap_words = 0;
+        if (cudaMalloc((void**)&h->d_raw, n_words * sizeof(uint32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            return evk_fail(h, EVK_ERR_NOMEM, "RAW staging of %zu words", n_words);
+        }
+        h->raw_cap_words = n_words;
+    }
+    const size_t nb = evk_evt2_blocks(n_words);
+    if (h->raw_cap_blocks < nb) {
+        if (h->d_raw_blk) cudaFree(h->d_raw_blk);
+        h->d_raw_blk = nullptr;
+        h->raw_cap_blocks = 0;
+        if (cudaMalloc((void**)&h->d_raw_blk, 2 * nb * sizeof(uint32_t)) != cudaSuccess) {
+            cudaGetLastError();
+            return evk_fail(h, EVK_ERR_NOMEM, "RAW block summaries");
+        }
+        h->raw_cap_blocks = nb;
+    }
+    EVK_CUDA(h, cudaMemcpyAsync(h->d_raw, words, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice,
+                                h->stream));
+    EVK_CUDA(h, evk_launch_evt2_decode(h->d_raw, n_words, h->d_raw_blk, h->d_n_points, h->d_events,
+                                       h->max_events, h->stream));
+    EVK_CUDA(h, cudaMemcpyAsync(&h->h_cnt->scratch[5], h->d_n_points, sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, h->stream));
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    const size_t n = (size_t)h->h_cnt->scratch[5];
+    if (n > h->max_events)
+        return evk_fail(h, EVK_ERR_CAPACITY, "%zu CD events exceed the handle capacity %zu", n,
+                        h->max_events);
+    h->n_events = n;
+    if (n_events) *n_events = n;
+    return EVK_OK;
+}
+
+// A Metavision RAW recording: ASCII header lines starting with '%', then the binary payload.
+int evk_load_raw(evk_handle* h, const char* path, size_t* n_events) {
+    EVK_TRY(check_handle(h));
+    if (!path) return evk_fail(h, EVK_ERR_INVALID, "path is NULL");
+    FILE* f = fopen(path, "rb");
+    if (!f) return evk_fail(h, EVK_ERR_IO, "cannot open %s", path);
+    std::vector<unsigned char> buf;
+    {
+        fseek(f, 0, SEEK_END);
+        const long sz = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        if (sz < 0) {
+            fclose(f);
+            return evk_fail(h, EVK_ERR_IO, "cannot size %s", path);
+        }
+        buf.resize((size_t)sz);
+        if (sz && fread(buf.data(), 1, (size_t)sz, f) != (size_t)sz) {
+            fclose(f);
+            return evk_fail(h, EVK_ERR_IO, "short read on %s", path);
+        }
+        fclose(f);
+    }
+    size_t pos = 0;
+    bool evt2 = false, other = false;
+    while (pos < buf.size() && buf[pos] == '%') {  // header lines
+        size_t eol = pos;
+        while (eol < buf.size() && buf[eol] != '\n') eol++;
+        std::string line(buf.begin() + pos, buf.begin() + eol);
+        for (auto& c : line) c = (char)tolower((unsigned char)c);
+        if (line.find("evt 2.0") != std::string::npos || line.find("evt2;") != std::string::npos ||
+            line.find("format evt2") != std::string::npos)
+            evt2 = true;
+        else if (line.find("% evt ") == 0 || line.find("% format ") == 0)
+            other = true;
+        pos = eol < buf.size() ? eol + 1 : eol;
+    }
+    if (other && !evt2)
+        return evk_fail(h, EVK_ERR_IO, "%s: only the EVT 2.0 payload format is decoded", path);
+    const size_t n_words = (buf.size() - pos) / 4;
+    std::vector<uint32_t> words(n_words);
+    if (n_words) memcpy(words.data(), buf.data() + pos, n_words * 4);  // (payload may be unaligned)
+    return evk_load_evt2(h, words.data(), n_words, n_events);
 }
 
 int evk_synth(evk_handle* h, const evk_synth_params* sp) {

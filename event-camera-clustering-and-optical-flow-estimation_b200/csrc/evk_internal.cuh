@@ -205,6 +205,11 @@ struct evk_handle {
     bool win_started = false;
     size_t win_pending = 0;  // events of the open window already on the device (d_win_stage)
     evk_event* d_win_stage = nullptr;  // [max_events], lazy
+    // RAW ingest staging (lazy, grow-only): EVT 2.0 words and the decoder's block summaries
+    uint32_t* d_raw = nullptr;
+    size_t raw_cap_words = 0;
+    uint32_t* d_raw_blk = nullptr;
+    size_t raw_cap_blocks = 0;
     size_t win_count = 0;
     // multi-GPU
     CommState* comm = nullptr;
@@ -331,3 +336,8 @@ cudaError_t evk_launch_init_first_k_walk(const KeyParams& kp, const KmLaunch& kl
                                          const evk_event* ev, size_t n_scan, float* cent,
                                          unsigned long long* found, cudaStream_t s);
 cudaError_t evk_launch_fill_u8(void* p, int v, size_t bytes, cudaStream_t s);
+// RAW EVT 2.0 decode (evk_evt2.cu): words on the device -> packed events, CD count in *total
+cudaError_t evk_launch_evt2_decode(const uint32_t* words, size_t n_words, uint32_t* blk,
+                                   unsigned long long* total, evk_event* out, size_t cap,
+                                   cudaStream_t s);
+size_t evk_evt2_blocks(size_t n_words);

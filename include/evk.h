@@ -158,6 +158,16 @@ EVK_API int evk_load_events_soa(evk_handle* h, const uint16_t* x, const uint16_t
 EVK_API int evk_load_coords_i32(evk_handle* h, const int32_t* xy, size_t n_pairs);
 /* rows "x,y,t,p" as ACCEL-era dumps (optics-clustering/test/event_raw_data8.csv) */
 EVK_API int evk_load_csv(evk_handle* h, const char* path);
+/* RAW EVT 2.0 words (Prophesee; the payload of the recordings the reference opens with
+ * Metavision::Camera::from_file(argv[1]), ACCEL/store.cpp:336, e.g. `traffic_data.raw`,
+ * ACCEL/Readme.md:21).  Replaces the SDK's CPU decoder in front of the event callback (:614-615):
+ * the 4-byte words are uploaded as they are and decoded to the 16-byte records on the device.
+ * Word layout: type = bits 31..28; 0x0 CD_OFF / 0x1 CD_ON: [27:22] t bits 5..0, [21:11] x,
+ * [10:0] y; 0x8 EVT_TIME_HIGH: [27:0] t bits 33..6; other types carry no CD event.
+ * n_events (may be NULL) receives the number of CD events decoded. */
+EVK_API int evk_load_evt2(evk_handle* h, const uint32_t* words, size_t n_words, size_t* n_events);
+/* a RAW file: '%'-prefixed ASCII header lines, then the EVT 2.0 payload */
+EVK_API int evk_load_raw(evk_handle* h, const char* path, size_t* n_events);
 /* generate on device (benchmarks; no host copy) */
 EVK_API int evk_synth(evk_handle* h, const evk_synth_params* sp);
 EVK_API int evk_num_events(const evk_handle* h, size_t* n);

@@ -535,3 +535,45 @@ int orc_max_threads(void) {
     return 1;
 #endif
 }
+
+/* ---- RAW EVT 2.0 (see evk_oracle.h) ----------------------------------------------------------- */
+size_t orc_evt2_decode(const uint32_t* words, size_t n_words, evk_event* out, size_t cap) {
+    uint64_t time_high = 0;
+    size_t n = 0;
+    for (size_t i = 0; i < n_words; i++) {
+        const uint32_t w = words[i];
+        const uint32_t type = w >> 28;
+        if (type == 0x8u) {
+            time_high = w & 0x0FFFFFFFu;
+        } else if (type <= 0x1u) {
+            if (n >= cap) break;
+            evk_event e;
+            e.x = (uint16_t)((w >> 11) & 0x7FFu);
+            e.y = (uint16_t)(w & 0x7FFu);
+            e.p = (int16_t)type;
+            e._pad = 0;
+            e.t = (int64_t)((time_high << 6) | ((w >> 22) & 0x3Fu));
+            out[n++] = e;
+        }
+    }
+    return n;
+}
+
+size_t orc_evt2_encode(const evk_event* ev, size_t n, uint32_t* words, size_t cap) {
+    size_t m = 0;
+    uint64_t time_high = ~0ull;
+    for (size_t i = 0; i < n; i++) {
+        const evk_event* e = &ev[i];
+        if (e->x >= 2048 || e->y >= 2048 || e->t < 0 || e->t >= (1ll << 34)) return (size_t)-1;
+        const uint64_t th = (uint64_t)e->t >> 6;
+        if (th != time_high) {
+            if (m >= cap) return m;
+            words[m++] = 0x80000000u | (uint32_t)(th & 0x0FFFFFFFu);
+            time_high = th;
+        }
+        if (m >= cap) return m;
+        words[m++] = ((e->p > 0 ? 1u : 0u) << 28) | (((uint32_t)e->t & 0x3Fu) << 22) |
+                     ((uint32_t)e->x << 11) | (uint32_t)e->y;
+    }
+    return m;
+}

@@ -99,6 +99,21 @@ void orc_synth_mt(const evk_synth_params* sp, evk_event* out, int threads);
 long orc_load_csv(const char* path, evk_event* out, size_t cap);
 int orc_max_threads(void);
 
+/* ---- RAW EVT 2.0 (third-party format: Prophesee Metavision "EVT 2.0", the payload of the
+ * `traffic_data.raw`-style recordings the reference opens with Metavision::Camera::from_file,
+ * ACCEL/store.cpp:336; the SDK itself is absent from /root/reference, version unpinned, so the
+ * published word layout is restated here) -------------------------------------------------------
+ * 32-bit little-endian words, type in bits 31..28:
+ *   0x0 CD_OFF / 0x1 CD_ON : [27:22] timestamp bits 5..0, [21:11] x, [10:0] y
+ *   0x8 EVT_TIME_HIGH      : [27:0]  timestamp bits 33..6   (t_us = time_high << 6 | low 6 bits)
+ *   0xA EXT_TRIGGER, 0xE OTHERS, 0xF CONTINUED : carry no CD event (skipped)
+ * decode: sequential scan keeping the last EVT_TIME_HIGH (0 before the first one); returns the
+ * number of CD events written (<= cap).  encode: one EVT_TIME_HIGH whenever bits 33..6 change
+ * (and at the start); events need x, y < 2048 and 0 <= t < 2^34; returns words written (<= cap)
+ * or (size_t)-1 when an event does not fit the format. */
+size_t orc_evt2_decode(const uint32_t* words, size_t n_words, evk_event* out, size_t cap);
+size_t orc_evt2_encode(const evk_event* ev, size_t n, uint32_t* words, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

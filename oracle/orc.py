@@ -62,6 +62,10 @@ def lib():
         L.orc_ref_analyze_coordinates.restype = C.c_int
         L.orc_ref_kmeans_trip.argtypes = [vp] * 7
         L.orc_ref_kmeans_trip.restype = C.c_float
+        L.orc_evt2_decode.argtypes = [vp, sz, vp, sz]
+        L.orc_evt2_decode.restype = sz
+        L.orc_evt2_encode.argtypes = [vp, sz, vp, sz]
+        L.orc_evt2_encode.restype = sz
         L.orc_downsample.argtypes = [vp, sz, C.POINTER(DsParams), vp, vp, C.POINTER(sz)]
         L.orc_downsample.restype = sz
         L.orc_downsample_mt.argtypes = [vp, sz, C.POINTER(DsParams), C.c_int, C.c_int, vp, vp,
@@ -241,3 +245,21 @@ def ref_kmeans_trip(data, centroids, output=None):
                                        _p(nc))
     return dict(centroids=cent, new_centroids=nc, assign=assign, cluster_index=ci,
                 scalar_sum=ss, output=out, error_max=float(em))
+
+
+def evt2_encode(ev):
+    """events -> RAW EVT 2.0 words (uint32)"""
+    ev = np.ascontiguousarray(ev, dtype=EVENT_DTYPE)
+    words = np.empty(2 * len(ev) + 1, dtype=np.uint32)
+    m = lib().orc_evt2_encode(_p(ev), len(ev), _p(words), len(words))
+    if m == C.c_size_t(-1).value:
+        raise ValueError("an event does not fit EVT 2.0 (x, y < 2048, 0 <= t < 2^34)")
+    return words[:m].copy()
+
+
+def evt2_decode(words):
+    """RAW EVT 2.0 words -> CD events"""
+    words = np.ascontiguousarray(words, dtype=np.uint32)
+    out = np.zeros(len(words), dtype=EVENT_DTYPE)
+    n = lib().orc_evt2_decode(_p(words), len(words), _p(out), len(out))
+    return out[:n].copy()

@@ -158,3 +158,23 @@ def test_edge_cases(orc):
     c2, counts, _, _ = orc.kmeans_update(pts, lab, cent)
     assert counts.tolist() == [1, 1, 0] and c2[2].tolist() == [100, 100]
     assert orc.kmeans_assign(pts, cent, 1.0).tolist() == [-1, -1]
+
+
+def test_evt2_codec(orc):
+    """RAW EVT 2.0 (third-party format restated in oracle/evk_oracle.h): known-answer words and
+    encode -> decode round trips"""
+    kw = np.array([0x80000003, (1 << 28) | (9 << 22) | (5 << 11) | 7,
+                   (0 << 28) | (63 << 22) | (2047 << 11) | 2047, 0xA0000000, 0xE1234567,
+                   0x80000004, (1 << 28) | (0 << 22) | (1 << 11) | 2], dtype=np.uint32)
+    d = orc.evt2_decode(kw)
+    assert [(int(e["x"]), int(e["y"]), int(e["p"]), int(e["t"])) for e in d] == \
+        [(5, 7, 1, 3 * 64 + 9), (2047, 2047, 0, 3 * 64 + 63), (1, 2, 1, 4 * 64)]
+    # CD words before the first EVT_TIME_HIGH decode with time-high 0
+    assert int(orc.evt2_decode(np.array([(1 << 28) | (5 << 22)], np.uint32))["t"][0]) == 5
+    ev = orc.synth(orc.synth_params(0xE7CA0003, 200_000, 1280, 720, 100_000_000, 64))
+    w = orc.evt2_encode(ev)
+    assert len(w) == len(ev) + len(np.unique(ev["t"] >> 6))  # one time-high word per 64 us step
+    assert orc.evt2_decode(w).tobytes() == ev.tobytes()
+    assert len(orc.evt2_decode(np.zeros(0, np.uint32))) == 0
+    with pytest.raises(ValueError):
+        orc.evt2_encode(orc.events_from_xy([2048], [0]))
