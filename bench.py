@@ -60,52 +60,109 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi SM clock / throttle reasons sampled DURING the timed region"""
+    """SM clock / throttle reasons sampled DURING the timed region.  The region is tens of
+    milliseconds long, so NVML is polled from a thread every ~2 ms (nvidia-smi -lms cannot sample
+    that fast); nvidia-smi is the fallback when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, False
+        self.source = "none"
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it lists indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            self.dev = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.source = "nvml"
+            # first NVML queries are slow: make them before the timed region
+            self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        n = self.nvml
+        bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown
+                if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else n.nvmlClocksThrottleReasonHwSlowdown,
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown",
+                                               getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0)),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown",
+                                               getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0)),
+                "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap",
+                                        getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0))}
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons",
+                              getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
+        def guarded(fn, default):
+            try:
+                return fn()
+            except Exception as e:  # a field this driver does not report
+                if not getattr(self, "_warned", False):
+                    self._warned = True
+                    print(f"clock sampler: {e!r}", file=sys.stderr)
+                return default
+        mx = self.mx
+        while not self.stop_flag:
+            sm = guarded(lambda: n.nvmlDeviceGetClockInfo(self.dev, n.NVML_CLOCK_SM), None)
+            pw = guarded(lambda: n.nvmlDeviceGetPowerUsage(self.dev) / 1000.0, 0.0)
+            r = guarded(lambda: get_reasons(self.dev), 0) if get_reasons else 0
+            if sm is not None:
+                self.rows.append([sm, mx, pw] + ["Active" if (r & b) else "Not Active"
+                                                 for b in bits.values()])
+            time.sleep(0.002)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        if self.nvml:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+        elif self.proc:
+            time.sleep(0.05)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source"]}
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
+                    if str(v).lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm),
-                "reasons": sorted(reasons)}
+                "reasons": sorted(reasons), "source": self.source}
 
 
 def peaks():
@@ -265,12 +322,14 @@ def _main(args, real_stdout):
             state["R"] = r
 
     h.set_profiling(True)
-    for _ in range(args.warmup):
-        step()
-    barrier()
+    # the timed region lasts tens of milliseconds: the sampler also covers the warm-up steps of the
+    # same workload right before it
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
     ds_main = ds_total = km_total = 0.0
     launches = 0
     h.timer_start()
