@@ -10,16 +10,17 @@
 // bits 33..6; every other type carries no CD event.
 //
 // Decode = an order-preserving stream compaction (CD words only) + a "last EVT_TIME_HIGH seen"
-// scan.  k_evt2_scan: per 4096-word block, CD count and last time-high.  k_evt2_prefix: one CTA
+// scan.  k_evt2_scan: per 2048-word block, CD count and last time-high.  k_evt2_prefix: one CTA
 // scans the block summaries (exclusive CD offsets, carried time-high).  k_evt2_decode: per block
-// the same local scans again, then every thread walks its 16 consecutive words and writes its CD
-// events at their final position.  HBM traffic: 8 B read + 16 B written per event.
+// the same local scans again, then every thread walks its 8 consecutive words and writes its CD
+// events into a shared-memory tile, which the block then copies out with fully coalesced 16-B
+// stores.  HBM traffic: 8 B read + 16 B written per event.
 #include "evk_internal.cuh"
 
 namespace {
 
 constexpr int kT = 256;              // threads per block
-constexpr int kWpt = 16;             // consecutive words per thread (four 16-B loads)
+constexpr int kWpt = 8;              // consecutive words per thread (two 16-B loads)
 constexpr int kWpb = kT * kWpt;      // words per block
 constexpr uint32_t kNoTh = 0xFFFFFFFFu;
 
@@ -154,21 +155,25 @@ __global__ void __launch_bounds__(kT)
     load16(words, n_words, (size_t)blockIdx.x * kWpb + (size_t)threadIdx.x * kWpt, w);
     summarise(w, cd, th);
     block_scan(cd, th, cd_ex, th_ex, tot_cd, tot_th);
-    size_t o = (size_t)blk_off[blockIdx.x] + cd_ex;
+    // stage the block's events in shared memory in stream order, then copy out coalesced
+    __shared__ uint4 s_ev[kWpb];
+    uint32_t o = cd_ex;
     uint64_t time_high = th_ex != kNoTh ? th_ex : blk_carry[blockIdx.x];
-    uint4* dst = reinterpret_cast<uint4*>(out);
 #pragma unroll
     for (int q = 0; q < kWpt; q++) {
         const uint32_t type = w[q] >> 28;
         if (type == 8u) time_high = w[q] & 0x0FFFFFFFu;
         if (type <= 1u) {
             const uint64_t t = (time_high << 6) | ((w[q] >> 22) & 0x3Fu);
-            if (o < cap)
-                dst[o] = make_uint4(((w[q] >> 11) & 0x7FFu) | ((w[q] & 0x7FFu) << 16), type,
-                                    (uint32_t)t, (uint32_t)(t >> 32));
-            o++;
+            s_ev[o++] = make_uint4(((w[q] >> 11) & 0x7FFu) | ((w[q] & 0x7FFu) << 16), type,
+                                   (uint32_t)t, (uint32_t)(t >> 32));
         }
     }
+    __syncthreads();
+    const size_t base = blk_off[blockIdx.x];
+    uint4* dst = reinterpret_cast<uint4*>(out);
+    for (uint32_t i = threadIdx.x; i < tot_cd; i += kT)
+        if (base + i < cap) __stcs(dst + base + i, s_ev[i]);
 }
 
 }  // namespace
