@@ -437,7 +437,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 reinterpret_cast<uint4*>(s_late + (par ^ 1) * kHash)[tid] =
                     make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
             uint32_t wbase = 0;
-            if (lane == 0 && wtot) wbase = atomicAdd(&s_cursor[par], wtot);
+            // one shared atomic per warp, written as PTX: the compiler's own warp-aggregation of an
+            // atomicAdd under a condition (leader election + redux) costs a dozen instructions
+            if (lane == 0)
+                asm volatile("atom.shared.add.u32 %0, [%1], %2;"
+                             : "=r"(wbase)
+                             : "r"(smem_u32(&s_cursor[par])), "r"(wtot)
+                             : "memory");
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
             {
                 const uint32_t pos0 = s_chunk_pos, nxt0 = s_next_base;
