@@ -24,6 +24,7 @@
 // copy torch already loaded, so both share one NCCL.
 #include <dlfcn.h>
 #include <nccl.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "evk_internal.cuh"
@@ -80,6 +81,18 @@ constexpr int kBlock = 256;
 
 }  // namespace
 
+// peer-memory mailbox of one rank (see "peer-memory exchange" below)
+constexpr int kMailWords = 2048;  // >= 254 * 5 + 3
+struct Mailbox {
+    unsigned long long sums[2][kMaxWorld][kMailWords];  // [parity][from rank][word]
+    unsigned long long sum_flag[2][kMaxWorld];          // seq of the partial above
+    unsigned long long ready_flag;                      // next rank: "my events of step seq are loaded"
+    unsigned long long cent_flag;                       // rank 0: "centroids of step seq are below"
+    unsigned long long seq;                             // my step counter
+    unsigned long long err;                             // a wait timed out
+    float cent[EVK_MAX_K * 2];
+};
+
 struct CommState {
     ncclComm_t comm = nullptr;
     int rank = 0, world = 1;
@@ -92,6 +105,12 @@ struct CommState {
     evk_event *sr = nullptr, *rr = nullptr;
     size_t stage_cap = 0;
     int last_mode = -1;
+    // peer-memory exchange (NVLink P2P through CUDA IPC): mailboxes and event buffers of all ranks
+    bool p2p = false;
+    Mailbox* mail = nullptr;                        // mine (device)
+    Mailbox* peer_mail[64] = {};                    // [r]: rank r's mailbox mapped into this process
+    const evk_event* peer_events[64] = {};          // [r]: rank r's event buffer
+    Mailbox** d_peer_mail = nullptr;                // the table above, on the device
     cudaGraphExec_t step_exec = nullptr;  // the fused sharded step as one graph
     FusedKey step_key{};
     int step_launches = 0;
@@ -163,13 +182,120 @@ __global__ void __launch_bounds__(32)
     }
 }
 
+// ---- peer-memory exchange ---------------------------------------------------------------------
+// The fused sharded step moves three small things between GPUs: a 4 MB boundary block to the
+// previous rank, K x 2 centroids from rank 0, and 2.6 KB of partial sums all-to-all.  Through NCCL
+// each costs a kernel launch and tens of microseconds of latency; here the ranks read and write
+// each other's memory directly over NVLink (buffers mapped with CUDA IPC) and synchronise with
+// sequence-number flags, so each exchange is part of an ordinary kernel of the step:
+//   k_p2p_tick     seq++; tell the previous rank "my events are loaded"
+//   k_p2p_push_cent rank 0 (beside its downsample): centroids into every mailbox
+//   k_p2p_pull     wait for the next rank's flag, PULL its boundary block behind my own events
+//   k_p2p_cent     wait for rank 0's centroids, copy them in
+//   k_p2p_allreduce push my partial sums into every rank's mailbox, wait for everybody's, add up
+// Every wait is bounded (about nine seconds of spinning): a timeout raises Mailbox::err, the pass is
+// abandoned by all ranks through the give-up flag, and the communicator falls back to NCCL.
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin until *flag >= want; false on timeout
+__device__ __forceinline__ bool wait_flag(const unsigned long long* flag, unsigned long long want) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < want) {
+        if (clock64() - t0 > (1ll << 34)) return false;  // about nine seconds: a peer is gone
+        __nanosleep(100);
+    }
+    return true;
+}
+
+__global__ void k_p2p_tick(Mailbox* mine, Mailbox* const* peers, int rank) {
+    const unsigned long long seq = mine->seq + 1;
+    mine->seq = seq;
+    if (rank > 0) st_release_sys(&peers[rank - 1]->ready_flag, seq);
+}
+
+// rank 0, beside its downsample: the centroids the walk kernel has just written go to every rank
+__global__ void __launch_bounds__(256)
+    k_p2p_push_cent(Mailbox* mine, Mailbox* const* peers, int world, const float* cent, int K) {
+    const unsigned long long seq = mine->seq;
+    for (int r = 1; r < world; r++)
+        for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) peers[r]->cent[i] = cent[i];
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x > 0 && (int)threadIdx.x < world)
+        st_release_sys(&peers[threadIdx.x]->cent_flag, seq);
+}
+
+// the next rank's first `halo` events -> behind my own (a pull: the reader knows where they go)
+__global__ void __launch_bounds__(256)
+    k_p2p_pull(Mailbox* mine, const evk_event* next_events, evk_event* dst, uint32_t halo) {
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        s_ok = wait_flag(&mine->ready_flag, mine->seq) ? 1 : 0;
+        if (!s_ok) mine->err = 1;
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    const uint4* src = reinterpret_cast<const uint4*>(next_events);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < halo; i += gridDim.x * blockDim.x)
+        d[i] = src[i];
+}
+
+__global__ void __launch_bounds__(256) k_p2p_cent(Mailbox* mine, float* cent, int K) {
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        s_ok = wait_flag(&mine->cent_flag, mine->seq) ? 1 : 0;
+        if (!s_ok) mine->err = 1;
+    }
+    __syncthreads();
+    if (!s_ok) return;
+    for (int i = threadIdx.x; i < 2 * K; i += blockDim.x) cent[i] = __ldcg(&mine->cent[i]);
+}
+
+// one-shot allreduce (sum) of acc[0..n): every rank pushes its partial into every mailbox
+__global__ void __launch_bounds__(1024)
+    k_p2p_allreduce(Mailbox* mine, Mailbox* const* peers, int rank, int world,
+                    unsigned long long* acc, int n) {
+    __shared__ int s_ok;
+    const unsigned long long seq = mine->seq;
+    const int par = (int)(seq & 1);
+    if (threadIdx.x == 0) s_ok = 1;
+    for (int r = 0; r < world; r++)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) peers[r]->sums[par][rank][i] = acc[i];
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) st_release_sys(&peers[threadIdx.x]->sum_flag[par][rank], seq);
+    if ((int)threadIdx.x < world && !wait_flag(&mine->sum_flag[par][threadIdx.x], seq)) {
+        s_ok = 0;
+        mine->err = 1;
+    }
+    __syncthreads();
+    if (!s_ok) {
+        if (threadIdx.x == 0) acc[n - 3] = 1ull << 32;  // give-up flag of the step (k_pack_step_stats)
+        return;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        unsigned long long sum = 0;
+        for (int r = 0; r < world; r++) sum += __ldcg(&mine->sums[par][r][i]);  // written by peers
+        acc[i] = sum;
+    }
+}
+
 // fused sharded step: [K * 5 + 0] = any reason to abandon the pass, [+1] = voxels, [+2] = repeated
+// (a peer-memory wait that timed out on this rank adds 2^32: the host then drops to NCCL everywhere)
 __global__ void k_pack_step_stats(const DsCounters* cnt, const unsigned long long* range,
                                   unsigned long long found_want, int check_found,
-                                  unsigned long long* tail) {
+                                  const Mailbox* mail, unsigned long long* tail) {
     unsigned long long flag = cnt->slab_violation | cnt->overflow | range[ST_FLAG];
     if (check_found && cnt->scratch[4] != found_want) flag |= 1;
-    tail[0] = flag ? 1 : 0;
+    tail[0] = (flag ? 1 : 0) + ((mail && mail->err) ? (1ull << 32) : 0ull);
     tail[1] = cnt->n_unique;
     tail[2] = cnt->n_repeated;
 }
@@ -485,6 +611,58 @@ int sharded_mix64(evk_handle* h, const evk_ds_params* p) {
     return EVK_OK;
 }
 
+// Map every rank's mailbox and event buffer into this process (CUDA IPC; the 64-byte handles travel
+// through one NCCL allgather).  Any failure leaves c->p2p false: the NCCL path is used instead.
+void p2p_setup(evk_handle* h, CommState* c) {
+    struct Handles {
+        cudaIpcMemHandle_t mail, events;
+    };
+    static_assert(sizeof(Handles) * kMaxWorld <= 8 * (ST_HIST + (size_t)kMaxWorld * (kMaxWorld + 3)),
+                  "the stats scratch doubles as the handle exchange buffer");
+    Handles mine;
+    memset(&mine, 0, sizeof mine);
+    Handles* d_all = reinterpret_cast<Handles*>(c->d_stats);
+    std::vector<Handles> all(c->world);
+    bool ok = cudaMalloc((void**)&c->mail, sizeof(Mailbox)) == cudaSuccess &&
+              cudaMemset(c->mail, 0, sizeof(Mailbox)) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.mail, c->mail) == cudaSuccess &&
+              cudaIpcGetMemHandle(&mine.events, h->d_events) == cudaSuccess;
+    // both collectives below are reached by every rank whatever happened above: a rank whose
+    // set-up failed publishes zero handles and votes "no" in the allreduce, and all fall back
+    bool coll = cudaMemcpy(d_all + c->rank, &mine, sizeof mine, cudaMemcpyHostToDevice) == cudaSuccess;
+    coll = g_nccl.AllGather(d_all + c->rank, d_all, sizeof(Handles), ncclUint8, c->comm,
+                            h->stream) == ncclSuccess && coll;
+    coll = cudaStreamSynchronize(h->stream) == cudaSuccess && coll;
+    coll = cudaMemcpy(all.data(), d_all, sizeof(Handles) * c->world, cudaMemcpyDeviceToHost) ==
+               cudaSuccess && coll;
+    ok = ok && coll;
+    for (int r = 0; ok && r < c->world; r++) {
+        if (r == c->rank) {
+            c->peer_mail[r] = c->mail;
+            c->peer_events[r] = h->d_events;
+            continue;
+        }
+        void *pm = nullptr, *pe = nullptr;
+        ok = cudaIpcOpenMemHandle(&pm, all[r].mail, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess &&
+             cudaIpcOpenMemHandle(&pe, all[r].events, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
+        c->peer_mail[r] = static_cast<Mailbox*>(pm);
+        c->peer_events[r] = static_cast<const evk_event*>(pe);
+    }
+    if (ok)
+        ok = cudaMalloc((void**)&c->d_peer_mail, sizeof(Mailbox*) * kMaxWorld) == cudaSuccess &&
+             cudaMemcpy(c->d_peer_mail, c->peer_mail, sizeof(Mailbox*) * kMaxWorld,
+                        cudaMemcpyHostToDevice) == cudaSuccess;
+    // all ranks agree: P2P only if it works everywhere
+    unsigned long long flag = ok ? 0 : 1;
+    if (cudaMemcpy(c->d_stats, &flag, 8, cudaMemcpyHostToDevice) == cudaSuccess &&
+        g_nccl.AllReduce(c->d_stats, c->d_stats, 1, ncclUint64, ncclSum, c->comm, h->stream) ==
+            ncclSuccess &&
+        cudaStreamSynchronize(h->stream) == cudaSuccess &&
+        cudaMemcpy(&flag, c->d_stats, 8, cudaMemcpyDeviceToHost) == cudaSuccess)
+        c->p2p = flag == 0;
+    cudaGetLastError();
+}
+
 int allreduce_acc(evk_handle* h, int K, int D) {
     (void)D;
     CommState* c = h->comm;
@@ -531,6 +709,7 @@ int evk_comm_init(evk_handle* h, int rank, int world, const uint8_t* id128) {
     }
     if ((size_t)c->halo * 4 > h->max_events) c->halo = (uint32_t)(h->max_events / 4);
     h->comm = c;
+    if (world > 1 && !getenv("EVK_NO_P2P")) p2p_setup(h, c);  // best effort: NCCL stays the fallback
     return EVK_OK;
 }
 
@@ -540,6 +719,14 @@ int evk_comm_destroy(evk_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (c->step_exec) cudaGraphExecDestroy(c->step_exec);
+    for (int r = 0; r < c->world; r++) {
+        if (r == c->rank) continue;
+        if (c->peer_mail[r]) cudaIpcCloseMemHandle(c->peer_mail[r]);
+        if (c->peer_events[r]) cudaIpcCloseMemHandle(const_cast<evk_event*>(c->peer_events[r]));
+    }
+    if (c->d_peer_mail) cudaFree(c->d_peer_mail);
+    if (c->mail) cudaFree(c->mail);
+    cudaGetLastError();
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
     void* ptrs[] = {c->d_stats, c->sk, c->rk, c->sf, c->rf, c->sx, c->rx, c->sr, c->rr};
     for (void* p : ptrs)
@@ -598,10 +785,11 @@ static int enqueue_fused_sharded(evk_handle* h, const KeyParams& kp, const evk_d
     unsigned long long* tail = h->d_acc + (size_t)km->K * 5;
     EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
     evk_prof_rec(h, 0);
-    // main stream: rank 0 walks the head of the global stream for the initial centroids; ONE
-    // NCCL group carries the boundary blocks and the centroid broadcast (collectives cannot
-    // start beside the downsample: its CTAs leave no shared memory on any SM)
-    if (init_first_k && c->rank == 0) {
+    // NCCL path: rank 0 walks the head of the global stream for the initial centroids first, then
+    // ONE group carries the boundary blocks and the centroid broadcast (collectives cannot start
+    // beside the downsample: its CTAs leave no shared memory on any SM).  Peer-memory path: the
+    // walk and the centroid exchange run on the side stream, beside the downsample.
+    if (init_first_k && c->rank == 0 && !c->p2p) {
         const size_t n_scan = n_own < (1u << 20) ? n_own : (1u << 20);
         if (n_scan)
             EVK_CUDA(h, evk_launch_init_first_k_walk(kp, kl, h->d_events, n_scan, h->d_cent,
@@ -611,18 +799,27 @@ static int enqueue_fused_sharded(evk_handle* h, const KeyParams& kp, const evk_d
         EVK_CUDA(h, cudaMemcpyAsync(h->d_cent + EVK_MAX_K * 2, h->d_cent,
                                     (size_t)km->K * 2 * sizeof(float), cudaMemcpyDeviceToDevice,
                                     h->stream));
-    EVK_NCCL(h, g_nccl.GroupStart());
-    if (c->rank > 0)
-        EVK_NCCL(h, g_nccl.Send(h->d_events, (size_t)halo * 16, ncclUint8, c->rank - 1, c->comm,
-                                h->stream));
-    if (c->rank < c->world - 1)
-        EVK_NCCL(h, g_nccl.Recv(h->d_events + n_own, (size_t)halo * 16, ncclUint8, c->rank + 1,
-                                c->comm, h->stream));
-    if (init_first_k)
-        EVK_NCCL(h, g_nccl.Broadcast(h->d_cent, h->d_cent, (size_t)km->K * 2, ncclFloat, 0,
-                                     c->comm, h->stream));
-    EVK_NCCL(h, g_nccl.GroupEnd());
-    EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+    if (c->p2p) {  // peer memory over NVLink: flags + direct loads / stores (see k_p2p_*)
+        k_p2p_tick<<<1, 1, 0, h->stream>>>(c->mail, c->d_peer_mail, c->rank);
+        EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));  // the side stream reads the new seq
+        if (c->rank < c->world - 1)
+            k_p2p_pull<<<64, 256, 0, h->stream>>>(c->mail, c->peer_events[c->rank + 1],
+                                                  h->d_events + n_own, halo);
+        EVK_CUDA(h, cudaGetLastError());
+    } else {
+        EVK_NCCL(h, g_nccl.GroupStart());
+        if (c->rank > 0)
+            EVK_NCCL(h, g_nccl.Send(h->d_events, (size_t)halo * 16, ncclUint8, c->rank - 1,
+                                    c->comm, h->stream));
+        if (c->rank < c->world - 1)
+            EVK_NCCL(h, g_nccl.Recv(h->d_events + n_own, (size_t)halo * 16, ncclUint8,
+                                    c->rank + 1, c->comm, h->stream));
+        if (init_first_k)
+            EVK_NCCL(h, g_nccl.Broadcast(h->d_cent, h->d_cent, (size_t)km->K * 2, ncclFloat, 0,
+                                         c->comm, h->stream));
+        EVK_NCCL(h, g_nccl.GroupEnd());
+        EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+    }
     // who keeps what (on the device), then the downsample on that range
     k_halo_range<<<1, 32, 0, h->stream>>>(kp, h->d_events, (uint32_t)n_own, halo, c->rank,
                                           c->world, c->d_stats);
@@ -631,6 +828,19 @@ static int enqueue_fused_sharded(evk_handle* h, const KeyParams& kp, const evk_d
     EVK_TRY(evk_downsample_slab(h, kp, ds->count_repeated, &ok, launches, false, c->d_stats));
     // side stream, beside the downsample: candidate lists, label map, quads
     EVK_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+    if (c->p2p && init_first_k) {
+        if (c->rank == 0) {
+            const size_t n_scan = n_own < (1u << 20) ? n_own : (1u << 20);
+            if (n_scan)
+                EVK_CUDA(h, evk_launch_init_first_k_walk(kp, kl, h->d_events, n_scan, h->d_cent,
+                                                         &h->d_cnt->scratch[4], h->side));
+            k_p2p_push_cent<<<1, 256, 0, h->side>>>(c->mail, c->d_peer_mail, c->world, h->d_cent,
+                                                    km->K);
+        } else {
+            k_p2p_cent<<<1, 256, 0, h->side>>>(c->mail, h->d_cent, km->K);
+        }
+        EVK_CUDA(h, cudaGetLastError());
+    }
     EVK_CUDA(h, evk_launch_km_image(kl, ds->width, ds->height, h->d_prune_lists, h->d_cent,
                                     nullptr, h->d_label_map, h->d_quads, h->d_acc, h->side));
     EVK_CUDA(h, cudaEventRecord(h->ev_join, h->side));
@@ -641,10 +851,17 @@ static int enqueue_fused_sharded(evk_handle* h, const KeyParams& kp, const evk_d
                                            h->d_xy, n_own + halo, &h->d_cnt->n_unique, true,
                                            h->d_acc, h->d_labels, h->sm_count, h->stream));
     k_pack_step_stats<<<1, 1, 0, h->stream>>>(h->d_cnt, c->d_stats, (unsigned long long)km->K,
-                                              init_first_k && c->rank == 0, tail);
+                                              init_first_k && c->rank == 0,
+                                              c->p2p ? c->mail : nullptr, tail);
     EVK_CUDA(h, cudaGetLastError());
-    EVK_NCCL(h, g_nccl.AllReduce(h->d_acc, h->d_acc, (size_t)km->K * 5 + 3, ncclUint64, ncclSum,
-                                 c->comm, h->stream));
+    if (c->p2p) {
+        k_p2p_allreduce<<<1, 1024, 0, h->stream>>>(c->mail, c->d_peer_mail, c->rank, c->world,
+                                                   h->d_acc, km->K * 5 + 3);
+        EVK_CUDA(h, cudaGetLastError());
+    } else {
+        EVK_NCCL(h, g_nccl.AllReduce(h->d_acc, h->d_acc, (size_t)km->K * 5 + 3, ncclUint64,
+                                     ncclSum, c->comm, h->stream));
+    }
     EVK_CUDA(h, cudaMemcpyAsync(c->h_stats, tail, 3 * 8, cudaMemcpyDeviceToHost, h->stream));
     EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
                                        h->stream));
@@ -729,6 +946,12 @@ int evk_downsample_kmeans_sharded(evk_handle* h, const evk_ds_params* ds, const 
         }
         EVK_CUDA(h, cudaGraphLaunch(c->step_exec, h->stream));
         EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (c->h_stats[0] >> 32) {  // a peer-memory wait timed out somewhere: NCCL from now on
+            c->p2p = false;
+            cudaGraphExecDestroy(c->step_exec);
+            c->step_exec = nullptr;
+            cudaGetLastError();
+        }
         if (c->h_stats[0] == 0) {
             h->n_unique = (size_t)h->h_cnt->n_unique;
             h->n_repeated = ds->count_repeated ? (size_t)h->h_cnt->n_repeated : 0;
