@@ -5,7 +5,7 @@
 // `traffic_data.raw` in ACCEL/Readme.md:21): the SDK decodes the RAW payload on the CPU and hands
 // EventCD ranges to the callback (:614-615).  Here the payload is uploaded as it is (4 B per event
 // instead of 16) and decoded by three small kernels, so the end-to-end path moves a quarter of the
-// bytes.  Format (Prophesee "EVT 2.0", restated in oracle/evk_oracle.h): type in bits 31..28;
+// bytes.  Format (Prophesee "EVT 2.0", word layout as in include/evk.h): type in bits 31..28;
 // CD_OFF 0x0 / CD_ON 0x1: [27:22] t bits 5..0, [21:11] x, [10:0] y; EVT_TIME_HIGH 0x8: [27:0] t
 // bits 33..6; every other type carries no CD event.
 //
