@@ -1,5 +1,8 @@
+"""A/B helper: CUDA-event time of the dominant downsample kernel on the C3 workload.
+EVK_LIB=<path to an alternative libevk.so> selects the build under test (one library per
+compile flag: see DESIGN.md section 7)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import evk_loader
 evk = evk_loader.load()
 n = 100_000_000

@@ -1,6 +1,7 @@
+"""A/B helper: wall time of evk_load_evt2 (H2D of 400 MB of RAW words + device decode)."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import evk_loader, torch
 from oracle import orc
 evk = evk_loader.load()
