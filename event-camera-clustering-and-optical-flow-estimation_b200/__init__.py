@@ -74,7 +74,7 @@ SYMBOLS = [
     "evk_get_stage_times", "evk_timer_start", "evk_timer_stop", "evk_sync", "evk_flush_l2",
     "evk_comm_unique_id", "evk_comm_init", "evk_comm_destroy", "evk_set_shard",
     "evk_downsample_sharded", "evk_kmeans_sharded", "evk_init_centroids_first_k_sharded",
-    "evk_downsample_kmeans_sharded",
+    "evk_downsample_kmeans_sharded", "evk_downsample_kmeans_submit", "evk_downsample_kmeans_wait",
 ]
 
 _lib = None
@@ -111,6 +111,8 @@ def lib():
         "evk_kmeans": [vp, C.POINTER(KmParams), C.POINTER(i32)],
         "evk_downsample_kmeans": [vp, C.POINTER(DsParams), C.POINTER(KmParams), i32, psz, psz,
                                   C.POINTER(i32)],
+        "evk_downsample_kmeans_submit": [vp, C.POINTER(DsParams), C.POINTER(KmParams), i32],
+        "evk_downsample_kmeans_wait": [vp, psz, psz, C.POINTER(i32)],
         "evk_get_labels": [vp, vp, sz],
         "evk_get_centroids": [vp, vp, vp],
         "evk_window_config": [vp, C.POINTER(DsParams), C.POINTER(KmParams), C.c_int64],
@@ -299,6 +301,19 @@ class Evk:
                                                C.byref(it)))
         self.n_unique = u.value
         self._km = km
+        return u.value, r.value, it.value
+
+    def downsample_kmeans_submit(self, ds, km, init_first_k=True):
+        """Queue the fused step on the handle's stream (evk_downsample_kmeans_submit)."""
+        self._ck(self._L.evk_downsample_kmeans_submit(self._h, C.byref(ds), C.byref(km),
+                                                      1 if init_first_k else 0))
+        self._km = km
+
+    def downsample_kmeans_wait(self):
+        """The step's one synchronisation. Returns (n_unique, n_repeated, iters_done)."""
+        u, r, it = C.c_size_t(0), C.c_size_t(0), C.c_int(0)
+        self._ck(self._L.evk_downsample_kmeans_wait(self._h, C.byref(u), C.byref(r), C.byref(it)))
+        self.n_unique = u.value
         return u.value, r.value, it.value
 
     def get_labels(self, n=None):

@@ -889,66 +889,99 @@ static int enqueue_fused(evk_handle* h, const KeyParams& kp, const evk_ds_params
     return EVK_OK;
 }
 
-int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
-                          int init_first_k, size_t* n_unique, size_t* n_repeated,
-                          int* iters_done) {
+// Submission half of the fused step.  A fusable shape goes out as one graph launch and the call
+// returns at once (h->step_pending = 1: results are collected by evk_downsample_kmeans_wait);
+// any other shape runs the three calls here, synchronously, and wait only reports their results.
+// Several submissions may be queued behind each other (a pipeline of slices on one stream): every
+// replay works on the events resident at ITS turn in stream order, wait reports the last one.
+int evk_downsample_kmeans_submit(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
+                                 int init_first_k) {
     EVK_TRY(check_handle(h));
     EVK_TRY(km_validate(h, km));
     KeyParams kp;
     EVK_TRY(evk_make_key_params(h, ds, &kp));
     h->shard_first = h->comm ? h->shard_first : 0;
-    if (!init_first_k && (!h->have_centroids || h->K != km->K || h->D != km->D))
+    // (a queued step leaves centroids behind: a warm start may follow it without a wait)
+    if (!init_first_k && h->step_pending != 1 &&
+        (!h->have_centroids || h->K != km->K || h->D != km->D))
         return evk_fail(h, EVK_ERR_STATE, "centroids for K=%d, D=%d have not been set", km->K, km->D);
     const bool fusable = km->D == 2 && !km->on_events && km->K <= 254 && h->n_events &&
                          km->iters == 1 && km->tol < 0.f &&
                          (ds->algo == EVK_ALGO_AUTO || ds->algo == EVK_ALGO_SLAB) &&
                          evk_slab_supported(h, kp) && ensure_images(h, ds->width, ds->height);
-    int st = EVK_OK;
-    bool done = false;
-    if (fusable) {
-        DeviceGuard g(h->device);
-        invalidate_results(h);
-        h->ds = *ds;
-        h->kp = kp;
-        h->have_ds = true;
-        // The whole pass is one CUDA graph, re-instantiated only when the shape of the call changes
-        // (event count, parameters, profiling): a replay costs one launch instead of a dozen.
-        FusedKey key;
-        memset(&key, 0, sizeof key);
-        key.n = h->n_events;
-        key.ds = *ds;
-        key.km = *km;
-        key.init = init_first_k ? 1 : 0;
-        key.profiling = h->profiling ? 1 : 0;
-        key.shard_first = h->shard_first;
-        int launches = 0;
-        if (h->fused_exec && memcmp(&key, &h->fused_key, sizeof key) == 0) {
-            launches = h->fused_launches;
-        } else {
-            if (h->fused_exec) cudaGraphExecDestroy(h->fused_exec);
-    if (h->loop_exec) cudaGraphExecDestroy(h->loop_exec);
-            h->fused_exec = nullptr;
-            cudaGraph_t graph = nullptr;
-            EVK_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            int st_enq = enqueue_fused(h, kp, ds, km, init_first_k, &launches);
-            cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-            if (st_enq != EVK_OK) {
-                if (graph) cudaGraphDestroy(graph);
-                cudaGetLastError();
-                return st_enq;
-            }
-            EVK_CUDA(h, ce);
-            ce = cudaGraphInstantiate(&h->fused_exec, graph, 0);
-            cudaGraphDestroy(graph);
-            EVK_CUDA(h, ce);
-            h->fused_key = key;
-            h->fused_launches = launches;
+    if (!fusable) {
+        if (h->step_pending == 1)
+            EVK_TRY(evk_downsample_kmeans_wait(h, nullptr, nullptr, nullptr));
+        h->step_pending = 0;
+        h->step_iters = 0;
+        EVK_TRY(step_unfused(h, ds, km, init_first_k, &h->step_iters));
+        h->step_pending = 2;  // finished: wait has nothing to collect from the device
+        return EVK_OK;
+    }
+    h->step_ds = *ds;
+    h->step_km = *km;
+    h->step_init = init_first_k;
+    h->step_iters = 0;
+    DeviceGuard g(h->device);
+    invalidate_results(h);
+    h->ds = *ds;
+    h->kp = kp;
+    h->have_ds = true;
+    // The whole pass is one CUDA graph, re-instantiated only when the shape of the call changes
+    // (event count, parameters, profiling): a replay costs one launch instead of a dozen.
+    FusedKey key;
+    memset(&key, 0, sizeof key);
+    key.n = h->n_events;
+    key.ds = *ds;
+    key.km = *km;
+    key.init = init_first_k ? 1 : 0;
+    key.profiling = h->profiling ? 1 : 0;
+    key.shard_first = h->shard_first;
+    int launches = 0;
+    if (h->fused_exec && memcmp(&key, &h->fused_key, sizeof key) == 0) {
+        launches = h->fused_launches;
+    } else {
+        if (h->fused_exec) cudaGraphExecDestroy(h->fused_exec);
+        h->fused_exec = nullptr;
+        cudaGraph_t graph = nullptr;
+        EVK_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int st_enq = enqueue_fused(h, kp, ds, km, init_first_k, &launches);
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        if (st_enq != EVK_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            return st_enq;
         }
-        EVK_CUDA(h, cudaGraphLaunch(h->fused_exec, h->stream));
+        EVK_CUDA(h, ce);
+        ce = cudaGraphInstantiate(&h->fused_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        EVK_CUDA(h, ce);
+        h->fused_key = key;
+        h->fused_launches = launches;
+    }
+    EVK_CUDA(h, cudaGraphLaunch(h->fused_exec, h->stream));
+    h->step_pending = 1;
+    return EVK_OK;
+}
+
+// Collection half: the step's single host synchronisation.  A stream the slab kernel rejected
+// (not time-ordered, events before t0, ...) is rerun here on the general path -- same results.
+int evk_downsample_kmeans_wait(evk_handle* h, size_t* n_unique, size_t* n_repeated,
+                               int* iters_done) {
+    EVK_TRY(check_handle(h));
+    if (!h->step_pending)
+        return evk_fail(h, EVK_ERR_STATE, "evk_downsample_kmeans_wait: no step has been submitted");
+    const int pending = h->step_pending;
+    h->step_pending = 0;
+    if (pending == 1) {
+        DeviceGuard g(h->device);
+        const evk_ds_params* ds = &h->step_ds;
+        const evk_km_params* km = &h->step_km;
+        const int init_first_k = h->step_init;
+        const int launches = h->fused_launches;
         EVK_CUDA(h, cudaStreamSynchronize(h->stream));
-        bool ok;
-        ok = h->h_cnt->slab_violation == 0 && h->h_cnt->overflow == 0 &&
-             (!init_first_k || h->h_cnt->scratch[4] == (unsigned long long)km->K);
+        const bool ok = h->h_cnt->slab_violation == 0 && h->h_cnt->overflow == 0 &&
+                        (!init_first_k || h->h_cnt->scratch[4] == (unsigned long long)km->K);
         if (ok) {
             h->n_unique = (size_t)h->h_cnt->n_unique;
             h->n_repeated = ds->count_repeated ? (size_t)h->h_cnt->n_repeated : 0;
@@ -969,19 +1002,32 @@ int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const evk_km_p
                 h->times.ds_main_ms = prof_ms(h, 5, 6);
                 h->times.km_total_ms = h->times.km_assign_ms = prof_ms(h, 3, 4);
             }
-            if (iters_done) *iters_done = 1;
-            done = true;
-        } else if (!init_first_k) {  // finalise has overwritten the caller's centroids
-            EVK_CUDA(h, cudaMemcpyAsync(h->d_cent, h->d_cent + EVK_MAX_K * 2,
-                                        (size_t)km->K * 2 * sizeof(float),
-                                        cudaMemcpyDeviceToDevice, h->stream));
+            h->step_iters = 1;
+        } else {
+            if (!init_first_k) {  // finalise has overwritten the caller's centroids
+                if (!h->have_centroids || h->K != km->K || h->D != km->D)
+                    return evk_fail(h, EVK_ERR_STATE,
+                                    "centroids for K=%d, D=%d have not been set", km->K, km->D);
+                EVK_CUDA(h, cudaMemcpyAsync(h->d_cent, h->d_cent + EVK_MAX_K * 2,
+                                            (size_t)km->K * 2 * sizeof(float),
+                                            cudaMemcpyDeviceToDevice, h->stream));
+            }
+            EVK_TRY(step_unfused(h, ds, km, init_first_k, &h->step_iters));
         }
     }
-    if (!done && st == EVK_OK) st = step_unfused(h, ds, km, init_first_k, iters_done);
-    if (st != EVK_OK) return st;
     if (n_unique) *n_unique = h->n_unique;
     if (n_repeated) *n_repeated = h->n_repeated;
+    if (iters_done) *iters_done = h->step_iters;
     return EVK_OK;
+}
+
+int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
+                          int init_first_k, size_t* n_unique, size_t* n_repeated,
+                          int* iters_done) {
+    EVK_TRY(check_handle(h));
+    if (h->step_pending) EVK_TRY(evk_downsample_kmeans_wait(h, nullptr, nullptr, nullptr));
+    EVK_TRY(evk_downsample_kmeans_submit(h, ds, km, init_first_k));
+    return evk_downsample_kmeans_wait(h, n_unique, n_repeated, iters_done);
 }
 
 int evk_get_labels(evk_handle* h, int32_t* labels, size_t cap) {

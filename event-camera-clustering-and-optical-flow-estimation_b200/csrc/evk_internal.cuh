@@ -179,6 +179,12 @@ struct evk_handle {
     cudaGraphExec_t fused_exec = nullptr;    // the fused step as one graph (evk_downsample_kmeans)
     FusedKey fused_key{};
     int fused_launches = 0;
+    // evk_downsample_kmeans_submit / _wait: 0 = nothing submitted, 1 = graph in flight, 2 = the
+    // step ran synchronously on the general path (wait only reports)
+    int step_pending = 0;
+    evk_ds_params step_ds{};
+    evk_km_params step_km{};
+    int step_init = 0, step_iters = 0;
     size_t image_pixels = 0;                 // capacity of both
     bool pix_valid = false;                  // d_pixcnt matches the current voxel shard
     float* d_shift = nullptr;                // [1]

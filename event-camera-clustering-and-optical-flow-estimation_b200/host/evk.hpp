@@ -84,6 +84,20 @@ class Handle {
         if (iters) *iters = it;
         return c;
     }
+    // the same step in two halves: queue it, do host work, collect (evk_downsample_kmeans_submit/_wait)
+    void submit_downsample_kmeans(const evk_ds_params& ds, const evk_km_params& km,
+                                  bool init_first_k) {
+        check(evk_downsample_kmeans_submit(h_, &ds, &km, init_first_k ? 1 : 0));
+        km_ = km;
+    }
+    Counts wait_downsample_kmeans(int* iters = nullptr) {
+        Counts c;
+        int it = 0;
+        check(evk_downsample_kmeans_wait(h_, &c.unique, &c.repeated, &it));
+        n_unique_ = c.unique;
+        if (iters) *iters = it;
+        return c;
+    }
     // labels and centroids
     std::vector<int32_t> labels() {
         std::size_t n = n_unique_;

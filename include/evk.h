@@ -205,6 +205,16 @@ EVK_API int evk_kmeans(evk_handle* h, const evk_km_params* p, int* iters_done);
 EVK_API int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
                                   int init_first_k, size_t* n_unique, size_t* n_repeated,
                                   int* iters_done);
+/* The same step in two halves, for callers that keep the device busy across slices (the reference
+ * blocks its producer thread in clFinish for every slice, ACCEL/store.cpp:397-411): submit returns
+ * as soon as the pass is queued on the handle's stream, wait is the step's one synchronisation and
+ * reports its counts.  Steps may be queued behind each other (each one works on the events resident
+ * at its turn in stream order); wait then reports the last one.  evk_downsample_kmeans ==
+ * submit + wait.  Shapes the fused pass does not take run synchronously inside submit. */
+EVK_API int evk_downsample_kmeans_submit(evk_handle* h, const evk_ds_params* ds,
+                                         const evk_km_params* km, int init_first_k);
+EVK_API int evk_downsample_kmeans_wait(evk_handle* h, size_t* n_unique, size_t* n_repeated,
+                                       int* iters_done);
 
 /* ---- return labels and centroids ----------------------------------------------------------- */
 /* Replaces clEnqueueReadBuffer(assign_buffer) (KM/assign_to_centers2.c:259-265).  labels[i] in

@@ -144,3 +144,44 @@ def test_fused_full_size(evk):
     assert (nf == nu).all() and (cf == cu).all()
     assert (lf == lu).all()
     assert (np.bincount(lf, minlength=K) == nf).all()
+
+
+def test_submit_wait_pipeline(evk, orc):
+    """evk_downsample_kmeans_submit / _wait: queued steps == the synchronous call, bit for bit;
+    a warm-started step may be queued behind a cold one; a rejected (unordered) stream is rerun
+    on the general path inside wait; wait without a submission is a state error."""
+    n, W, H, K = 600_000, 1280, 720, 16
+    ev = orc.synth(orc.synth_params(0xE7CA0003, n, W, H, 100_000_000, 16))
+    ds, km = evk.ds_params(W, H, 2, 2, 500, 0, 1), evk.km_params(K, 2, iters=1)
+    with evk.Evk(n) as h:
+        h.load_events(ev)
+        ref = fused(evk, h, ds, km, None)
+        with pytest.raises(evk.EvkError):
+            h.downsample_kmeans_wait()
+        for _ in range(3):
+            h.downsample_kmeans_submit(ds, km, True)
+        U, R, it = h.downsample_kmeans_wait()
+        keys, _, first = h.get_voxels(reps=False)
+        got = (U, R, it, keys, first, h.get_labels(), h.get_centroids(K, 2))
+        assert h.stage_times().ds_algo_used == evk.ALGO_SLAB
+        same(ref, got)
+        # cold step, then a warm-started one queued behind it == two synchronous calls
+        h.downsample_kmeans(ds, km, True)
+        h.downsample_kmeans(ds, km, False)
+        want = h.get_centroids(K, 2)
+        want_lab = h.get_labels()
+        h.downsample_kmeans_submit(ds, km, True)
+        h.downsample_kmeans_submit(ds, km, False)
+        h.downsample_kmeans_wait()
+        c = h.get_centroids(K, 2)
+        assert (c[0] == want[0]).all() and (c[1] == want[1]).all()
+        assert (h.get_labels() == want_lab).all()
+        # unordered stream: the slab pass gives up, wait reruns the general path
+        shuffled = ev[np.random.default_rng(3).permutation(n)]
+        h.load_events(shuffled)
+        a = unfused(evk, h, ds, km, None)
+        h.downsample_kmeans_submit(ds, km, True)
+        U, R, it = h.downsample_kmeans_wait()
+        assert h.stage_times().ds_algo_used == evk.ALGO_TABLE
+        keys, _, first = h.get_voxels(reps=False)
+        same(a, (U, R, it, keys, first, h.get_labels(), h.get_centroids(K, 2)))

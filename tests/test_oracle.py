@@ -178,3 +178,23 @@ def test_evt2_codec(orc):
     assert len(orc.evt2_decode(np.zeros(0, np.uint32))) == 0
     with pytest.raises(ValueError):
         orc.evt2_encode(orc.events_from_xy([2048], [0]))
+
+
+def test_host_evt2_writer_matches_oracle_codec(orc):
+    """<package>/evt2.py (the vectorised writer bench.py uses to make RAW input) == the oracle's
+    encoder word for word, and the oracle decodes its output back to the same events."""
+    import importlib.util
+    import os
+    import evk_loader
+    spec = importlib.util.spec_from_file_location("evk_evt2", os.path.join(evk_loader.PKG_DIR, "evt2.py"))
+    evt2 = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(evt2)
+    for seed, n, W, H, rate in ((1, 100_000, 1280, 720, 100_000_000), (2, 5000, 346, 260, 10_000),
+                                (3, 1, 346, 260, 10_000)):
+        ev = orc.synth(orc.synth_params(seed, n, W, H, rate, 8))
+        w = evt2.encode_evt2(ev)
+        assert (w == orc.evt2_encode(ev)).all()
+        assert orc.evt2_decode(w).tobytes() == ev.tobytes()
+    assert len(evt2.encode_evt2(ev[:0])) == 0
+    with pytest.raises(ValueError):
+        evt2.encode_evt2(orc.events_from_xy([2048], [0]))
