@@ -56,6 +56,23 @@ class SynthParams(C.Structure):
     ]
 
 
+class AecParams(C.Structure):
+    _fields_ = [
+        ("use_init", C.c_int32), ("sz_buffer", C.c_int32), ("radius", C.c_double),
+        ("kappa", C.c_int32), ("min_n", C.c_int32), ("alpha", C.c_double),
+        ("rand_seed", C.c_uint32), ("max_clusters", C.c_int32), ("max_points", C.c_int32),
+        ("_pad", C.c_int32),
+    ]
+
+
+AEC_CLUSTER_DTYPE = np.dtype([("id", "<i4"), ("n", "<i4"), ("mu", "<f8", (2,)),
+                              ("centroid", "<f8", (2,))], align=True)
+AEC_FLOW_DTYPE = np.dtype([("id", "<i4"), ("n", "<i4"), ("centroid", "<f8", (2,)),
+                           ("prev", "<f8", (2,)), ("has_arrow", "<i4"), ("_pad", "<i4"),
+                           ("arrow_end", "<f8", (2,))], align=True)
+assert AEC_CLUSTER_DTYPE.itemsize == 40 and AEC_FLOW_DTYPE.itemsize == 64
+
+
 class StageTimes(C.Structure):
     _fields_ = [
         ("ds_total_ms", C.c_float), ("ds_main_ms", C.c_float), ("ds_compact_ms", C.c_float),
@@ -75,6 +92,8 @@ SYMBOLS = [
     "evk_comm_unique_id", "evk_comm_init", "evk_comm_destroy", "evk_set_shard",
     "evk_downsample_sharded", "evk_kmeans_sharded", "evk_init_centroids_first_k_sharded",
     "evk_downsample_kmeans_sharded", "evk_downsample_kmeans_submit", "evk_downsample_kmeans_wait",
+    "evk_aec_create", "evk_aec_destroy", "evk_aec_update", "evk_aec_update_voxels",
+    "evk_aec_get_clusters", "evk_aec_get_points", "evk_aec_report",
 ]
 
 _lib = None
@@ -114,6 +133,13 @@ def lib():
         "evk_downsample_kmeans_submit": [vp, C.POINTER(DsParams), C.POINTER(KmParams), i32],
         "evk_downsample_kmeans_wait": [vp, psz, psz, C.POINTER(i32)],
         "evk_get_labels": [vp, vp, sz],
+        "evk_aec_create": [vp, C.POINTER(AecParams)],
+        "evk_aec_destroy": [vp],
+        "evk_aec_update": [vp, vp, sz],
+        "evk_aec_update_voxels": [vp, C.c_double, sz, sz, sz],
+        "evk_aec_get_clusters": [vp, vp, sz, psz, C.POINTER(i32)],
+        "evk_aec_get_points": [vp, sz, vp, vp, vp, vp, sz, psz],
+        "evk_aec_report": [vp, vp, sz, psz],
         "evk_get_centroids": [vp, vp, vp],
         "evk_window_config": [vp, C.POINTER(DsParams), C.POINTER(KmParams), C.c_int64],
         "evk_window_push": [vp, vp, vp, C.POINTER(i32)],
@@ -315,6 +341,65 @@ class Evk:
         self._ck(self._L.evk_downsample_kmeans_wait(self._h, C.byref(u), C.byref(r), C.byref(it)))
         self.n_unique = u.value
         return u.value, r.value, it.value
+
+    # ---- consumer: asynchronous event clustering (evk_aec_*) ---------------------------------
+    def aec_create(self, init=None, rand_seed=1, max_clusters=0, max_points=0):
+        """init=None: the default-constructed AEClustering of the reference app; else a dict
+        with sz_buffer, radius, kappa, alpha, min_n (AEClustering::init)"""
+        p = AecParams()
+        p.use_init = 0 if init is None else 1
+        if init is not None:
+            p.sz_buffer, p.radius, p.kappa = init["sz_buffer"], init["radius"], init["kappa"]
+            p.alpha, p.min_n = init["alpha"], init["min_n"]
+        p.rand_seed, p.max_clusters, p.max_points = rand_seed, max_clusters, max_points
+        self._ck(self._L.evk_aec_create(self._h, C.byref(p)))
+
+    def aec_update(self, e):
+        """e: (n, 4) float64 rows {t, x, y, p}"""
+        e = np.ascontiguousarray(e, dtype=np.float64).reshape(-1, 4)
+        self._ck(self._L.evk_aec_update(self._h, _p(e), len(e)))
+
+    def aec_update_voxels(self, t, start=0, step=1, count=None):
+        if count is None:
+            nu = getattr(self, "n_unique", 0)
+            count = (nu - start + step - 1) // step if nu > start else 0
+        self._ck(self._L.evk_aec_update_voxels(self._h, float(t), start, step, count))
+        return count
+
+    def aec_clusters(self):
+        """(records of AEC_CLUSTER_DTYPE in list order, last updated cluster index)"""
+        n, last = C.c_size_t(0), C.c_int(0)
+        self._ck(self._L.evk_aec_get_clusters(self._h, None, 0, C.byref(n), C.byref(last)))
+        out = np.zeros(n.value, AEC_CLUSTER_DTYPE)
+        if n.value:
+            self._ck(self._L.evk_aec_get_clusters(self._h, _p(out), len(out), C.byref(n),
+                                                  C.byref(last)))
+        return out, last.value
+
+    def aec_points(self, c):
+        """(event ids, xy[n,2], t, pol) of cluster c, oldest first"""
+        n = C.c_size_t(0)
+        self._ck(self._L.evk_aec_get_points(self._h, c, None, None, None, None, 0, C.byref(n)))
+        k = n.value
+        ids, xy, t, pol = np.zeros(k, np.int32), np.zeros((k, 2)), np.zeros(k), np.zeros(k, np.uint8)
+        if k:
+            self._ck(self._L.evk_aec_get_points(self._h, c, _p(ids), _p(xy), _p(t), _p(pol), k,
+                                                C.byref(n)))
+        return ids, xy, t, pol.astype(np.int32)
+
+    def aec_state(self):
+        """everything observable, shaped like oracle.aec's state()"""
+        cl, last = self.aec_clusters()
+        pts = [self.aec_points(c) for c in range(len(cl))]
+        return dict(ids=cl["id"].copy(), n=cl["n"].copy(), mu=cl["mu"].copy(),
+                    cen=cl["centroid"].copy(), pts=pts, last=last)
+
+    def aec_report(self):
+        """per-slice report: records of AEC_FLOW_DTYPE (clusters with n >= min_n)"""
+        out = np.zeros(1024, AEC_FLOW_DTYPE)
+        n = C.c_size_t(0)
+        self._ck(self._L.evk_aec_report(self._h, _p(out), len(out), C.byref(n)))
+        return out[: n.value].copy()
 
     def get_labels(self, n=None):
         if n is None:

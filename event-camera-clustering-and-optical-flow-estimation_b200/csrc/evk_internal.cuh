@@ -105,6 +105,7 @@ struct DsCounters {  // device-side counters, mirrored into pinned host memory a
 };
 
 struct CommState;
+struct AecHost;  // evk_aec.cu
 
 struct FusedKey {  // what the captured fused-step graph depends on
     size_t n;
@@ -219,6 +220,8 @@ struct evk_handle {
     size_t win_count = 0;
     // multi-GPU
     CommState* comm = nullptr;
+    // asynchronous event clustering consumer (evk_aec.cu), created by evk_aec_create
+    AecHost* aec = nullptr;
     uint64_t shard_first = 0;
     std::string err;
 };

@@ -235,6 +235,64 @@ EVK_API int evk_window_push(evk_handle* h, const evk_event* begin, const evk_eve
                             int* windows_done);
 EVK_API int evk_window_flush(evk_handle* h, int* windows_done);
 
+/* ---- consumer: asynchronous event clustering ----------------------------- */
+/* The reference hands every unique coordinate a slice keeps to AEClustering::update and draws one
+ * centroid + flow arrow per cluster afterwards (ACCEL/store.cpp:435-445,461-521; ACCEL/
+ * AEClustering.{h,cpp}, ACCEL/MyCluster.{h,cpp}).  These calls keep that consumer on the device:
+ * the same sequential algorithm, state for state (cluster order, ids, moving averages to the last
+ * bit, stored events), so the voxels never cross PCIe.  One consumer per handle. */
+typedef struct {
+    int32_t use_init;  /* 0: `new AEClustering` with init() never called, what the reference app does
+                        *    (store.cpp:42; AEClustering.cpp:7-18: szBuffer 800, radius 40, alpha 0.5,
+                        *    minN 10, kappa 0 -> the sampling test never fires);
+                        * 1: AEClustering::init(sz_buffer, radius, kappa, alpha, min_n), :20-26 */
+    int32_t sz_buffer; /* events remembered: older ones are forgotten (AEClustering.cpp:137-146)   */
+    double radius;     /* Manhattan radius around a cluster's moving average                      */
+    int32_t kappa;     /* stored events sampled per cluster above min_n (MyCluster.cpp:72-103)    */
+    int32_t min_n;     /* clusters with fewer events are neither sampled nor reported             */
+    double alpha;      /* moving average: mu = (1 - alpha) mu + alpha pix (MyCluster.cpp:200-202) */
+    uint32_t rand_seed;/* std::srand value; 1 = a process that never calls srand (the reference)  */
+    int32_t max_clusters; /* capacity: simultaneous clusters, <= 1024; 0 = 1024                   */
+    int32_t max_points;   /* capacity: stored events per cluster; 0 = 4096                        */
+    int32_t _pad;
+} evk_aec_params;
+typedef struct {
+    int32_t id, n;       /* getClusterId(), getN()                                                */
+    double mu[2];        /* getMu(): the moving average                                           */
+    double centroid[2];  /* getClusterCentroid(): mean of the stored events (NaN when n = 0)      */
+} evk_aec_cluster;
+typedef struct {         /* one cluster of the per-slice report, ACCEL/store.cpp:466-521          */
+    int32_t id, n;
+    double centroid[2];  /* cen                                                                   */
+    double prev[2];      /* centroid_prev[id] before this report (0,0 = none yet)                 */
+    int32_t has_arrow;   /* prev x and y both > 0 (:498): the flow arrow prev -> arrow_end is drawn */
+    int32_t _pad;
+    double arrow_end[2]; /* prev + (cen - prev), :499-500                                         */
+} evk_aec_flow;
+/* new AEClustering (+ init); replaces the consumer the handle already has, if any */
+EVK_API int evk_aec_create(evk_handle* h, const evk_aec_params* p);
+EVK_API int evk_aec_destroy(evk_handle* h);
+/* n calls of AEClustering::update (AEClustering.h:37) in order; e = n x {t, x, y, p} doubles in host
+ * memory, the std::deque<double> of the reference.  EVK_ERR_CAPACITY when max_clusters or
+ * max_points is exceeded (the consumer is then unusable until re-created). */
+EVK_API int evk_aec_update(evk_handle* h, const double* e, size_t n);
+/* The hand-off loop (ACCEL/store.cpp:435-445) without leaving the device: `count` updates with the
+ * representatives of the current voxel shard at canonical positions start, start + step, ...;
+ * every event carries pseudo-time t (the reference uses uniqueCount / 1000.0) and polarity 0.
+ * As written the reference steps the FLAT x,y array by 4 up to the PAIR count (SURVEY appendix A,
+ * D4): that is step = 2, count = ceil(n_unique / 4); step = 1, count = n_unique feeds them all. */
+EVK_API int evk_aec_update_voxels(evk_handle* h, double t, size_t start, size_t step, size_t count);
+/* eclustering->clusters in list order + getLastUpdatedClusterIdx(); out may be NULL (count only) */
+EVK_API int evk_aec_get_clusters(evk_handle* h, evk_aec_cluster* out, size_t cap, size_t* n,
+                                 int* last_updated);
+/* the stored events of one cluster, oldest first: getDatId / getDat / getDatT / getDatPol */
+EVK_API int evk_aec_get_points(evk_handle* h, size_t cluster, int32_t* ids, double* xy, double* t,
+                               uint8_t* pol, size_t cap, size_t* n);
+/* The per-slice report (ACCEL/store.cpp:461-521): one record per cluster with n >= min_n, list
+ * order; centroid_prev[id] then becomes the centroid (16384 ids as in the reference, :188). Call it
+ * once per slice: it advances centroid_prev whether or not `out` has room. */
+EVK_API int evk_aec_report(evk_handle* h, evk_aec_flow* out, size_t cap, size_t* n);
+
 /* ---- profiling / measurement --------------------------------------------------------------- */
 EVK_API int evk_set_profiling(evk_handle* h, int enabled);
 EVK_API int evk_get_stage_times(const evk_handle* h, evk_stage_times* out);

@@ -107,6 +107,14 @@ class Oracle(_Base):
         super().__init__(init, rand_seed)
         self.centroid_prev = np.zeros((16384, 2))   # store.cpp:188-193
 
+    def coverage(self):
+        """(merges, largest merged cluster, rand draws) so far -- tests assert the hard paths ran"""
+        out = (C.c_long * 3)()
+        self._L.orc_aec_coverage.argtypes = [C.c_void_p, C.c_void_p]
+        self._L.orc_aec_coverage.restype = None
+        self._L.orc_aec_coverage(self._h, out)
+        return tuple(out)
+
     def report(self):
         """per-slice report (store.cpp:461-521): rows {id, n, cen_x, cen_y, prev_x, prev_y,
         has_arrow, end_x, end_y}"""

@@ -54,6 +54,7 @@ typedef struct orc_aec {
     /* glibc random() TYPE_3 state (std::rand, MyCluster.cpp:88) */
     int32_t r[31];
     int rf, rb;
+    long n_merges, max_merged, n_draws; /* test-coverage counters */
 } orc_aec;
 
 /* glibc srandom_r / random_r, TYPE_3 (x^31 + x^3 + 1): what std::rand() is in the reference build */
@@ -171,6 +172,7 @@ static double cl_sampling(orc_aec* a, const aec_cluster* k, double x, double y) 
     } else {
         for (int ii = 0; ii < a->kappa; ii++) {
             const int idx = glibc_rand(a) % k->n;
+            a->n_draws++;
             const double foo = manhattan(x, y, k->d[idx].x, k->d[idx].y);
             if (foo < ma) ma = foo;
         }
@@ -186,6 +188,8 @@ static void cl_erase(orc_aec* a, int pos) {
 static void aec_merge(orc_aec* a, const int* assigned, int m) {
     int aux_n = 0;
     for (int ii = 0; ii < m; ii++) aux_n += a->c[assigned[ii]].n;
+    a->n_merges++;
+    if (aux_n > a->max_merged) a->max_merged = aux_n;
     double aux_mu[2] = {0.0, 0.0};
     for (int ii = 0; ii < m; ii++) {
         const aec_cluster* k = &a->c[assigned[ii]];
@@ -276,6 +280,11 @@ void orc_aec_update(orc_aec* a, const double* e, long n) {
     for (long i = 0; i < n; i++) aec_update_one(a, e + 4 * i);
 }
 int orc_aec_n_clusters(const orc_aec* a) { return a->nc; }
+void orc_aec_coverage(const orc_aec* a, long* out3) {
+    out3[0] = a->n_merges;
+    out3[1] = a->max_merged;
+    out3[2] = a->n_draws;
+}
 int orc_aec_last_updated(const orc_aec* a) { return a->last_updated; }
 /* getClusterCentroid, MyCluster.cpp:171-186: sequential sums in deque order, then one division */
 static void cl_centroid(const aec_cluster* k, double* cen) {
