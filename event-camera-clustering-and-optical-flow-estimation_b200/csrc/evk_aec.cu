@@ -111,8 +111,8 @@ __device__ __forceinline__ double manhattan(double x, double y, double mx, doubl
 // Remove the clusters at the (ascending) positions lst[0..k) from the list, keeping the order of
 // the others (std::deque::erase, AEClustering.cpp:116-121,208-210); their storage slots go back
 // to the free stack.  Warp-synchronous; returns the new cluster count.
-__device__ int aec_erase(const AecSmem& s, AecDev* S, const int* lst, int k, int nc, int lane,
-                         int* n_free) {
+__device__ __forceinline__ int aec_erase(const AecSmem& s, const AecDev* S, const int* lst, int k,
+                                         int nc, int lane, int* n_free) {
     for (int base = 0; base < nc; base += 32) {
         const int i = base + lane;
         int below = 0;
@@ -157,7 +157,7 @@ __device__ int aec_erase(const AecSmem& s, AecDev* S, const int* lst, int k, int
 
 // AEClustering::merge_clusters_ (AEClustering.cpp:148-211) for the clusters at positions
 // s.asg[0..m).  Returns false when the merged cluster does not fit a storage ring.
-__device__ bool aec_merge(const AecSmem& s, AecDev* S, int m, int lane) {
+__device__ __forceinline__ bool aec_merge(const AecSmem& s, const AecDev* S, int m, int lane) {
     const int cap = S->cap;
     int aux_n = 0;
     for (int ii = 0; ii < m; ii++) aux_n += s.n[s.asg[ii]];
@@ -260,10 +260,15 @@ __device__ bool aec_merge(const AecSmem& s, AecDev* S, int m, int lane) {
 }
 
 // n calls of AEClustering::update, in order.  ev = n x {t, x, y, p} doubles on the device.
-__global__ void __launch_bounds__(32) k_aec_update(AecDev* S, const double* __restrict__ ev,
+__global__ void __launch_bounds__(32) k_aec_update(AecDev* S_global, const double* __restrict__ ev,
                                                    long long n) {
     extern __shared__ __align__(16) unsigned char aec_raw[];
     const int lane = threadIdx.x;
+    // the header (parameters, array pointers) is read ONCE into registers: through the pointer every
+    // use would be a dependent global load in front of the access it addresses
+    AecDev* const Sg = S_global;
+    const AecDev hdr = *Sg;
+    const AecDev* const S = &hdr;
     const int ring = S->sz_buffer + 1;
     const AecSmem s = carve(aec_raw, ring);
     if (S->error) return;
@@ -284,14 +289,26 @@ __global__ void __launch_bounds__(32) k_aec_update(AecDev* S, const double* __re
         s.ft[i] = S->c_n[i] > 0 ? S->p_t[(size_t)S->c_slot[i] * cap + S->c_head[i]] : 0.0;
     }
     for (int i = lane; i < ring; i += 32) s.tb[i] = S->tbuf[i];
-    if (lane < 31) s.r[lane] = S->r[lane];
+    if (lane < 31) s.r[lane] = Sg->r[lane];
     int rf = S->rf, rb = S->rb;
     __syncwarp();
     const unsigned lt = (1u << lane) - 1u;
     int err = AEC_OK;
     long long e = 0;
+    // the next event is fetched while the current one is processed (a dependent L2 round trip per
+    // event otherwise)
+    const double2* ev2 = reinterpret_cast<const double2*>(ev);
+    double2 nx_a = make_double2(0, 0), nx_b = make_double2(0, 0);
+    if (n > 0) {
+        nx_a = ev2[0];
+        nx_b = ev2[1];
+    }
     for (; e < n; e++) {
-        const double et = ev[4 * e], x = ev[4 * e + 1], y = ev[4 * e + 2], pv = ev[4 * e + 3];
+        const double et = nx_a.x, x = nx_a.y, y = nx_b.x, pv = nx_b.y;
+        if (e + 1 < n) {
+            nx_a = ev2[2 * (e + 1)];
+            nx_b = ev2[2 * (e + 1) + 1];
+        }
         if (t0 < 0) t0 = et;  // AEClustering.cpp:49-51
         const double t = __dsub_rn(et, t0);
         // updateBuffer_, AEClustering.cpp:137-146
@@ -446,30 +463,30 @@ __global__ void __launch_bounds__(32) k_aec_update(AecDev* S, const double* __re
     __syncwarp();
     // ---- state out ----
     for (int i = lane; i < nc; i += 32) {
-        S->c_mux[i] = s.mux[i];
-        S->c_muy[i] = s.muy[i];
-        S->c_n[i] = s.n[i];
-        S->c_head[i] = s.head[i];
-        S->c_slot[i] = s.slot[i];
-        S->c_id[i] = s.id[i];
+        Sg->c_mux[i] = s.mux[i];
+        Sg->c_muy[i] = s.muy[i];
+        Sg->c_n[i] = s.n[i];
+        Sg->c_head[i] = s.head[i];
+        Sg->c_slot[i] = s.slot[i];
+        Sg->c_id[i] = s.id[i];
     }
-    for (int i = lane; i < ring; i += 32) S->tbuf[i] = s.tb[i];
-    if (lane < 31) S->r[lane] = s.r[lane];
+    for (int i = lane; i < ring; i += 32) Sg->tbuf[i] = s.tb[i];
+    if (lane < 31) Sg->r[lane] = s.r[lane];
     if (lane == 0) {
-        S->nc = nc;
-        S->n_free = n_free;
-        S->tb_head = tb_head;
-        S->tb_n = tb_n;
-        S->event_id = event_id;
-        S->next_id = next_id;
-        S->last = last;
-        S->t0 = t0;
-        S->rf = rf;
-        S->rb = rb;
-        S->events_done += e;
+        Sg->nc = nc;
+        Sg->n_free = n_free;
+        Sg->tb_head = tb_head;
+        Sg->tb_n = tb_n;
+        Sg->event_id = event_id;
+        Sg->next_id = next_id;
+        Sg->last = last;
+        Sg->t0 = t0;
+        Sg->rf = rf;
+        Sg->rb = rb;
+        Sg->events_done = hdr.events_done + e;
         if (err) {
-            S->error = err;
-            S->error_event = S->events_done;
+            Sg->error = err;
+            Sg->error_event = hdr.events_done + e;
         }
     }
 }

@@ -113,6 +113,30 @@ class Handle {
     }
     std::size_t n_unique() const { return n_unique_; }
 
+    // ---- consumer: the reference's `AEClustering *eclustering` (ACCEL/store.cpp:42) on the device
+    void aec_create(const evk_aec_params& p) { check(evk_aec_create(h_, &p)); }
+    // eclustering->update(ev_data) for n events {t, x, y, p} (AEClustering.h:37)
+    void aec_update(const double* e, std::size_t n) { check(evk_aec_update(h_, e, n)); }
+    // the hand-off loop of the slice callback (ACCEL/store.cpp:435-445) without leaving the device
+    void aec_update_voxels(double t, std::size_t start, std::size_t step, std::size_t count) {
+        check(evk_aec_update_voxels(h_, t, start, step, count));
+    }
+    std::vector<evk_aec_cluster> aec_clusters(int* last_updated = nullptr) {
+        std::size_t n = 0;
+        check(evk_aec_get_clusters(h_, nullptr, 0, &n, last_updated));
+        std::vector<evk_aec_cluster> c(n);
+        if (n) check(evk_aec_get_clusters(h_, c.data(), n, &n, last_updated));
+        return c;
+    }
+    // centroid + flow arrow per cluster with >= minN events (ACCEL/store.cpp:461-521)
+    std::vector<evk_aec_flow> aec_report() {
+        std::vector<evk_aec_flow> f(1024);
+        std::size_t n = 0;
+        check(evk_aec_report(h_, f.data(), f.size(), &n));
+        f.resize(n);
+        return f;
+    }
+
   private:
     evk_handle* h_ = nullptr;
     std::size_t n_unique_ = 0;
@@ -125,6 +149,7 @@ struct Slice {
     std::size_t n_events = 0, n_unique = 0, n_repeated = 0;
     std::vector<float> centroids;   // K x D
     std::vector<uint64_t> counts;   // K
+    std::vector<evk_aec_flow> flow; // enable_aec(): one centroid + arrow per reported cluster
 };
 
 // Replays the reference's streaming structure: events arrive in arbitrary chunks, a slice is
@@ -136,6 +161,20 @@ class Pipeline {
         : h_(max_events_per_slice, device), ds_(ds), km_(km), slice_us_(slice_us) {}
 
     void on_new_slice(std::function<void(const Slice&)> fn) { cb_ = std::move(fn); }
+
+    // Attach the reference's consumer (ACCEL/store.cpp:42,435-521): after every slice the unique
+    // voxels are handed to the asynchronous event clustering on the device and Slice::flow holds
+    // its report.  literal_stride reproduces the hand-off as written (every 2nd pair, a quarter of
+    // the slice); otherwise every voxel is handed over.
+    // max_per_slice bounds the hand-off (the reference's kernel emits at most 8192 pairs per
+    // launch, so its loop makes at most 2048 updates per slice).
+    void enable_aec(const evk_aec_params& p, bool literal_stride = false,
+                    std::size_t max_per_slice = 2048) {
+        h_.aec_create(p);
+        aec_ = true;
+        aec_literal_ = literal_stride;
+        aec_max_ = max_per_slice;
+    }
 
     // the event callback: a borrowed range, valid only during the call
     void add_events(const evk_event* begin, const evk_event* end) {
@@ -175,6 +214,14 @@ class Pipeline {
             }
             s.n_unique = c.unique;
             s.n_repeated = c.repeated;
+            if (aec_) {  // pseudo-time = cumulative unique count / 1000.0 (ACCEL/store.cpp:440)
+                unique_total_ += c.unique;
+                const double t = static_cast<double>(unique_total_) / 1000.0;
+                std::size_t cnt = aec_literal_ ? (c.unique + 3) / 4 : c.unique;
+                if (cnt > aec_max_) cnt = aec_max_;
+                h_.aec_update_voxels(t, 0, aec_literal_ ? 2 : 1, cnt);
+                s.flow = h_.aec_report();
+            }
             if (cb_) cb_(s);
             buf_.clear();
         }
@@ -184,7 +231,8 @@ class Pipeline {
     evk_ds_params ds_;
     evk_km_params km_;
     int64_t slice_us_, t0_ = 0;
-    bool started_ = false, warm_ = false;
+    bool started_ = false, warm_ = false, aec_ = false, aec_literal_ = false;
+    std::size_t unique_total_ = 0, aec_max_ = 2048;
     std::vector<evk_event> buf_;
     std::function<void(const Slice&)> cb_;
 };

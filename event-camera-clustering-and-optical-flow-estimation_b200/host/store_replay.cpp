@@ -1,6 +1,8 @@
 // store_replay.cpp — the reference's streaming sample without the SDK: replays a CSV dump
 // ("x,y,t,p" rows) or a synthetic stream in 50 ms slices through evk::Pipeline and prints one line
-// per slice (events, unique voxels, repeated, centroids of the K clusters).
+// per slice (events, unique voxels, repeated, centroids of the K clusters) and, with a third argument
+// "aec", the report of the reference's own consumer (AEClustering: centroid + flow arrow per
+// cluster, ACCEL/store.cpp:461-521) computed on the device.
 //
 // Mirrors main() of ACCEL/metavision_sdk_get_started5_opencl_store.cpp:179-643:
 //   Camera::from_file(argv[1])              -> CSV path in argv[1] (or "synth:<n_events>")
@@ -81,6 +83,12 @@ int main(int argc, char** argv) {
     try {
         evk::Pipeline pipe(ev.size(), ds, km, 50000);
         int n_slices = 0;
+        if (argc > 3 && std::strcmp(argv[3], "aec") == 0) {
+            evk_aec_params ap{};  // use_init = 0: the default-constructed consumer of the reference
+            ap.rand_seed = 1;
+            ap.max_points = 1 << 15;
+            pipe.enable_aec(ap, /*literal_stride=*/true);
+        }
         pipe.on_new_slice([&](const evk::Slice& s) {
             std::printf("slice %d t=%lld us events=%zu unique=%zu repeated=%zu", n_slices++,
                         (long long)s.t_begin_us, s.n_events, s.n_unique, s.n_repeated);
@@ -88,6 +96,10 @@ int main(int argc, char** argv) {
                 std::printf(" c%zu=(%.1f,%.1f)x%llu", k, s.centroids[2 * k], s.centroids[2 * k + 1],
                             (unsigned long long)s.counts[k]);
             std::printf("\n");
+            for (const evk_aec_flow& f : s.flow)
+                if (f.has_arrow)
+                    std::printf("  cluster %d n=%d (%.1f,%.1f) -> (%.1f,%.1f)\n", f.id, f.n,
+                                f.prev[0], f.prev[1], f.arrow_end[0], f.arrow_end[1]);
         });
         // the SDK delivers events in uneven buffers; do the same
         size_t at = 0, chunk = 1000;

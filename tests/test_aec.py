@@ -210,3 +210,46 @@ def test_cuda_capacity_and_state_errors(evk, orc):
         h.aec_update(e[:100])
         with pytest.raises(evk.EvkError):
             h.aec_update_voxels(0.0)                      # no voxel shard on this handle
+
+
+@pytest.mark.gpu
+def test_cpp_host_replay_with_consumer(evk, orc):
+    """store_replay ... aec: the C++ host layer runs the reference's whole slice callback --
+    downsample, as-written hand-off (every 2nd pair, <= 2048 per slice), asynchronous event
+    clustering, flow arrows -- and its arrows equal the oracle's fed from the oracle's downsample"""
+    import re
+    import subprocess
+    exe = os.path.join(evk_loader.PKG_DIR, "store_replay")
+    assert os.path.exists(exe), "host demo not built"
+    r = subprocess.run([exe, "synth:1500000", "8", "aec"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr
+    got, cur = [], None
+    for line in r.stdout.splitlines():
+        if line.startswith("slice "):
+            cur = []
+            got.append(cur)
+        elif line.startswith("  cluster "):
+            cur.append(tuple(float(v) for v in re.findall(r"-?\d+\.?\d*", line)))
+    ev = orc.synth(orc.synth_params(0xE7CA0005, 1_500_000, 1280, 720, 10_000_000, 8))
+    o = aec.Oracle(None)
+    total, want = 0, []
+    for s in range(3):
+        e0 = ev[(ev["t"] >= s * 50_000) & (ev["t"] < (s + 1) * 50_000)]
+        ok, of, _ = orc.downsample(e0, orc.ds_params(1280, 720, 4, 4, 1000, s * 50_000, 1))
+        reps = e0[of]
+        U = len(ok)
+        total += U
+        cnt = min((U + 3) // 4, 2048)
+        e = np.zeros((cnt, 4))
+        e[:, 0], e[:, 1], e[:, 2] = total / 1000.0, reps["x"][::2][:cnt], reps["y"][::2][:cnt]
+        o.update(e)
+        rep = o.report()
+        want.append([(r_[0], r_[1], round(r_[4], 1), round(r_[5], 1), round(r_[7], 1),
+                      round(r_[8], 1)) for r_ in rep if r_[6]])
+    assert len(got) == 3
+    assert sum(len(w) for w in want) > 0
+    for g, w in zip(got, want):
+        assert len(g) == len(w)
+        for a, b in zip(g, w):
+            assert a[:2] == b[:2] and np.allclose(a[2:], b[2:], atol=0.051)
