@@ -84,7 +84,7 @@ class StageTimes(C.Structure):
 # every symbol include/evk.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "evk_create", "evk_destroy", "evk_last_error", "evk_version", "evk_load_events",
-    "evk_append_events", "evk_load_events_soa", "evk_load_coords_i32", "evk_load_csv", "evk_load_evt2", "evk_load_raw", "evk_synth",
+    "evk_append_events", "evk_load_events_soa", "evk_load_coords_i32", "evk_load_csv", "evk_load_evt2", "evk_load_evt3", "evk_load_raw", "evk_synth",
     "evk_num_events", "evk_get_events", "evk_downsample", "evk_get_voxels", "evk_set_centroids",
     "evk_init_centroids_first_k", "evk_kmeans", "evk_downsample_kmeans", "evk_get_labels", "evk_get_centroids",
     "evk_window_config", "evk_window_push", "evk_window_flush", "evk_set_profiling",
@@ -119,6 +119,7 @@ def lib():
         "evk_load_coords_i32": [vp, vp, sz],
         "evk_load_csv": [vp, C.c_char_p],
         "evk_load_evt2": [vp, vp, sz, psz],
+        "evk_load_evt3": [vp, vp, sz, psz],
         "evk_load_raw": [vp, C.c_char_p, psz],
         "evk_synth": [vp, C.POINTER(SynthParams)],
         "evk_num_events": [vp, psz],
@@ -261,6 +262,13 @@ class Evk:
         words = np.ascontiguousarray(words, dtype=np.uint32)
         n = C.c_size_t(0)
         self._ck(self._L.evk_load_evt2(self._h, _p(words), len(words), C.byref(n)))
+        return n.value
+
+    def load_evt3(self, words):
+        """RAW EVT 3.0 words (uint16) -> events on the device; returns the number of CD events"""
+        words = np.ascontiguousarray(words, dtype=np.uint16)
+        n = C.c_size_t(0)
+        self._ck(self._L.evk_load_evt3(self._h, _p(words), len(words), C.byref(n)))
         return n.value
 
     def load_evt2_ptr(self, ptr, n_words):

@@ -26,7 +26,8 @@
 //     head is oldest" equals a stable merge on the running maximum of each list's times, so every
 //     stored event finds its output position with binary searches instead of a sequential walk;
 //   * std::rand() (MyCluster.cpp:88) is the glibc TYPE_3 additive generator, kept in shared memory
-//     and advanced by lane 0 in the reference's draw order (clusters in list order, kappa each).
+//     with 31 values generated per step (the recurrence unrolled eleven times), consumed in the
+//     reference's draw order (clusters in list order, kappa each).
 // All arithmetic is IEEE double with one rounding per operation (__dmul_rn / __dadd_rn: no FMA
 // contraction), as the reference's x86-64 build evaluates it.
 //
@@ -40,6 +41,7 @@ namespace {
 
 constexpr int kMaxC = 1024;      // simultaneous clusters (one lane each, 32 per pass)
 constexpr int kMaxKappa = 256;   // draws per sampled cluster
+constexpr int kDrawCap = 2048;   // draws generated per batch of sampled clusters
 constexpr int kMaxIds = 16384;   // centroid_prev[16384][2], store.cpp:188
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -55,8 +57,7 @@ struct AecDev {  // device-resident header; the arrays follow it in the same all
     int tb_head, tb_n, n_free;
     int error;
     long long error_event, events_done;
-    int32_t r[31];  // glibc random() TYPE_3 state
-    int rf, rb;
+    long long rcount;  // glibc random() TYPE_3: index of the next value of r[i] = r[i-31] + r[i-3]
     // arrays
     double* tbuf;                                // [sz_buffer + 1] ring
     int *c_slot, *c_id, *c_n, *c_head;           // [kMaxC] by position in the cluster list
@@ -69,13 +70,14 @@ struct AecDev {  // device-resident header; the arrays follow it in the same all
     int* m_id;
     unsigned char* m_pol;
     double* prev;                                // [kMaxIds][2]
+    uint32_t* rhist;                             // [128] the last 128 values of r[], ring by i & 127
     int n_report;                                // records written by the last report
 };
 
 struct AecSmem {  // carved out of dynamic shared memory
     double *mux, *muy, *ft, *tb;
     int *n, *head, *slot, *id, *asg, *rem, *draw;
-    int32_t* r;
+    uint32_t *hist, *hit;  // generator history ring [128]; sampling hits by 32 positions [32]
 };
 __device__ __forceinline__ AecSmem carve(unsigned char* raw, int ring) {
     AecSmem s;
@@ -92,11 +94,12 @@ __device__ __forceinline__ AecSmem carve(unsigned char* raw, int ring) {
     s.asg = i + 4 * kMaxC;
     s.rem = i + 5 * kMaxC;
     s.draw = i + 6 * kMaxC;
-    s.r = reinterpret_cast<int32_t*>(s.draw + kMaxKappa);
+    s.hist = reinterpret_cast<uint32_t*>(s.draw + kDrawCap);
+    s.hit = s.hist + 128;
     return s;
 }
 size_t aec_smem_bytes(int ring) {
-    return sizeof(double) * (3 * kMaxC + (size_t)ring) + sizeof(int) * (6 * kMaxC + kMaxKappa + 32);
+    return sizeof(double) * (3 * kMaxC + (size_t)ring) + sizeof(int) * (6 * kMaxC + kDrawCap + 128 + 32);
 }
 
 __device__ __forceinline__ double warp_min(double v) {
@@ -108,26 +111,37 @@ __device__ __forceinline__ double manhattan(double x, double y, double mx, doubl
     return __dadd_rn(fabs(__dsub_rn(x, mx)), fabs(__dsub_rn(y, my)));
 }
 
-// Remove the clusters at the (ascending) positions lst[0..k) from the list, keeping the order of
-// the others (std::deque::erase, AEClustering.cpp:116-121,208-210); their storage slots go back
-// to the free stack.  Warp-synchronous; returns the new cluster count.
-__device__ __forceinline__ int aec_erase(const AecSmem& s, const AecDev* S, const int* lst, int k,
-                                         int nc, int lane, int* n_free) {
-    for (int base = 0; base < nc; base += 32) {
+// exclusive prefix sum of v over the lanes; *total = sum over the warp
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int* total) {
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int u = __shfl_up_sync(kFull, inc, d);
+        if (lane >= d) inc += u;
+    }
+    *total = __shfl_sync(kFull, inc, 31);
+    return inc - v;
+}
+
+// Remove the clusters whose bits are set in `gone` (lane c holds the mask of positions
+// 32c .. 32c+31) from the list, keeping the order of the others (std::deque::erase,
+// AEClustering.cpp:116-121,208-210); their storage slots go back to the free stack.
+// Warp-synchronous; returns the new cluster count.
+__device__ __forceinline__ int aec_erase(const AecSmem& s, const AecDev* S, unsigned gone, int nc,
+                                         int lane, int* n_free) {
+    int k;
+    const int before = warp_excl_scan(__popc(gone), lane, &k);  // removed positions in earlier chunks
+    const unsigned lt = (1u << lane) - 1u;
+    const unsigned chunks = __ballot_sync(kFull, gone != 0);
+    const int first_ch = __ffs(chunks) - 1;  // positions before the first removal stay put
+    for (int ch = first_ch, base = first_ch << 5; base < nc; ch++, base += 32) {
         const int i = base + lane;
-        int below = 0;
-        bool gone = false;
+        const unsigned gm = __shfl_sync(kFull, gone, ch);
+        const int below = __shfl_sync(kFull, before, ch) + __popc(gm & lt);
+        const bool g = (gm >> lane) & 1u;
         double mx = 0, my = 0, ft = 0;
         int cn = 0, hd = 0, sl = 0, id = 0;
         if (i < nc) {
-            int lo = 0, hi = k;  // below = #{removed positions < i}
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (lst[mid] < i) lo = mid + 1;
-                else hi = mid;
-            }
-            below = lo;
-            gone = lo < k && lst[lo] == i;
             mx = s.mux[i];
             my = s.muy[i];
             ft = s.ft[i];
@@ -136,11 +150,10 @@ __device__ __forceinline__ int aec_erase(const AecSmem& s, const AecDev* S, cons
             sl = s.slot[i];
             id = s.id[i];
         }
-        const unsigned mg = __ballot_sync(kFull, gone);
-        if (gone) S->free_slots[*n_free + __popc(mg & ((1u << lane) - 1u))] = sl;
-        *n_free += __popc(mg);
+        if (g) S->free_slots[*n_free + __popc(gm & lt)] = sl;
+        *n_free += __popc(gm);
         __syncwarp();
-        if (i < nc && !gone && below) {
+        if (i < nc && !g && below) {
             const int j = i - below;
             s.mux[j] = mx;
             s.muy[j] = my;
@@ -153,6 +166,17 @@ __device__ __forceinline__ int aec_erase(const AecSmem& s, const AecDev* S, cons
         __syncwarp();
     }
     return nc - k;
+}
+
+// positions of the set bits of `mask` (lane c: positions 32c..) in ascending order -> lst[]
+__device__ __forceinline__ void aec_list(unsigned mask, int lane, int* lst) {
+    int tot;
+    int o = warp_excl_scan(__popc(mask), lane, &tot);
+    while (mask) {
+        lst[o++] = (lane << 5) + __ffs(mask) - 1;
+        mask &= mask - 1;
+    }
+    __syncwarp();
 }
 
 // AEClustering::merge_clusters_ (AEClustering.cpp:148-211) for the clusters at positions
@@ -169,8 +193,7 @@ __device__ __forceinline__ bool aec_merge(const AecSmem& s, const AecDev* S, int
         aux0 = __dadd_rn(aux0, __dmul_rn(w, s.mux[c]));
         aux1 = __dadd_rn(aux1, __dmul_rn(w, s.muy[c]));
     }
-    // offsets of the lists in the scratch arrays (s.rem is free here: update() returns right after
-    // a merge, the empty clusters it found stay)
+    // offsets of the lists in the scratch arrays
     if (lane == 0) {
         int off = 0;
         for (int ii = 0; ii < m; ii++) {
@@ -217,7 +240,6 @@ __device__ __forceinline__ bool aec_merge(const AecSmem& s, const AecDev* S, int
         if (g < aux_n) {
             int k = 0;
             while (k + 1 < m && s.rem[k + 1] <= g) k++;
-            // (empty lists share an offset with their successor: skip to the last list starting here)
             const double key = S->m_kp[g];
             int rank = g - s.rem[k];
             for (int j = 0; j < m; j++) {
@@ -259,6 +281,32 @@ __device__ __forceinline__ bool aec_merge(const AecSmem& s, const AecDev* S, int
     return true;
 }
 
+// glibc random_r, TYPE_3: r[i] = r[i-31] + r[i-3].  Substituting the second term eleven times gives
+// r[i] = r[i-33] + sum_{j=0..10} r[i-31-3j]: every index is at least 31 back, so 31 consecutive
+// outputs are independent of each other -- one per lane from a 128-entry history ring.
+// Writes `count` draws (rand() values) to out[]; *rcount = index of the next value to generate.
+__device__ __forceinline__ void aec_rand_fill(uint32_t* hist, long long* rcount, int count, int* out,
+                                              int lane) {
+    long long K = *rcount;
+    for (int done = 0; done < count; done += 31, K += 31) {
+        uint32_t v = 0;
+        const bool act = lane < 31 && done + lane < count;
+        if (act) {
+            const long long i = K + lane;
+            v = hist[(i - 33) & 127];
+#pragma unroll
+            for (int j = 0; j <= 10; j++) v += hist[(i - 31 - 3 * j) & 127];
+        }
+        __syncwarp();
+        if (act) {
+            hist[(K + lane) & 127] = v;
+            out[done + lane] = (int)(v >> 1);
+        }
+        __syncwarp();
+    }
+    *rcount += count;
+}
+
 // n calls of AEClustering::update, in order.  ev = n x {t, x, y, p} doubles on the device.
 __global__ void __launch_bounds__(32) k_aec_update(AecDev* S_global, const double* __restrict__ ev,
                                                    long long n) {
@@ -276,6 +324,7 @@ __global__ void __launch_bounds__(32) k_aec_update(AecDev* S_global, const doubl
     int nc = S->nc, n_free = S->n_free, tb_head = S->tb_head, tb_n = S->tb_n;
     int event_id = S->event_id, next_id = S->next_id, last = S->last;
     double t0 = S->t0;
+    long long rcount = S->rcount;
     const int sz = S->sz_buffer, kappa = S->kappa, min_n = S->min_n, cap = S->cap;
     const int max_c = S->max_clusters;
     const double radius = S->radius, alpha = S->alpha, om_alpha = 1 - S->alpha;
@@ -289,8 +338,8 @@ __global__ void __launch_bounds__(32) k_aec_update(AecDev* S_global, const doubl
         s.ft[i] = S->c_n[i] > 0 ? S->p_t[(size_t)S->c_slot[i] * cap + S->c_head[i]] : 0.0;
     }
     for (int i = lane; i < ring; i += 32) s.tb[i] = S->tbuf[i];
-    if (lane < 31) s.r[lane] = Sg->r[lane];
-    int rf = S->rf, rb = S->rb;
+    for (int i = lane; i < 128; i += 32) s.hist[i] = S->rhist[i];
+    s.hit[lane] = 0;
     __syncwarp();
     const unsigned lt = (1u << lane) - 1u;
     int err = AEC_OK;
@@ -324,9 +373,10 @@ __global__ void __launch_bounds__(32) k_aec_update(AecDev* S_global, const doubl
         }
         __syncwarp();
         const double tmin = s.tb[tb_head];
-        // ---- proximity pass over the cluster list, AEClustering.cpp:69-94 ----
-        int na = 0, nr = 0;
-        for (int base = 0; base < nc; base += 32) {
+        // ---- proximity pass over the cluster list, AEClustering.cpp:69-94: lane c keeps the three
+        //      masks of positions 32c .. 32c+31 (empty / near the moving average / to be sampled)
+        unsigned my_rem = 0, my_near = 0, my_samp = 0;
+        for (int ch = 0, base = 0; base < nc; ch++, base += 32) {
             const int i = base + lane;
             bool rem = false, near = false, samp = false;
             if (i < nc) {
@@ -345,55 +395,69 @@ __global__ void __launch_bounds__(32) k_aec_update(AecDev* S_global, const doubl
                     if (cn > 0) s.ft[i] = ft;
                 }
                 rem = cn == 0;
-                if (!rem) {
-                    near = manhattan(x, y, s.mux[i], s.muy[i]) <= radius;
-                    samp = !near && cn > min_n;
-                }
+                near = !rem && manhattan(x, y, s.mux[i], s.muy[i]) <= radius;
+                samp = !rem && !near && cn > min_n;
             }
-            const unsigned m_rem = __ballot_sync(kFull, rem);
-            unsigned m_near = __ballot_sync(kFull, near);
-            unsigned m_samp = __ballot_sync(kFull, samp);
-            while (m_samp) {  // manhattanDistanceWithSampling, clusters in list order
-                const int b = __ffs(m_samp) - 1;
-                m_samp &= m_samp - 1;
-                const int j = base + b, cn = s.n[j], hd = s.head[j];
-                const size_t o = (size_t)s.slot[j] * cap;
-                double ma = DBL_MAX;
-                if (kappa > cn) {
-                    for (int q = lane; q < cn; q += 32) {
-                        int idx = hd + q;
-                        if (idx >= cap) idx -= cap;
-                        ma = fmin(ma, manhattan(x, y, S->p_x[o + idx], S->p_y[o + idx]));
-                    }
-                } else {
-                    if (lane == 0) {
-                        for (int ii = 0; ii < kappa; ii++) {  // glibc random_r, TYPE_3
-                            const uint32_t v = (uint32_t)s.r[rf] + (uint32_t)s.r[rb];
-                            s.r[rf] = (int32_t)v;
-                            rf = rf == 30 ? 0 : rf + 1;
-                            rb = rb == 30 ? 0 : rb + 1;
-                            s.draw[ii] = (int)(v >> 1);
-                        }
-                    }
-                    rf = __shfl_sync(kFull, rf, 0);
-                    rb = __shfl_sync(kFull, rb, 0);
-                    __syncwarp();
-                    for (int q = lane; q < kappa; q += 32) {
-                        int idx = hd + s.draw[q] % cn;
-                        if (idx >= cap) idx -= cap;
-                        ma = fmin(ma, manhattan(x, y, S->p_x[o + idx], S->p_y[o + idx]));
-                    }
-                    __syncwarp();
-                }
-                ma = warp_min(ma);
-                if (ma <= radius) m_near |= 1u << b;
+            const unsigned b_rem = __ballot_sync(kFull, rem);
+            const unsigned b_near = __ballot_sync(kFull, near);
+            const unsigned b_samp = __ballot_sync(kFull, samp);
+            if (lane == ch) {
+                my_rem = b_rem;
+                my_near = b_near;
+                my_samp = b_samp;
             }
-            if (rem) s.rem[nr + __popc(m_rem & lt)] = i;
-            if ((m_near >> lane) & 1u) s.asg[na + __popc(m_near & lt)] = i;
-            nr += __popc(m_rem);
-            na += __popc(m_near);
         }
-        __syncwarp();
+        // ---- manhattanDistanceWithSampling (MyCluster.cpp:72-103) for the flagged clusters, in
+        //      list order: one lane per cluster, the draws of a batch generated up front
+        if (kappa > 0 && __any_sync(kFull, my_samp != 0)) {
+            __syncwarp();
+            const int F = __reduce_add_sync(kFull, __popc(my_samp));
+            aec_list(my_samp, lane, s.asg);  // s.asg[f] = position of the f-th flagged cluster
+            for (int f0 = 0; f0 < F;) {
+                // batch: as many clusters as fit the draw buffer (those with kappa > n draw none)
+                int f1 = f0, nd = 0;
+                while (f1 < F) {
+                    const int d = kappa > s.n[s.asg[f1]] ? 0 : kappa;
+                    if (nd + d > kDrawCap) break;
+                    s.rem[f1] = nd;  // draw offset of cluster f1 inside the batch
+                    nd += d;
+                    f1++;
+                }
+                __syncwarp();
+                aec_rand_fill(s.hist, &rcount, nd, s.draw, lane);
+                for (int fb = f0; fb < f1; fb += 32) {
+                    const int f = fb + lane;
+                    if (f < f1) {
+                        const int j = s.asg[f], cn = s.n[j], hd = s.head[j];
+                        const size_t o = (size_t)s.slot[j] * cap;
+                        double ma = DBL_MAX;
+                        if (kappa > cn) {
+                            for (int q = 0; q < cn; q++) {
+                                int idx = hd + q;
+                                if (idx >= cap) idx -= cap;
+                                ma = fmin(ma, manhattan(x, y, S->p_x[o + idx], S->p_y[o + idx]));
+                            }
+                        } else {
+                            const int* dr = s.draw + s.rem[f];
+#pragma unroll 5
+                            for (int q = 0; q < kappa; q++) {
+                                int idx = hd + dr[q] % cn;
+                                if (idx >= cap) idx -= cap;
+                                ma = fmin(ma, manhattan(x, y, S->p_x[o + idx], S->p_y[o + idx]));
+                            }
+                        }
+                        if (ma <= radius) atomicOr(&s.hit[j >> 5], 1u << (j & 31));
+                    }
+                }
+                __syncwarp();
+                f0 = f1;
+            }
+            my_near |= s.hit[lane];
+            s.hit[lane] = 0;
+            __syncwarp();
+        }
+        const int na = __reduce_add_sync(kFull, __popc(my_near));
+        const int nr = __reduce_add_sync(kFull, __popc(my_rem));
         // ---- no proximity -> new cluster; else join the first one, AEClustering.cpp:97-110 ----
         if (na == 0) {
             if (nc >= max_c || nc >= kMaxC || n_free == 0) {
@@ -423,7 +487,11 @@ __global__ void __launch_bounds__(32) k_aec_update(AecDev* S_global, const doubl
             nc++;
             __syncwarp();
         } else {
-            const int a0 = s.asg[0], cn = s.n[a0];
+            const unsigned chs = __ballot_sync(kFull, my_near != 0);
+            const int ch0 = __ffs(chs) - 1;
+            const unsigned m0 = __shfl_sync(kFull, my_near, ch0);
+            const int a0 = (ch0 << 5) + __ffs(m0) - 1;
+            const int cn = s.n[a0];
             if (cn >= cap) {
                 err = AEC_ERR_POINTS;
                 break;
@@ -445,19 +513,23 @@ __global__ void __launch_bounds__(32) k_aec_update(AecDev* S_global, const doubl
             last = a0;
             __syncwarp();
             if (na >= 2) {  // proximity to more than one cluster -> merge, then return (:103-107)
+                aec_list(my_near, lane, s.asg);
                 if (!aec_merge(s, S, na, lane)) {
                     err = AEC_ERR_POINTS;
                     break;
                 }
-                nc = aec_erase(s, S, s.asg + 1, na - 1, nc, lane, &n_free);
+                if (lane == ch0) my_near &= ~(1u << (a0 & 31));  // every assigned cluster but the first
+                nc = aec_erase(s, S, my_near, nc, lane, &n_free);
                 continue;
             }
         }
         if (nr) {  // AEClustering.cpp:113-121
-            int below = 0;
-            for (int q = 0; q < nr && s.rem[q] < last; q++) below++;
-            last -= below;
-            nc = aec_erase(s, S, s.rem, nr, nc, lane, &n_free);
+            // lastUpdatedCluster_ moves down by the removed positions below it
+            const int lch = last >> 5;
+            const int below = lane < lch ? __popc(my_rem)
+                              : (lane == lch ? __popc(my_rem & ((1u << (last & 31)) - 1u)) : 0);
+            last -= __reduce_add_sync(kFull, below);
+            nc = aec_erase(s, S, my_rem, nc, lane, &n_free);
         }
     }
     __syncwarp();
@@ -471,7 +543,7 @@ __global__ void __launch_bounds__(32) k_aec_update(AecDev* S_global, const doubl
         Sg->c_id[i] = s.id[i];
     }
     for (int i = lane; i < ring; i += 32) Sg->tbuf[i] = s.tb[i];
-    if (lane < 31) Sg->r[lane] = s.r[lane];
+    for (int i = lane; i < 128; i += 32) S->rhist[i] = s.hist[i];
     if (lane == 0) {
         Sg->nc = nc;
         Sg->n_free = n_free;
@@ -481,8 +553,7 @@ __global__ void __launch_bounds__(32) k_aec_update(AecDev* S_global, const doubl
         Sg->next_id = next_id;
         Sg->last = last;
         Sg->t0 = t0;
-        Sg->rf = rf;
-        Sg->rb = rb;
+        Sg->rcount = rcount;
         Sg->events_done = hdr.events_done + e;
         if (err) {
             Sg->error = err;
@@ -590,26 +661,20 @@ __global__ void k_aec_init(AecDev* S, unsigned seed) {
     if (i < S->max_clusters) S->free_slots[i] = S->max_clusters - 1 - i;  // slot 0 on top
     for (int q = i; q < 2 * kMaxIds; q += gridDim.x * blockDim.x) S->prev[q] = 0.0;
     for (int q = i; q <= S->sz_buffer; q += gridDim.x * blockDim.x) S->tbuf[q] = 0.0;
-    if (i == 0) {  // glibc srandom_r, TYPE_3
+    if (i == 0) {  // glibc srandom_r, TYPE_3: r[0..30] seeded, r[31..33] = r[0..2], 310 values discarded
         int32_t word = seed ? (int32_t)seed : 1;
-        int32_t r[31];
-        r[0] = word;
+        uint32_t* h = S->rhist;  // ring indexed by i & 127
+        h[0] = (uint32_t)word;
         for (int k = 1; k < 31; k++) {
             const long long hi = word / 127773, lo = word % 127773;
             long long w = 16807 * lo - 2836 * hi;
             if (w < 0) w += 2147483647;
             word = (int32_t)w;
-            r[k] = word;
+            h[k] = (uint32_t)word;
         }
-        int rf = 3, rb = 0;
-        for (int k = 0; k < 310; k++) {
-            r[rf] = (int32_t)((uint32_t)r[rf] + (uint32_t)r[rb]);
-            rf = rf == 30 ? 0 : rf + 1;
-            rb = rb == 30 ? 0 : rb + 1;
-        }
-        for (int k = 0; k < 31; k++) S->r[k] = r[k];
-        S->rf = rf;
-        S->rb = rb;
+        for (int k = 31; k < 34; k++) h[k] = h[k - 31];
+        for (int k = 34; k < 344; k++) h[k & 127] = h[(k - 31) & 127] + h[(k - 3) & 127];
+        S->rcount = 344;  // rand() number j is r[344 + j] >> 1
     }
 }
 
@@ -749,6 +814,7 @@ int evk_aec_create(evk_handle* h, const evk_aec_params* p) {
     const size_t o_head = take(4 * kMaxC), o_free = take(4 * (size_t)hd.max_clusters);
     const size_t o_pid = take(4 * np), o_mid = take(4 * (size_t)hd.cap);
     const size_t o_ppol = take(np), o_mpol = take((size_t)hd.cap);
+    const size_t o_rh = take(4 * 128);
     unsigned char* base = nullptr;
     if (cudaMalloc(&base, off) != cudaSuccess) {
         cudaGetLastError();
@@ -774,6 +840,7 @@ int evk_aec_create(evk_handle* h, const evk_aec_params* p) {
     hd.m_id = (int*)(base + o_mid);
     hd.p_pol = base + o_ppol;
     hd.m_pol = base + o_mpol;
+    hd.rhist = (uint32_t*)(base + o_rh);
     hd.n_free = hd.max_clusters;
     AecHost* a = new AecHost;
     a->d = (AecDev*)base;

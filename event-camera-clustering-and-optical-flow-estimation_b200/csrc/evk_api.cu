@@ -388,8 +388,10 @@ int evk_load_csv(evk_handle* h, const char* path) {
     return st;
 }
 
-// RAW EVT 2.0 words: uploaded as they are (4 B per event), decoded on the device (evk_evt2.cu)
-int evk_load_evt2(evk_handle* h, const uint32_t* words, size_t n_words, size_t* n_events) {
+// RAW sensor words: uploaded as they are, decoded on the device.  fmt 2: EVT 2.0, 32-bit words,
+// 4 B per event (evk_evt2.cu); fmt 3: EVT 3.0, 16-bit words (evk_evt3.cu).
+static int load_raw_words(evk_handle* h, int fmt, const void* words, size_t n_words,
+                          size_t* n_events) {
     EVK_TRY(check_handle(h));
     if (n_words && !words) return evk_fail(h, EVK_ERR_INVALID, "words is NULL");
     DeviceGuard g(h->device);
@@ -397,31 +399,39 @@ int evk_load_evt2(evk_handle* h, const uint32_t* words, size_t n_words, size_t* 
     h->n_events = 0;
     if (n_events) *n_events = 0;
     if (!n_words) return EVK_OK;
-    if (h->raw_cap_words < n_words) {
+    const size_t bytes = n_words * (fmt == 2 ? 4 : 2);
+    const size_t n_u32 = (bytes + 3) / 4;
+    if (h->raw_cap_words < n_u32) {
         if (h->d_raw) cudaFree(h->d_raw);
         h->d_raw = nullptr;
         h->raw_cap_words = 0;
-        if (cudaMalloc((void**)&h->d_raw, n_words * sizeof(uint32_t)) != cudaSuccess) {
+        if (cudaMalloc((void**)&h->d_raw, (n_u32 + 4) * sizeof(uint32_t)) != cudaSuccess) {
             cudaGetLastError();
             return evk_fail(h, EVK_ERR_NOMEM, "RAW staging of %zu words", n_words);
         }
-        h->raw_cap_words = n_words;
+        h->raw_cap_words = n_u32;
     }
-    const size_t nb = evk_evt2_blocks(n_words);
-    if (h->raw_cap_blocks < nb) {
+    // block summaries: 2 u32 per block (EVT 2.0) or 7 (EVT 3.0); capacity counted in pairs
+    const size_t nb = fmt == 2 ? evk_evt2_blocks(n_words) : evk_evt3_blocks(n_words);
+    const size_t pairs = fmt == 2 ? nb : (7 * nb + 1) / 2;
+    if (h->raw_cap_blocks < pairs) {
         if (h->d_raw_blk) cudaFree(h->d_raw_blk);
         h->d_raw_blk = nullptr;
         h->raw_cap_blocks = 0;
-        if (cudaMalloc((void**)&h->d_raw_blk, 2 * nb * sizeof(uint32_t)) != cudaSuccess) {
+        if (cudaMalloc((void**)&h->d_raw_blk, 2 * pairs * sizeof(uint32_t)) != cudaSuccess) {
             cudaGetLastError();
             return evk_fail(h, EVK_ERR_NOMEM, "RAW block summaries");
         }
-        h->raw_cap_blocks = nb;
+        h->raw_cap_blocks = pairs;
     }
-    EVK_CUDA(h, cudaMemcpyAsync(h->d_raw, words, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice,
-                                h->stream));
-    EVK_CUDA(h, evk_launch_evt2_decode(h->d_raw, n_words, h->d_raw_blk, h->d_n_points, h->d_events,
-                                       h->max_events, h->stream));
+    EVK_CUDA(h, cudaMemcpyAsync(h->d_raw, words, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (fmt == 2)
+        EVK_CUDA(h, evk_launch_evt2_decode(h->d_raw, n_words, h->d_raw_blk, h->d_n_points,
+                                           h->d_events, h->max_events, h->stream));
+    else
+        EVK_CUDA(h, evk_launch_evt3_decode(reinterpret_cast<const uint16_t*>(h->d_raw), n_words,
+                                           h->d_raw_blk, h->d_n_points, h->d_events,
+                                           h->max_events, h->stream));
     EVK_CUDA(h, cudaMemcpyAsync(&h->h_cnt->scratch[5], h->d_n_points, sizeof(unsigned long long),
                                 cudaMemcpyDeviceToHost, h->stream));
     EVK_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -432,6 +442,12 @@ int evk_load_evt2(evk_handle* h, const uint32_t* words, size_t n_words, size_t* 
     h->n_events = n;
     if (n_events) *n_events = n;
     return EVK_OK;
+}
+int evk_load_evt2(evk_handle* h, const uint32_t* words, size_t n_words, size_t* n_events) {
+    return load_raw_words(h, 2, words, n_words, n_events);
+}
+int evk_load_evt3(evk_handle* h, const uint16_t* words, size_t n_words, size_t* n_events) {
+    return load_raw_words(h, 3, words, n_words, n_events);
 }
 
 // A Metavision RAW recording: ASCII header lines starting with '%', then the binary payload.
@@ -457,7 +473,7 @@ int evk_load_raw(evk_handle* h, const char* path, size_t* n_events) {
         fclose(f);
     }
     size_t pos = 0;
-    bool evt2 = false, other = false;
+    bool evt2 = false, evt3 = false, other = false;
     while (pos < buf.size() && buf[pos] == '%') {  // header lines
         size_t eol = pos;
         while (eol < buf.size() && buf[eol] != '\n') eol++;
@@ -466,12 +482,22 @@ int evk_load_raw(evk_handle* h, const char* path, size_t* n_events) {
         if (line.find("evt 2.0") != std::string::npos || line.find("evt2;") != std::string::npos ||
             line.find("format evt2") != std::string::npos)
             evt2 = true;
+        else if (line.find("evt 3.0") != std::string::npos || line.find("evt3;") != std::string::npos ||
+                 line.find("format evt3") != std::string::npos)
+            evt3 = true;
         else if (line.find("% evt ") == 0 || line.find("% format ") == 0)
             other = true;
         pos = eol < buf.size() ? eol + 1 : eol;
     }
-    if (other && !evt2)
-        return evk_fail(h, EVK_ERR_IO, "%s: only the EVT 2.0 payload format is decoded", path);
+    if (other && !evt2 && !evt3)
+        return evk_fail(h, EVK_ERR_IO, "%s: only the EVT 2.0 and EVT 3.0 payload formats are decoded",
+                        path);
+    if (evt3) {
+        const size_t n16 = (buf.size() - pos) / 2;
+        std::vector<uint16_t> w16(n16);
+        if (n16) memcpy(w16.data(), buf.data() + pos, n16 * 2);
+        return evk_load_evt3(h, w16.data(), n16, n_events);
+    }
     const size_t n_words = (buf.size() - pos) / 4;
     std::vector<uint32_t> words(n_words);
     if (n_words) memcpy(words.data(), buf.data() + pos, n_words * 4);  // (payload may be unaligned)

@@ -350,3 +350,8 @@ cudaError_t evk_launch_evt2_decode(const uint32_t* words, size_t n_words, uint32
                                    unsigned long long* total, evk_event* out, size_t cap,
                                    cudaStream_t s);
 size_t evk_evt2_blocks(size_t n_words);
+// RAW EVT 3.0 decode (evk_evt3.cu): 16-bit words; blk = scratch of 7 * evk_evt3_blocks() u32
+cudaError_t evk_launch_evt3_decode(const uint16_t* words, size_t n_words, uint32_t* blk,
+                                   unsigned long long* total, evk_event* out, size_t cap,
+                                   cudaStream_t s);
+size_t evk_evt3_blocks(size_t n_words);

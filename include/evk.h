@@ -166,7 +166,15 @@ EVK_API int evk_load_csv(evk_handle* h, const char* path);
  * [10:0] y; 0x8 EVT_TIME_HIGH: [27:0] t bits 33..6; other types carry no CD event.
  * n_events (may be NULL) receives the number of CD events decoded. */
 EVK_API int evk_load_evt2(evk_handle* h, const uint32_t* words, size_t n_words, size_t* n_events);
-/* a RAW file: '%'-prefixed ASCII header lines, then the EVT 2.0 payload */
+/* RAW EVT 3.0 words (16 bit; the format current Prophesee sensors record): type = bits 15..12;
+ * 0x0 EVT_ADDR_Y [10:0] y; 0x2 EVT_ADDR_X [11] p, [10:0] x (one event); 0x3 VECT_BASE_X [11] p,
+ * [10:0] x; 0x4 VECT_12 / 0x5 VECT_8: one event at base + i per set mask bit, then base += 12 / 8;
+ * 0x6 EVT_TIME_LOW t bits 11..0; 0x8 EVT_TIME_HIGH t bits 23..12 (a lower value than the previous
+ * one counts a 2^24 us wrap); other types carry no CD event.  Decoded on the device as a scan over
+ * the decoder state (evk_evt3.cu). */
+EVK_API int evk_load_evt3(evk_handle* h, const uint16_t* words, size_t n_words, size_t* n_events);
+/* a RAW file: '%'-prefixed ASCII header lines ("% evt 2.0" / "% evt 3.0" / "% format EVT3;..."),
+ * then the payload in that format */
 EVK_API int evk_load_raw(evk_handle* h, const char* path, size_t* n_events);
 /* generate on device (benchmarks; no host copy) */
 EVK_API int evk_synth(evk_handle* h, const evk_synth_params* sp);

@@ -577,3 +577,121 @@ size_t orc_evt2_encode(const evk_event* ev, size_t n, uint32_t* words, size_t ca
     }
     return m;
 }
+
+/* ---- RAW EVT 3.0 (third-party format: Prophesee "EVT 3.0"; the Metavision SDK that decodes it
+ * for the reference -- Camera::from_file, ACCEL/store.cpp:336 -- is absent from /root/reference
+ * and its version is unpinned, so the published word layout is restated here; PARITY UNPINNED by
+ * the reference: pinned only by known-answer words and encode/decode round trips).
+ * 16-bit words, type = bits 15..12: 0x0 EVT_ADDR_Y [10:0] y; 0x2 EVT_ADDR_X [11] p [10:0] x (one
+ * event); 0x3 VECT_BASE_X [11] p [10:0] x; 0x4 VECT_12 [11:0] mask, 0x5 VECT_8 [7:0] mask (an event
+ * at base + i per set bit, then base += 12 / 8); 0x6 EVT_TIME_LOW t[11:0]; 0x8 EVT_TIME_HIGH
+ * t[23:12], a value lower than the previous EVT_TIME_HIGH counts one 2^24 us wrap; every other type
+ * carries no CD event.  State before the first word of each kind: 0. */
+size_t orc_evt3_decode(const uint16_t* words, size_t n_words, evk_event* out, size_t cap) {
+    uint32_t th = 0, tl = 0, y = 0, base = 0, pol = 0;
+    uint64_t wraps = 0;
+    int have_th = 0;
+    size_t n = 0;
+    for (size_t i = 0; i < n_words; i++) {
+        const uint32_t w = words[i], type = w >> 12, v = w & 0xFFFu;
+        if (type == 0x0) y = v & 0x7FFu;
+        else if (type == 0x6) tl = v;
+        else if (type == 0x8) {
+            if (have_th && v < th) wraps++;
+            th = v;
+            have_th = 1;
+        } else if (type == 0x3) {
+            base = v & 0x7FFu;
+            pol = (v >> 11) & 1u;
+        } else if (type == 0x2 || type == 0x4 || type == 0x5) {
+            const int64_t t = (int64_t)((wraps << 24) | ((uint64_t)th << 12) | tl);
+            if (type == 0x2) {
+                if (n < cap) {
+                    evk_event e = {(uint16_t)(v & 0x7FFu), (uint16_t)y, (int16_t)((v >> 11) & 1u), 0, t};
+                    out[n] = e;
+                }
+                n++;
+            } else {
+                const uint32_t bits = type == 0x4 ? 12u : 8u;
+                for (uint32_t b = 0; b < bits; b++)
+                    if (v & (1u << b)) {
+                        if (n < cap) {
+                            evk_event e = {(uint16_t)((base + b) & 0x7FFFu), (uint16_t)y, (int16_t)pol, 0, t};
+                            out[n] = e;
+                        }
+                        n++;
+                    }
+                base = (base + bits) & 0x7FFFu;
+            }
+        }
+    }
+    return n; /* may exceed cap: the number of CD events in the stream */
+}
+
+/* A writer that uses every word kind: time words only when they change, a row word when the row
+ * changes, runs of same-time same-row same-polarity events with increasing columns as vectors
+ * (VECT_8 when the run spans < 8 columns, else VECT_12; a vector that continues exactly where the
+ * previous one stopped reuses the running base without a new VECT_BASE_X), single events as
+ * EVT_ADDR_X.  Events must be time-ordered with gaps < 2^24 us and start below 2^24 us (the wrap
+ * count is implicit in the format).  Returns the number of words, or (size_t)-1. */
+size_t orc_evt3_encode(const evk_event* ev, size_t n, uint16_t* words, size_t cap) {
+    size_t m = 0;
+    int64_t cur_hi = -1, cur_tl = -1, cur_y = -1, prev_t = 0;
+    int64_t vec_next = -1; /* running vector base, valid while t, y, p stay the same */
+    int vec_pol = 0;
+#define PUT(w)                        \
+    do {                              \
+        if (m >= cap) return m;       \
+        words[m++] = (uint16_t)(w);   \
+    } while (0)
+    for (size_t i = 0; i < n;) {
+        const evk_event* e = &ev[i];
+        const int pol = e->p > 0;
+        if (e->x >= 2048 || e->y >= 2048 || e->t < 0) return (size_t)-1;
+        if (i == 0 ? e->t >= (1ll << 24) : (e->t < prev_t || e->t - prev_t >= (1ll << 24) - 4096))
+            return (size_t)-1;
+        prev_t = e->t;
+        if ((e->t >> 12) != cur_hi) {
+            cur_hi = e->t >> 12;
+            PUT(0x8000u | (uint32_t)(cur_hi & 0xFFF));
+            vec_next = -1;
+        }
+        if ((e->t & 0xFFF) != cur_tl) {
+            cur_tl = e->t & 0xFFF;
+            PUT(0x6000u | (uint32_t)cur_tl);
+            vec_next = -1;
+        }
+        if (e->y != cur_y) {
+            cur_y = e->y;
+            PUT(0x0000u | (uint32_t)cur_y);
+            vec_next = -1;
+        }
+        /* the run of events that fit one vector word starting at column x0 */
+        int64_t x0 = e->x;
+        const int cont = vec_next >= 0 && vec_pol == pol && e->x >= vec_next && e->x - vec_next < 12;
+        if (cont) x0 = vec_next;
+        size_t j = i + 1;
+        while (j < n && ev[j].t == e->t && ev[j].y == e->y && (ev[j].p > 0) == pol &&
+               ev[j].x > ev[j - 1].x && ev[j].x - x0 < 12)
+            j++;
+        if (j - i >= 2 || cont) {
+            uint32_t mask = 0;
+            for (size_t k = i; k < j; k++) mask |= 1u << (ev[k].x - x0);
+            if (!cont) PUT(0x3000u | ((uint32_t)pol << 11) | (uint32_t)x0);
+            if (mask < 256u && !cont) {
+                PUT(0x5000u | mask);
+                vec_next = x0 + 8;
+            } else {
+                PUT(0x4000u | mask);
+                vec_next = x0 + 12;
+            }
+            vec_pol = pol;
+            i = j;
+        } else {
+            PUT(0x2000u | ((uint32_t)pol << 11) | (uint32_t)e->x);
+            i++; /* (an EVT_ADDR_X word leaves the vector base alone) */
+        }
+    }
+#undef PUT
+    return m;
+}

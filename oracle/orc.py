@@ -66,6 +66,10 @@ def lib():
         L.orc_evt2_decode.restype = sz
         L.orc_evt2_encode.argtypes = [vp, sz, vp, sz]
         L.orc_evt2_encode.restype = sz
+        L.orc_evt3_decode.argtypes = [vp, sz, vp, sz]
+        L.orc_evt3_decode.restype = sz
+        L.orc_evt3_encode.argtypes = [vp, sz, vp, sz]
+        L.orc_evt3_encode.restype = sz
         L.orc_downsample.argtypes = [vp, sz, C.POINTER(DsParams), vp, vp, C.POINTER(sz)]
         L.orc_downsample.restype = sz
         L.orc_downsample_mt.argtypes = [vp, sz, C.POINTER(DsParams), C.c_int, C.c_int, vp, vp,
@@ -263,3 +267,23 @@ def evt2_decode(words):
     out = np.zeros(len(words), dtype=EVENT_DTYPE)
     n = lib().orc_evt2_decode(_p(words), len(words), _p(out), len(out))
     return out[:n].copy()
+
+
+def evt3_encode(ev):
+    """events (time-ordered) -> RAW EVT 3.0 words (uint16)"""
+    ev = np.ascontiguousarray(ev, dtype=EVENT_DTYPE)
+    words = np.empty(5 * len(ev) + 4, dtype=np.uint16)
+    m = lib().orc_evt3_encode(_p(ev), len(ev), _p(words), len(words))
+    if m == C.c_size_t(-1).value:
+        raise ValueError("events do not fit EVT 3.0 (x, y < 2048, time-ordered, gaps < 2^24 us)")
+    assert m < len(words)
+    return words[:m].copy()
+
+
+def evt3_decode(words):
+    """RAW EVT 3.0 words -> CD events"""
+    words = np.ascontiguousarray(words, dtype=np.uint16)
+    n = lib().orc_evt3_decode(_p(words), len(words), None, 0)
+    out = np.zeros(n, dtype=EVENT_DTYPE)
+    lib().orc_evt3_decode(_p(words), len(words), _p(out), n)
+    return out

@@ -70,7 +70,7 @@ def test_raw_file_and_pipeline(evk, orc):
         assert a == b and (ka == kb).all() and (fa == fb).all()
         assert (ca == cb).all() and (na == nb).all()
         with open(path, "wb") as f:
-            f.write(b"% evt 3.0\n% end\n" + w.tobytes())
+            f.write(b"% evt 2.1\n% end\n" + w.tobytes())   # (EVT 3.0: tests/test_gpu_evt3.py)
         with pytest.raises(evk.EvkError) as e:
             h.load_raw(path)
         assert e.value.status == -6

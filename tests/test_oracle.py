@@ -198,3 +198,46 @@ def test_host_evt2_writer_matches_oracle_codec(orc):
     assert len(evt2.encode_evt2(ev[:0])) == 0
     with pytest.raises(ValueError):
         evt2.encode_evt2(orc.events_from_xy([2048], [0]))
+
+
+def test_evt3_codec_known_answers_and_round_trips(orc):
+    """RAW EVT 3.0 (third-party format, SDK absent: parity unpinned by the reference): hand-derived
+    known-answer words for every word kind (row, single event, vector base, VECT_12, VECT_8 with the
+    running base, time low / high, a 2^24 us wrap, ignored types) and encode -> decode round trips"""
+    kw = np.array([0x8001, 0x6005, 0x0007, 0x2000 | 0x800 | 5,      # th=1 tl=5 y=7, ON event at x=5
+                   0x3000 | 10, 0x4000 | 0b101,                     # base 10 OFF: x=10, 12; base -> 22
+                   0x5000 | 0x80,                                   # VECT_8: x = 22 + 7; base -> 30
+                   0xA123, 0xE000, 0x7ABC,                          # trigger / others / continued
+                   0x8000, 0x2003,                                  # th 1 -> 0: one wrap
+                   0x4001], np.uint16)                              # vector again: x = 30
+    d = orc.evt3_decode(kw)
+    assert [(int(e["x"]), int(e["y"]), int(e["p"]), int(e["t"])) for e in d] == [
+        (5, 7, 1, 4101), (10, 7, 0, 4101), (12, 7, 0, 4101), (29, 7, 0, 4101),
+        (3, 7, 0, (1 << 24) + 5), (30, 7, 0, (1 << 24) + 5)]
+    assert len(orc.evt3_decode(np.zeros(0, np.uint16))) == 0
+    # events before any time / row word decode with zero state
+    assert orc.evt3_decode(np.array([0x2000 | 9], np.uint16)).tolist() == [(9, 0, 0, 0, 0)]
+    ev = orc.synth(orc.synth_params(0xE7CA0003, 200_000, 1280, 720, 100_000_000, 64))
+    ev["p"] = ev["p"] > 0
+    w = orc.evt3_encode(ev)
+    assert orc.evt3_decode(w).tobytes() == ev.tobytes()
+    # dense rows: sorted columns per (t, row, polarity) -> vector words incl. continued bases
+    r = np.random.default_rng(1)
+    n = 100_000
+    t = np.sort(r.integers(0, 3000, n)).astype(np.int64)
+    y, x, p = r.integers(0, 8, n), r.integers(0, 200, n), r.integers(0, 2, n)
+    o = np.lexsort((x, p, y, t))
+    dense = np.zeros(n, orc.EVENT_DTYPE)
+    dense["t"], dense["y"], dense["x"], dense["p"] = t[o], y[o], x[o], p[o]
+    w = orc.evt3_encode(dense)
+    kinds = np.bincount(w >> 12, minlength=16)
+    assert kinds[0x3] > 1000 and kinds[0x4] > 1000 and kinds[0x5] > 1000 and kinds[0x2] > 1000
+    assert kinds[0x4] + kinds[0x5] > kinds[0x3]          # some vectors continue a running base
+    assert orc.evt3_decode(w).tobytes() == dense.tobytes()
+    # a stream longer than 2^24 us: wraps are counted from the EVT_TIME_HIGH words
+    long_ev = np.zeros(5000, orc.EVENT_DTYPE)
+    long_ev["t"] = np.arange(5000, dtype=np.int64) * 20_000          # 100 s > 5 wraps
+    long_ev["x"], long_ev["y"] = np.arange(5000) % 1280, np.arange(5000) % 720
+    assert orc.evt3_decode(orc.evt3_encode(long_ev)).tobytes() == long_ev.tobytes()
+    with pytest.raises(ValueError):
+        orc.evt3_encode(orc.events_from_xy([2048], [0]))
