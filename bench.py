@@ -61,102 +61,108 @@ def parse():
     return ap.parse_args()
 
 
+_POLL_SRC = r"""
+import sys, time
+import pynvml as n
+n.nvmlInit()
+dev = n.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+mx = n.nvmlDeviceGetMaxClockInfo(dev, n.NVML_CLOCK_SM)
+def pick(*names):
+    for k in names:
+        if hasattr(n, k):
+            return getattr(n, k)
+    return 0
+bits = [pick("nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+        pick("nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+        pick("nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+        pick("nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap")]
+reasons = pick("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons")
+n.nvmlDeviceGetClockInfo(dev, n.NVML_CLOCK_SM)
+print("ready", flush=True)
+while True:
+    t = time.time()
+    sm = n.nvmlDeviceGetClockInfo(dev, n.NVML_CLOCK_SM)
+    try:
+        r = reasons(dev) if reasons else 0
+    except Exception:
+        r = 0
+    try:
+        pw = n.nvmlDeviceGetPowerUsage(dev) / 1000.0
+    except Exception:
+        pw = 0.0
+    print(t, sm, mx, pw, *[1 if (r & b) else 0 for b in bits], flush=True)
+    time.sleep(0.001)
+"""
+
+
 class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed region.  The region is tens of
-    milliseconds long, so NVML is polled from a thread every ~2 ms (nvidia-smi -lms cannot sample
-    that fast); nvidia-smi is the fallback when pynvml is missing."""
+    milliseconds long, so NVML is polled every ~1-2 ms (nvidia-smi -lms cannot sample that fast) --
+    from a separate PROCESS, so that this process's interpreter lock (the timed loop is a tight loop
+    of C-ABI calls) cannot starve the sampler.  Rows carry wall-clock stamps; stop(t0, t1) keeps the
+    rows taken inside [t0, t1].  nvidia-smi is the fallback when pynvml is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.rows, self.proc, self.nvml, self.stop_flag = index, [], None, None, False
-        self.source = "none"
+        self.index, self.rows, self.proc, self.source = index, [], None, "none"
 
     def start(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        idx = self.index  # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES indices
+        if vis and all(v.strip().isdigit() for v in vis.split(",")):
+            idx = int(vis.split(",")[self.index])
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it lists indices
-            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
-            idx = self.index
-            if vis and all(v.strip().isdigit() for v in vis.split(",")):
-                idx = int(vis.split(",")[self.index])
-            self.dev = pynvml.nvmlDeviceGetHandleByIndex(idx)
-            self.nvml = pynvml
+            self.proc = subprocess.Popen([sys.executable, "-c", _POLL_SRC, str(idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            if self.proc.stdout.readline().strip() != "ready":   # first NVML queries are slow
+                raise RuntimeError("sampler did not start")
             self.source = "nvml"
-            # first NVML queries are slow: make them before the timed region
-            self.mx = pynvml.nvmlDeviceGetMaxClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
-            pynvml.nvmlDeviceGetClockInfo(self.dev, pynvml.NVML_CLOCK_SM)
-            self.t = threading.Thread(target=self._poll, daemon=True)
-            self.t.start()
-            return
         except Exception:
-            self.nvml = None
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "20"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.source = "nvidia-smi"
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _poll(self):
-        n = self.nvml
-        bits = {"hw_slowdown": n.nvmlClocksEventReasonHwSlowdown
-                if hasattr(n, "nvmlClocksEventReasonHwSlowdown") else n.nvmlClocksThrottleReasonHwSlowdown,
-                "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown",
-                                               getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0)),
-                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown",
-                                               getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0)),
-                "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap",
-                                        getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0))}
-        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons",
-                              getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons", None))
-        def guarded(fn, default):
+            if self.proc:
+                self.proc.kill()
             try:
-                return fn()
-            except Exception as e:  # a field this driver does not report
-                if not getattr(self, "_warned", False):
-                    self._warned = True
-                    print(f"clock sampler: {e!r}", file=sys.stderr)
-                return default
-        mx = self.mx
-        while not self.stop_flag:
-            sm = guarded(lambda: n.nvmlDeviceGetClockInfo(self.dev, n.NVML_CLOCK_SM), None)
-            pw = guarded(lambda: n.nvmlDeviceGetPowerUsage(self.dev) / 1000.0, 0.0)
-            r = guarded(lambda: get_reasons(self.dev), 0) if get_reasons else 0
-            if sm is not None:
-                self.rows.append([sm, mx, pw] + ["Active" if (r & b) else "Not Active"
-                                                 for b in bits.values()])
-            time.sleep(0.002)
+                self.proc = subprocess.Popen(
+                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                     "--format=csv,noheader,nounits", "-lms", "20"],
+                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.source = "nvidia-smi"
+            except Exception:
+                self.proc = None
+                return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            if self.source == "nvml":
+                f = line.split()
+                self.rows.append([float(f[0])] + f[1:4] + ["Active" if v == "1" else "Not Active"
+                                                           for v in f[4:8]])
+            else:
+                self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
 
-    def stop(self):
-        if self.nvml:
-            self.stop_flag = True
-            self.t.join(timeout=1)
-        elif self.proc:
-            time.sleep(0.05)
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
-        else:
+    def stop(self, t0=None, t1=None):
+        if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock source"]}
+        time.sleep(0.02)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        self.t.join(timeout=1)
+        rows = self.rows
+        if t0 is not None:
+            inside = [r for r in rows if t0 <= r[0] <= t1]
+            rows = inside or rows   # (a region shorter than one poll: keep the surrounding rows)
         sm, mx, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1])); pw.append(float(r[2]))
-                for n, v in zip(names, r[3:7]):
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for n, v in zip(names, r[4:8]):
                     if str(v).lower().startswith("active"):
                         reasons.add(n)
             except Exception:
@@ -164,6 +170,7 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm),
+                "window": "timed steps + the synchronous stage-time pass of the same steps",
                 "reasons": sorted(reasons), "source": self.source}
 
 
@@ -205,6 +212,51 @@ def cpu_port(n_sample, steps, threads):
         best = dt if best is None else min(best, dt)
         U = len(keys)
     return n_sample / best / 1e6, threads, U, best
+
+
+def consumer_leg(evk):
+    """SURVEY 8f rank 1, the reference's consumer of the downsampled coordinates (asynchronous event
+    clustering, ACCEL/AEClustering.cpp): sequential by definition, so the figure is microseconds per
+    event.  The CUDA path (evk_aec_update through the C-ABI, host buffers, one call per 1250-event
+    slice) beside the reference's OWN code (oracle/_ref/libref_aec.so: its sources compiled where
+    they lie; one host thread) on the reference app's configuration; states must be equal."""
+    import numpy as np
+    from oracle import aec
+    r = np.random.default_rng(31)
+    n, sl = 20_000, 1250
+    c0 = r.uniform([100, 100], [1180, 620], size=(6, 2))
+    v = r.uniform(-300, 300, size=(6, 2))
+    t = np.floor(np.arange(n) / sl) * 0.05 + 5.0          # one pseudo-time per 50 ms slice
+    k = r.integers(0, 6, n)
+    xy = c0[k] + v[k] * (t - 5.0)[:, None] + r.normal(0, 8, size=(n, 2))
+    noise = r.random(n) < 0.25
+    xy[noise] = r.uniform([0, 0], [1280, 720], size=(int(noise.sum()), 2))
+    e = np.zeros((n, 4))
+    e[:, 0], e[:, 1:3] = t, np.clip(np.rint(xy), 0, [1279, 719])
+    out = {"workload": f"{n} events in {sl}-event slices (one pseudo-time per slice), default-"
+                       "constructed AEClustering (szBuffer 800, radius 40, alpha 0.5, minN 10)",
+           "unit": "us/event"}
+    with evk.Evk(1024) as h:
+        h.aec_create(None)
+        h.aec_update(e[:sl])
+        h.aec_create(None)
+        t0 = time.perf_counter()
+        for i in range(0, n, sl):
+            h.aec_update(e[i:i + sl])
+        out["value"] = (time.perf_counter() - t0) / n * 1e6
+        st = h.aec_state()
+    kind, cls = ("reference", aec.Reference) if aec.ref_available() else ("port", aec.Oracle)
+    o = cls(None)
+    t0 = time.perf_counter()
+    for i in range(0, n, sl):
+        o.update(e[i:i + sl])
+    out["cpu_baseline"] = {"value": (time.perf_counter() - t0) / n * 1e6, "unit": "us/event",
+                           "cores": 1, "kind": kind}
+    so = o.state()
+    out["clusters"] = int(len(st["ids"]))
+    out["state_equal"] = bool((st["ids"] == so["ids"]).all() and (st["n"] == so["n"]).all()
+                              and (st["mu"] == so["mu"]).all())
+    return out
 
 
 def run_reference(args, rank, out):
@@ -339,6 +391,7 @@ def _main(args, real_stdout):
     # unfused runs synchronise inside every step.
     pipelined = world == 1 and not args.unfused and not args.sync_steps
     launches = 0
+    clk_t0 = time.time()
     h.timer_start()
     if pipelined:
         for _ in range(args.steps):
@@ -362,7 +415,7 @@ def _main(args, real_stdout):
         launches += t.ds_launches + t.km_launches + (1 if args.unfused else 0)
     sync_ms_per_step = (time.perf_counter() - sync_t0) * 1e3 / args.steps
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(clk_t0, time.time()) if rank == 0 else None
     algo_used = h.stage_times().ds_algo_used
     tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -479,6 +532,7 @@ def _main(args, real_stdout):
                 "value": mev, "unit": "Mevents/s", "cores": threads, "kind": "port",
                 "sample": f"first {n_sample} events of the workload stream (U={Us}), best of 2 "
                           f"passes ({best:.2f} s each), generation excluded"}
+            line["consumer"] = consumer_leg(evk)
         print(json.dumps(line), file=real_stdout, flush=True)
     h.close()
     if world > 1:

@@ -85,9 +85,9 @@ class StageTimes(C.Structure):
 SYMBOLS = [
     "evk_create", "evk_destroy", "evk_last_error", "evk_version", "evk_load_events",
     "evk_append_events", "evk_load_events_soa", "evk_load_coords_i32", "evk_load_csv", "evk_load_evt2", "evk_load_evt3", "evk_load_raw", "evk_synth",
-    "evk_num_events", "evk_get_events", "evk_downsample", "evk_get_voxels", "evk_set_centroids",
+    "evk_num_events", "evk_get_events", "evk_downsample", "evk_get_voxels", "evk_num_voxels", "evk_set_centroids",
     "evk_init_centroids_first_k", "evk_kmeans", "evk_downsample_kmeans", "evk_get_labels", "evk_get_centroids",
-    "evk_window_config", "evk_window_push", "evk_window_flush", "evk_set_profiling",
+    "evk_window_config", "evk_window_config_events", "evk_window_push", "evk_window_flush", "evk_set_profiling",
     "evk_get_stage_times", "evk_timer_start", "evk_timer_stop", "evk_sync", "evk_flush_l2",
     "evk_comm_unique_id", "evk_comm_init", "evk_comm_destroy", "evk_set_shard",
     "evk_downsample_sharded", "evk_kmeans_sharded", "evk_init_centroids_first_k_sharded",
@@ -126,6 +126,7 @@ def lib():
         "evk_get_events": [vp, vp, sz, sz],
         "evk_downsample": [vp, C.POINTER(DsParams), psz, psz],
         "evk_get_voxels": [vp, vp, vp, vp, sz],
+        "evk_num_voxels": [vp, psz, psz],
         "evk_set_centroids": [vp, vp, i32, i32],
         "evk_init_centroids_first_k": [vp, C.POINTER(KmParams)],
         "evk_kmeans": [vp, C.POINTER(KmParams), C.POINTER(i32)],
@@ -143,6 +144,7 @@ def lib():
         "evk_aec_report": [vp, vp, sz, psz],
         "evk_get_centroids": [vp, vp, vp],
         "evk_window_config": [vp, C.POINTER(DsParams), C.POINTER(KmParams), C.c_int64],
+        "evk_window_config_events": [vp, C.POINTER(DsParams), C.POINTER(KmParams), sz],
         "evk_window_push": [vp, vp, vp, C.POINTER(i32)],
         "evk_window_flush": [vp, C.POINTER(i32)],
         "evk_set_profiling": [vp, i32],
@@ -303,8 +305,14 @@ class Evk:
         self.n_unique = u.value
         return u.value, r.value
 
+    def num_voxels(self):
+        """(n_unique, n_repeated) of the current voxel shard"""
+        u, r = C.c_size_t(0), C.c_size_t(0)
+        self._ck(self._L.evk_num_voxels(self._h, C.byref(u), C.byref(r)))
+        return u.value, r.value
+
     def get_voxels(self, keys=True, reps=True, first=True):
-        n = self.n_unique
+        n = self.n_unique = self.num_voxels()[0]
         k = np.zeros(n, dtype=np.uint64) if keys else None
         r = np.zeros(n, dtype=EVENT_DTYPE) if reps else None
         f = np.zeros(n, dtype=np.uint32) if first else None
@@ -425,6 +433,11 @@ class Evk:
     # ---- streaming windows
     def window_config(self, ds, km, window_us):
         self._ck(self._L.evk_window_config(self._h, C.byref(ds), C.byref(km), window_us))
+        self._km = km
+
+    def window_config_events(self, ds, km, n_events):
+        """windows of exactly n_events events (the reslicer's make_n_events condition)"""
+        self._ck(self._L.evk_window_config_events(self._h, C.byref(ds), C.byref(km), n_events))
         self._km = km
 
     def window_push(self, ev):

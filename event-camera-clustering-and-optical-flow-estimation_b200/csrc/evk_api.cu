@@ -604,6 +604,15 @@ int evk_downsample(evk_handle* h, const evk_ds_params* p, size_t* n_unique, size
     return EVK_OK;
 }
 
+// the counters of the current voxel shard (the blocking reads of unique_count / repeated_count,
+// ACCEL/store.cpp:418-430): what the last downsample, fused step or completed window produced
+int evk_num_voxels(const evk_handle* h, size_t* n_unique, size_t* n_repeated) {
+    if (!h) return EVK_ERR_INVALID;
+    if (n_unique) *n_unique = h->have_voxels ? h->n_unique : 0;
+    if (n_repeated) *n_repeated = h->have_voxels ? h->n_repeated : 0;
+    return h->have_voxels ? EVK_OK : EVK_ERR_STATE;
+}
+
 int evk_get_voxels(evk_handle* h, uint64_t* keys, evk_event* reps, uint32_t* first_idx, size_t cap) {
     EVK_TRY(check_handle(h));
     if (!h->have_voxels) return evk_fail(h, EVK_ERR_STATE, "evk_downsample has not run");
@@ -1103,11 +1112,26 @@ int evk_window_config(evk_handle* h, const evk_ds_params* ds, const evk_km_param
     h->win_ds = *ds;
     h->win_km = *km;
     h->win_us = window_us;
+    h->win_events = 0;
     h->win_cfg = true;
     h->win_started = false;
     h->win_pending = 0;
     h->win_count = 0;
     h->have_centroids = false;
+    return EVK_OK;
+}
+
+// Condition::make_n_events(nevents) of the reslicer (SAMP/store.cpp:336): a window is complete after
+// exactly n_events events; its time bins start at its first event.
+int evk_window_config_events(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
+                             size_t n_events) {
+    EVK_TRY(check_handle(h));
+    if (n_events == 0) return evk_fail(h, EVK_ERR_INVALID, "n_events must be > 0");
+    if (n_events > h->max_events)
+        return evk_fail(h, EVK_ERR_CAPACITY, "window of %zu events exceeds the handle capacity %zu",
+                        n_events, h->max_events);
+    EVK_TRY(evk_window_config(h, ds, km, 1));
+    h->win_events = n_events;
     return EVK_OK;
 }
 
@@ -1145,6 +1169,21 @@ int evk_window_push(evk_handle* h, const evk_event* begin, const evk_event* end,
     if ((!begin && end != begin) || end < begin) return evk_fail(h, EVK_ERR_INVALID, "bad event range");
     int done = 0;
     const evk_event* p = begin;
+    while (h->win_events && p != end) {  // count-based windows
+        if (h->win_pending == 0) h->win_start = p->t;
+        const size_t m = std::min((size_t)(end - p), h->win_events - h->win_pending);
+        DeviceGuard g(h->device);
+        if (!h->d_win_stage)
+            EVK_CUDA(h, cudaMalloc((void**)&h->d_win_stage, h->max_events * sizeof(evk_event)));
+        EVK_CUDA(h, cudaMemcpyAsync(h->d_win_stage + h->win_pending, p, m * sizeof(evk_event),
+                                    cudaMemcpyHostToDevice, h->stream));
+        h->win_pending += m;
+        p += m;
+        if (h->win_pending == h->win_events) {
+            EVK_TRY(window_run(h));
+            done++;
+        }
+    }
     while (p != end) {
         if (!h->win_started) {
             h->win_started = true;
@@ -1190,7 +1229,7 @@ int evk_window_flush(evk_handle* h, int* windows_done) {
     if (h->win_pending) {
         EVK_TRY(window_run(h));
         done = 1;
-        h->win_start += h->win_us;
+        if (!h->win_events) h->win_start += h->win_us;
     }
     if (windows_done) *windows_done = done;
     return EVK_OK;

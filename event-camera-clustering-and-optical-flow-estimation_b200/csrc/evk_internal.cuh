@@ -209,6 +209,7 @@ struct evk_handle {
     evk_ds_params win_ds{};
     evk_km_params win_km{};
     int64_t win_us = 0, win_start = 0;
+    size_t win_events = 0;  // > 0: windows of exactly this many events (evk_window_config_events)
     bool win_started = false;
     size_t win_pending = 0;  // events of the open window already on the device (d_win_stage)
     evk_event* d_win_stage = nullptr;  // [max_events], lazy

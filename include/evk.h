@@ -193,6 +193,10 @@ EVK_API int evk_downsample(evk_handle* h, const evk_ds_params* p, size_t* n_uniq
  * Any of keys / reps / first_idx may be NULL.  cap = capacity of the arrays in records. */
 EVK_API int evk_get_voxels(evk_handle* h, uint64_t* keys, evk_event* reps, uint32_t* first_idx,
                            size_t cap);
+/* The counters of the current voxel shard -- what the last evk_downsample, fused step or completed
+ * window produced (the reads of unique_count / repeated_count, ACCEL/store.cpp:418-430).
+ * EVK_ERR_STATE (and zeros) when there is none. */
+EVK_API int evk_num_voxels(const evk_handle* h, size_t* n_unique, size_t* n_repeated);
 
 /* ---- cluster ------------------------------------------------------------------------------- */
 /* Replaces the host-initialised float centroids[16] (KM/assign_to_centers2.c:131). K*D floats. */
@@ -239,6 +243,10 @@ EVK_API int evk_get_centroids(evk_handle* h, float* c, uint64_t* counts);
  * the number of windows completed by this call (may be NULL). */
 EVK_API int evk_window_config(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
                               int64_t window_us);
+/* The reslicer's other condition, make_n_events(nevents) (SAMP/store.cpp:336, ACCEL/store.cpp:350):
+ * a window is complete after exactly n_events events; its time bins start at its first event. */
+EVK_API int evk_window_config_events(evk_handle* h, const evk_ds_params* ds,
+                                     const evk_km_params* km, size_t n_events);
 EVK_API int evk_window_push(evk_handle* h, const evk_event* begin, const evk_event* end,
                             int* windows_done);
 EVK_API int evk_window_flush(evk_handle* h, int* windows_done);

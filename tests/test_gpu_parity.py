@@ -329,6 +329,39 @@ def test_streaming_windows(evk, orc):
     np.testing.assert_allclose(cents[-1], last, rtol=CENT_RTOL, atol=0)
 
 
+def test_streaming_windows_by_event_count(evk, orc):
+    """the reslicer's make_n_events condition (SAMP/store.cpp:336): windows of exactly n events,
+    time bins starting at the window's first event, centroids warm-started across windows"""
+    n, W, H, K, per = 330_000, 346, 260, 8, 100_000
+    ev = orc.synth(orc.synth_params(0xE7CA0006, n, W, H, 2_000_000, K))
+    ds = evk.ds_params(W, H, 4, 4, 1000, 0, 1)
+    km = evk.km_params(K, 2, iters=2)
+    got = []
+    with evk.Evk(per) as h:
+        h.window_config_events(ds, km, per)
+        done = 0
+        for a, b in zip([0, 7, 99_999, 100_000, 250_001], [7, 99_999, 100_000, 250_001, n]):
+            d = h.window_push(ev[a:b])
+            done += d
+            if d:
+                got.append((h.get_voxels(reps=False)[0].copy(), h.get_centroids(K, 2)[0].copy()))
+        assert done == 3
+        assert h.window_flush() == 1            # the 30 000-event remainder
+        got.append((h.get_voxels(reps=False)[0].copy(), h.get_centroids(K, 2)[0].copy()))
+        with pytest.raises(evk.EvkError):
+            h.window_config_events(ds, km, per + 1)   # beyond the handle capacity
+    cent = None
+    for w in range(4):
+        e = ev[w * per:(w + 1) * per]
+        ok, of, _ = orc.downsample(e, orc.ds_params(W, H, 4, 4, 1000, int(e["t"][0]), 1))
+        assert (got[w][0] == ok).all()
+        pts = orc.points(e, of, 2)
+        if cent is None:
+            cent = pts[:K].copy()
+        cent, _, _, _ = orc.kmeans(pts, cent, iters=2)
+        np.testing.assert_allclose(got[w][1], cent, rtol=CENT_RTOL, atol=0)
+
+
 def test_full_size_properties(evk, orc):
     """BASELINE config C3 at full size (100 M Gen4 events): size-independent properties —
     slab and table agree on counts and on an order-independent checksum of the key set, the
