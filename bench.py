@@ -387,13 +387,17 @@ def _main(args, real_stdout):
     # ---- timed region: K steps, inputs resident in HBM -----------------------------------------
     # One GPU, fused step: the K steps are QUEUED (evk_downsample_kmeans_submit) and collected by
     # one evk_downsample_kmeans_wait -- a slice pipeline never idles the device between slices
-    # (the synchronous call costs one host wake-up + relaunch, ~40 us, per step).  Sharded and
-    # unfused runs synchronise inside every step.
-    pipelined = world == 1 and not args.unfused and not args.sync_steps
+    # (the synchronous call costs one host wake-up + relaunch per step); sharded runs queue
+    # evk_downsample_kmeans_sharded_submit the same way.  Unfused runs synchronise inside every step.
+    pipelined = not args.unfused and not args.sync_steps
     launches = 0
     clk_t0 = time.time()
     h.timer_start()
-    if pipelined:
+    if pipelined and world > 1:
+        for _ in range(args.steps):
+            h.downsample_kmeans_sharded_submit(ds, km, True, owner)
+        state["U_local"], state["U"], _ = h.downsample_kmeans_sharded_wait()
+    elif pipelined:
         for _ in range(args.steps):
             h.downsample_kmeans_submit(ds, km, True)
         u, r, _ = h.downsample_kmeans_wait()
@@ -510,8 +514,9 @@ def _main(args, real_stdout):
                          "measured": "CUDA events around every stage, second pass of the same "
                                      "K steps run synchronously (one host sync per step)",
                          "ms_per_step_synchronous": sync_ms_per_step},
-            "submission": ("pipelined: K x evk_downsample_kmeans_submit + one "
-                           "evk_downsample_kmeans_wait" if pipelined
+            "submission": ("pipelined: K x evk_downsample_kmeans%s_submit + one "
+                           "evk_downsample_kmeans%s_wait" % (("_sharded",) * 2 if world > 1 else ("", ""))
+                           if pipelined
                            else "synchronous: one host sync per step"),
             "step_roofline": {"algorithmic_bytes": step_bytes,
                               "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,

@@ -92,6 +92,7 @@ SYMBOLS = [
     "evk_comm_unique_id", "evk_comm_init", "evk_comm_destroy", "evk_set_shard",
     "evk_downsample_sharded", "evk_kmeans_sharded", "evk_init_centroids_first_k_sharded",
     "evk_downsample_kmeans_sharded", "evk_downsample_kmeans_submit", "evk_downsample_kmeans_wait",
+    "evk_downsample_kmeans_sharded_submit", "evk_downsample_kmeans_sharded_wait",
     "evk_aec_create", "evk_aec_destroy", "evk_aec_update", "evk_aec_update_voxels",
     "evk_aec_get_clusters", "evk_aec_get_points", "evk_aec_report",
 ]
@@ -135,6 +136,9 @@ def lib():
         "evk_downsample_kmeans_submit": [vp, C.POINTER(DsParams), C.POINTER(KmParams), i32],
         "evk_downsample_kmeans_wait": [vp, psz, psz, C.POINTER(i32)],
         "evk_get_labels": [vp, vp, sz],
+        "evk_downsample_kmeans_sharded_submit": [vp, C.POINTER(DsParams), C.POINTER(KmParams), i32,
+                                                 i32],
+        "evk_downsample_kmeans_sharded_wait": [vp, psz, psz, C.POINTER(i32)],
         "evk_aec_create": [vp, C.POINTER(AecParams)],
         "evk_aec_destroy": [vp],
         "evk_aec_update": [vp, vp, sz],
@@ -509,6 +513,19 @@ class Evk:
                                                        C.byref(ul), C.byref(ug), C.byref(it)))
         self.n_unique = ul.value
         self._km = km
+        return ul.value, ug.value, it.value
+
+    def downsample_kmeans_sharded_submit(self, ds, km, init_first_k=True, owner_mode=0):
+        self._ck(self._L.evk_downsample_kmeans_sharded_submit(
+            self._h, C.byref(ds), C.byref(km), 1 if init_first_k else 0, owner_mode))
+        self._km = km
+
+    def downsample_kmeans_sharded_wait(self):
+        """(n_unique_local, n_unique_global, iters_done) of the last queued sharded step"""
+        ul, ug, it = C.c_size_t(0), C.c_size_t(0), C.c_int(0)
+        self._ck(self._L.evk_downsample_kmeans_sharded_wait(self._h, C.byref(ul), C.byref(ug),
+                                                            C.byref(it)))
+        self.n_unique = ul.value
         return ul.value, ug.value, it.value
 
     def kmeans_sharded(self, km):

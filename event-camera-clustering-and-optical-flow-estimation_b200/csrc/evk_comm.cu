@@ -112,6 +112,8 @@ struct CommState {
     const evk_event* peer_events[64] = {};          // [r]: rank r's event buffer
     Mailbox** d_peer_mail = nullptr;                // the table above, on the device
     cudaGraphExec_t step_exec = nullptr;  // the fused sharded step as one graph
+    int step_owner = 0;                   // evk_downsample_kmeans_sharded_submit: owner mode,
+    bool step_fusable = false;            // and whether the submission went out as the graph
     FusedKey step_key{};
     int step_launches = 0;
 };
@@ -877,9 +879,14 @@ static int enqueue_fused_sharded(evk_handle* h, const KeyParams& kp, const evk_d
 // (after giving its first partial bin to the previous rank and keeping the next rank's) stays on
 // the device.  Anything the fused pass does not take -- other ownership mode, D > 2, several
 // iterations, an unordered stream on any rank -- runs the separate sharded calls.
-int evk_downsample_kmeans_sharded(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
-                                  int init_first_k, int owner_mode, size_t* n_unique_local,
-                                  size_t* n_unique_global, int* iters_done) {
+// Submission half of the fused sharded step: a fusable shape goes out as one graph launch per rank
+// and returns (h->step_pending = 1); steps may be queued behind each other -- every flag of the
+// peer-memory exchange is a device-side sequence number and the mailboxes are double-buffered by
+// step parity, and no rank can run more than one step ahead of its slowest peer (it needs that
+// peer's partial sums to finish a step).  Other shapes run the three calls synchronously here.
+int evk_downsample_kmeans_sharded_submit(evk_handle* h, const evk_ds_params* ds,
+                                         const evk_km_params* km, int init_first_k,
+                                         int owner_mode) {
     if (!h) return EVK_ERR_INVALID;
     if (!h->comm) return evk_fail(h, EVK_ERR_COMM, "evk_comm_init has not been called");
     EVK_TRY(evk_km_validate(h, km));
@@ -887,7 +894,8 @@ int evk_downsample_kmeans_sharded(evk_handle* h, const evk_ds_params* ds, const 
     EVK_TRY(evk_make_key_params(h, ds, &kp));
     CommState* c = h->comm;
     EVK_CUDA(h, cudaSetDevice(h->device));
-    if (!init_first_k && (!h->have_centroids || h->K != km->K || h->D != km->D))
+    if (!init_first_k && h->step_pending != 1 &&
+        (!h->have_centroids || h->K != km->K || h->D != km->D))
         return evk_fail(h, EVK_ERR_STATE, "centroids for K=%d, D=%d have not been set", km->K, km->D);
     const size_t n_own = h->n_events;
     const uint32_t halo = c->halo;
@@ -902,49 +910,87 @@ int evk_downsample_kmeans_sharded(evk_handle* h, const evk_ds_params* ds, const 
         probe_shape.sm_count = h->sm_count;
         fusable = evk_slab_supported(&probe_shape, kp);
     }
-    bool done = false;
-    if (fusable) {
-        if (n_own + halo > h->max_events)
-            return evk_fail(h, EVK_ERR_CAPACITY,
-                            "sharded downsample needs max_events >= n_events + %u (halo)", halo);
-        if (!evk_ensure_images(h, ds->width, ds->height))
-            return evk_fail(h, EVK_ERR_NOMEM, "pixel images");
-        evk_invalidate_results(h);
-        h->ds = *ds;
-        h->kp = kp;
-        h->have_ds = true;
-        // one CUDA graph (NCCL operations included), re-captured only when the call's shape changes
-        FusedKey key;
-        memset(&key, 0, sizeof key);
-        key.n = n_own;
-        key.ds = *ds;
-        key.km = *km;
-        key.init = init_first_k ? 1 : 0;
-        key.profiling = h->profiling ? 1 : 0;
-        key.shard_first = h->shard_first;
-        int launches = 0;
-        if (c->step_exec && memcmp(&key, &c->step_key, sizeof key) == 0) {
-            launches = c->step_launches;
-        } else {
-            if (c->step_exec) cudaGraphExecDestroy(c->step_exec);
-            c->step_exec = nullptr;
-            cudaGraph_t graph = nullptr;
-            EVK_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            const int st_enq = enqueue_fused_sharded(h, kp, ds, km, init_first_k, &launches);
-            cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-            if (st_enq != EVK_OK) {
-                if (graph) cudaGraphDestroy(graph);
-                cudaGetLastError();
-                return st_enq;
-            }
-            EVK_CUDA(h, ce);
-            ce = cudaGraphInstantiate(&c->step_exec, graph, 0);
-            cudaGraphDestroy(graph);
-            EVK_CUDA(h, ce);
-            c->step_key = key;
-            c->step_launches = launches;
+    h->step_ds = *ds;
+    h->step_km = *km;
+    h->step_init = init_first_k;
+    h->step_iters = 0;
+    c->step_owner = owner_mode;
+    c->step_fusable = fusable;
+    if (!fusable) {
+        if (h->step_pending == 1)
+            EVK_TRY(evk_downsample_kmeans_sharded_wait(h, nullptr, nullptr, nullptr));
+        h->step_pending = 0;
+        EVK_TRY(evk_downsample_sharded(h, ds, owner_mode, nullptr, nullptr));
+        if (init_first_k) EVK_TRY(evk_init_centroids_first_k_sharded(h, km));
+        EVK_TRY(evk_kmeans_sharded(h, km, &h->step_iters));
+        h->step_pending = 2;
+        return EVK_OK;
+    }
+    if (n_own + halo > h->max_events)
+        return evk_fail(h, EVK_ERR_CAPACITY,
+                        "sharded downsample needs max_events >= n_events + %u (halo)", halo);
+    if (!evk_ensure_images(h, ds->width, ds->height))
+        return evk_fail(h, EVK_ERR_NOMEM, "pixel images");
+    evk_invalidate_results(h);
+    h->ds = *ds;
+    h->kp = kp;
+    h->have_ds = true;
+    // one CUDA graph (NCCL operations included), re-captured only when the call's shape changes
+    FusedKey key;
+    memset(&key, 0, sizeof key);
+    key.n = n_own;
+    key.ds = *ds;
+    key.km = *km;
+    key.init = init_first_k ? 1 : 0;
+    key.profiling = h->profiling ? 1 : 0;
+    key.shard_first = h->shard_first;
+    int launches = 0;
+    if (c->step_exec && memcmp(&key, &c->step_key, sizeof key) == 0) {
+        launches = c->step_launches;
+    } else {
+        if (h->step_pending == 1)  // the graph in flight is about to be replaced
+            EVK_TRY(evk_downsample_kmeans_sharded_wait(h, nullptr, nullptr, nullptr));
+        if (c->step_exec) cudaGraphExecDestroy(c->step_exec);
+        c->step_exec = nullptr;
+        cudaGraph_t graph = nullptr;
+        EVK_CUDA(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        const int st_enq = enqueue_fused_sharded(h, kp, ds, km, init_first_k, &launches);
+        cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+        if (st_enq != EVK_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            return st_enq;
         }
-        EVK_CUDA(h, cudaGraphLaunch(c->step_exec, h->stream));
+        EVK_CUDA(h, ce);
+        ce = cudaGraphInstantiate(&c->step_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        EVK_CUDA(h, ce);
+        c->step_key = key;
+        c->step_launches = launches;
+    }
+    EVK_CUDA(h, cudaGraphLaunch(c->step_exec, h->stream));
+    h->step_pending = 1;
+    return EVK_OK;
+}
+
+// Collection half: the step's one host synchronisation; a step the fast path gave up on (unordered
+// stream somewhere, peer-memory time-out) is rerun on the general path -- every rank sees the same
+// flags, so every rank takes the same branch.
+int evk_downsample_kmeans_sharded_wait(evk_handle* h, size_t* n_unique_local,
+                                       size_t* n_unique_global, int* iters_done) {
+    if (!h) return EVK_ERR_INVALID;
+    if (!h->comm) return evk_fail(h, EVK_ERR_COMM, "evk_comm_init has not been called");
+    if (!h->step_pending)
+        return evk_fail(h, EVK_ERR_STATE, "evk_downsample_kmeans_sharded_wait: nothing submitted");
+    CommState* c = h->comm;
+    const int pending = h->step_pending;
+    h->step_pending = 0;
+    if (pending == 1) {
+        EVK_CUDA(h, cudaSetDevice(h->device));
+        const evk_ds_params* ds = &h->step_ds;
+        const evk_km_params* km = &h->step_km;
+        const int init_first_k = h->step_init;
+        const int launches = c->step_launches;
         EVK_CUDA(h, cudaStreamSynchronize(h->stream));
         if (c->h_stats[0] >> 32) {  // a peer-memory wait timed out somewhere: NCCL from now on
             c->p2p = false;
@@ -976,22 +1022,35 @@ int evk_downsample_kmeans_sharded(evk_handle* h, const evk_ds_params* ds, const 
                     h->times.km_total_ms = h->times.km_assign_ms = ms;
                 cudaGetLastError();
             }
-            if (iters_done) *iters_done = 1;
-            done = true;
-        } else if (!init_first_k) {  // finalise has overwritten the caller's centroids
-            EVK_CUDA(h, cudaMemcpyAsync(h->d_cent, h->d_cent + EVK_MAX_K * 2,
-                                        (size_t)km->K * 2 * sizeof(float),
-                                        cudaMemcpyDeviceToDevice, h->stream));
+            h->step_iters = 1;
+        } else {
+            if (!init_first_k) {  // finalise has overwritten the caller's centroids
+                if (!h->have_centroids || h->K != km->K || h->D != km->D)
+                    return evk_fail(h, EVK_ERR_STATE,
+                                    "centroids for K=%d, D=%d have not been set", km->K, km->D);
+                EVK_CUDA(h, cudaMemcpyAsync(h->d_cent, h->d_cent + EVK_MAX_K * 2,
+                                            (size_t)km->K * 2 * sizeof(float),
+                                            cudaMemcpyDeviceToDevice, h->stream));
+            }
+            EVK_TRY(evk_downsample_sharded(h, ds, EVK_OWNER_MIX64, nullptr, nullptr));
+            if (init_first_k) EVK_TRY(evk_init_centroids_first_k_sharded(h, km));
+            EVK_TRY(evk_kmeans_sharded(h, km, &h->step_iters));
         }
-    }
-    if (!done) {
-        EVK_TRY(evk_downsample_sharded(h, ds, fusable ? EVK_OWNER_MIX64 : owner_mode, nullptr, nullptr));
-        if (init_first_k) EVK_TRY(evk_init_centroids_first_k_sharded(h, km));
-        EVK_TRY(evk_kmeans_sharded(h, km, iters_done));
     }
     if (n_unique_local) *n_unique_local = h->n_unique;
     if (n_unique_global) *n_unique_global = (size_t)c->h_stats[ST_U];
+    if (iters_done) *iters_done = h->step_iters;
     return EVK_OK;
+}
+
+int evk_downsample_kmeans_sharded(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
+                                  int init_first_k, int owner_mode, size_t* n_unique_local,
+                                  size_t* n_unique_global, int* iters_done) {
+    if (!h) return EVK_ERR_INVALID;
+    if (h->step_pending && h->comm)
+        EVK_TRY(evk_downsample_kmeans_sharded_wait(h, nullptr, nullptr, nullptr));
+    EVK_TRY(evk_downsample_kmeans_sharded_submit(h, ds, km, init_first_k, owner_mode));
+    return evk_downsample_kmeans_sharded_wait(h, n_unique_local, n_unique_global, iters_done);
 }
 
 int evk_init_centroids_first_k_sharded(evk_handle* h, const evk_km_params* p) {

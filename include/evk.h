@@ -341,6 +341,14 @@ EVK_API int evk_downsample_kmeans_sharded(evk_handle* h, const evk_ds_params* ds
                                           const evk_km_params* km, int init_first_k,
                                           int owner_mode, size_t* n_unique_local,
                                           size_t* n_unique_global, int* iters_done);
+/* The same step in two halves (see evk_downsample_kmeans_submit / _wait): every rank queues its
+ * pass, steps may be queued behind each other, wait is the one synchronisation.  Ranks must make
+ * the same sequence of calls. */
+EVK_API int evk_downsample_kmeans_sharded_submit(evk_handle* h, const evk_ds_params* ds,
+                                                 const evk_km_params* km, int init_first_k,
+                                                 int owner_mode);
+EVK_API int evk_downsample_kmeans_sharded_wait(evk_handle* h, size_t* n_unique_local,
+                                               size_t* n_unique_global, int* iters_done);
 /* broadcast-free deterministic init: the K globally lowest first indices */
 EVK_API int evk_init_centroids_first_k_sharded(evk_handle* h, const evk_km_params* p);
 

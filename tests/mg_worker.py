@@ -100,8 +100,19 @@ def main():
             assert (counts == ocnt1).all() and np.allclose(cent, oc1, rtol=1e-5, atol=0)
             lab = h.get_labels()
             assert (lab == ol1[np.searchsorted(of, first)]).all()
+        # the same step queued three times behind each other, one wait: same result
+        h.synth(evk.synth_params(seed, n, W, H, rate, blobs, first_index=rank * n))
+        for _ in range(3):
+            h.downsample_kmeans_sharded_submit(ds, km1, True, evk.OWNER_TIME_RANGE)
+        ul2, ug2, it2 = h.downsample_kmeans_sharded_wait()
+        assert (ul2, ug2, it2) == (ul, ug, 1)
+        keys2, _, first2 = h.get_voxels(reps=False)
+        assert (np.sort(first2) == np.sort(first)).all()
+        cent2, counts2 = h.get_centroids(K, 2)
+        assert (counts2 == counts).all() and (cent2 == cent).all()
+        assert (h.get_labels() == ol1[np.searchsorted(of, first2)]).all()
         if rank == 0:
-            print(f"mg ok: {name} fused sharded step world={world} U={ug}", flush=True)
+            print(f"mg ok: {name} fused sharded step world={world} U={ug} (also queued x3)", flush=True)
         # unordered stream: the time-range scheme must detect it on every rank and fall back
         rng = np.random.default_rng(5)
         perm = rng.permutation(total)
