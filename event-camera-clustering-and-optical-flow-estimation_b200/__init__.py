@@ -95,6 +95,7 @@ SYMBOLS = [
     "evk_downsample_kmeans_sharded_submit", "evk_downsample_kmeans_sharded_wait",
     "evk_aec_create", "evk_aec_destroy", "evk_aec_update", "evk_aec_update_voxels",
     "evk_aec_get_clusters", "evk_aec_get_points", "evk_aec_report",
+    "evk_ts_create", "evk_ts_destroy", "evk_ts_corners", "evk_ts_get_corners", "evk_ts_get_surface",
 ]
 
 _lib = None
@@ -146,6 +147,11 @@ def lib():
         "evk_aec_get_clusters": [vp, vp, sz, psz, C.POINTER(i32)],
         "evk_aec_get_points": [vp, sz, vp, vp, vp, vp, sz, psz],
         "evk_aec_report": [vp, vp, sz, psz],
+        "evk_ts_create": [vp, i32, i32],
+        "evk_ts_destroy": [vp],
+        "evk_ts_corners": [vp, i32, psz],
+        "evk_ts_get_corners": [vp, vp, sz],
+        "evk_ts_get_surface": [vp, vp, sz],
         "evk_get_centroids": [vp, vp, vp],
         "evk_window_config": [vp, C.POINTER(DsParams), C.POINTER(KmParams), C.c_int64],
         "evk_window_config_events": [vp, C.POINTER(DsParams), C.POINTER(KmParams), sz],
@@ -420,6 +426,26 @@ class Evk:
         n = C.c_size_t(0)
         self._ck(self._L.evk_aec_report(self._h, _p(out), len(out), C.byref(n)))
         return out[: n.value].copy()
+
+    # ---- time surface + corner test (evk_ts_*) ----------------------------------------------
+    def ts_create(self, width, height):
+        self._ck(self._L.evk_ts_create(self._h, width, height))
+        self._ts_shape = (height, width)
+
+    def ts_corners(self, literal_break=True):
+        """one callback range = the resident events: stamp the surface, test every event;
+        returns the stream indices of the corner events"""
+        n = C.c_size_t(0)
+        self._ck(self._L.evk_ts_corners(self._h, 1 if literal_break else 0, C.byref(n)))
+        idx = np.zeros(n.value, np.uint32)
+        if n.value:
+            self._ck(self._L.evk_ts_get_corners(self._h, _p(idx), len(idx)))
+        return idx
+
+    def ts_surface(self):
+        out = np.zeros(self._ts_shape, np.int64)
+        self._ck(self._L.evk_ts_get_surface(self._h, _p(out), out.size))
+        return out
 
     def get_labels(self, n=None):
         if n is None:

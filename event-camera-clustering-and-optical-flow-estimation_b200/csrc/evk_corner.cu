@@ -1,0 +1,284 @@
+// evk_corner.cu — time surface + per-event corner test on the device.
+//
+// Reference: the event callback of the corner tracker, event-cam-tracking/
+// event-cam-fast-corner-tracker/metavision_time_surface_periodic_group_track.cpp (FCT below):
+//   :786       Metavision::MostRecentTimestampBuffer time_surface(height, width, 1), zero-initialised
+//   :888-923   every event of the callback range stamps its pixel: surface[y][x] = t (stream order,
+//              the last one wins)
+//   :931-1057  then every event of the range is tested against the UPDATED surface (the update
+//              inside that loop is commented out, :935): a streak of 3..6 newest pixels on the
+//              16-pixel circle of radius 3 (:44) AND a streak of 4..8 on the 20-pixel circle of
+//              radius 4 (:45) -- the Arc*-style test of the event-based FAST family
+//   :948-955   an event closer than 4 pixels to the border BREAKS the loop (the rest of the range is
+//              not tested); the evident intent is `continue`.  Both are offered (literal_break).
+// Because the surface is frozen while the range is tested, the tests are independent: one thread per
+// event, 36 gathers from an L2-resident int64 image (7.4 MB for Gen4) -- a gather / issue-bound
+// kernel, not an HBM-bound one.  Algorithmic bytes per event: 16 (read the event) + 8 (stamp) +
+// 36 x 8 (circle reads, L2) + 1 (flag).
+//   k_ts_stamp_idx   atomicMax of (stream index + 1) per pixel: which event stamps last; also the
+//                    index of the first border event (atomicMin)
+//   k_ts_stamp_t     the winner writes its timestamp and clears the index image (self-cleaning: no
+//                    memset per call)
+//   k_corner_detect  the two streak tests per event, flag + per-block corner count
+//   k_corner_prefix / k_corner_scatter   ordered compaction of the corner events' stream indices
+#include "evk_internal.cuh"
+
+namespace {
+
+constexpr int kT = 256;
+
+__constant__ int c_circle3[16][2] = {{0, 3},  {1, 3},  {2, 2},  {3, 1},   {3, 0},   {3, -1},
+                                     {2, -2}, {1, -3}, {0, -3}, {-1, -3}, {-2, -2}, {-3, -1},
+                                     {-3, 0}, {-3, 1}, {-2, 2}, {-1, 3}};
+__constant__ int c_circle4[20][2] = {{0, 4},   {1, 4},  {2, 3},  {3, 2},  {4, 1},  {4, 0},  {4, -1},
+                                     {3, -2},  {2, -3}, {1, -4}, {0, -4}, {-1, -4}, {-2, -3}, {-3, -2},
+                                     {-4, -1}, {-4, 0}, {-4, 1}, {-3, 2}, {-2, 3}, {-1, 4}};
+
+struct TsScalars {
+    unsigned long long first_border;  // stream index of the first event within 4 px of the border
+    unsigned long long n_corners;
+};
+
+__device__ __forceinline__ bool is_border(uint32_t x, uint32_t y, int W, int H) {
+    return x < 4u || x >= (uint32_t)(W - 4) || y < 4u || y >= (uint32_t)(H - 4);
+}
+
+__global__ void __launch_bounds__(kT)
+    k_ts_stamp_idx(const evk_event* __restrict__ ev, size_t n, int W, int H, uint32_t* last_idx,
+                   TsScalars* sc) {
+    const size_t i = (size_t)blockIdx.x * kT + threadIdx.x;
+    if (i >= n) return;
+    const uint4 e = ld_event(ev + i);
+    const uint32_t x = ev_x(e), y = ev_y(e);
+    if (x < (uint32_t)W && y < (uint32_t)H) atomicMax(&last_idx[(size_t)y * W + x], (uint32_t)i + 1u);
+    if (is_border(x, y, W, H)) atomicMin(&sc->first_border, (unsigned long long)i);
+}
+
+__global__ void __launch_bounds__(kT)
+    k_ts_stamp_t(const evk_event* __restrict__ ev, size_t n, int W, int H, uint32_t* last_idx,
+                 long long* surf) {
+    const size_t i = (size_t)blockIdx.x * kT + threadIdx.x;
+    if (i >= n) return;
+    const uint4 e = ld_event(ev + i);
+    const uint32_t x = ev_x(e), y = ev_y(e);
+    if (x >= (uint32_t)W || y >= (uint32_t)H) return;
+    const size_t p = (size_t)y * W + x;
+    if (last_idx[p] == (uint32_t)i + 1u) {
+        surf[p] = ev_t(e);
+        last_idx[p] = 0u;
+    }
+}
+
+// the streak test of FCT:958-1003 (circle of N pixels, streak sizes SMIN..SMAX) on the N surface
+// values t[] read around the event
+template <int N, int SMIN, int SMAX>
+__device__ __forceinline__ bool streak(const long long (&t)[N]) {
+    for (int i = 0; i < N; i++) {
+        const int im1 = i == 0 ? N - 1 : i - 1;
+        if (t[i] < t[im1]) continue;  // (the same for every streak size)
+        for (int sz = SMIN; sz <= SMAX; sz++) {
+            int a = i + sz - 1, b = i + sz;
+            if (a >= N) a -= N;
+            if (b >= N) b -= N;
+            if (t[a] < t[b]) continue;
+            long long min_t = t[i];
+            int k = i;
+            for (int j = 1; j < sz; j++) {
+                k = k + 1 == N ? 0 : k + 1;
+                min_t = t[k] < min_t ? t[k] : min_t;
+            }
+            bool ok = true;
+            for (int j = sz; j < N; j++) {
+                k = k + 1 == N ? 0 : k + 1;
+                if (t[k] >= min_t) {
+                    ok = false;
+                    break;
+                }
+            }
+            if (ok) return true;
+        }
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(kT)
+    k_corner_detect(const evk_event* __restrict__ ev, size_t n, int W, int H,
+                    const long long* __restrict__ surf, const TsScalars* sc, int literal_break,
+                    uint8_t* flags, uint32_t* blk_cnt) {
+    const size_t i = (size_t)blockIdx.x * kT + threadIdx.x;
+    const size_t limit = literal_break ? (size_t)min(sc->first_border, (unsigned long long)n) : n;
+    bool corner = false;
+    if (i < limit) {
+        const uint4 e = ld_event(ev + i);
+        const int x = (int)ev_x(e), y = (int)ev_y(e);
+        if (!is_border((uint32_t)x, (uint32_t)y, W, H)) {
+            long long t3[16];
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                t3[k] = surf[(size_t)(y + c_circle3[k][0]) * W + (x + c_circle3[k][1])];
+            if (streak<16, 3, 6>(t3)) {
+                long long t4[20];
+#pragma unroll
+                for (int k = 0; k < 20; k++)
+                    t4[k] = surf[(size_t)(y + c_circle4[k][0]) * W + (x + c_circle4[k][1])];
+                corner = streak<20, 4, 8>(t4);
+            }
+        }
+    }
+    if (i < n) flags[i] = corner ? 1 : 0;
+    const int c = __syncthreads_count(corner);
+    if (threadIdx.x == 0) blk_cnt[blockIdx.x] = (uint32_t)c;
+}
+
+// one CTA: exclusive scan of the per-block corner counts, in place; total -> sc->n_corners
+__global__ void __launch_bounds__(1024)
+    k_corner_prefix(uint32_t* blk, uint32_t nb, TsScalars* sc) {
+    __shared__ unsigned long long s_sum[1024];
+    const uint32_t per = (nb + 1023) / 1024;
+    const uint32_t b0 = min(nb, threadIdx.x * per), b1 = min(nb, b0 + per);
+    unsigned long long sum = 0;
+    for (uint32_t b = b0; b < b1; b++) sum += blk[b];
+    s_sum[threadIdx.x] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned long long a = 0;
+        if ((int)threadIdx.x >= o) a = s_sum[threadIdx.x - o];
+        __syncthreads();
+        s_sum[threadIdx.x] += a;
+        __syncthreads();
+    }
+    unsigned long long off = threadIdx.x ? s_sum[threadIdx.x - 1] : 0ull;
+    for (uint32_t b = b0; b < b1; b++) {
+        const uint32_t c = blk[b];
+        blk[b] = (uint32_t)off;
+        off += c;
+    }
+    if (threadIdx.x == 1023) sc->n_corners = s_sum[1023];
+}
+
+__global__ void __launch_bounds__(kT)
+    k_corner_scatter(const uint8_t* __restrict__ flags, size_t n, const uint32_t* __restrict__ blk_off,
+                     uint32_t* out) {
+    __shared__ uint32_t s_w[kT / 32];
+    const size_t i = (size_t)blockIdx.x * kT + threadIdx.x;
+    const bool c = i < n && flags[i];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(0xffffffffu, c);
+    if (lane == 0) s_w[wid] = __popc(bal);
+    __syncthreads();
+    uint32_t base = blk_off[blockIdx.x];
+    for (int k = 0; k < wid; k++) base += s_w[k];
+    if (c) out[base + __popc(bal & ((1u << lane) - 1u))] = (uint32_t)i;
+}
+
+}  // namespace
+
+struct TsHost {
+    int W = 0, H = 0;
+    long long* d_surf = nullptr;     // [H][W] most recent timestamp per pixel
+    uint32_t* d_last = nullptr;      // [H][W] scratch: index + 1 of the last event at the pixel
+    uint8_t* d_flags = nullptr;      // [max_events]
+    uint32_t* d_blk = nullptr;       // [max_events / kT + 1]
+    uint32_t* d_corners = nullptr;   // [max_events] stream indices of the corner events
+    TsScalars* d_sc = nullptr;
+    size_t n_corners = 0;
+    bool have = false;
+};
+
+extern "C" {
+
+int evk_ts_destroy(evk_handle* h) {
+    if (!h || !h->ts) return EVK_OK;
+    TsHost* t = h->ts;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* ptrs[] = {t->d_surf, t->d_last, t->d_flags, t->d_blk, t->d_corners, t->d_sc};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete t;
+    h->ts = nullptr;
+    return EVK_OK;
+}
+
+int evk_ts_create(evk_handle* h, int width, int height) {
+    if (!h) return EVK_ERR_INVALID;
+    if (width < 9 || height < 9 || width > 65535 || height > 65535)
+        return evk_fail(h, EVK_ERR_INVALID, "evk_ts_create: %d x %d", width, height);
+    evk_ts_destroy(h);
+    cudaSetDevice(h->device);
+    TsHost* t = new TsHost;
+    t->W = width;
+    t->H = height;
+    const size_t px = (size_t)width * height, ne = h->max_events ? h->max_events : 1;
+    cudaError_t ce = cudaMalloc((void**)&t->d_surf, px * sizeof(long long));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&t->d_last, px * sizeof(uint32_t));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&t->d_flags, ne);
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&t->d_blk, (ne / kT + 2) * sizeof(uint32_t));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&t->d_corners, ne * sizeof(uint32_t));
+    if (ce == cudaSuccess) ce = cudaMalloc((void**)&t->d_sc, sizeof(TsScalars));
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(t->d_surf, 0, px * sizeof(long long), h->stream);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(t->d_last, 0, px * sizeof(uint32_t), h->stream);
+    h->ts = t;
+    if (ce != cudaSuccess) {
+        cudaGetLastError();
+        evk_ts_destroy(h);
+        return evk_fail(h, EVK_ERR_NOMEM, "evk_ts_create: %s", cudaGetErrorString(ce));
+    }
+    return EVK_OK;
+}
+
+int evk_ts_corners(evk_handle* h, int literal_break, size_t* n_corners) {
+    if (!h) return EVK_ERR_INVALID;
+    if (!h->ts) return evk_fail(h, EVK_ERR_STATE, "evk_ts_create has not been called");
+    TsHost* t = h->ts;
+    cudaSetDevice(h->device);
+    const size_t n = h->n_events;
+    t->n_corners = 0;
+    t->have = true;
+    if (n_corners) *n_corners = 0;
+    if (n == 0) return EVK_OK;
+    const unsigned nb = (unsigned)((n + kT - 1) / kT);
+    const TsScalars init = {~0ull, 0ull};
+    EVK_CUDA(h, cudaMemcpyAsync(t->d_sc, &init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+    k_ts_stamp_idx<<<nb, kT, 0, h->stream>>>(h->d_events, n, t->W, t->H, t->d_last, t->d_sc);
+    k_ts_stamp_t<<<nb, kT, 0, h->stream>>>(h->d_events, n, t->W, t->H, t->d_last, t->d_surf);
+    k_corner_detect<<<nb, kT, 0, h->stream>>>(h->d_events, n, t->W, t->H, t->d_surf, t->d_sc,
+                                              literal_break, t->d_flags, t->d_blk);
+    k_corner_prefix<<<1, 1024, 0, h->stream>>>(t->d_blk, nb, t->d_sc);
+    k_corner_scatter<<<nb, kT, 0, h->stream>>>(t->d_flags, n, t->d_blk, t->d_corners);
+    EVK_CUDA(h, cudaGetLastError());
+    TsScalars sc;
+    EVK_CUDA(h, cudaMemcpyAsync(&sc, t->d_sc, sizeof sc, cudaMemcpyDeviceToHost, h->stream));
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    t->n_corners = (size_t)sc.n_corners;
+    if (n_corners) *n_corners = t->n_corners;
+    return EVK_OK;
+}
+
+int evk_ts_get_corners(evk_handle* h, uint32_t* event_index, size_t cap) {
+    if (!h) return EVK_ERR_INVALID;
+    if (!h->ts || !h->ts->have) return evk_fail(h, EVK_ERR_STATE, "evk_ts_corners has not run");
+    TsHost* t = h->ts;
+    if (t->n_corners == 0) return EVK_OK;
+    if (!event_index || cap < t->n_corners)
+        return evk_fail(h, EVK_ERR_CAPACITY, "%zu corners, room for %zu", t->n_corners, cap);
+    cudaSetDevice(h->device);
+    EVK_CUDA(h, cudaMemcpyAsync(event_index, t->d_corners, t->n_corners * sizeof(uint32_t),
+                                cudaMemcpyDeviceToHost, h->stream));
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EVK_OK;
+}
+
+int evk_ts_get_surface(evk_handle* h, int64_t* out, size_t cap_pixels) {
+    if (!h) return EVK_ERR_INVALID;
+    if (!h->ts) return evk_fail(h, EVK_ERR_STATE, "evk_ts_create has not been called");
+    TsHost* t = h->ts;
+    const size_t px = (size_t)t->W * t->H;
+    if (!out || cap_pixels < px) return evk_fail(h, EVK_ERR_CAPACITY, "surface of %zu pixels", px);
+    cudaSetDevice(h->device);
+    EVK_CUDA(h, cudaMemcpyAsync(out, t->d_surf, px * sizeof(int64_t), cudaMemcpyDeviceToHost,
+                                h->stream));
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EVK_OK;
+}
+
+}  // extern "C"

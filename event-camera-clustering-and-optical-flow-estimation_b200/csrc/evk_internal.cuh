@@ -106,6 +106,7 @@ struct DsCounters {  // device-side counters, mirrored into pinned host memory a
 
 struct CommState;
 struct AecHost;  // evk_aec.cu
+struct TsHost;   // evk_corner.cu
 
 struct FusedKey {  // what the captured fused-step graph depends on
     size_t n;
@@ -223,6 +224,8 @@ struct evk_handle {
     CommState* comm = nullptr;
     // asynchronous event clustering consumer (evk_aec.cu), created by evk_aec_create
     AecHost* aec = nullptr;
+    // time surface + corner test (evk_corner.cu), created by evk_ts_create
+    TsHost* ts = nullptr;
     uint64_t shard_first = 0;
     std::string err;
 };

@@ -309,6 +309,25 @@ EVK_API int evk_aec_get_points(evk_handle* h, size_t cluster, int32_t* ids, doub
  * once per slice: it advances centroid_prev whether or not `out` has room. */
 EVK_API int evk_aec_report(evk_handle* h, evk_aec_flow* out, size_t cap, size_t* n);
 
+/* ---- time surface + corner test ----------------------------------------- */
+/* The event callback of the reference's corner tracker (event-cam-tracking/
+ * event-cam-fast-corner-tracker/metavision_time_surface_periodic_group_track.cpp, FCT): a
+ * Metavision::MostRecentTimestampBuffer (:786) stamped by every event (:888-923), then every event
+ * of the callback range tested for an Arc*-style corner on the circles of radius 3 and 4 against
+ * the updated surface (:931-1057).  One time surface per handle, zero-initialised. */
+EVK_API int evk_ts_create(evk_handle* h, int width, int height);
+EVK_API int evk_ts_destroy(evk_handle* h);
+/* One callback range = the events resident in the handle (evk_load_events ...): stamp, then test.
+ * literal_break != 0 reproduces FCT:948-955 as written (the first event within 4 px of the border
+ * ends the range's tests); 0 skips that event only.  Timestamps must stay below 2^53 (the reference
+ * compares them as doubles). */
+EVK_API int evk_ts_corners(evk_handle* h, int literal_break, size_t* n_corners);
+/* stream indices (ascending) of the corner events of the last evk_ts_corners = the events pushed to
+ * `corners` at FCT:1050 */
+EVK_API int evk_ts_get_corners(evk_handle* h, uint32_t* event_index, size_t cap);
+/* the surface, row-major [height][width] */
+EVK_API int evk_ts_get_surface(evk_handle* h, int64_t* out, size_t cap_pixels);
+
 /* ---- profiling / measurement --------------------------------------------------------------- */
 EVK_API int evk_set_profiling(evk_handle* h, int enabled);
 EVK_API int evk_get_stage_times(const evk_handle* h, evk_stage_times* out);

@@ -695,3 +695,72 @@ size_t orc_evt3_encode(const evk_event* ev, size_t n, uint16_t* words, size_t ca
 #undef PUT
     return m;
 }
+
+/* ---- time surface + corner test --------------------------------------------
+ * Restates the event callback of the reference's corner tracker, event-cam-tracking/
+ * event-cam-fast-corner-tracker/metavision_time_surface_periodic_group_track.cpp:883-1063 (the code
+ * sits inside a lambda of main() that needs the Metavision SDK, so it cannot be compiled here:
+ * PARITY UNPINNED by the reference, pinned by hand-derived known answers only).
+ *   :888-923   every event of the callback range stamps its pixel of the MostRecentTimestampBuffer
+ *              (:786, zero-initialised): surface[y][x] = t, in stream order (the last one wins)
+ *   :931-1057  then every event of the range is tested against the UPDATED surface: a streak of
+ *              3..6 newest pixels on the 16-pixel circle of radius 3 (:44) whose neighbours on both
+ *              sides are older-or-equal and whose oldest member is strictly newer than every other
+ *              pixel of the circle, and likewise a streak of 4..8 on the 20-pixel circle of radius
+ *              4 (:45); circle entry [k][0] is added to y, [k][1] to x (:962)
+ *   :948-955   events closer than 4 pixels to the border: the loop BREAKS there, i.e. the rest of
+ *              the range is not tested (literal_break != 0); the evident intent is to skip that
+ *              event only (literal_break == 0)
+ * flags[i] = 1 when event i is a corner.  Returns the number of corners. */
+static const int orc_circle3[16][2] = {{0, 3},  {1, 3},   {2, 2},   {3, 1},  {3, 0},  {3, -1},
+                                       {2, -2}, {1, -3},  {0, -3},  {-1, -3}, {-2, -2}, {-3, -1},
+                                       {-3, 0}, {-3, 1},  {-2, 2},  {-1, 3}};
+static const int orc_circle4[20][2] = {{0, 4},   {1, 4},   {2, 3},   {3, 2},  {4, 1},  {4, 0},  {4, -1},
+                                       {3, -2},  {2, -3},  {1, -4},  {0, -4}, {-1, -4}, {-2, -3}, {-3, -2},
+                                       {-4, -1}, {-4, 0},  {-4, 1},  {-3, 2}, {-2, 3}, {-1, 4}};
+static int orc_streak(const int64_t* s, int W, int x, int y, const int (*c)[2], int n, int smin,
+                      int smax) {
+#define TS(k) s[(size_t)(y + c[(k)][0]) * W + (x + c[(k)][1])]
+    for (int i = 0; i < n; i++) {
+        for (int sz = smin; sz <= smax; sz++) {
+            if (TS(i) < TS((i - 1 + n) % n)) continue;
+            if (TS((i + sz - 1) % n) < TS((i + sz) % n)) continue;
+            double min_t = (double)TS(i);
+            for (int j = 1; j < sz; j++) {
+                const double tj = (double)TS((i + j) % n);
+                if (tj < min_t) min_t = tj;
+            }
+            int did_break = 0;
+            for (int j = sz; j < n; j++) {
+                const double tj = (double)TS((i + j) % n);
+                if (tj >= min_t) {
+                    did_break = 1;
+                    break;
+                }
+            }
+            if (!did_break) return 1;
+        }
+    }
+#undef TS
+    return 0;
+}
+size_t orc_ts_corners(const evk_event* ev, size_t n, int W, int H, int64_t* surface,
+                      int literal_break, uint8_t* flags) {
+    for (size_t i = 0; i < n; i++)
+        if (ev[i].x < W && ev[i].y < H) surface[(size_t)ev[i].y * W + ev[i].x] = ev[i].t;
+    size_t nc = 0;
+    memset(flags, 0, n);
+    for (size_t i = 0; i < n; i++) {
+        const int x = ev[i].x, y = ev[i].y;
+        if (x < 4 || x >= W - 4 || y < 4 || y >= H - 4) {
+            if (literal_break) break;
+            continue;
+        }
+        if (orc_streak(surface, W, x, y, orc_circle3, 16, 3, 6) &&
+            orc_streak(surface, W, x, y, orc_circle4, 20, 4, 8)) {
+            flags[i] = 1;
+            nc++;
+        }
+    }
+    return nc;
+}

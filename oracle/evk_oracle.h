@@ -118,6 +118,9 @@ size_t orc_evt2_decode(const uint32_t* words, size_t n_words, evk_event* out, si
 size_t orc_evt2_encode(const evk_event* ev, size_t n, uint32_t* words, size_t cap);
 /* RAW EVT 3.0 (16-bit words; see evk_oracle.c): decode returns the number of CD events in the stream
  * (which may exceed cap), encode the number of words or (size_t)-1 */
+/* time surface + corner test of the reference's corner tracker (see evk_oracle.c) */
+size_t orc_ts_corners(const evk_event* ev, size_t n, int W, int H, int64_t* surface,
+                      int literal_break, uint8_t* flags);
 size_t orc_evt3_decode(const uint16_t* words, size_t n_words, evk_event* out, size_t cap);
 size_t orc_evt3_encode(const evk_event* ev, size_t n, uint16_t* words, size_t cap);
 

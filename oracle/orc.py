@@ -66,6 +66,8 @@ def lib():
         L.orc_evt2_decode.restype = sz
         L.orc_evt2_encode.argtypes = [vp, sz, vp, sz]
         L.orc_evt2_encode.restype = sz
+        L.orc_ts_corners.argtypes = [vp, sz, C.c_int, C.c_int, vp, C.c_int, vp]
+        L.orc_ts_corners.restype = sz
         L.orc_evt3_decode.argtypes = [vp, sz, vp, sz]
         L.orc_evt3_decode.restype = sz
         L.orc_evt3_encode.argtypes = [vp, sz, vp, sz]
@@ -287,3 +289,15 @@ def evt3_decode(words):
     out = np.zeros(n, dtype=EVENT_DTYPE)
     lib().orc_evt3_decode(_p(words), len(words), _p(out), n)
     return out
+
+
+def ts_corners(ev, W, H, surface, literal_break=True):
+    """one callback range of the reference's corner tracker: stamps `surface` (int64 [H, W], in
+    place) with every event, then tests every event -> indices of the corner events"""
+    ev = np.ascontiguousarray(ev, dtype=EVENT_DTYPE)
+    assert surface.dtype == np.int64 and surface.shape == (H, W) and surface.flags.c_contiguous
+    flags = np.zeros(max(len(ev), 1), np.uint8)
+    n = lib().orc_ts_corners(_p(ev), len(ev), W, H, _p(surface), 1 if literal_break else 0, _p(flags))
+    idx = np.flatnonzero(flags[:len(ev)]).astype(np.uint32)
+    assert len(idx) == n
+    return idx
