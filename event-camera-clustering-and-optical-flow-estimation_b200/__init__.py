@@ -73,6 +73,12 @@ AEC_FLOW_DTYPE = np.dtype([("id", "<i4"), ("n", "<i4"), ("centroid", "<f8", (2,)
 assert AEC_CLUSTER_DTYPE.itemsize == 40 and AEC_FLOW_DTYPE.itemsize == 64
 
 
+class DbscanParams(C.Structure):
+    _fields_ = [("eps", C.c_double), ("min_pts", C.c_int32), ("min_cluster", C.c_int32),
+                ("max_cluster", C.c_int32), ("D", C.c_int32), ("t_scale", C.c_double),
+                ("t0_us", C.c_int64)]
+
+
 class StageTimes(C.Structure):
     _fields_ = [
         ("ds_total_ms", C.c_float), ("ds_main_ms", C.c_float), ("ds_compact_ms", C.c_float),
@@ -95,6 +101,7 @@ SYMBOLS = [
     "evk_downsample_kmeans_sharded_submit", "evk_downsample_kmeans_sharded_wait",
     "evk_aec_create", "evk_aec_destroy", "evk_aec_update", "evk_aec_update_voxels",
     "evk_aec_get_clusters", "evk_aec_get_points", "evk_aec_report",
+    "evk_dbscan_points", "evk_dbscan_voxels", "evk_dbscan_get", "evk_dbscan_destroy",
     "evk_ts_create", "evk_ts_destroy", "evk_ts_corners", "evk_ts_get_corners", "evk_ts_get_surface",
 ]
 
@@ -147,6 +154,10 @@ def lib():
         "evk_aec_get_clusters": [vp, vp, sz, psz, C.POINTER(i32)],
         "evk_aec_get_points": [vp, sz, vp, vp, vp, vp, sz, psz],
         "evk_aec_report": [vp, vp, sz, psz],
+        "evk_dbscan_points": [vp, vp, sz, C.POINTER(DbscanParams), psz, psz],
+        "evk_dbscan_voxels": [vp, C.POINTER(DbscanParams), psz, psz],
+        "evk_dbscan_get": [vp, vp, sz, vp, vp, sz, vp, sz],
+        "evk_dbscan_destroy": [vp],
         "evk_ts_create": [vp, i32, i32],
         "evk_ts_destroy": [vp],
         "evk_ts_corners": [vp, i32, psz],
@@ -426,6 +437,34 @@ class Evk:
         n = C.c_size_t(0)
         self._ck(self._L.evk_aec_report(self._h, _p(out), len(out), C.byref(n)))
         return out[: n.value].copy()
+
+    # ---- DBSCAN (evk_dbscan_*) ----------------------------------------------------------------
+    def _dbscan_results(self, n_points, nc, ne):
+        labels = np.zeros(n_points, np.int32)
+        sizes, seeds = np.zeros(nc, np.uint32), np.zeros(nc, np.uint32)
+        extra = np.zeros((ne, 2), np.uint32)
+        self._ck(self._L.evk_dbscan_get(self._h, _p(labels), n_points, _p(sizes), _p(seeds), nc,
+                                        _p(extra), ne))
+        return labels, sizes, seeds, extra
+
+    def dbscan_points(self, points, eps, min_pts, min_cluster=1, max_cluster=2**31 - 1):
+        """points (n, 2) or (n, 3) -> (labels, sizes, seeds, extra pairs (point, cluster))"""
+        pts = np.asarray(points, dtype=np.float32)
+        if pts.shape[1] == 2:
+            pts = np.concatenate([pts, np.zeros((len(pts), 1), np.float32)], axis=1)
+        pts = np.ascontiguousarray(pts)
+        p = DbscanParams(eps, min_pts, min_cluster, max_cluster, 3, 0.0, 0)
+        nc, ne = C.c_size_t(0), C.c_size_t(0)
+        self._ck(self._L.evk_dbscan_points(self._h, _p(pts), len(pts), C.byref(p), C.byref(nc),
+                                           C.byref(ne)))
+        return self._dbscan_results(len(pts), nc.value, ne.value)
+
+    def dbscan_voxels(self, eps, min_pts, min_cluster=1, max_cluster=2**31 - 1, D=2, t_scale=0.0,
+                      t0_us=0):
+        p = DbscanParams(eps, min_pts, min_cluster, max_cluster, D, t_scale, t0_us)
+        nc, ne = C.c_size_t(0), C.c_size_t(0)
+        self._ck(self._L.evk_dbscan_voxels(self._h, C.byref(p), C.byref(nc), C.byref(ne)))
+        return self._dbscan_results(self.num_voxels()[0], nc.value, ne.value)
 
     # ---- time surface + corner test (evk_ts_*) ----------------------------------------------
     def ts_create(self, width, height):

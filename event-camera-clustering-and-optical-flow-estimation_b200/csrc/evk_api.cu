@@ -276,6 +276,7 @@ int evk_destroy(evk_handle* h) {
     evk_comm_destroy(h);
     evk_aec_destroy(h);
     evk_ts_destroy(h);
+    evk_dbscan_destroy(h);
     // graphs first: they reference the buffers, events and streams released below
     if (h->fused_exec) chk(cudaGraphExecDestroy(h->fused_exec), "fused graph");
     if (h->loop_exec) chk(cudaGraphExecDestroy(h->loop_exec), "loop graph");

@@ -107,6 +107,7 @@ struct DsCounters {  // device-side counters, mirrored into pinned host memory a
 struct CommState;
 struct AecHost;  // evk_aec.cu
 struct TsHost;   // evk_corner.cu
+struct DbHost;   // evk_dbscan.cu
 
 struct FusedKey {  // what the captured fused-step graph depends on
     size_t n;
@@ -226,6 +227,8 @@ struct evk_handle {
     AecHost* aec = nullptr;
     // time surface + corner test (evk_corner.cu), created by evk_ts_create
     TsHost* ts = nullptr;
+    // DBSCAN buffers and last results (evk_dbscan.cu), created on first use
+    DbHost* db = nullptr;
     uint64_t shard_first = 0;
     std::string err;
 };

@@ -328,6 +328,36 @@ EVK_API int evk_ts_get_corners(evk_handle* h, uint32_t* event_index, size_t cap)
 /* the surface, row-major [height][width] */
 EVK_API int evk_ts_get_surface(evk_handle* h, int64_t* out, size_t cap_pixels);
 
+/* ---- density clustering of the downsampled cloud ------------------------- */
+/* DBSCAN as the reference runs it on voxel-grid-downsampled clouds (event-cam-clustering/
+ * point-cloud-clustering/DBSCAN_simple.h:27-140, parameters as pcl_cluster.cpp:112-120): the same
+ * clusters, member for member, as its sequential seed-queue walk -- computed as core flags,
+ * connected components of core points (seed = lowest-index core point) and border assignment. */
+typedef struct {
+    double eps;           /* setClusterTolerance: neighbours are points with distance^2 <= eps^2      */
+    int32_t min_pts;      /* setCorePointMinPts: neighbours (the point itself included) of a core point */
+    int32_t min_cluster;  /* setMinClusterSize / setMaxClusterSize: clusters outside are dropped      */
+    int32_t max_cluster;
+    int32_t D;            /* evk_dbscan_voxels only: 2 = (x, y); 3 = (x, y, (t - t0_us) * t_scale)    */
+    double t_scale;
+    int64_t t0_us;
+} evk_dbscan_params;
+/* a cloud of n points, xyz = n x 3 floats in host memory (pcl::PointCloud<pcl::PointXYZ>) */
+EVK_API int evk_dbscan_points(evk_handle* h, const float* xyz, size_t n, const evk_dbscan_params* p,
+                              size_t* n_clusters, size_t* n_extra);
+/* the current voxel shard: point i = the representative of the i-th voxel in canonical order */
+EVK_API int evk_dbscan_voxels(evk_handle* h, const evk_dbscan_params* p, size_t* n_clusters,
+                              size_t* n_extra);
+/* Results of the last run.  Clusters are ordered largest first (DBSCAN_simple.h:89; ties: lowest
+ * seed first).  labels[i] = position in that order of the first kept cluster that holds point i
+ * (lowest seed), -1 = noise or member of dropped clusters only; sizes / seeds per cluster (seed = its lowest-index core point); extra_pairs = (point,
+ * cluster) pairs of the second memberships the reference creates when a border point held by an
+ * earlier cluster neighbours a later cluster's seed point (:45-50).  Any pointer may be NULL. */
+EVK_API int evk_dbscan_get(evk_handle* h, int32_t* labels, size_t cap_points, uint32_t* sizes,
+                           uint32_t* seeds, size_t cap_clusters, uint32_t* extra_pairs,
+                           size_t cap_extra);
+EVK_API int evk_dbscan_destroy(evk_handle* h);
+
 /* ---- profiling / measurement --------------------------------------------------------------- */
 EVK_API int evk_set_profiling(evk_handle* h, int enabled);
 EVK_API int evk_get_stage_times(const evk_handle* h, evk_stage_times* out);
