@@ -87,6 +87,8 @@ struct Mailbox {
     unsigned long long sums[2][kMaxWorld][kMailWords];  // [parity][from rank][word]
     unsigned long long sum_flag[2][kMaxWorld];          // seq of the partial above
     unsigned long long ready_flag;                      // next rank: "my events of step seq are loaded"
+    unsigned long long keep_count;                      // next rank: how many of its leading events are mine
+                                                        // (>= halo: its first bin does not end in the block)
     unsigned long long cent_flag;                       // rank 0: "centroids of step seq are below"
     unsigned long long seq;                             // my step counter
     unsigned long long err;                             // a wait timed out
@@ -220,6 +222,77 @@ __global__ void k_p2p_tick(Mailbox* mine, Mailbox* const* peers, int rank) {
     const unsigned long long seq = mine->seq + 1;
     mine->seq = seq;
     if (rank > 0) st_release_sys(&peers[rank - 1]->ready_flag, seq);
+}
+
+// The fused step's tick: one warp.  seq++; the events at the head of my shard that still belong to the
+// previous rank's last time bin are counted HERE (a 32-way search over my own, local events) and the
+// count travels with the flag, so the receiver pulls exactly those events and needs no search of its
+// own (k_halo_range's two searches would otherwise sit between the pull and the downsample).
+__global__ void __launch_bounds__(32)
+    k_p2p_tick_range(KeyParams kp, const evk_event* ev, uint32_t n_own, uint32_t halo, int rank,
+                     int world, Mailbox* mine, Mailbox* const* peers, unsigned long long* stats) {
+    const int lane = threadIdx.x;
+    const unsigned long long seq = mine->seq + 1;
+    __syncwarp();
+    if (lane == 0) mine->seq = seq;
+    unsigned long long flag = n_own < halo ? 1 : 0, skip = 0;
+    if (!flag && rank > 0) {
+        const int64_t t0v = ev[0].t;
+        if (t0v < kp.t0) {
+            flag = 1;
+        } else {
+            const uint64_t b0 = evk_tbin(kp, t0v);
+            uint32_t lo = 0, hi = halo;  // first offset whose bin differs from the first event's
+            while (lo < hi) {
+                const uint32_t span = hi - lo;
+                const uint32_t p = lo + (uint32_t)((uint64_t)span * (uint32_t)(lane + 1) / 33u);
+                const int64_t t = ev[p].t;
+                const bool differs = !(t >= kp.t0 && evk_tbin(kp, t) == b0);
+                const uint32_t m = __ballot_sync(0xffffffffu, differs);
+                const int f = m ? __ffs(m) - 1 : 32;
+                const uint32_t p_f = __shfl_sync(0xffffffffu, p, f < 32 ? f : 0);
+                const uint32_t p_b = __shfl_sync(0xffffffffu, p, f > 0 ? f - 1 : 0);
+                if (f < 32) hi = p_f;
+                if (f > 0) lo = p_b + 1;
+            }
+            skip = lo;
+            if (skip >= halo || skip >= n_own) flag = 1;  // first bin does not end inside the block
+        }
+    }
+    if (lane == 0) {
+        stats[ST_FLAG] = flag;
+        stats[ST_SKIP] = flag ? 0 : skip;
+        stats[ST_KEEP] = 0;
+        if (rank > 0) {
+            peers[rank - 1]->keep_count = flag ? (unsigned long long)halo : skip;
+            st_release_sys(&peers[rank - 1]->ready_flag, seq);
+        }
+    }
+}
+
+// the events of the next rank that belong to my last bin -> behind my own: exactly keep_count of them
+__global__ void __launch_bounds__(256)
+    k_p2p_pull_exact(Mailbox* mine, const evk_event* next_events, evk_event* dst, uint32_t halo,
+                     unsigned long long* stats) {
+    __shared__ unsigned long long s_keep;
+    if (threadIdx.x == 0) {
+        unsigned long long keep = halo;  // (time-out: give up)
+        if (wait_flag(&mine->ready_flag, mine->seq))
+            keep = *reinterpret_cast<volatile unsigned long long*>(&mine->keep_count);
+        else
+            mine->err = 1;
+        s_keep = keep;
+        if (blockIdx.x == 0) {
+            if (keep >= halo) stats[ST_FLAG] = 1;
+            else stats[ST_KEEP] = keep;
+        }
+    }
+    __syncthreads();
+    const unsigned long long keep = s_keep;
+    if (keep >= halo) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < keep)
+        reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(next_events)[i];
 }
 
 // rank 0, beside its downsample: the centroids the walk kernel has just written go to every rank
@@ -802,11 +875,15 @@ static int enqueue_fused_sharded(evk_handle* h, const KeyParams& kp, const evk_d
                                     (size_t)km->K * 2 * sizeof(float), cudaMemcpyDeviceToDevice,
                                     h->stream));
     if (c->p2p) {  // peer memory over NVLink: flags + direct loads / stores (see k_p2p_*)
-        k_p2p_tick<<<1, 1, 0, h->stream>>>(c->mail, c->d_peer_mail, c->rank);
+        // who keeps what is decided by the SENDER of a boundary block (a search over its own events)
+        // and travels with the flag; the receiver pulls exactly its share
+        k_p2p_tick_range<<<1, 32, 0, h->stream>>>(kp, h->d_events, (uint32_t)n_own, halo, c->rank,
+                                                  c->world, c->mail, c->d_peer_mail, c->d_stats);
         EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));  // the side stream reads the new seq
         if (c->rank < c->world - 1)
-            k_p2p_pull<<<64, 256, 0, h->stream>>>(c->mail, c->peer_events[c->rank + 1],
-                                                  h->d_events + n_own, halo);
+            // (one 16-B load per thread: the whole share is in flight over NVLink at once)
+            k_p2p_pull_exact<<<(halo + 255) / 256, 256, 0, h->stream>>>(
+                c->mail, c->peer_events[c->rank + 1], h->d_events + n_own, halo, c->d_stats);
         EVK_CUDA(h, cudaGetLastError());
     } else {
         EVK_NCCL(h, g_nccl.GroupStart());
@@ -821,11 +898,11 @@ static int enqueue_fused_sharded(evk_handle* h, const KeyParams& kp, const evk_d
                                          c->comm, h->stream));
         EVK_NCCL(h, g_nccl.GroupEnd());
         EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+        // who keeps what (on the device), then the downsample on that range
+        k_halo_range<<<1, 32, 0, h->stream>>>(kp, h->d_events, (uint32_t)n_own, halo, c->rank,
+                                              c->world, c->d_stats);
+        EVK_CUDA(h, cudaGetLastError());
     }
-    // who keeps what (on the device), then the downsample on that range
-    k_halo_range<<<1, 32, 0, h->stream>>>(kp, h->d_events, (uint32_t)n_own, halo, c->rank,
-                                          c->world, c->d_stats);
-    EVK_CUDA(h, cudaGetLastError());
     bool ok = false;
     EVK_TRY(evk_downsample_slab(h, kp, ds->count_repeated, &ok, launches, false, c->d_stats));
     // side stream, beside the downsample: candidate lists, label map, quads
