@@ -52,6 +52,8 @@ def test_struct_layouts(evk):
     assert evk.EVENT_DTYPE.itemsize == 16 and evk.EVENT_DTYPE.fields["t"][1] == 8
     assert C.sizeof(evk.DsParams) == 48 and C.sizeof(evk.KmParams) == 32
     assert C.sizeof(evk.SynthParams) == 56 and C.sizeof(evk.StageTimes) == 36
+    assert C.sizeof(evk.AecParams) == 48 and C.sizeof(evk.DbscanParams) == 40
+    assert evk.AEC_CLUSTER_DTYPE.itemsize == 40 and evk.AEC_FLOW_DTYPE.itemsize == 64
 
 
 def test_no_cpu_fallback(evk):
