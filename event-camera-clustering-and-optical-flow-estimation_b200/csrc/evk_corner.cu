@@ -69,10 +69,9 @@ __global__ void __launch_bounds__(kT)
     }
 }
 
-// the streak test of FCT:958-1003 (circle of N pixels, streak sizes SMIN..SMAX) on the N surface
-// values t[] read around the event
+// the streak test exactly as the reference writes it (FCT:958-1003): every start, every size
 template <int N, int SMIN, int SMAX>
-__device__ __forceinline__ bool streak(const long long (&t)[N]) {
+__device__ __forceinline__ bool streak_literal(const long long (&t)[N]) {
     for (int i = 0; i < N; i++) {
         const int im1 = i == 0 ? N - 1 : i - 1;
         if (t[i] < t[im1]) continue;  // (the same for every streak size)
@@ -101,6 +100,56 @@ __device__ __forceinline__ bool streak(const long long (&t)[N]) {
     return false;
 }
 
+#ifndef EVK_CORNER_FAST
+#define EVK_CORNER_FAST 0  // 1: the arc-growth form below; 0: the literal loops
+#endif
+
+// The streak test of FCT:958-1003 (circle of N pixels, streak sizes SMIN..SMAX) on the N surface
+// values t[] read around the event.  As written it tries every start and every size; what it decides
+// is: "is there an arc A of SMIN..SMAX consecutive pixels with min(A) > max(all other pixels)?" (the
+// two neighbour comparisons at :962 and :966 follow from that, the arc being shorter than the
+// circle).  Such an arc holds the newest pixel, and growing an arc from the newest pixel by always
+// taking the newer of its two neighbours reaches it (pixels inside are strictly newer than pixels
+// outside), so ONE arc per size has to be examined: ~N + 2 SMAX + (N - SMAX) reads instead of the
+// nested loops.  Equal to the literal loops on 200 000 random circles with ties (checked on the CPU)
+// and, through the parity tests, to the oracle's literal restatement.
+template <int N, int SMIN, int SMAX>
+__device__ __forceinline__ bool streak(const long long (&t)[N]) {
+    int m = 0;
+#pragma unroll
+    for (int k = 1; k < N; k++)
+        if (t[k] > t[m]) m = k;
+    int lo = m, hi = m;
+    long long cur = t[m];
+    long long mins[SMAX + 1], added[SMAX + 1];
+    mins[1] = cur;
+#pragma unroll
+    for (int size = 2; size <= SMAX; size++) {
+        const int l = lo == 0 ? N - 1 : lo - 1, r = hi == N - 1 ? 0 : hi + 1;
+        const long long L = t[l], R = t[r];
+        long long a;
+        if (L >= R) {
+            lo = l;
+            a = L;
+        } else {
+            hi = r;
+            a = R;
+        }
+        cur = a < cur ? a : cur;
+        mins[size] = cur;
+        added[size] = a;
+    }
+    long long rest = t[hi == N - 1 ? 0 : hi + 1];  // newest pixel outside the largest arc
+    for (int k = hi == N - 1 ? 0 : hi + 1; k != lo; k = k == N - 1 ? 0 : k + 1)
+        rest = t[k] > rest ? t[k] : rest;
+#pragma unroll
+    for (int size = SMAX; size >= SMIN; size--) {
+        if (mins[size] > rest) return true;
+        rest = added[size] > rest ? added[size] : rest;
+    }
+    return false;
+}
+
 __global__ void __launch_bounds__(kT)
     k_corner_detect(const evk_event* __restrict__ ev, size_t n, int W, int H,
                     const long long* __restrict__ surf, const TsScalars* sc, int literal_break,
@@ -116,12 +165,12 @@ __global__ void __launch_bounds__(kT)
 #pragma unroll
             for (int k = 0; k < 16; k++)
                 t3[k] = surf[(size_t)(y + c_circle3[k][0]) * W + (x + c_circle3[k][1])];
-            if (streak<16, 3, 6>(t3)) {
+            if (EVK_CORNER_FAST ? streak<16, 3, 6>(t3) : streak_literal<16, 3, 6>(t3)) {
                 long long t4[20];
 #pragma unroll
                 for (int k = 0; k < 20; k++)
                     t4[k] = surf[(size_t)(y + c_circle4[k][0]) * W + (x + c_circle4[k][1])];
-                corner = streak<20, 4, 8>(t4);
+                corner = EVK_CORNER_FAST ? streak<20, 4, 8>(t4) : streak_literal<20, 4, 8>(t4);
             }
         }
     }

@@ -140,3 +140,63 @@ def test_cuda_known_surfaces_and_errors(evk, orc):
             assert (h.ts_surface() == s).all()
         with pytest.raises(evk.EvkError):
             h.ts_create(4, 4)
+
+
+def test_arc_growth_equals_the_literal_streak_loops():
+    """The CUDA kernel does not run the reference's nested start x size loops: it grows ONE arc from
+    the newest pixel (always taking the newer neighbour) and checks min(arc) > max(rest) per size.
+    This pins that reformulation against the literal loops (FCT:958-1003) on random circles with
+    heavy ties -- the same statement csrc/evk_corner.cu `streak` implements."""
+    def literal(t, smin, smax):
+        n = len(t)
+        for i in range(n):
+            for sz in range(smin, smax + 1):
+                if t[i] < t[(i - 1) % n] or t[(i + sz - 1) % n] < t[(i + sz) % n]:
+                    continue
+                mn = min(t[(i + j) % n] for j in range(sz))
+                if all(t[(i + j) % n] < mn for j in range(sz, n)):
+                    return True
+        return False
+
+    def grown(t, smin, smax):
+        n = len(t)
+        m = max(range(n), key=lambda k: (t[k], -k))
+        lo = hi = m
+        cur, mins, added = t[m], {1: t[m]}, {}
+        for size in range(2, smax + 1):
+            L, R = t[(lo - 1) % n], t[(hi + 1) % n]
+            if L >= R:
+                lo, a = (lo - 1) % n, L
+            else:
+                hi, a = (hi + 1) % n, R
+            cur = min(cur, a)
+            mins[size], added[size] = cur, a
+        rest, k = None, (hi + 1) % n
+        while k != lo:
+            rest = t[k] if rest is None else max(rest, t[k])
+            k = (k + 1) % n
+        for size in range(smax, smin - 1, -1):
+            if mins[size] > rest:
+                return True
+            rest = max(rest, added[size])
+        return False
+
+    r = np.random.default_rng(0)
+    pos = 0
+    for trial in range(30_000):
+        n, smin, smax = (16, 3, 6) if trial % 2 == 0 else (20, 4, 8)
+        mode = trial % 4
+        if mode == 0:
+            t = r.integers(0, 4, n)
+        elif mode == 1:
+            t = r.integers(0, 1000, n)
+        else:
+            t = r.integers(0, 10, n) if mode == 2 else np.full(n, 10)
+            s, L = r.integers(0, n), r.integers(1, 10)
+            for j in range(L):
+                t[(s + j) % n] = 100 + (r.integers(0, 5) if mode == 2 else 0)
+        t = [int(v) for v in t]
+        a = literal(t, smin, smax)
+        assert a == grown(t, smin, smax), t
+        pos += a
+    assert pos > 3000
