@@ -876,6 +876,7 @@ int evk_aec_update(evk_handle* h, const double* e, size_t n) {
 
 int evk_aec_update_voxels(evk_handle* h, double t, size_t start, size_t step, size_t count) {
     EVK_TRY(aec_check(h));
+    EVK_TRY(evk_collect_pending(h));
     if (!h->have_voxels) return evk_fail(h, EVK_ERR_STATE, "evk_aec_update_voxels: no voxel shard");
     if (step == 0) return evk_fail(h, EVK_ERR_INVALID, "evk_aec_update_voxels: step = 0");
     if (count && (start >= h->n_unique || (count - 1) > (h->n_unique - 1 - start) / step))

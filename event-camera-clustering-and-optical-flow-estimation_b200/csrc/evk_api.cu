@@ -597,8 +597,17 @@ int evk_downsample_local(evk_handle* h, const evk_ds_params* p) {
     return EVK_OK;
 }
 
+// A queued fused step (evk_downsample_kmeans[_sharded]_submit) is collected before anything reads or
+// replaces its results: the getters and the separate calls never see half a step.
+int evk_collect_pending(evk_handle* h) {
+    if (!h || !h->step_pending) return EVK_OK;
+    if (h->step_sharded) return evk_downsample_kmeans_sharded_wait(h, nullptr, nullptr, nullptr);
+    return evk_downsample_kmeans_wait(h, nullptr, nullptr, nullptr);
+}
+
 int evk_downsample(evk_handle* h, const evk_ds_params* p, size_t* n_unique, size_t* n_repeated) {
     EVK_TRY(check_handle(h));
+    EVK_TRY(evk_collect_pending(h));
     h->shard_first = h->comm ? h->shard_first : 0;
     EVK_TRY(evk_downsample_local(h, p));
     if (n_unique) *n_unique = h->n_unique;
@@ -610,6 +619,11 @@ int evk_downsample(evk_handle* h, const evk_ds_params* p, size_t* n_unique, size
 // ACCEL/store.cpp:418-430): what the last downsample, fused step or completed window produced
 int evk_num_voxels(const evk_handle* h, size_t* n_unique, size_t* n_repeated) {
     if (!h) return EVK_ERR_INVALID;
+    if (h->step_pending == 1) {  // (const handle: cannot collect) a queued step has not been waited for
+        if (n_unique) *n_unique = 0;
+        if (n_repeated) *n_repeated = 0;
+        return EVK_ERR_STATE;
+    }
     if (n_unique) *n_unique = h->have_voxels ? h->n_unique : 0;
     if (n_repeated) *n_repeated = h->have_voxels ? h->n_repeated : 0;
     return h->have_voxels ? EVK_OK : EVK_ERR_STATE;
@@ -617,6 +631,7 @@ int evk_num_voxels(const evk_handle* h, size_t* n_unique, size_t* n_repeated) {
 
 int evk_get_voxels(evk_handle* h, uint64_t* keys, evk_event* reps, uint32_t* first_idx, size_t cap) {
     EVK_TRY(check_handle(h));
+    EVK_TRY(evk_collect_pending(h));
     if (!h->have_voxels) return evk_fail(h, EVK_ERR_STATE, "evk_downsample has not run");
     const size_t n = h->n_unique;
     if (cap < n) return evk_fail(h, EVK_ERR_CAPACITY, "cap %zu < %zu voxels", cap, n);
@@ -870,6 +885,7 @@ int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_done,
 
 int evk_kmeans(evk_handle* h, const evk_km_params* p, int* iters_done) {
     EVK_TRY(check_handle(h));
+    EVK_TRY(evk_collect_pending(h));
     return evk_kmeans_run(h, p, iters_done, nullptr);
 }
 
@@ -999,6 +1015,7 @@ int evk_downsample_kmeans_submit(evk_handle* h, const evk_ds_params* ds, const e
     }
     EVK_CUDA(h, cudaGraphLaunch(h->fused_exec, h->stream));
     h->step_pending = 1;
+    h->step_sharded = false;
     return EVK_OK;
 }
 
@@ -1070,6 +1087,7 @@ int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const evk_km_p
 
 int evk_get_labels(evk_handle* h, int32_t* labels, size_t cap) {
     EVK_TRY(check_handle(h));
+    EVK_TRY(evk_collect_pending(h));
     if (!h->km_last.K) return evk_fail(h, EVK_ERR_STATE, "evk_kmeans has not run");
     const size_t n = h->n_labels;
     if (cap < n) return evk_fail(h, EVK_ERR_CAPACITY, "cap %zu < %zu labels", cap, n);
@@ -1090,6 +1108,7 @@ int evk_get_labels(evk_handle* h, int32_t* labels, size_t cap) {
 
 int evk_get_centroids(evk_handle* h, float* c, uint64_t* counts) {
     EVK_TRY(check_handle(h));
+    EVK_TRY(evk_collect_pending(h));
     if (!h->have_centroids) return evk_fail(h, EVK_ERR_STATE, "no centroids");
     DeviceGuard g(h->device);
     if (c)

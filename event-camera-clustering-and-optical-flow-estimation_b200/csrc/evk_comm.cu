@@ -1047,6 +1047,7 @@ int evk_downsample_kmeans_sharded_submit(evk_handle* h, const evk_ds_params* ds,
     }
     EVK_CUDA(h, cudaGraphLaunch(c->step_exec, h->stream));
     h->step_pending = 1;
+    h->step_sharded = true;
     return EVK_OK;
 }
 

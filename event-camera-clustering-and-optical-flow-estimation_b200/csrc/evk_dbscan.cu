@@ -394,6 +394,7 @@ int evk_dbscan_points(evk_handle* h, const float* xyz, size_t n, const evk_dbsca
 int evk_dbscan_voxels(evk_handle* h, const evk_dbscan_params* p, size_t* n_clusters,
                       size_t* n_extra) {
     EVK_TRY(db_check(h, p));
+    EVK_TRY(evk_collect_pending(h));
     if (!h->have_voxels) return evk_fail(h, EVK_ERR_STATE, "evk_dbscan_voxels: no voxel shard");
     if (p->D != 2 && p->D != 3) return evk_fail(h, EVK_ERR_INVALID, "dbscan: D must be 2 or 3");
     if (p->D == 3 && (h->comm || h->reps_valid))

@@ -188,6 +188,7 @@ struct evk_handle {
     evk_ds_params step_ds{};
     evk_km_params step_km{};
     int step_init = 0, step_iters = 0;
+    bool step_sharded = false;  // the pending step was queued by the sharded submit
     size_t image_pixels = 0;                 // capacity of both
     bool pix_valid = false;                  // d_pixcnt matches the current voxel shard
     float* d_shift = nullptr;                // [1]
@@ -257,6 +258,7 @@ extern "C" int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_
 // host helpers of evk_api.cu used by the sharded step (evk_comm.cu)
 struct KmLaunch;
 int evk_km_validate(evk_handle* h, const evk_km_params* p);
+extern "C" int evk_collect_pending(evk_handle* h);  // wait for a queued fused step, if any
 bool evk_ensure_images(evk_handle* h, int width, int height);
 void evk_invalidate_results(evk_handle* h);
 

@@ -34,6 +34,9 @@
 
 namespace {
 
+#ifndef EVK_SLAB_VIOLX
+#define EVK_SLAB_VIOLX 1  // how the out-of-bin check is written (A/B'd: see DESIGN.md section 7)
+#endif
 #ifndef EVK_SLAB_THREADS
 #define EVK_SLAB_THREADS 1024
 #endif
@@ -351,10 +354,22 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 const uint32_t li = j * NT + tid;
                 const uint4 ev = tile[li];
                 const uint32_t x = ev.x & 0xFFFFu, y = ev.x >> 16;
+#if EVK_SLAB_VIOLX == 1
+                const bool gate = (base + li < hi) & (x < (uint32_t)kp.width) & (y < (uint32_t)kp.height);
+                const bool inbin = (uint64_t)(ev_t(ev) - t_lo) < (uint64_t)kp.vt;
+                const bool ok = gate & inbin;
+                viol |= (uint32_t)(gate != ok);  // a gated-in event that is not of this bin
+#elif EVK_SLAB_VIOLX == 2
+                bool ok = (base + li < hi) & (x < (uint32_t)kp.width) & (y < (uint32_t)kp.height);
+                const bool inbin = (uint64_t)(ev_t(ev) - t_lo) < (uint64_t)kp.vt;
+                viol |= (uint32_t)(ok & !inbin);
+                ok &= inbin;
+#else
                 bool ok = (base + li < hi) & (x < (uint32_t)kp.width) & (y < (uint32_t)kp.height);
                 const bool inbin = (uint64_t)(ev_t(ev) - t_lo) < (uint64_t)kp.vt;
                 if (ok & !inbin) viol = 1;  // not an event of this bin
                 ok &= inbin;
+#endif
                 uint32_t cell;
                 if (POW2) cell = (y >> kp.sy) * kp.NX + (x >> kp.sx);
                 else cell = (kp.sy >= 0 ? y >> kp.sy : __umulhi(y, kp.my)) * kp.NX +

@@ -165,6 +165,14 @@ def test_submit_wait_pipeline(evk, orc):
         got = (U, R, it, keys, first, h.get_labels(), h.get_centroids(K, 2))
         assert h.stage_times().ds_algo_used == evk.ALGO_SLAB
         same(ref, got)
+        # a getter collects a queued step by itself (no explicit wait): same results
+        h.downsample_kmeans_submit(ds, km, True)
+        with pytest.raises(evk.EvkError):
+            h.num_voxels()                      # (const query: refuses while a step is in flight)
+        lab2 = h.get_labels(len(ref[5]))
+        assert (lab2 == ref[5]).all() and h.num_voxels() == (ref[0], ref[1])
+        with pytest.raises(evk.EvkError):
+            h.downsample_kmeans_wait()          # already collected
         # cold step, then a warm-started one queued behind it == two synchronous calls
         h.downsample_kmeans(ds, km, True)
         h.downsample_kmeans(ds, km, False)
