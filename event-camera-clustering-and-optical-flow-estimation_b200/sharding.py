@@ -1,7 +1,7 @@
 """Host-side statement of the multi-GPU sharding rules of csrc/evk_comm.cu.
 
 Pure arithmetic on numpy arrays — no device work, no oracle: which rank owns what.  The CUDA
-library implements the same rules on the device (k_halo_range, owner_of); bench.py uses
+library implements the same rules on the device (k_halo_range / k_p2p_tick_range, owner_of); bench.py uses
 `shard_range`, and tests/test_sharding_gloo.py runs the whole exchange protocol over these
 functions on CPU with world_size 2 (gloo) against the single-process answer.
 """
@@ -50,6 +50,18 @@ def time_range_split(t_own, t_halo, rank, world, t0_us, vt_us):
         if keep >= len(t_halo):
             ok = False
     return skip, keep, ok
+
+
+def boundary_share(t_own, rank, t0_us, vt_us):
+    """The sender's half of the peer-memory exchange (csrc/evk_comm.cu k_p2p_tick_range): how many of
+    this rank's leading events belong to the previous rank's last time bin.  The count travels with
+    the "my events are loaded" flag and the previous rank pulls exactly that many events
+    (k_p2p_pull_exact), so no rank searches a received block.  Returns (share, ok); rank 0 sends
+    nothing.  Equal to time_range_split's (skip, ok) of this rank and to its predecessor's keep."""
+    if rank == 0:
+        return 0, True
+    skip, _, ok = time_range_split(t_own, t_own[:0], rank, rank + 1, t0_us, vt_us)
+    return skip, ok
 
 
 def mix64(z):

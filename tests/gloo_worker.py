@@ -46,6 +46,14 @@ def main():
     halo = heads[rank + 1] if rank < world - 1 else own[:0]
     skip, keep, ok = sh.time_range_split(own["t"], halo["t"], rank, world, 0, vt)
     assert ok
+    # the peer-memory form of the same exchange: every sender counts its own boundary share and
+    # publishes it; the receiver takes exactly that many events of the next shard -- same split
+    share, ok2 = sh.boundary_share(own["t"], rank, 0, vt)
+    shares = allgather((share, ok2), world)
+    assert all(q[1] for q in shares) and share == skip
+    assert keep == (shares[rank + 1][0] if rank < world - 1 else 0)
+    pulled = heads[rank + 1][:shares[rank + 1][0]] if rank < world - 1 else own[:0]
+    assert pulled.tobytes() == halo[:keep].tobytes()
     mine = np.concatenate([own[skip:], halo[:keep]])
     k, f, r = orc.downsample(mine, p)
     f = f.astype(np.int64) + lo + skip  # global first indices
