@@ -6,6 +6,11 @@
  *     load events -> voxel-hash downsample -> k-means assign + centroid update
  *                 -> return labels and centroids
  *
+ * and, widening into the path's callers on either side: RAW EVT 2.0 / 3.0
+ * ingest (evk_load_evt2 / _evt3 / _raw), the reference's consumer of the downsampled coordinates
+ * (evk_aec_*: asynchronous event clustering + per-slice flow arrows), the corner tracker's time
+ * surface + corner test (evk_ts_*) and DBSCAN on the downsampled cloud (evk_dbscan_*).
+ *
  * The reference has no library / plugin API for this path: every call is inlined in main()
  * of three sample programs.  Each entry point below therefore cites the reference call site it
  * replaces (paths relative to the reference root; abbreviations:
@@ -23,6 +28,8 @@
  *    ACCEL/store.cpp:389);
  *  - one handle is used from one thread at a time (the reference does pack -> launch -> wait ->
  *    consume on the single SDK decoding thread, ACCEL/store.cpp:370-615);
+ *  - calls return when their results are complete, except the *_submit halves of the fused step,
+ *    which only queue it on the handle's stream; the matching *_wait (or any getter) collects it;
  *  - there is NO CPU fallback: without a CUDA device evk_create fails with EVK_ERR_CUDA.
  */
 #ifndef EVK_H_
