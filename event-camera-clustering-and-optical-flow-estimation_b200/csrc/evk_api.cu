@@ -995,6 +995,9 @@ int evk_downsample_kmeans_submit(evk_handle* h, const evk_ds_params* ds, const e
     if (h->fused_exec && memcmp(&key, &h->fused_key, sizeof key) == 0) {
         launches = h->fused_launches;
     } else {
+        if (h->step_pending == 1) {  // the graph in flight is about to be replaced: let it finish
+            EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+        }
         if (h->fused_exec) cudaGraphExecDestroy(h->fused_exec);
         h->fused_exec = nullptr;
         cudaGraph_t graph = nullptr;

@@ -229,7 +229,10 @@ EVK_API int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const 
  * as soon as the pass is queued on the handle's stream, wait is the step's one synchronisation and
  * reports its counts.  Steps may be queued behind each other (each one works on the events resident
  * at its turn in stream order); wait then reports the last one.  evk_downsample_kmeans ==
- * submit + wait.  Shapes the fused pass does not take run synchronously inside submit. */
+ * submit + wait.  Shapes the fused pass does not take run synchronously inside submit.
+ * Loading the next slice's events behind a queued step is allowed (the copy is stream-ordered
+ * behind the step); results that refer back to the events -- the representatives of
+ * evk_get_voxels -- must then be read before that load. */
 EVK_API int evk_downsample_kmeans_submit(evk_handle* h, const evk_ds_params* ds,
                                          const evk_km_params* km, int init_first_k);
 EVK_API int evk_downsample_kmeans_wait(evk_handle* h, size_t* n_unique, size_t* n_repeated,
