@@ -73,3 +73,34 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".cu", ".cuh", ".py", ".hpp", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle/" not in txt and "liborc" not in txt and "import orc" not in txt, f
+
+
+def test_null_handle_is_rejected_everywhere(evk):
+    """no entry point dereferences a NULL handle (no GPU needed: nothing is computed)"""
+    L = evk.lib()
+    n = C.c_size_t(0)
+    i = C.c_int(0)
+    calls = [
+        lambda: L.evk_aec_create(None, None), lambda: L.evk_aec_update(None, None, 0),
+        lambda: L.evk_aec_update_voxels(None, 0.0, 0, 1, 0),
+        lambda: L.evk_aec_get_clusters(None, None, 0, C.byref(n), C.byref(i)),
+        lambda: L.evk_aec_get_points(None, 0, None, None, None, None, 0, C.byref(n)),
+        lambda: L.evk_aec_report(None, None, 0, C.byref(n)),
+        lambda: L.evk_ts_create(None, 1280, 720), lambda: L.evk_ts_corners(None, 1, C.byref(n)),
+        lambda: L.evk_ts_get_corners(None, None, 0), lambda: L.evk_ts_get_surface(None, None, 0),
+        lambda: L.evk_dbscan_points(None, None, 0, None, C.byref(n), C.byref(n)),
+        lambda: L.evk_dbscan_voxels(None, None, C.byref(n), C.byref(n)),
+        lambda: L.evk_dbscan_get(None, None, 0, None, None, 0, None, 0),
+        lambda: L.evk_load_evt3(None, None, 0, C.byref(n)),
+        lambda: L.evk_downsample_kmeans_submit(None, None, None, 1),
+        lambda: L.evk_downsample_kmeans_wait(None, C.byref(n), C.byref(n), C.byref(i)),
+        lambda: L.evk_downsample_kmeans_sharded_submit(None, None, None, 1, 0),
+        lambda: L.evk_downsample_kmeans_sharded_wait(None, C.byref(n), C.byref(n), C.byref(i)),
+        lambda: L.evk_window_config_events(None, None, None, 10),
+        lambda: L.evk_num_voxels(None, C.byref(n), C.byref(n)),
+    ]
+    for k, f in enumerate(calls):
+        assert f() < 0, k
+    # the destroy calls are no-ops on NULL
+    assert L.evk_aec_destroy(None) == 0 and L.evk_ts_destroy(None) == 0
+    assert L.evk_dbscan_destroy(None) == 0
