@@ -97,3 +97,33 @@ def test_evt3_arbitrary_ordered_streams(evk, orc, handle, seed, n, rows, cols, d
     w = orc.evt3_encode(ev)
     assert handle.load_evt3(w) == n
     assert handle.get_events().tobytes() == ev.tobytes()
+
+
+@settings(max_examples=40, **SET)
+@given(seed=st.integers(0, 2**31), n=st.integers(1, 60000), W=st.integers(9, 700),
+       H=st.integers(9, 500), vx=st.integers(1, 9), vy=st.integers(1, 9),
+       vt=st.sampled_from([1, 7, 64, 500, 1000, 12345]), up=st.integers(0, 1),
+       dt_max=st.integers(0, 6), hot=st.sampled_from([0.0, 0.3, 0.95]), K=st.integers(1, 40),
+       algo=st.sampled_from(["auto", "table", "sort"]))
+def test_hot_path_arbitrary_shapes(evk, orc, handle, seed, n, W, H, vx, vy, vt, up, dt_max, hot, K,
+                                   algo):
+    """the hot path itself on arbitrary sensors, voxel sizes, time bins and duplicate densities:
+    every downsample algorithm and the fused step equal the oracle bit for bit"""
+    from test_gpu_stress import make_stream
+    ev = make_stream(np.random.default_rng(seed), n, W, H, dt_max, hot)
+    ok, of, orr = orc.downsample(ev, orc.ds_params(W, H, vx, vy, vt, 0, up))
+    a = {"auto": evk.ALGO_AUTO, "table": evk.ALGO_TABLE, "sort": evk.ALGO_SORT}[algo]
+    ds = evk.ds_params(W, H, vx, vy, vt, 0, up, algo=a)
+    handle.load_events(ev)
+    U, R = handle.downsample(ds)
+    keys, reps, first = handle.get_voxels()
+    assert (U, R) == (len(ok), orr) and (keys == ok).all() and (first == of).all()
+    assert reps.tobytes() == ev[of].tobytes()
+    K = min(K, len(ok))
+    pts = orc.points(ev, of, 2)
+    oc, ol, ocnt, _ = orc.kmeans(pts, pts[:K], iters=1)
+    U, R, it = handle.downsample_kmeans(evk.ds_params(W, H, vx, vy, vt, 0, up), evk.km_params(K, 2, iters=1),
+                                        True)
+    assert (U, R, it) == (len(ok), orr, 1)
+    cent, counts = handle.get_centroids(K, 2)
+    assert (counts == ocnt).all() and (cent == oc).all() and (handle.get_labels() == ol).all()
