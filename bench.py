@@ -14,8 +14,15 @@ ownership; --owner mix64 = hash ownership with an NCCL all-to-all of voxels) and
 partial sums are allreduced.
 
 `value`  : events resident in HBM, timed with CUDA events on the library's stream.
-`e2e`    : the same step through the C-ABI from pinned HOST memory: H2D of the events and D2H of
-           centroids + counts inside the timed region.
+`e2e`    : the same step through the C-ABI with HOST buffers, everything the reference reads back
+           inside the timed region: H2D of the events (pinned), the step, D2H of the unique voxels'
+           keys (ACCEL/store.cpp:412-422 reads the unique coordinates every slice), of the labels
+           (KM/assign_to_centers2.c:259-265 reads the assignments) and of centroids + counts.  Two
+           handles alternate so that one slice's read-back overlaps the next slice's upload (PCIe is
+           full duplex); `e2e_serial` is the same on ONE handle, `e2e_centroids` reads back
+           centroids + counts only (round 1's e2e), `h2d_only` is the bare copy (the host limit).
+`c5`, `c1`: BASELINE configs[4] (50 ms windows pushed from host memory: per-window latency) and
+           configs[0] (the reference's CPU-runnable case) beside their CPU timings.
 `roofline`: dominant kernel, algorithmic bytes / its CUDA-event duration, against
            MEASURED_PEAKS.json hbm_gbs (fallback 6650 GB/s).
 `cpu_baseline`: the CPU oracle (a port of the reference's semantics; the reference's own OpenCL
@@ -58,7 +65,47 @@ def parse():
     ap.add_argument("--algo", default="auto", choices=["auto", "table", "sort", "slab"])
     ap.add_argument("--sync-steps", action="store_true",
                     help="one host synchronisation per timed step instead of a queued pipeline")
+    ap.add_argument("--config", default="c3", choices=["c3", "c4"],
+                    help="c3: weak scaling, --events per GPU (default); c4: ONE 1 B-event stream "
+                         "strong-scaled over the GPUs (BASELINE configs[3])")
+    ap.add_argument("--c4-events", type=int, default=1_000_000_000)
+    ap.add_argument("--no-extras", action="store_true", help="skip the c5 / c1 / c4 / consumer legs")
+    ap.add_argument("--c5-windows", type=int, default=200)
     return ap.parse_args()
+
+
+def host_threads():
+    """threads this process may use on the box -- never OMP_NUM_THREADS (torchrun exports 1)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def pin_to_gpu_numa(local_rank):
+    """Bind this rank (and the pinned buffers it allocates afterwards) to the NUMA node of its GPU:
+    8 ranks pinning 1.6 GB each on node 0 halve the host->device rate of the far GPUs."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        node = int(open(base + "/numa_node").read())
+        cpus = open(base + "/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                ids.update(range(int(a), int(b) + 1))
+            elif part:
+                ids.add(int(part))
+        allowed = set(os.sched_getaffinity(0))
+        ids &= allowed
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return {"gpu": bdf, "numa_node": node, "cpus": len(ids) or len(allowed)}
+    except Exception as e:   # containers without sysfs: leave the affinity alone
+        return {"error": str(e)[:80]}
 
 
 _POLL_SRC = r"""
@@ -195,7 +242,7 @@ def cpu_port(n_sample, steps, threads):
     """CPU oracle (port) on a bounded prefix of the same stream. Returns Mev/s, description."""
     from oracle import orc
     orc.build()
-    threads = threads or orc.max_threads()
+    threads = threads or host_threads()
     ev = orc.synth(orc.synth_params(SEED, n_sample, W, H, RATE, N_BLOBS), threads=threads)
     p = orc.ds_params(W, H, VOX[0], VOX[1], VOX[2], 0, VOX[3])
     best = None
@@ -259,31 +306,71 @@ def consumer_leg(evk):
     return out
 
 
-def run_reference(args, rank, out):
+def cpu_c1(threads_list):
+    """BASELINE configs[0], the reference's CPU-runnable case: 1 M synthetic DAVIS346 events,
+    4x4 px x 1 ms voxels, k-means K = 8 (one iteration), on the CPU oracle."""
+    import numpy as np
+    from oracle import orc
+    orc.build()
+    n, w, h, k = 1_000_000, 346, 260, 8
+    ev = orc.synth(orc.synth_params(0xE7CA0001, n, w, h, 10_000_000, 8))
+    p = orc.ds_params(w, h, 4, 4, 1000, 0, 1)
+    out = {}
+    for t in threads_list:
+        best = None
+        for _ in range(3):
+            t0 = time.perf_counter()
+            keys, first, rep = orc.downsample(ev, p, threads=t, canonical=False)
+            pts = orc.points(ev, first, 2)
+            init = pts[np.argsort(first, kind="stable")[:k]]
+            orc.kmeans(pts, init, iters=1, threads=t)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        out[t] = (n / best / 1e6, best * 1e3, len(keys))
+    return out
+
+
+def run_reference(args, rank, world, out):
+    """The reference arm: the reference's CPU semantics (oracle port; its OpenCL / Metavision host
+    code cannot be built here) on ALL host threads of the box, rank 0 only.  The CPU rate does not
+    depend on how many GPUs the other arm uses: the sample is a prefix of the same stream."""
     if rank != 0:
         return
+    threads = host_threads()
     n_sample = min(args.cpu_sample, args.events)
-    mev, threads, U, best = cpu_port(n_sample, args.steps + args.warmup, 0)
+    mev, threads, U, best = cpu_port(n_sample, args.steps + args.warmup, threads)
     sample = (f"first {n_sample} events of the workload stream (U={U}), best of "
               f"{args.steps + args.warmup} passes, generation excluded")
     line = {
         "impl": "reference", "metric": "Mevents/s downsample+k-means iteration", "value": mev,
         "unit": "Mevents/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": best * 1e3, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": best * 1e3, "higher_is_better": True,
+        "scaling": "strong" if args.config == "c4" else "weak",
         "vs_baseline": None, "dtype": "u64 keys / f32 distances", "data": "synthetic",
         "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": mev, "unit": "Mevents/s", "cores": threads, "kind": "port",
-                         "sample": sample},
+                         "sample": sample,
+                         "threads_source": "sched_getaffinity (OMP_NUM_THREADS is ignored: torchrun "
+                                           "exports 1)"},
         "e2e": {"value": mev, "unit": "Mevents/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference's OpenCL/Metavision code cannot be built here; this is the CPU oracle "
-                "port of its semantics on all host threads",
+                "port of its semantics on all host threads of the box (one host whatever N is)",
     }
     print(json.dumps(line), file=out, flush=True)
 
 
 def workload_config(args, world):
+    if args.config == "c4":
+        per = args.c4_events // world
+        return {"workload": f"C4 synthetic Prophesee Gen4 {W}x{H}, ONE {args.c4_events}-event stream "
+                            f"at {RATE // 1_000_000} Mev/s index-sharded over {world} GPUs ({per} "
+                            f"events/GPU, strong scaling), voxels {VOX[0]}x{VOX[1]} px x {VOX[2]} us"
+                            f"{' x polarity' if VOX[3] else ''}, k-means K={K} D={D}, 1 iteration",
+                "events_per_gpu": per, "events_total": per * world, "K": K, "D": D,
+                "voxel": list(VOX), "seed": hex(SEED), "parallelism": f"index-sharded x{world}",
+                "l2_policy": "inputs larger than L2; no flush needed"}
     return {"workload": f"C3 synthetic Prophesee Gen4 {W}x{H}, {args.events} events/GPU at "
                         f"{RATE // 1_000_000} Mev/s, voxels {VOX[0]}x{VOX[1]} px x {VOX[2]} us"
                         f"{' x polarity' if VOX[3] else ''}, k-means K={K} D={D}, 1 iteration",
@@ -304,12 +391,77 @@ def main():
         real_stdout.flush()
 
 
+def c5_leg(evk, torch, device, n_windows):
+    """BASELINE configs[4]: 50 ms windows at 100 Mev/s (5 M events each) pushed from pinned host
+    memory through evk_window_push -- per-window latency = H2D + downsample + two warm-started
+    k-means iterations + the host synchronisation.  Windows are tumbling 50 ms slices, which is
+    what the reference's reslicer produces (ACCEL/store.cpp:329,349-352: make_n_us(50000))."""
+    import numpy as np
+    per, win_us = 5_000_000, 50_000
+    ds = evk.ds_params(W, H, VOX[0], VOX[1], VOX[2], 0, VOX[3])
+    km = evk.km_params(K, D, iters=2)
+    gen = evk.Evk(per, device=device)
+    h = evk.Evk(per + 1, device=device)
+    bufs = [torch.empty(per * 16, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    h.window_config(ds, km, win_us)
+    lat = []
+    for w in range(n_windows + 3):
+        buf = bufs[w & 1]
+        gen.synth(evk.synth_params(SEED, per, W, H, RATE, N_BLOBS, first_index=w * per))
+        buf.numpy().view(evk.EVENT_DTYPE)[:] = gen.get_events()
+        t0 = time.perf_counter()
+        # window w completes when the first event of window w+1 arrives: push the window, then
+        # flush it (the reslicer's callback fires on the slice boundary)
+        done = h.window_push_ptr(buf.data_ptr(), per)
+        done += h.window_flush()
+        dt = (time.perf_counter() - t0) * 1e3
+        assert done == 1, done
+        if w >= 3:
+            lat.append(dt)
+    u, r = h.num_voxels()
+    h.close()
+    gen.close()
+    lat.sort()
+    return {"windows": len(lat), "events_per_window": per, "window_ms": 50.0,
+            "p50_ms": lat[len(lat) // 2], "p99_ms": lat[min(len(lat) - 1, int(len(lat) * 0.99))],
+            "max_ms": lat[-1], "mean_ms": sum(lat) / len(lat),
+            "real_time_factor": 50.0 / lat[len(lat) // 2],
+            "includes": "H2D of the window's 80 MB from pinned host memory, downsample, 2 warm-started "
+                        "k-means iterations, one host synchronisation (evk_window_push + _flush)",
+            "windows_are": "tumbling 50 ms slices (the reference's make_n_us(50000) reslicer)",
+            "last_window_voxels": u}
+
+
+def c1_leg(evk, device):
+    """BASELINE configs[0] on the GPU (fused step) beside the CPU oracle, one and all threads"""
+    n, w, hh, k = 1_000_000, 346, 260, 8
+    with evk.Evk(n, device=device) as h:
+        h.synth(evk.synth_params(0xE7CA0001, n, w, hh, 10_000_000, 8))
+        ds = evk.ds_params(w, hh, 4, 4, 1000, 0, 1)
+        km = evk.km_params(k, 2, iters=1)
+        for _ in range(3):
+            h.downsample_kmeans(ds, km, True)
+        h.timer_start()
+        for _ in range(20):
+            h.downsample_kmeans_submit(ds, km, True)
+        u, r, _ = h.downsample_kmeans_wait()
+        ms = h.timer_stop() / 20
+    T = host_threads()
+    cpu = cpu_c1([1, T] if T > 1 else [1])
+    return {"workload": "C1: 1 M synthetic DAVIS346 (346x260) events, 4x4 px x 1 ms voxels, K=8, "
+                        "1 iteration (BASELINE configs[0], the reference's CPU-runnable case)",
+            "gpu_ms_per_step": ms, "gpu_Mevents_per_s": n / ms / 1e3, "unique_voxels": u,
+            "cpu_baseline_c1": {"unit": "Mevents/s", "kind": "port",
+                                "single_thread": {"value": cpu[1][0], "ms": cpu[1][1], "cores": 1},
+                                "all_threads": {"value": cpu[T][0], "ms": cpu[T][1], "cores": T}}}
+
+
 def _main(args, real_stdout):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference(args, rank, real_stdout)
+        run_reference(args, rank, world, real_stdout)
         return
     import numpy as np
     import torch
@@ -320,6 +472,7 @@ def _main(args, real_stdout):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa = pin_to_gpu_numa(local_rank) if world > 1 else {"note": "single rank: not pinned"}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -328,7 +481,14 @@ def _main(args, real_stdout):
             dist.barrier()
         torch.cuda.synchronize()
 
-    n = args.events
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    strong = args.config == "c4"
+    n = args.c4_events // world if strong else args.events
     algo = {"auto": evk.ALGO_AUTO, "table": evk.ALGO_TABLE, "sort": evk.ALGO_SORT,
             "slab": evk.ALGO_SLAB}[args.algo]
     ds = evk.ds_params(W, H, VOX[0], VOX[1], VOX[2], 0, VOX[3], algo=algo,
@@ -355,23 +515,24 @@ def _main(args, real_stdout):
 
     state = {}
 
-    def step():
+    def step(hh=None):
+        hh = hh or h
         if world > 1 and args.unfused:
-            ul, ug = h.downsample_sharded(ds, owner)
-            h.init_centroids_first_k_sharded(km)
-            h.kmeans_sharded(km)
+            ul, ug = hh.downsample_sharded(ds, owner)
+            hh.init_centroids_first_k_sharded(km)
+            hh.kmeans_sharded(km)
             state["U_local"], state["U"] = ul, ug
         elif world > 1:
-            ul, ug, _ = h.downsample_kmeans_sharded(ds, km, True, owner)
+            ul, ug, _ = hh.downsample_kmeans_sharded(ds, km, True, owner)
             state["U_local"], state["U"] = ul, ug
         elif args.unfused:
-            u, r = h.downsample(ds)
-            h.init_centroids_first_k(km)
-            h.kmeans(km)
+            u, r = hh.downsample(ds)
+            hh.init_centroids_first_k(km)
+            hh.kmeans(km)
             state["U_local"] = state["U"] = u
             state["R"] = r
         else:
-            u, r, _ = h.downsample_kmeans(ds, km, True)
+            u, r, _ = hh.downsample_kmeans(ds, km, True)
             state["U_local"] = state["U"] = u
             state["R"] = r
 
@@ -421,40 +582,93 @@ def _main(args, real_stdout):
     barrier()
     clocks = sampler.stop(clk_t0, time.time()) if rank == 0 else None
     algo_used = h.stage_times().ds_algo_used
-    tt = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms_per_step = float(tt.item()) / args.steps
+    ms_per_step = max_over_ranks(total_ms) / args.steps
     value = n * world / (ms_per_step * 1e-3) / 1e6
 
-    # ---- end to end from pinned host memory through the C-ABI --------------------------------
+    # ---- end to end through the C-ABI with host buffers ----------------------------------------
+    # (a) everything the reference reads back (e2e), (b) centroids + counts only, (c) the bare H2D
+    U_cap = state["U_local"] + (1 << 16)
     host = torch.empty(n * 16, dtype=torch.uint8, pin_memory=True)
     host_np = host.numpy().view(evk.EVENT_DTYPE)
     host_np[:] = h.get_events()
-    cent = np.zeros((K, D), np.float32)
     e2e_steps = max(1, args.e2e_steps)
+    d2h_full = lambda u: 8 * u + 4 * u + K * D * 4 + K * 8 + 64
 
-    def e2e_step():
+    def timed(fn, reps):
+        fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return max_over_ranks((time.perf_counter() - t0) / reps)
+
+    def e2e_centroids_step():
         h.load_events_ptr(host.data_ptr(), n)
         step()
-        c, cnt = h.get_centroids(K, D)   # D2H + sync
-        return c
+        return h.get_centroids(K, D)[0]   # D2H + sync
 
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        cent = e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = n * world / float(te.item()) / 1e6
+    cent = e2e_centroids_step()
+    e2e_cent_s = timed(e2e_centroids_step, e2e_steps)
+
+    def h2d_only():
+        h.load_events_ptr(host.data_ptr(), n)
+        h.sync()
+
+    h2d_s = timed(h2d_only, e2e_steps)
+
+    out_keys = [torch.empty(U_cap, dtype=torch.int64, pin_memory=True) for _ in range(2)]
+    out_lab = [torch.empty(U_cap, dtype=torch.int32, pin_memory=True) for _ in range(2)]
+
+    def read_back(hh, slot):
+        u = hh.num_voxels()[0]
+        hh.get_voxels_ptr(out_keys[slot].data_ptr(), 0, 0, U_cap)   # canonical order, D2H + sync
+        hh.get_labels_ptr(out_lab[slot].data_ptr(), U_cap)
+        return u, hh.get_centroids(K, D)[0]
+
+    def e2e_serial_step():
+        h.load_events_ptr(host.data_ptr(), n)
+        step()
+        return read_back(h, 0)
+
+    u_s, cent_s = e2e_serial_step()
+    assert u_s == state["U_local"] and (cent_s == cent).all()
+    e2e_serial_s = timed(e2e_serial_step, e2e_steps)
+
+    # two handles alternate: slice i's read-back (D2H) overlaps slice i+1's upload (H2D)
+    e2e_pipe_s = None
+    if world == 1 and not args.unfused:
+        h2 = evk.Evk(n, device=local_rank)
+        hs = [h, h2]
+
+        def e2e_pipe(reps):
+            for i in range(reps + 1):
+                if i < reps:
+                    a = hs[i & 1]
+                    a.load_events_ptr(host.data_ptr(), n)         # asynchronous (pinned source)
+                    a.downsample_kmeans_submit(ds, km, True)      # asynchronous
+                if i > 0:
+                    b = hs[(i - 1) & 1]
+                    b.downsample_kmeans_wait()
+                    u, c = read_back(b, (i - 1) & 1)
+                    assert u == state["U_local"]
+            return c
+
+        cp = e2e_pipe(2)
+        assert (cp == cent).all(), "pipelined e2e changed the result"
+        torch.cuda.synchronize()
+        reps = max(4, 2 * e2e_steps)
+        t0 = time.perf_counter()
+        e2e_pipe(reps)
+        torch.cuda.synchronize()
+        e2e_pipe_s = (time.perf_counter() - t0) / reps
+        h2.close()
+    e2e_s = e2e_pipe_s if e2e_pipe_s is not None else e2e_serial_s
+    e2e_val = n * world / e2e_s / 1e6
 
     # ---- end to end from the sensor's RAW EVT 2.0 words (4 B per event over PCIe) --------------
     e2e_raw = None
-    if world == 1:
+    if world == 1 and not args.no_extras and args.config == "c3":
         spec2 = importlib.util.spec_from_file_location(
             "evk_evt2", os.path.join(evk_loader.PKG_DIR, "evt2.py"))
         evt2 = importlib.util.module_from_spec(spec2)
@@ -479,14 +693,15 @@ def _main(args, real_stdout):
         raw_s = (time.perf_counter() - t0) / e2e_steps
         e2e_raw = {"value": n / raw_s / 1e6, "unit": "Mevents/s", "ms_per_step": raw_s * 1e3,
                    "h2d_bytes_per_step": 4 * n_words, "d2h_bytes_per_step": K * D * 4 + K * 8 + 64,
-                   "input": "RAW EVT 2.0 words (evk_load_evt2), decoded on the device"}
+                   "input": "RAW EVT 2.0 words (evk_load_evt2), decoded on the device; centroids "
+                            "+ counts read back"}
 
     if rank == 0:
         peak, peak_src = peaks()
         U = state["U_local"]
         ds_ms, km_ms = ds_main / args.steps, km_total / args.steps
         ds_bytes, km_bytes = 16.0 * n + 16.0 * U, 20.0 * U
-        names = {evk.ALGO_SLAB: "k_slab_main", evk.ALGO_TABLE: "k_table_insert",
+        names = {evk.ALGO_SLAB: "k_slab_pipe", evk.ALGO_TABLE: "k_table_insert",
                  evk.ALGO_SORT: "sort+unique"}
         traffic = ncu_traffic()
         fused = not args.unfused and algo_used == evk.ALGO_SLAB
@@ -496,10 +711,12 @@ def _main(args, real_stdout):
             kern, a_bytes, a_ms = "k_km_assign_tiles", km_bytes, km_ms
         achieved = a_bytes / (a_ms * 1e-3) / 1e9 if a_ms > 0 else 0.0
         step_bytes = 16.0 * n + 36.0 * U
+        tr = traffic.get(kern) if isinstance(traffic.get(kern), dict) else {"bytes": traffic.get(kern)}
         line = {
             "metric": "Mevents/s downsample+k-means iteration", "value": value,
             "unit": "Mevents/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "u64 keys / f32 distances / exact u64 sums",
             "data": "synthetic", "config": workload_config(args, world),
             "unique_voxels_per_gpu": U, "repeated": state.get("R"),
@@ -508,9 +725,12 @@ def _main(args, real_stdout):
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "frac_of_8000_nominal": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": a_bytes, "kernel_ms": a_ms,
-                         "traffic": traffic.get(kern)},
+                         "traffic": tr.get("bytes"), "traffic_source": tr.get("source")},
             "stage_ms": {"downsample_dominant_kernel": ds_ms, "downsample_total": ds_total / args.steps,
                          "kmeans_iteration": km_ms, "fused": fused,
+                         "kmeans_byte_model": "20 B/voxel algorithmic (16-B record + label); the "
+                                              "kernel itself reads 4 B (xy) + writes 4 B per voxel, "
+                                              "so its 20U/t figure may exceed the HBM peak",
                          "measured": "CUDA events around every stage, second pass of the same "
                                      "K steps run synchronously (one host sync per step)",
                          "ms_per_step_synchronous": sync_ms_per_step},
@@ -521,25 +741,45 @@ def _main(args, real_stdout):
             "step_roofline": {"algorithmic_bytes": step_bytes,
                               "achieved": step_bytes / (ms_per_step * 1e-3) / 1e9,
                               "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                              "frac_of_8000_nominal": step_bytes / (ms_per_step * 1e-3) / 1e9 / 8000.0,
                               "note": "16N+36U bytes over the whole step (ms_per_step)"},
             "e2e": {"value": e2e_val, "unit": "Mevents/s", "h2d_bytes_per_step": 16 * n,
-                    "d2h_bytes_per_step": K * D * 4 + K * 8 + 64, "steps": e2e_steps,
-                    "ms_per_step": float(te.item()) * 1e3,
-                    "result_read": "centroids + counts (+ voxel counters)"},
+                    "d2h_bytes_per_step": d2h_full(U), "steps": e2e_steps,
+                    "ms_per_step": e2e_s * 1e3,
+                    "result_read": "unique voxel keys (canonical order) + labels + centroids + counts",
+                    "mode": ("two handles alternating (read-back of slice i overlaps upload of "
+                             "slice i+1)" if e2e_pipe_s is not None else "one handle, serial")},
+            "e2e_serial": {"value": n * world / e2e_serial_s / 1e6, "unit": "Mevents/s",
+                           "ms_per_step": e2e_serial_s * 1e3, "h2d_bytes_per_step": 16 * n,
+                           "d2h_bytes_per_step": d2h_full(U),
+                           "result_read": "keys + labels + centroids + counts, one handle"},
+            "e2e_centroids": {"value": n * world / e2e_cent_s / 1e6, "unit": "Mevents/s",
+                              "ms_per_step": e2e_cent_s * 1e3, "h2d_bytes_per_step": 16 * n,
+                              "d2h_bytes_per_step": K * D * 4 + K * 8 + 64,
+                              "result_read": "centroids + counts (+ voxel counters)"},
+            "h2d_only": {"ms_per_step": h2d_s * 1e3, "GBps_per_gpu": 16 * n / h2d_s / 1e9,
+                         "GBps_all_gpus": 16 * n * world / h2d_s / 1e9,
+                         "note": "bare evk_load_events from pinned host memory on every rank at once: "
+                                 "the host-side limit of any e2e number", "numa": numa},
             "gpu_launches": launches, "clocks": clocks,
         }
         if e2e_raw:
             line["e2e_raw_evt2"] = e2e_raw
+    h.close()
+    if rank == 0 and world == 1 and not args.no_extras and args.config == "c3":
+        line["extra_keys"] = {"c5": c5_leg(evk, torch, local_rank, args.c5_windows),
+                              "c1": c1_leg(evk, local_rank)}
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             n_sample = min(args.cpu_sample, n)
-            mev, threads, Us, best = cpu_port(n_sample, 2, 0)
+            mev, threads, Us, best = cpu_port(n_sample, 2, host_threads())
             line["cpu_baseline"] = {
                 "value": mev, "unit": "Mevents/s", "cores": threads, "kind": "port",
                 "sample": f"first {n_sample} events of the workload stream (U={Us}), best of 2 "
                           f"passes ({best:.2f} s each), generation excluded"}
-            line["consumer"] = consumer_leg(evk)
+            if not args.no_extras:
+                line["consumer"] = consumer_leg(evk)
         print(json.dumps(line), file=real_stdout, flush=True)
-    h.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -342,6 +342,15 @@ class Evk:
                                         None if f is None else _p(f), n))
         return k, r, f
 
+    def get_voxels_ptr(self, keys_addr, reps_addr, first_addr, cap):
+        """evk_get_voxels into caller-owned (pinned) host buffers given by address (0 = skip)"""
+        self._ck(self._L.evk_get_voxels(self._h, C.c_void_p(keys_addr or None),
+                                        C.c_void_p(reps_addr or None),
+                                        C.c_void_p(first_addr or None), cap))
+
+    def get_labels_ptr(self, addr, cap):
+        self._ck(self._L.evk_get_labels(self._h, C.c_void_p(addr), cap))
+
     # ---- cluster
     def set_centroids(self, c):
         c = np.ascontiguousarray(c, dtype=np.float32)
@@ -514,6 +523,13 @@ class Evk:
         done = C.c_int(0)
         b = ev.ctypes.data
         self._ck(self._L.evk_window_push(self._h, b, b + ev.nbytes, C.byref(done)))
+        return done.value
+
+    def window_push_ptr(self, addr, n):
+        """n records in a (pinned) host buffer at `addr`"""
+        done = C.c_int(0)
+        self._ck(self._L.evk_window_push(self._h, C.c_void_p(addr), C.c_void_p(addr + 16 * n),
+                                         C.byref(done)))
         return done.value
 
     def window_flush(self):

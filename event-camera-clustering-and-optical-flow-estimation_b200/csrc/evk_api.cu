@@ -42,19 +42,6 @@ size_t next_pow2(size_t v) {
     return p;
 }
 
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-    }
-    ~DeviceGuard() {
-        int cur = -1;
-        cudaGetDevice(&cur);
-        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
-    }
-};
-
 void prof_rec(evk_handle* h, int i) { evk_prof_rec(h, i); }
 float prof_ms(evk_handle* h, int a, int b) {
     float ms = 0.f;
@@ -89,6 +76,12 @@ bool ensure_images(evk_handle* h, int width, int height) {
     const size_t need = (size_t)width * (size_t)height;
     if (need > (64ull << 20)) return false;
     if (h->image_pixels < need) {
+        // cached graphs (fused step, Lloyd loop, sharded step) hold the old pointers: their keys
+        // carry image_gen, so the next call of each re-captures.  A graph may still be in flight.
+        DeviceGuard g(h->device);
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        if (h->side) cudaStreamSynchronize(h->side);
+        h->image_gen++;
         if (h->d_label_map) cudaFree(h->d_label_map);
         if (h->d_pixcnt) cudaFree(h->d_pixcnt);
         h->d_label_map = nullptr;
@@ -230,7 +223,8 @@ int evk_create(evk_handle** out, int device, size_t max_events) {
     ALLOC(h->d_tkeys, h->table_cap * sizeof(uint64_t));
     ALLOC(h->d_tfirst, h->table_cap * sizeof(uint32_t));
     // the slab kernel hands out output slots in CTA-private chunks: room for the unfilled tails
-    h->out_cap = m + (size_t)EVK_SLAB_CHUNK * (3 * (size_t)h->sm_count + 4);
+    h->out_cap = m + (size_t)EVK_SLAB_CHUNK *
+                         (3 * (size_t)h->sm_count * evk_slab_ctas_per_sm() + 4);
     ALLOC(h->d_keys, h->out_cap * sizeof(uint64_t));
     ALLOC(h->d_first, h->out_cap * sizeof(uint32_t));
     ALLOC(h->d_xy, h->out_cap * sizeof(uint32_t));
@@ -245,6 +239,8 @@ int evk_create(evk_handle** out, int device, size_t max_events) {
     ALLOC(h->d_prune_lists, EVK_PRUNE_TILES * 16);
     ALLOC(h->d_quads, EVK_MAX_QUADS);
     ALLOC(h->d_n_points, sizeof(unsigned long long));
+    ALLOC(h->d_sticky, sizeof(unsigned long long));
+    ALLOC(h->d_t0, sizeof(long long));
     ALLOC(h->d_cand, 2 * h->cand_cap * sizeof(uint32_t));
     ALLOC(h->d_flush, h->flush_bytes);
 #undef ALLOC
@@ -258,6 +254,8 @@ int evk_create(evk_handle** out, int device, size_t max_events) {
         return bail(EVK_ERR_CUDA);
     cudaMemsetAsync(h->d_acc, 0, EVK_MAX_K * 5 * sizeof(unsigned long long), h->stream);
     cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream);
+    cudaMemsetAsync(h->d_sticky, 0, sizeof(unsigned long long), h->stream);
+    cudaMemsetAsync(h->d_slab_scratch, 0, evk_slab_scratch_bytes(h->sm_count), h->stream);
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return bail(EVK_ERR_CUDA);
     *out = h;
     return EVK_OK;
@@ -285,7 +283,7 @@ int evk_destroy(evk_handle* h) {
                     h->d_sort_c, h->d_sk_in,  h->d_sk_out, h->d_si_in,  h->d_si_out, h->d_sv_tmp,
                     h->d_bin_start, h->d_slab_scratch, h->d_cnt, h->d_cent,   h->d_acc,    h->d_counts, h->d_shift,
                     h->d_cand,   h->d_flush, h->d_prune_lists, h->d_label_map, h->d_pixcnt, h->d_quads,
-                    h->d_win_stage, h->d_n_points, h->d_raw, h->d_raw_blk};
+                    h->d_win_stage, h->d_n_points, h->d_raw, h->d_raw_blk, h->d_sticky, h->d_t0};
     for (void* p : ptrs)
         if (p) chk(cudaFree(p), "free");
     if (h->h_cnt) chk(cudaFreeHost(h->h_cnt), "free host");
@@ -307,6 +305,8 @@ int evk_destroy(evk_handle* h) {
 static int append_host(evk_handle* h, const evk_event* begin, const evk_event* end, bool replace) {
     EVK_TRY(check_handle(h));
     if ((!begin && end != begin) || end < begin) return evk_fail(h, EVK_ERR_INVALID, "bad event range");
+    // a queued step publishes first indices into the events it ran on: collect it before they change
+    EVK_TRY(evk_collect_pending(h));
     DeviceGuard g(h->device);
     const size_t n = (size_t)(end - begin);
     const size_t at = replace ? 0 : h->n_events;
@@ -333,6 +333,7 @@ int evk_load_events_soa(evk_handle* h, const uint16_t* x, const uint16_t* y, con
     EVK_TRY(check_handle(h));
     if (n && (!x || !y)) return evk_fail(h, EVK_ERR_INVALID, "x / y are NULL");
     if (n > h->max_events) return evk_fail(h, EVK_ERR_CAPACITY, "too many events");
+    EVK_TRY(evk_collect_pending(h));
     DeviceGuard g(h->device);
     invalidate_results(h);
     h->n_events = n;
@@ -355,6 +356,7 @@ int evk_load_coords_i32(evk_handle* h, const int32_t* xy, size_t n_pairs) {
     EVK_TRY(check_handle(h));
     if (n_pairs && !xy) return evk_fail(h, EVK_ERR_INVALID, "xy is NULL");
     if (n_pairs > h->max_events) return evk_fail(h, EVK_ERR_CAPACITY, "too many coordinates");
+    EVK_TRY(evk_collect_pending(h));
     DeviceGuard g(h->device);
     invalidate_results(h);
     h->n_events = n_pairs;
@@ -396,6 +398,7 @@ static int load_raw_words(evk_handle* h, int fmt, const void* words, size_t n_wo
                           size_t* n_events) {
     EVK_TRY(check_handle(h));
     if (n_words && !words) return evk_fail(h, EVK_ERR_INVALID, "words is NULL");
+    EVK_TRY(evk_collect_pending(h));
     DeviceGuard g(h->device);
     invalidate_results(h);
     h->n_events = 0;
@@ -511,6 +514,7 @@ int evk_synth(evk_handle* h, const evk_synth_params* sp) {
     if (!sp || sp->rate_eps == 0 || sp->width < 1 || sp->height < 1 || sp->n_blobs < 1)
         return evk_fail(h, EVK_ERR_INVALID, "bad synth params");
     if (sp->n_events > h->max_events) return evk_fail(h, EVK_ERR_CAPACITY, "too many events");
+    EVK_TRY(evk_collect_pending(h));
     DeviceGuard g(h->device);
     invalidate_results(h);
     h->n_events = (size_t)sp->n_events;
@@ -556,6 +560,7 @@ int evk_downsample_local(evk_handle* h, const evk_ds_params* p) {
         if (evk_slab_supported(h, kp)) EVK_TRY(evk_downsample_slab(h, kp, p->count_repeated, &ok, &launches));
         if (!ok) {  // not partitioned by time bin (or unsupported shape): general path
             algo = EVK_ALGO_TABLE;
+            EVK_CUDA(h, cudaMemsetAsync(h->d_sticky, 0, sizeof(unsigned long long), h->stream));
             EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
             prof_rec(h, 0);
         } else {
@@ -746,7 +751,10 @@ int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_done,
     // three or more iterations (or a tolerance stop) the iterations run on the W x H histogram of
     // the representatives and the voxel list is touched twice in total (histogram, final labels);
     // else every iteration is one two-level pass over the voxel list.
-    const bool image = xy && h->have_ds && p->D == 2 && p->K <= 254 &&
+    // (EVK_KEY_REF_HASH8192 gates inclusively, x <= width: its representatives may lie one pixel
+    // outside the W x H images, so that key function takes the per-point scan)
+    const bool in_frame = xy && h->have_ds && h->kp.keyfn == EVK_KEY_VOXEL;
+    const bool image = in_frame && p->D == 2 && p->K <= 254 &&
                        ensure_images(h, h->ds.width, h->ds.height);
     const bool on_hist = image && (p->iters >= 3 || p->tol >= 0.f);
     if (on_hist && p->tol < 0.f && !reduce && n) {
@@ -763,6 +771,7 @@ int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_done,
         key.profiling = h->profiling ? 1 : 0;
         key.max_dist = p->max_dist;
         key.cap = h->out_cap;
+        key.image_gen = h->image_gen;
         EVK_CUDA(h, evk_launch_set_u64(h->d_n_points, (unsigned long long)n, h->stream));
         if (!h->loop_exec || memcmp(&key, &h->loop_key, sizeof key) != 0) {
             if (h->loop_exec) {
@@ -841,7 +850,7 @@ int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_done,
                                                 h->d_label_map, xy, n, nullptr, true, h->d_acc,
                                                 h->d_labels, h->sm_count, h->stream);
         } else {
-            if (xy && h->have_ds)  // voxels are gated to the frame: exact candidate pruning applies
+            if (in_frame)  // voxels are gated to the frame: exact candidate pruning applies
                 ce = evk_launch_km_assign_pruned(kl, h->ds.width, h->ds.height, h->d_prune_lists,
                                                  xy, n, h->d_cent, h->d_acc, h->d_labels,
                                                  h->sm_count, h->stream);
@@ -909,14 +918,14 @@ static int enqueue_fused(evk_handle* h, const KeyParams& kp, const evk_ds_params
     prof_rec(h, 0);
     EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
     bool ok = false;
-    EVK_TRY(evk_downsample_slab(h, kp, ds->count_repeated, &ok, launches, false));
+    EVK_TRY(evk_downsample_slab(h, kp, ds->count_repeated, &ok, launches, false, nullptr, h->d_t0));
     // side stream: everything that depends on the centroids only (first-K walk over the head
     // of the stream, candidate lists, label map, quads) runs beside the downsample
     EVK_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
     if (init_first_k) {
         const size_t n_scan = h->n_events < (1u << 20) ? h->n_events : (1u << 20);
         EVK_CUDA(h, evk_launch_init_first_k_walk(kp, kl, h->d_events, n_scan, h->d_cent,
-                                                 &h->d_cnt->scratch[4], h->side));
+                                                 &h->d_cnt->scratch[4], h->side, h->d_t0));
         (*launches)++;
     } else {  // warm start: keep a copy in case the stream check sends us to the general path
         EVK_CUDA(h, cudaMemcpyAsync(h->d_cent + EVK_MAX_K * 2, h->d_cent,
@@ -954,6 +963,7 @@ int evk_downsample_kmeans_submit(evk_handle* h, const evk_ds_params* ds, const e
     EVK_TRY(km_validate(h, km));
     KeyParams kp;
     EVK_TRY(evk_make_key_params(h, ds, &kp));
+    DeviceGuard g(h->device);  // before anything that may allocate (ensure_images)
     h->shard_first = h->comm ? h->shard_first : 0;
     // (a queued step leaves centroids behind: a warm start may follow it without a wait)
     if (!init_first_k && h->step_pending != 1 &&
@@ -962,7 +972,8 @@ int evk_downsample_kmeans_submit(evk_handle* h, const evk_ds_params* ds, const e
     const bool fusable = km->D == 2 && !km->on_events && km->K <= 254 && h->n_events &&
                          km->iters == 1 && km->tol < 0.f &&
                          (ds->algo == EVK_ALGO_AUTO || ds->algo == EVK_ALGO_SLAB) &&
-                         evk_slab_supported(h, kp) && ensure_images(h, ds->width, ds->height);
+                         kp.keyfn == EVK_KEY_VOXEL && evk_slab_supported(h, kp) &&
+                         ensure_images(h, ds->width, ds->height);
     if (!fusable) {
         if (h->step_pending == 1)
             EVK_TRY(evk_downsample_kmeans_wait(h, nullptr, nullptr, nullptr));
@@ -976,7 +987,6 @@ int evk_downsample_kmeans_submit(evk_handle* h, const evk_ds_params* ds, const e
     h->step_km = *km;
     h->step_init = init_first_k;
     h->step_iters = 0;
-    DeviceGuard g(h->device);
     invalidate_results(h);
     h->ds = *ds;
     h->kp = kp;
@@ -987,11 +997,15 @@ int evk_downsample_kmeans_submit(evk_handle* h, const evk_ds_params* ds, const e
     memset(&key, 0, sizeof key);
     key.n = h->n_events;
     key.ds = *ds;
+    key.ds.t0_us = 0;  // the time origin is a device-side value (d_t0): windows replay one graph
     key.km = *km;
     key.init = init_first_k ? 1 : 0;
     key.profiling = h->profiling ? 1 : 0;
     key.shard_first = h->shard_first;
+    key.image_gen = h->image_gen;
     int launches = 0;
+    EVK_CUDA(h, evk_launch_set_u64(reinterpret_cast<unsigned long long*>(h->d_t0),
+                                   (unsigned long long)ds->t0_us, h->stream));
     if (h->fused_exec && memcmp(&key, &h->fused_key, sizeof key) == 0) {
         launches = h->fused_launches;
     } else {
@@ -1017,6 +1031,7 @@ int evk_downsample_kmeans_submit(evk_handle* h, const evk_ds_params* ds, const e
         h->fused_launches = launches;
     }
     EVK_CUDA(h, cudaGraphLaunch(h->fused_exec, h->stream));
+    h->steps_queued = h->step_pending == 1 ? h->steps_queued + 1 : 1;
     h->step_pending = 1;
     h->step_sharded = false;
     return EVK_OK;
@@ -1037,7 +1052,23 @@ int evk_downsample_kmeans_wait(evk_handle* h, size_t* n_unique, size_t* n_repeat
         const evk_km_params* km = &h->step_km;
         const int init_first_k = h->step_init;
         const int launches = h->fused_launches;
+        const int queued = h->steps_queued;
+        h->steps_queued = 0;
+        if (queued > 1)  // earlier queued steps: did the fast path reject any of them?
+            EVK_CUDA(h, cudaMemcpyAsync(&h->h_cnt->scratch[5], h->d_sticky, sizeof(unsigned long long),
+                                        cudaMemcpyDeviceToHost, h->stream));
         EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (queued > 1) {
+            // (the last step's own rejection is handled below by the rerun; it counts once here)
+            const unsigned long long rejected = h->h_cnt->scratch[5];
+            const unsigned long long last = h->h_cnt->slab_violation ? 1ull : 0ull;
+            if (rejected) EVK_CUDA(h, cudaMemsetAsync(h->d_sticky, 0, sizeof(unsigned long long), h->stream));
+            if (rejected > last)
+                return evk_fail(h, EVK_ERR_STATE,
+                                "%llu of %d queued steps were rejected by the time-slab path (slices "
+                                "must be time-ordered to be queued): resubmit them one at a time",
+                                rejected - last, queued);
+        }
         const bool ok = h->h_cnt->slab_violation == 0 && h->h_cnt->overflow == 0 &&
                         (!init_first_k || h->h_cnt->scratch[4] == (unsigned long long)km->K);
         if (ok) {
@@ -1062,6 +1093,7 @@ int evk_downsample_kmeans_wait(evk_handle* h, size_t* n_unique, size_t* n_repeat
             }
             h->step_iters = 1;
         } else {
+            EVK_CUDA(h, cudaMemsetAsync(h->d_sticky, 0, sizeof(unsigned long long), h->stream));
             if (!init_first_k) {  // finalise has overwritten the caller's centroids
                 if (!h->have_centroids || h->K != km->K || h->D != km->D)
                     return evk_fail(h, EVK_ERR_STATE,
@@ -1191,6 +1223,7 @@ int evk_window_push(evk_handle* h, const evk_event* begin, const evk_event* end,
     EVK_TRY(check_handle(h));
     if (!h->win_cfg) return evk_fail(h, EVK_ERR_STATE, "evk_window_config has not been called");
     if ((!begin && end != begin) || end < begin) return evk_fail(h, EVK_ERR_INVALID, "bad event range");
+    EVK_TRY(evk_collect_pending(h));
     int done = 0;
     const evk_event* p = begin;
     while (h->win_events && p != end) {  // count-based windows

@@ -765,7 +765,7 @@ int evk_comm_init(evk_handle* h, int rank, int world, const uint8_t* id128) {
         return evk_fail(h, EVK_ERR_INVALID, "bad communicator shape rank=%d world=%d", rank, world);
     if (!load_nccl()) return evk_fail(h, EVK_ERR_COMM, "libnccl.so.2 not found: %s", dlerror());
     if (h->comm) evk_comm_destroy(h);
-    EVK_CUDA(h, cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     CommState* c = new CommState();
     c->rank = rank;
     c->world = world;
@@ -791,7 +791,7 @@ int evk_comm_init(evk_handle* h, int rank, int world, const uint8_t* id128) {
 int evk_comm_destroy(evk_handle* h) {
     if (!h || !h->comm) return EVK_OK;
     CommState* c = h->comm;
-    cudaSetDevice(h->device);
+    DeviceGuard dev_guard(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (c->step_exec) cudaGraphExecDestroy(c->step_exec);
     for (int r = 0; r < c->world; r++) {
@@ -826,7 +826,7 @@ int evk_downsample_sharded(evk_handle* h, const evk_ds_params* p, int owner_mode
     if (!h->comm) return evk_fail(h, EVK_ERR_COMM, "evk_comm_init has not been called");
     if (!p) return evk_fail(h, EVK_ERR_INVALID, "ds params are NULL");
     CommState* c = h->comm;
-    EVK_CUDA(h, cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     bool done = false;
     if (owner_mode == EVK_OWNER_TIME_RANGE) {
         EVK_TRY(sharded_time_range(h, p, &done));
@@ -970,7 +970,7 @@ int evk_downsample_kmeans_sharded_submit(evk_handle* h, const evk_ds_params* ds,
     KeyParams kp;
     EVK_TRY(evk_make_key_params(h, ds, &kp));
     CommState* c = h->comm;
-    EVK_CUDA(h, cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     if (!init_first_k && h->step_pending != 1 &&
         (!h->have_centroids || h->K != km->K || h->D != km->D))
         return evk_fail(h, EVK_ERR_STATE, "centroids for K=%d, D=%d have not been set", km->K, km->D);
@@ -1021,6 +1021,7 @@ int evk_downsample_kmeans_sharded_submit(evk_handle* h, const evk_ds_params* ds,
     key.init = init_first_k ? 1 : 0;
     key.profiling = h->profiling ? 1 : 0;
     key.shard_first = h->shard_first;
+    key.image_gen = h->image_gen;
     int launches = 0;
     if (c->step_exec && memcmp(&key, &c->step_key, sizeof key) == 0) {
         launches = c->step_launches;
@@ -1064,7 +1065,7 @@ int evk_downsample_kmeans_sharded_wait(evk_handle* h, size_t* n_unique_local,
     const int pending = h->step_pending;
     h->step_pending = 0;
     if (pending == 1) {
-        EVK_CUDA(h, cudaSetDevice(h->device));
+        DeviceGuard dev_guard(h->device);
         const evk_ds_params* ds = &h->step_ds;
         const evk_km_params* km = &h->step_km;
         const int init_first_k = h->step_init;
@@ -1102,6 +1103,7 @@ int evk_downsample_kmeans_sharded_wait(evk_handle* h, size_t* n_unique_local,
             }
             h->step_iters = 1;
         } else {
+            EVK_CUDA(h, cudaMemsetAsync(h->d_sticky, 0, sizeof(unsigned long long), h->stream));
             if (!init_first_k) {  // finalise has overwritten the caller's centroids
                 if (!h->have_centroids || h->K != km->K || h->D != km->D)
                     return evk_fail(h, EVK_ERR_STATE,
@@ -1138,7 +1140,7 @@ int evk_init_centroids_first_k_sharded(evk_handle* h, const evk_km_params* p) {
         return evk_fail(h, EVK_ERR_INVALID, "bad k-means params");
     if (!h->have_ds) return evk_fail(h, EVK_ERR_STATE, "evk_downsample_sharded has not run");
     CommState* c = h->comm;
-    EVK_CUDA(h, cudaSetDevice(h->device));
+    DeviceGuard dev_guard(h->device);
     // the K globally lowest first indices are the first K distinct keys of rank 0's shard
     unsigned long long* d_found = c->d_stats + 5;
     EVK_CUDA(h, cudaMemsetAsync(d_found, 0, 8, h->stream));

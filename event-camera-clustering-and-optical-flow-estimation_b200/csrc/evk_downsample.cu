@@ -309,23 +309,126 @@ int evk_downsample_sort(evk_handle* h, const KeyParams& kp, int* launches) {
     return EVK_OK;
 }
 
-// canonical order: permutation that sorts the voxel shard by first stream index
+// ---- canonical order ------------------------------------------------------------------------
+// perm[i] = emission position of the voxel with the i-th lowest first stream index.  First indices
+// are distinct event indices inside the handle's shard, so the rank of a voxel is a population
+// count: one bit per event ("is a representative"), an exclusive prefix of the word popcounts, and
+// rank(f) = prefix[f / 32] + popc(word & below(f)).  Three light passes over the voxel list and a
+// 1-bit-per-event map instead of a radix sort of the first indices (4 passes over 8-byte pairs).
+namespace {
+constexpr int kScanWords = 16;  // flag words per thread in the prefix passes
+
+__global__ void __launch_bounds__(kBlock)
+    k_perm_flag(const uint32_t* __restrict__ first, size_t n, uint32_t base, uint32_t* flags) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t f = first[i] - base;
+        atomicOr(&flags[f >> 5], 1u << (f & 31));
+    }
+}
+
+// pass 1: popcount of each block of kBlock * kScanWords flag words
+__global__ void __launch_bounds__(kBlock)
+    k_perm_blocksum(const uint32_t* __restrict__ flags, size_t words, uint32_t* blk) {
+    __shared__ int s_warp[kBlock / 32 + 1];
+    const size_t w0 = ((size_t)blockIdx.x * kBlock + threadIdx.x) * kScanWords;
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kScanWords; j++)
+        if (w0 + j < words) c += __popc(flags[w0 + j]);
+    int total;
+    block_excl_scan(c, total, s_warp);
+    if (threadIdx.x == 0) blk[blockIdx.x] = (uint32_t)total;
+}
+
+// pass 2: exclusive scan of the block sums, one CTA, carried across chunks of kBlock
+__global__ void __launch_bounds__(kBlock) k_perm_blockscan(uint32_t* blk, size_t n_blocks) {
+    __shared__ int s_warp[kBlock / 32 + 1];
+    uint32_t carry = 0;
+    for (size_t b0 = 0; b0 < n_blocks; b0 += kBlock) {
+        const size_t b = b0 + threadIdx.x;
+        const int v = b < n_blocks ? (int)blk[b] : 0;
+        int total;
+        const int off = block_excl_scan(v, total, s_warp);
+        if (b < n_blocks) blk[b] = carry + (uint32_t)off;
+        carry += (uint32_t)total;
+    }
+}
+
+// pass 3: exclusive prefix per flag word
+__global__ void __launch_bounds__(kBlock)
+    k_perm_wordprefix(const uint32_t* __restrict__ flags, size_t words,
+                      const uint32_t* __restrict__ blk, uint32_t* prefix) {
+    __shared__ int s_warp[kBlock / 32 + 1];
+    const size_t w0 = ((size_t)blockIdx.x * kBlock + threadIdx.x) * kScanWords;
+    uint32_t v[kScanWords];
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kScanWords; j++) {
+        v[j] = w0 + j < words ? flags[w0 + j] : 0u;
+        c += __popc(v[j]);
+    }
+    int total;
+    uint32_t run = blk[blockIdx.x] + (uint32_t)block_excl_scan(c, total, s_warp);
+#pragma unroll
+    for (int j = 0; j < kScanWords; j++) {
+        if (w0 + j < words) prefix[w0 + j] = run;
+        run += __popc(v[j]);
+    }
+}
+
+__global__ void __launch_bounds__(kBlock)
+    k_perm_scatter(const uint32_t* __restrict__ first, size_t n, uint32_t base,
+                   const uint32_t* __restrict__ flags, const uint32_t* __restrict__ prefix,
+                   uint32_t* perm) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint32_t f = first[i] - base;
+        const uint32_t w = f >> 5;
+        const uint32_t rank = prefix[w] + __popc(flags[w] & ((1u << (f & 31)) - 1u));
+        perm[rank] = (uint32_t)i;
+    }
+}
+}  // namespace
+
 int evk_ensure_perm(evk_handle* h) {
     if (h->perm_valid) return EVK_OK;
     const size_t n = h->n_unique;
+    const size_t m = h->max_events;
     if (!h->d_perm) {
-        const size_t m = h->max_events;
         EVK_CUDA(h, cudaMalloc(&h->d_perm, m * sizeof(uint32_t)));
-        EVK_CUDA(h, cudaMalloc(&h->d_sort_a, m * sizeof(uint32_t)));
-        EVK_CUDA(h, cudaMalloc(&h->d_sort_b, m * sizeof(uint32_t)));
-        size_t bytes = 0;
-        EVK_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->d_first, h->d_sort_b,
-                                                    h->d_sort_a, h->d_perm, (int64_t)m, 0, 32,
-                                                    h->stream));
-        EVK_CUDA(h, cudaMalloc(&h->d_sort_tmp, bytes));
-        h->sort_tmp_bytes = bytes;
+        EVK_CUDA(h, cudaMalloc(&h->d_sort_a, (m + 64) * sizeof(uint32_t)));
+        EVK_CUDA(h, cudaMalloc(&h->d_sort_b, (m + 64) * sizeof(uint32_t)));
     }
-    if (n) {
+    if (n && !h->reps_valid) {
+        // local voxels: first indices lie in [shard_first, shard_first + max_events)
+        const uint32_t base = (uint32_t)h->shard_first;
+        const size_t words = (m + 31) / 32 + 1;
+        const size_t per_block = (size_t)kBlock * kScanWords;
+        const size_t n_blocks = (words + per_block - 1) / per_block;
+        uint32_t* flags = h->d_sort_a;            // [words]
+        uint32_t* prefix = h->d_sort_b;           // [words]
+        uint32_t* blk = h->d_sort_a + words + 4;  // [n_blocks]  (words + n_blocks << m)
+        if (words + 4 + n_blocks > m + 64) return evk_fail(h, EVK_ERR_CAPACITY, "perm scratch");
+        EVK_CUDA(h, cudaMemsetAsync(flags, 0, words * sizeof(uint32_t), h->stream));
+        const int grid = grid_for(n, kBlock, h->sm_count);
+        k_perm_flag<<<grid, kBlock, 0, h->stream>>>(h->d_first, n, base, flags);
+        k_perm_blocksum<<<(unsigned)n_blocks, kBlock, 0, h->stream>>>(flags, words, blk);
+        k_perm_blockscan<<<1, kBlock, 0, h->stream>>>(blk, n_blocks);
+        k_perm_wordprefix<<<(unsigned)n_blocks, kBlock, 0, h->stream>>>(flags, words, blk, prefix);
+        k_perm_scatter<<<grid, kBlock, 0, h->stream>>>(h->d_first, n, base, flags, prefix, h->d_perm);
+        EVK_CUDA(h, cudaGetLastError());
+    } else if (n) {
+        // voxels received from peers (hash ownership): first indices span the whole global stream;
+        // radix sort of (first index, position) pairs -- library code, off the hot path
+        if (!h->d_sort_tmp) {
+            size_t bytes = 0;
+            EVK_CUDA(h, cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->d_first, h->d_sort_b,
+                                                        h->d_sort_a, h->d_perm, (int64_t)m, 0, 32,
+                                                        h->stream));
+            EVK_CUDA(h, cudaMalloc(&h->d_sort_tmp, bytes));
+            h->sort_tmp_bytes = bytes;
+        }
         k_iota<<<grid_for(n, kBlock, h->sm_count), kBlock, 0, h->stream>>>(h->d_sort_a, n);
         EVK_CUDA(h, cudaGetLastError());
         size_t bytes = h->sort_tmp_bytes;

@@ -115,6 +115,7 @@ struct FusedKey {  // what the captured fused-step graph depends on
     evk_km_params km;
     int init, profiling;
     uint64_t shard_first;
+    uint64_t image_gen;  // bumped when the pixel images are reallocated (their pointers are baked in)
 };
 
 struct evk_handle {
@@ -177,6 +178,7 @@ struct evk_handle {
         int width, height, K, iters, need_hist, profiling;
         float max_dist;
         size_t cap;
+        uint64_t image_gen;
     } loop_key{};
     unsigned long long* d_n_points = nullptr;  // point count read by the loop graph's kernels
     cudaGraphExec_t fused_exec = nullptr;    // the fused step as one graph (evk_downsample_kmeans)
@@ -185,11 +187,17 @@ struct evk_handle {
     // evk_downsample_kmeans_submit / _wait: 0 = nothing submitted, 1 = graph in flight, 2 = the
     // step ran synchronously on the general path (wait only reports)
     int step_pending = 0;
+    // steps queued since the last wait, and a device counter of queued steps the fast path rejected
+    // (never cleared by the per-step memset): wait reports them instead of silently skipping a slice
+    int steps_queued = 0;
+    unsigned long long* d_sticky = nullptr;
+    long long* d_t0 = nullptr;  // time origin of the queued fused step (read by its kernels)
     evk_ds_params step_ds{};
     evk_km_params step_km{};
     int step_init = 0, step_iters = 0;
     bool step_sharded = false;  // the pending step was queued by the sharded submit
     size_t image_pixels = 0;                 // capacity of both
+    uint64_t image_gen = 0;                  // generation of the image allocations (graph keys)
     bool pix_valid = false;                  // d_pixcnt matches the current voxel shard
     float* d_shift = nullptr;                // [1]
     float* h_shift = nullptr;                // pinned
@@ -232,6 +240,20 @@ struct evk_handle {
     DbHost* db = nullptr;
     uint64_t shard_first = 0;
     std::string err;
+};
+
+// makes the handle's device current for the scope of an entry point and restores the caller's
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
 };
 
 // ---- error handling -------------------------------------------------------------------------
@@ -283,11 +305,15 @@ int evk_downsample_sort(evk_handle* h, const KeyParams& kp, int* launches);
 // downsample: time-slab kernel.  sync = false: everything is only enqueued; the caller copies the
 // counters, synchronises and reads slab_violation / overflow itself.
 // range (device, sharded runs): [0] give-up flag, [3] events to skip, [4] events to keep behind n.
+// t0_dev (device): when not null the time origin is read from there instead of kp.t0, so that a
+// captured graph can be replayed for slices with different origins (streaming windows).
 int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, bool* ok,
                         int* launches, bool sync = true,
-                        const unsigned long long* range = nullptr);
+                        const unsigned long long* range = nullptr,
+                        const long long* t0_dev = nullptr);
 bool evk_slab_supported(const evk_handle* h, const KeyParams& kp);
 size_t evk_slab_scratch_bytes(int sm_count);
+int evk_slab_ctas_per_sm();
 // canonical order
 int evk_ensure_perm(evk_handle* h);
 cudaError_t evk_launch_gather_voxels(const evk_handle* h, uint64_t* keys, evk_event* reps,
@@ -352,7 +378,8 @@ cudaError_t evk_launch_init_from_cand(const KmLaunch& kl, const uint32_t* cand, 
                                       const evk_event* reps, float* cent, cudaStream_t s);
 cudaError_t evk_launch_init_first_k_walk(const KeyParams& kp, const KmLaunch& kl,
                                          const evk_event* ev, size_t n_scan, float* cent,
-                                         unsigned long long* found, cudaStream_t s);
+                                         unsigned long long* found, cudaStream_t s,
+                                         const long long* t0_dev = nullptr);
 cudaError_t evk_launch_fill_u8(void* p, int v, size_t bytes, cudaStream_t s);
 // RAW EVT 2.0 decode (evk_evt2.cu): words on the device -> packed events, CD count in *total
 cudaError_t evk_launch_evt2_decode(const uint32_t* words, size_t n_words, uint32_t* blk,

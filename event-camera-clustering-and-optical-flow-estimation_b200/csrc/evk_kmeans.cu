@@ -652,8 +652,9 @@ __global__ void __launch_bounds__(kBlock)
 // host when the walk ran out (it then falls back to the rank-by-first-index path).
 __global__ void __launch_bounds__(32)
     k_init_first_k_walk(KeyParams kp, KmLaunch kl, const evk_event* __restrict__ ev, size_t n_scan,
-                        float* cent, unsigned long long* found_out) {
+                        float* cent, unsigned long long* found_out, const long long* t0_dev) {
     __shared__ uint64_t s_keys[EVK_MAX_K];
+    if (t0_dev) kp.t0 = *t0_dev;  // (replayed graphs: the time origin is a device-side value)
     const int lane = threadIdx.x;
     int found = 0;
     for (size_t base = 0; base < n_scan && found < kl.K; base += 32) {
@@ -889,7 +890,8 @@ cudaError_t evk_launch_init_from_cand(const KmLaunch& kl, const uint32_t* cand, 
 
 cudaError_t evk_launch_init_first_k_walk(const KeyParams& kp, const KmLaunch& kl,
                                          const evk_event* ev, size_t n_scan, float* cent,
-                                         unsigned long long* found, cudaStream_t s) {
-    k_init_first_k_walk<<<1, 32, 0, s>>>(kp, kl, ev, n_scan, cent, found);
+                                         unsigned long long* found, cudaStream_t s,
+                                         const long long* t0_dev) {
+    k_init_first_k_walk<<<1, 32, 0, s>>>(kp, kl, ev, n_scan, cent, found, t0_dev);
     return cudaGetLastError();
 }
