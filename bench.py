@@ -701,7 +701,7 @@ def _main(args, real_stdout):
         U = state["U_local"]
         ds_ms, km_ms = ds_main / args.steps, km_total / args.steps
         ds_bytes, km_bytes = 16.0 * n + 16.0 * U, 20.0 * U
-        names = {evk.ALGO_SLAB: "k_slab_pipe", evk.ALGO_TABLE: "k_table_insert",
+        names = {evk.ALGO_SLAB: "k_slab_main", evk.ALGO_TABLE: "k_table_insert",
                  evk.ALGO_SORT: "sort+unique"}
         traffic = ncu_traffic()
         fused = not args.unfused and algo_used == evk.ALGO_SLAB

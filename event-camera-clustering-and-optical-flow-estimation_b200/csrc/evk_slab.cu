@@ -6,9 +6,12 @@
 //   s_map    2 bits per spatial cell: "seen" and "hit at least twice" (the kernel's
 //            repeated_count semantics, ACCEL/build/coordinate_processor.cl:73-75), 16 cells per
 //            word so one load answers both (115 KB for Gen4 2x2 px + polarity)
-//   s_ev     a 3-stage ring of 2048-event tiles (32 KB each) filled by TMA bulk copies
-//            (cp.async.bulk + mbarrier complete_tx) issued two tiles ahead by an elected thread,
-//            across bin boundaries (bins are dealt round-robin, so the order is known)
+//   s_ev     a 2-stage ring of 3072-event tiles (48 KB each) filled by TMA bulk copies
+//            (cp.async.bulk + mbarrier complete_tx) issued by an elected thread across bin
+//            boundaries (bins are dealt round-robin, so the order is known).  The classify pass
+//            drains a tile into registers, so its slot is refilled one barrier later (tile + 2):
+//            the prefetch distance of a three-stage ring at two thirds of the memory, which is
+//            what lets a tile hold three events per thread (round 2: -3.8 %, profiles/r02)
 //   s_late   two small tables (one per tile parity) for the rare events that lose a claim race
 // Per tile:  classify  one bitmap load per event: seen -> duplicate of an earlier tile
 //            -- barrier: every read of the tile precedes every claim of the tile --
@@ -18,7 +21,8 @@
 //                      where a 32-bit atomicMin keeps the lowest index of the cell
 //            -- barrier --
 //            resolve   a claimant probes s_late once: a late peer with a lower index replaces it
-//                      as representative (lowest stream index wins); then warp ballot
+//                      as representative (lowest stream index wins; its coordinates are
+//                      re-read from global memory: rare, L2-resident); then warp ballot
 //                      + one shared atomic per warp claim output slots and the 16-B record goes
 //                      to HBM from registers
 // Two block barriers per tile and no global atomic: output slots come from a CTA-private chunk of
@@ -40,20 +44,17 @@ namespace {
 #ifndef EVK_SLAB_THREADS
 #define EVK_SLAB_THREADS 1024
 #endif
-#ifndef EVK_SLAB_LOGTILE
-#define EVK_SLAB_LOGTILE 11
-#endif
 #ifndef EVK_SLAB_PER
-#define EVK_SLAB_PER ((1 << EVK_SLAB_LOGTILE) / EVK_SLAB_THREADS)
+#define EVK_SLAB_PER 3
 #endif
 #ifndef EVK_SLAB_STAGES
-#define EVK_SLAB_STAGES 3
+#define EVK_SLAB_STAGES 2
 #endif
 #ifndef EVK_SLAB_KEEP_BITS
-#define EVK_SLAB_KEEP_BITS 0  // 1: the claim pass reuses the classify pass's word index and bit
+#define EVK_SLAB_KEEP_BITS 1  // 1: the claim pass reuses the classify pass's word index and bit
 #endif
 #ifndef EVK_SLAB_EARLY_FREE
-#define EVK_SLAB_EARLY_FREE 0  // 1: a ring slot is refilled right after the classify pass drained it
+#define EVK_SLAB_EARLY_FREE 1  // 1: a ring slot is refilled right after the classify pass drained it
 #endif                         //    (a late peer's coordinates are then re-read from global memory)
 constexpr int kThreads = EVK_SLAB_THREADS;  // CTA size (the hardware maximum by default)
 constexpr int kCtasPerSm = kThreads <= 512 ? 2 : 1;
@@ -74,6 +75,13 @@ static_assert(kChunk >= 2 * kTile, "a fresh chunk must absorb a whole tile");
 static_assert(kThreads * kPer == kTile, "tile = events per thread x CTA size");
 static_assert(kThreads >= kHash / 4, "one 16-B store per thread clears a late-peer table");
 
+// what a CTA leaves behind for the fix-up pass: the two output chunks it may have left partly
+// filled (the current one and the one claimed ahead, never written to)
+struct ChunkTail {
+    uint32_t cur_base, cur_filled;    // current chunk: first slot, slots written
+    uint32_t next_base, next_filled;  // chunk claimed ahead (kNoChunk-based if none); always 0 filled
+};
+
 struct SlabArgs {
     KeyParams kp;
     const evk_event* ev;
@@ -83,7 +91,7 @@ struct SlabArgs {
     uint32_t* first;
     uint32_t* xy;
     DsCounters* cnt;
-    uint32_t* chunk_list;   // [2 * grid] pairs (base, filled)
+    ChunkTail* chunk_list;  // [grid]
     uint32_t first_offset;  // added to every emitted first index (global index of event 0)
     uint32_t words;         // bitmap words per bin
     uint32_t max_bins;
@@ -93,7 +101,6 @@ struct SlabArgs {
     // so that the halo exchange and the downsample need no host round trip in between.
     const unsigned long long* range;
     const long long* t0_dev;  // not null: the time origin (overrides kp.t0; replayed graphs)
-    uint32_t* rep_bits;       // k_slab_duo: per-CTA "hit twice" bitmaps in global memory (zero)
 };
 
 // the event range the kernels work on
@@ -527,698 +534,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
     if (viol) atomicOr(&cnt->slab_violation, 1u);
     if (tid == 0) {  // publish the two chunks this CTA leaves partly filled
         if (pend_chunk != kNoChunk) s_next_base = pend_chunk * kChunk;
-        uint32_t* cl = a.chunk_list + 4 * blockIdx.x;
-        cl[0] = s_chunk_end - kChunk;
-        cl[1] = kChunk - (s_chunk_end - s_chunk_pos);
-        cl[2] = s_next_base;
-        cl[3] = 0;
+        ChunkTail ct;
+        ct.cur_base = s_chunk_end - kChunk;
+        ct.cur_filled = kChunk - (s_chunk_end - s_chunk_pos);
+        ct.next_base = s_next_base;
+        ct.next_filled = 0;
+        a.chunk_list[blockIdx.x] = ct;
     }
 }
-
-// ---- software-pipelined variant (round 2) -------------------------------------------------------
-// Same data structures and the same claim protocol as k_slab_main, re-scheduled so that neither
-// barrier interval of a tile is latency-only:
-//   prep(T)     ring -> registers: gate, in-bin check, cell -> candidate word      (no map access)
-//   mapread(T)  one bitmap load per candidate: seen -> duplicate of an earlier tile (+ "hit twice")
-//   claim(T)    one returning atomicOr per unseen event; same-tile losers go to the late-peer table
-//   emit(T)     claimant vs late peer, warp-aggregated output slots, the 16-B record to HBM
-// Per iteration:  [S1(T-1)] mapread(T) emit(T-1) [B0(T)] claim(T) prep(T+1) late(T) [S1(T)]
-// so the ALU-heavy prep of the next tile overlaps the shared-memory atomics of this one, and the
-// output stores of the previous tile overlap the bitmap loads of this one.  A ring slot is read by
-// prep only (a late peer's coordinates are re-read from global memory: rare, L2-resident), so it
-// is free one barrier after it was consumed: a TWO-stage ring of 3072-event tiles has the
-// prefetch distance the three-stage ring of 2048-event tiles had, and the per-tile overhead
-// (barriers, cursor atomic, bookkeeping) is spread over 1.5x the events.
-#ifndef EVK_PIPE_PER
-#define EVK_PIPE_PER 3
-#endif
-#ifndef EVK_PIPE_STAGES
-#define EVK_PIPE_STAGES 2
-#endif
-#ifndef EVK_PIPE_EMIT_PHASE
-#define EVK_PIPE_EMIT_PHASE 0  // 0: emit(T-1) beside mapread(T); 1: beside claim(T) / prep(T+1)
-#endif
-namespace pipe {
-constexpr int NT = 1024;
-constexpr int kPer = EVK_PIPE_PER;
-constexpr int kStages = EVK_PIPE_STAGES;
-constexpr int TILE = NT * kPer;
-constexpr int kLogIdx = 12;             // index-in-tile field of a candidate word
-constexpr uint32_t kIdxMask = (1u << kLogIdx) - 1u;
-constexpr int kLogHash = 11;            // late-peer table: 2048 slots per parity; a tile has at most
-constexpr int kHash = 1 << kLogHash;    // TILE / 2 = 1536 late cells (each shares a cell with a claimant)
-static_assert(TILE <= (1 << kLogIdx), "index field too narrow");
-static_assert(TILE / 2 < kHash, "late-peer table must never fill up");
-static_assert(kChunk >= 2 * TILE, "a fresh chunk must absorb a whole tile");
-static_assert(NT >= kHash / 4, "one 16-B store per thread clears a late-peer table");
-
-__device__ __forceinline__ uint32_t hslot(uint32_t cell) {
-    return (cell * 0x9E3779B1u) >> (32 - kLogHash);
-}
-
-template <bool COUNT_REP, bool POW2>
-__global__ void __launch_bounds__(NT, 1) k_slab_pipe(SlabArgs a) {
-    constexpr int kTmaThread = NT - 32;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint4* s_ev = reinterpret_cast<uint4*>(smem_raw);                       // [kStages][TILE]
-    uint32_t* s_late = reinterpret_cast<uint32_t*>(s_ev + kStages * TILE);  // [2][kHash]
-    uint32_t* s_map = s_late + 2 * kHash;                                   // [words]
-    __shared__ __align__(8) uint64_t s_bar[kStages];
-    __shared__ uint32_t s_cursor[2];
-    __shared__ uint32_t s_chunk_pos, s_chunk_end, s_next_base;
-
-    DsCounters* cnt = a.cnt;
-    if (cnt->slab_violation) return;
-    const KeyParams& kp = a.kp;
-    const int64_t t0 = a.t0_dev ? *a.t0_dev : a.kp.t0;  // (replayed graphs: device-side origin)
-    const uint32_t nb = (uint32_t)cnt->scratch[0];
-    const uint64_t tb0 = cnt->scratch[2];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const SlabRange rg = slab_range(a);
-    const evk_event* const evs = rg.ev;
-    const uint32_t first_offset = rg.first_offset;
-
-    for (int i = tid; i < 2 * kHash; i += NT) s_late[i] = kEmpty;
-    for (uint32_t i = tid; i < a.words; i += NT) s_map[i] = 0;
-    if (tid == 0) {
-        for (int s = 0; s < kStages; s++) mbar_init(&s_bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_cursor[0] = s_cursor[1] = 0;
-        const uint32_t c0 = (uint32_t)atomicAdd(&cnt->scratch[3], 2ull);
-        s_chunk_pos = c0 * kChunk;
-        s_chunk_end = s_chunk_pos + kChunk;
-        s_next_base = (c0 + 1) * kChunk;
-    }
-    __syncthreads();
-    uint32_t pend_chunk = kNoChunk, book_par = 2, viol = 0;
-    auto book = [&]() {  // thread 0, once every warp has claimed its output slots of a tile
-        if (book_par > 1) return;
-        if (pend_chunk != kNoChunk) {
-            s_next_base = pend_chunk * kChunk;
-            pend_chunk = kNoChunk;
-        }
-        const uint32_t c = s_cursor[book_par];
-        const uint32_t room = s_chunk_end - s_chunk_pos;
-        if (c >= room) {
-            const uint32_t nb0 = s_next_base;
-            s_chunk_pos = nb0 + (c - room);
-            s_chunk_end = nb0 + kChunk;
-            s_next_base = kNoChunk;
-            pend_chunk = (uint32_t)atomicAdd(&cnt->scratch[3], 1ull);
-        } else {
-            s_chunk_pos += c;
-        }
-        s_cursor[book_par] = 0;
-        book_par = 2;
-    };
-
-    // the TMA thread runs kStages tiles ahead of the prep stream
-    TileIt tma;
-    tma.b = blockIdx.x;
-    tma.hi = tma.base = 0;
-    uint32_t tma_seq = 0;
-    auto fetch = [&]() {
-        if (tma.b >= nb) return;
-        const uint32_t cntev = min((uint32_t)TILE, tma.hi - tma.base);
-        uint64_t* bar = &s_bar[tma_seq % kStages];
-        mbar_expect_tx(bar, cntev * 16u);
-        tma_load_1d(s_ev + (tma_seq % kStages) * TILE, evs + tma.base, cntev * 16u, bar);
-        tma_seq++;
-        tma.base += TILE;
-        if (tma.base >= tma.hi) {
-            tma.b += gridDim.x;
-            it_enter(tma, a.bin_start, nb);
-        }
-    };
-    if (tid == kTmaThread) {
-        it_enter(tma, a.bin_start, nb);
-#pragma unroll
-        for (int s = 0; s < kStages; s++) fetch();
-    }
-
-    // consumer-side tile stream (every thread walks it identically)
-    auto enter = [&](TileIt& it) {
-        while (it.b < nb) {
-            const uint32_t lo = a.bin_start[it.b], hi = a.bin_start[it.b + 1];
-            if (hi < lo) viol = 1;  // ranges do not partition the stream: not time-ordered
-            if (hi > lo) {
-                it.base = lo;
-                it.hi = hi;
-                return;
-            }
-            it.b += gridDim.x;
-        }
-    };
-
-    uint32_t pc[kPer], pxy[kPer];  // prepped tile: candidate word (cell << kLogIdx | index) or kEmpty
-    auto prep = [&](const TileIt& t, uint32_t sq) {
-        const uint32_t stage = sq % kStages;
-        mbar_wait(&s_bar[stage], (sq / kStages) & 1);
-        const uint4* tile = s_ev + stage * TILE;
-        const int64_t t_lo = t0 + (int64_t)((tb0 + t.b) * (uint64_t)kp.vt);
-#pragma unroll
-        for (int j = 0; j < kPer; j++) {
-            const uint32_t li = j * NT + tid;
-            const uint4 ev = tile[li];
-            const uint32_t x = ev.x & 0xFFFFu, y = ev.x >> 16;
-            const bool gate = (t.base + li < t.hi) & (x < (uint32_t)kp.width) & (y < (uint32_t)kp.height);
-            const bool inbin = (uint64_t)(ev_t(ev) - t_lo) < (uint64_t)kp.vt;
-            const bool ok = gate & inbin;
-            viol |= (uint32_t)(gate != ok);  // a gated-in event that is not of this bin
-            uint32_t cell;
-            if (POW2) cell = (y >> kp.sy) * kp.NX + (x >> kp.sx);
-            else cell = (kp.sy >= 0 ? y >> kp.sy : __umulhi(y, kp.my)) * kp.NX +
-                        (kp.sx >= 0 ? x >> kp.sx : __umulhi(x, kp.mx));
-            if (kp.use_p) cell = cell * 2u + ev_pbit(ev);
-            pc[j] = ok ? ((cell << kLogIdx) | li) : kEmpty;
-            pxy[j] = ev.x;
-        }
-    };
-
-    uint32_t cv[kPer], cxy[kPer], cvp[kPer], cxyp[kPer];
-    // emit the previous tile: claimant vs late peer, output slots, records to HBM
-    auto emit = [&](const TileIt& t, uint32_t par) {
-        const uint32_t* late_tbl = s_late + par * kHash;
-        const uint64_t key_base = (tb0 + t.b) * kp.cells;
-        uint32_t bal[kPer], wtot = 0, w0[kPer];
-#pragma unroll
-        for (int j = 0; j < kPer; j++)
-            w0[j] = cvp[j] != kEmpty ? late_tbl[hslot(cvp[j] >> kLogIdx)] : kEmpty;
-#pragma unroll
-        for (int j = 0; j < kPer; j++) {
-            if (w0[j] != kEmpty) {
-                const uint32_t cell = cvp[j] >> kLogIdx;
-                uint32_t s = hslot(cell), w = w0[j];
-                for (;;) {
-                    if ((w >> kLogIdx) == cell) {
-                        if (w < cvp[j]) {  // a late peer with a lower index is the representative
-                            cvp[j] = w;
-                            cxyp[j] = __ldg(reinterpret_cast<const uint32_t*>(
-                                evs + (t.base + (w & kIdxMask))));
-                        }
-                        break;
-                    }
-                    s = (s + 1) & (kHash - 1);
-                    w = late_tbl[s];
-                    if (w == kEmpty) break;
-                }
-            }
-            bal[j] = __ballot_sync(0xffffffffu, cvp[j] != kEmpty);
-            wtot += __popc(bal[j]);
-        }
-        uint32_t wbase = 0;
-        if (lane == 0)
-            asm volatile("atom.shared.add.u32 %0, [%1], %2;"
-                         : "=r"(wbase)
-                         : "r"(smem_u32(&s_cursor[par])), "r"(wtot)
-                         : "memory");
-        wbase = __shfl_sync(0xffffffffu, wbase, 0);
-        const uint32_t pos0 = s_chunk_pos, nxt0 = s_next_base;
-        const uint32_t room = s_chunk_end - pos0;
-        const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-        for (int j = 0; j < kPer; j++) {
-            if (cvp[j] != kEmpty) {
-                const uint32_t o = wbase + __popc(bal[j] & lt);
-                const uint32_t p = o < room ? pos0 + o : nxt0 + (o - room);
-                a.keys[p] = key_base + (cvp[j] >> kLogIdx);
-                a.first[p] = t.base + (cvp[j] & kIdxMask) + first_offset;
-                a.xy[p] = cxyp[j];
-            }
-            wbase += __popc(bal[j]);
-        }
-        if (tid == 0) book_par = par;
-    };
-
-    TileIt cur, prv;
-    cur.b = blockIdx.x;
-    cur.hi = cur.base = 0;
-    enter(cur);
-    prv = cur;
-    bool have_cur = cur.b < nb, have_prev = false;
-    uint32_t sq = 0, map_bin = cur.b;  // (the map starts out clean for the first bin)
-    if (have_cur) prep(cur, 0);
-    prod_sync<NT>();  // ring slot 0 has been consumed by every thread
-
-    while (have_cur) {
-        const uint32_t par = sq & 1;
-        if (tid == kTmaThread) fetch();  // tile sq + kStages into the slot prep(sq) has drained
-        if (cur.b != map_bin) {  // a new bin: count the old one's repeated cells, clear the bitmap
-            uint32_t r = 0;
-            for (uint32_t i = tid; i < a.words; i += NT) {
-                if (COUNT_REP) r += __popc(s_map[i] >> 16);
-                s_map[i] = 0;
-            }
-            if (COUNT_REP) {
-                r = __reduce_add_sync(0xffffffffu, r);
-                if (lane == 0 && r) atomicAdd(&cnt->n_repeated, (unsigned long long)r);
-            }
-            map_bin = cur.b;
-            prod_sync<NT>();
-        }
-        // ---- phase A: bitmap reads of this tile, output of the previous one
-#pragma unroll
-        for (int j = 0; j < kPer; j++) {
-            const uint32_t cell = pc[j] >> kLogIdx;
-            const uint32_t w = COUNT_REP ? cell >> 4 : cell >> 5;
-            const uint32_t sbit = 1u << (cell & (COUNT_REP ? 15u : 31u));
-            const bool ok = pc[j] != kEmpty;
-            const uint32_t wv = ok ? s_map[w] : 0xFFFFFFFFu;
-            if (COUNT_REP) {  // duplicate of an earlier tile's voxel: mark it "hit twice"
-                const uint32_t need = (wv & sbit) && !(wv & (sbit << 16)) && ok;
-                sred_or_if(&s_map[w], sbit << 16, need);
-            }
-            cv[j] = (wv & sbit) ? kEmpty : pc[j];
-            cxy[j] = pxy[j];
-        }
-#if EVK_PIPE_EMIT_PHASE == 0
-        if (have_prev) emit(prv, par ^ 1);
-#else
-        // this tile's late table was last read by emit() one barrier ago: clean it
-        if (tid < kHash / 4)
-            reinterpret_cast<uint4*>(s_late + par * kHash)[tid] =
-                make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-        if (tid == 0) book();
-#endif
-        prod_sync<NT>();  // B0: every bitmap read of this tile precedes every claim below
-#if EVK_PIPE_EMIT_PHASE == 0
-        if (tid == 0) book();
-#endif
-        // ---- phase B: claims of this tile, prep of the next one
-        uint32_t old[kPer];
-#pragma unroll
-        for (int j = 0; j < kPer; j++) {
-            old[j] = 0;
-            if (cv[j] == kEmpty) continue;
-            const uint32_t cell = cv[j] >> kLogIdx;
-            uint32_t* wp = COUNT_REP ? &s_map[cell >> 4] : &s_map[cell >> 5];
-            const uint32_t sbit = 1u << (cell & (COUNT_REP ? 15u : 31u));
-            old[j] = atomicOr(wp, sbit) & sbit;
-        }
-#if EVK_PIPE_EMIT_PHASE == 0
-        // the table the NEXT tile will use was last read by emit() above: clean it
-        if (tid < kHash / 4)
-            reinterpret_cast<uint4*>(s_late + (par ^ 1) * kHash)[tid] =
-                make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-#endif
-        TileIt nxt = cur;
-        nxt.base += TILE;
-        if (nxt.base >= nxt.hi) {
-            nxt.b += gridDim.x;
-            enter(nxt);
-        }
-        const bool have_next = nxt.b < nb;
-        if (have_next) prep(nxt, sq + 1);
-#if EVK_PIPE_EMIT_PHASE == 1
-        if (have_prev) emit(prv, par ^ 1);
-#endif
-        {
-            uint32_t* late_tbl = s_late + par * kHash;
-#pragma unroll
-            for (int j = 0; j < kPer; j++) {  // a peer of this tile claimed the cell first (rare)
-                if (!old[j]) continue;
-                const uint32_t cell = cv[j] >> kLogIdx;
-                if (COUNT_REP) atomicOr(&s_map[cell >> 4], 1u << (16 + (cell & 15)));
-                uint32_t s = hslot(cell);
-                for (;;) {
-                    const uint32_t o = atomicCAS(&late_tbl[s], kEmpty, cv[j]);
-                    if (o == kEmpty) break;
-                    if ((o >> kLogIdx) == cell) {  // keep the lowest index of the cell
-                        atomicMin(&late_tbl[s], cv[j]);
-                        break;
-                    }
-                    s = (s + 1) & (kHash - 1);
-                }
-                cv[j] = kEmpty;
-            }
-        }
-        prod_sync<NT>();  // S1: every claim of the tile is in the bitmap, its late table is complete
-#pragma unroll
-        for (int j = 0; j < kPer; j++) {
-            cvp[j] = cv[j];
-            cxyp[j] = cxy[j];
-        }
-        prv = cur;
-        have_prev = true;
-        cur = nxt;
-        have_cur = have_next;
-        sq++;
-    }
-#if EVK_PIPE_EMIT_PHASE == 1
-    if (tid == 0) book();  // the tile emitted during the last iteration
-    prod_sync<NT>();
-#endif
-    if (have_prev) emit(prv, (sq - 1) & 1);
-    prod_sync<NT>();
-    if (tid == 0) book();
-    if (COUNT_REP) {  // the last bin's repeated cells
-        uint32_t r = 0;
-        for (uint32_t i = tid; i < a.words; i += NT) r += __popc(s_map[i] >> 16);
-        r = __reduce_add_sync(0xffffffffu, r);
-        if (lane == 0 && r) atomicAdd(&cnt->n_repeated, (unsigned long long)r);
-    }
-    if (viol) atomicOr(&cnt->slab_violation, 1u);
-    if (tid == 0) {  // publish the two chunks this CTA leaves partly filled
-        if (pend_chunk != kNoChunk) s_next_base = pend_chunk * kChunk;
-        uint32_t* cl = a.chunk_list + 4 * blockIdx.x;
-        cl[0] = s_chunk_end - kChunk;
-        cl[1] = kChunk - (s_chunk_end - s_chunk_pos);
-        cl[2] = s_next_base;
-        cl[3] = 0;
-    }
-}
-}  // namespace pipe
-
-// ---- two CTAs per SM (round 2) ------------------------------------------------------------------
-// k_slab_main keeps one 1024-thread CTA per SM and every warp of the SM meets at two barriers per
-// tile: issue slots idle while the claim phase waits on shared-memory atomics (ncu: 68 % issue
-// active).  k_slab_duo runs the same classify / claim / resolve protocol with TWO independent
-// 512-thread CTAs per SM, each on its own time bin: one CTA's barrier waits are filled by the
-// other's work.  What makes two bins fit in 228 KB:
-//   * the bin bitmap is 1 bit per cell ("seen", 57.6 KB for Gen4 2x2 px + polarity); the "hit
-//     twice" bits move to a per-CTA bitmap in global memory that stays L2-resident (17 MB for all
-//     CTAs) and is only ever touched by fire-and-forget RED.OR (one per duplicate event) and by
-//     one count-and-clear pass per bin;
-//   * a ring slot is read by the classify pass only (a late peer's coordinates are re-read from
-//     global memory: rare, L2-resident), so it is refilled one barrier after it was consumed: two
-//     stages of 1536-event tiles give the prefetch distance three stages of 1024 would.
-// The rare paths (late-peer insert, probe collisions) are ONE divergent loop per warp and tile
-// instead of one region per event row.
-#ifndef EVK_DUO_THREADS
-#define EVK_DUO_THREADS 512
-#endif
-#ifndef EVK_DUO_PER
-#define EVK_DUO_PER 3
-#endif
-#ifndef EVK_DUO_STAGES
-#define EVK_DUO_STAGES 2
-#endif
-namespace duo {
-constexpr int NT = EVK_DUO_THREADS;
-constexpr int kCtas = 1024 / NT;  // resident CTAs per SM
-constexpr int kPer = EVK_DUO_PER;
-constexpr int kStages = EVK_DUO_STAGES;
-constexpr int TILE = NT * kPer;
-constexpr int kLogIdx = TILE > 2048 ? 12 : 11;  // index-in-tile field of a candidate word
-// where the "hit twice" bits live: 0 = upper half of the shared bitmap words (16 cells per word),
-// 1 = a per-CTA bitmap in global memory (1 bit per cell in shared memory: two CTAs per SM fit;
-// measured slower: 45 M scattered RED.OR per step cost an SM about a cycle each)
-#ifndef EVK_DUO_REP_L2
-#define EVK_DUO_REP_L2 0
-#endif
-constexpr bool kRepL2 = EVK_DUO_REP_L2 != 0;
-constexpr uint32_t kIdxMask = (1u << kLogIdx) - 1u;
-constexpr int ceil_log2(int v) { return v <= 1 ? 0 : 1 + ceil_log2((v + 1) / 2); }
-constexpr int kLogHash = ceil_log2(TILE / 2 + 1);  // a tile has at most TILE / 2 late cells
-constexpr int kHash = 1 << kLogHash;
-constexpr uint32_t kRepStride = 29696;  // words of one CTA's "hit twice" bitmap in global memory
-static_assert(TILE <= (1 << kLogIdx), "index field too narrow");
-static_assert(TILE / 2 < kHash, "late-peer table must never fill up");
-static_assert(kChunk >= 2 * TILE, "a fresh chunk must absorb a whole tile");
-static_assert(NT >= kHash / 4, "one 16-B store per thread clears a late-peer table");
-static_assert(kPer <= 4, "slot selection below is written for up to four events per thread");
-
-__device__ __forceinline__ uint32_t hslot(uint32_t cell) {
-    return (cell * 0x9E3779B1u) >> (32 - kLogHash);
-}
-__device__ __forceinline__ void red_or_global_if(uint32_t* addr, uint32_t v, bool pred) {
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q red.global.or.b32 [%0], %1; }" ::"l"(addr),
-                 "r"(v), "r"((uint32_t)pred)
-                 : "memory");
-}
-template <int N>
-__device__ __forceinline__ uint32_t pick(const uint32_t (&v)[N], int j) {
-    uint32_t r = v[0];
-#pragma unroll
-    for (int q = 1; q < N; q++) r = j == q ? v[q] : r;
-    return r;
-}
-
-template <bool COUNT_REP, bool POW2>
-__global__ void __launch_bounds__(NT, kCtas) k_slab_duo(SlabArgs a) {
-    constexpr int kTmaThread = NT - 32;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint4* s_ev = reinterpret_cast<uint4*>(smem_raw);                       // [kStages][TILE]
-    uint32_t* s_late = reinterpret_cast<uint32_t*>(s_ev + kStages * TILE);  // [2][kHash]
-    uint32_t* s_map = s_late + 2 * kHash;                                   // [words] 1 bit / cell
-    __shared__ __align__(8) uint64_t s_bar[kStages];
-    __shared__ uint32_t s_cursor[2];
-    __shared__ uint32_t s_chunk_pos, s_chunk_end, s_next_base;
-
-    DsCounters* cnt = a.cnt;
-    if (cnt->slab_violation) return;
-    const KeyParams& kp = a.kp;
-    const int64_t t0 = a.t0_dev ? *a.t0_dev : a.kp.t0;  // (replayed graphs: device-side origin)
-    const uint32_t nb = (uint32_t)cnt->scratch[0];
-    const uint64_t tb0 = cnt->scratch[2];
-    const int tid = threadIdx.x, lane = tid & 31;
-    const SlabRange rg = slab_range(a);
-    const evk_event* const evs = rg.ev;
-    const uint32_t first_offset = rg.first_offset;
-    uint32_t* const rep = a.rep_bits + (size_t)blockIdx.x * kRepStride;  // zero between bins
-
-    for (int i = tid; i < 2 * kHash; i += NT) s_late[i] = kEmpty;
-    for (uint32_t i = tid; i < a.words; i += NT) s_map[i] = 0;
-    if (tid == 0) {
-        for (int s = 0; s < kStages; s++) mbar_init(&s_bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_cursor[0] = s_cursor[1] = 0;
-        const uint32_t c0 = (uint32_t)atomicAdd(&cnt->scratch[3], 2ull);
-        s_chunk_pos = c0 * kChunk;
-        s_chunk_end = s_chunk_pos + kChunk;
-        s_next_base = (c0 + 1) * kChunk;
-    }
-    __syncthreads();
-    uint32_t pend_chunk = kNoChunk, book_par = 2, tile_seq = 0, viol = 0;
-    auto book = [&]() {  // thread 0, once every warp has claimed its output slots of a tile
-        if (book_par > 1) return;
-        if (pend_chunk != kNoChunk) {
-            s_next_base = pend_chunk * kChunk;
-            pend_chunk = kNoChunk;
-        }
-        const uint32_t c = s_cursor[book_par];
-        const uint32_t room = s_chunk_end - s_chunk_pos;
-        if (c >= room) {
-            const uint32_t nb0 = s_next_base;
-            s_chunk_pos = nb0 + (c - room);
-            s_chunk_end = nb0 + kChunk;
-            s_next_base = kNoChunk;
-            pend_chunk = (uint32_t)atomicAdd(&cnt->scratch[3], 1ull);
-        } else {
-            s_chunk_pos += c;
-        }
-        s_cursor[book_par] = 0;
-        book_par = 2;
-    };
-
-    TileIt tma;
-    tma.b = blockIdx.x;
-    tma.hi = tma.base = 0;
-    uint32_t tma_seq = 0;
-    auto fetch = [&]() {
-        if (tma.b >= nb) return;
-        const uint32_t cntev = min((uint32_t)TILE, tma.hi - tma.base);
-        uint64_t* bar = &s_bar[tma_seq % kStages];
-        mbar_expect_tx(bar, cntev * 16u);
-        tma_load_1d(s_ev + (tma_seq % kStages) * TILE, evs + tma.base, cntev * 16u, bar);
-        tma_seq++;
-        tma.base += TILE;
-        if (tma.base >= tma.hi) {
-            tma.b += gridDim.x;
-            it_enter(tma, a.bin_start, nb);
-        }
-    };
-    if (tid == kTmaThread) {
-        it_enter(tma, a.bin_start, nb);
-#pragma unroll
-        for (int s = 0; s < kStages; s++) fetch();
-    }
-
-    // count the finished bin's "hit twice" cells and leave its global bitmap clean
-    auto count_rep = [&]() {
-        uint32_t r = 0;
-        for (uint32_t i = tid; i < a.words; i += NT) {
-            if (kRepL2) {
-                const uint32_t v = __ldcg(rep + i);
-                if (v) {
-                    r += __popc(v);
-                    rep[i] = 0;
-                }
-            } else {
-                r += __popc(s_map[i] >> 16);
-            }
-        }
-        r = __reduce_add_sync(0xffffffffu, r);
-        if (lane == 0 && r) atomicAdd(&cnt->n_repeated, (unsigned long long)r);
-    };
-
-    bool first_bin = true;
-    for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
-        const uint32_t lo = a.bin_start[b], hi = a.bin_start[b + 1];
-        if (hi < lo) viol = 1;  // ranges do not partition the stream: not time-ordered
-        if (hi <= lo) continue;
-        const uint64_t tb = tb0 + b;
-        const int64_t t_lo = t0 + (int64_t)(tb * (uint64_t)kp.vt);
-        const uint64_t key_base = tb * kp.cells;
-        prod_sync<NT>();  // every thread has left the previous bin (bitmap, cursor, REDs issued)
-        if (tid == 0) book();
-        if (!first_bin) {
-            if (COUNT_REP) count_rep();
-            for (uint32_t i = tid; i < a.words; i += NT) s_map[i] = 0;
-        }
-        first_bin = false;
-        prod_sync<NT>();
-
-        for (uint32_t base = lo; base < hi; base += TILE, tile_seq++) {
-            const uint32_t stage = tile_seq % kStages, par = tile_seq & 1;
-            const uint4* tile = s_ev + stage * TILE;
-            uint32_t* late_tbl = s_late + par * kHash;
-            mbar_wait(&s_bar[stage], (tile_seq / kStages) & 1);
-            // ---- classify: cv = candidate word (cell << kLogIdx | index in tile) or kEmpty
-            uint32_t cv[kPer], cxy[kPer];
-#pragma unroll
-            for (int j = 0; j < kPer; j++) {
-                const uint32_t li = j * NT + tid;
-                const uint4 ev = tile[li];
-                const uint32_t x = ev.x & 0xFFFFu, y = ev.x >> 16;
-                const bool gate = (base + li < hi) & (x < (uint32_t)kp.width) & (y < (uint32_t)kp.height);
-                const bool inbin = (uint64_t)(ev_t(ev) - t_lo) < (uint64_t)kp.vt;
-                const bool ok = gate & inbin;
-                viol |= (uint32_t)(gate != ok);  // a gated-in event that is not of this bin
-                uint32_t cell;
-                if (POW2) cell = (y >> kp.sy) * kp.NX + (x >> kp.sx);
-                else cell = (kp.sy >= 0 ? y >> kp.sy : __umulhi(y, kp.my)) * kp.NX +
-                            (kp.sx >= 0 ? x >> kp.sx : __umulhi(x, kp.mx));
-                if (kp.use_p) cell = cell * 2u + ev_pbit(ev);
-                const bool wide = COUNT_REP && !kRepL2;  // 16 cells per word, "hit twice" bits on top
-                const uint32_t w = wide ? cell >> 4 : cell >> 5;
-                const uint32_t sbit = 1u << (cell & (wide ? 15u : 31u));
-                const uint32_t wv = ok ? s_map[w] : 0xFFFFFFFFu;  // gated events: nothing to do
-                const bool seen = (wv & sbit) != 0;
-                // duplicate of an earlier tile's voxel: the cell has been hit (at least) twice
-                if (COUNT_REP && kRepL2) red_or_global_if(rep + w, sbit, seen & ok);
-                if (wide) sred_or_if(&s_map[w], sbit << 16, seen && !(wv & (sbit << 16)) && ok);
-                cv[j] = seen ? kEmpty : ((cell << kLogIdx) | li);
-                cxy[j] = ev.x;
-            }
-            prod_sync<NT>();  // B0: every bitmap read of this tile precedes every claim below
-            // the ring slot has been drained into registers: refill it (kStages tiles ahead)
-            if (tid == kTmaThread) fetch();
-            if (tid == 0) book();
-            // ---- claim: one returning atomic per unseen event
-            uint32_t lm = 0;  // bit j: a peer of this tile claimed the cell of event j first
-#pragma unroll
-            for (int j = 0; j < kPer; j++) {
-                if (cv[j] == kEmpty) continue;
-                const uint32_t cell = cv[j] >> kLogIdx;
-                const bool wide = COUNT_REP && !kRepL2;
-                const uint32_t sbit = 1u << (cell & (wide ? 15u : 31u));
-                if (atomicOr(&s_map[wide ? cell >> 4 : cell >> 5], sbit) & sbit) lm |= 1u << j;
-            }
-            while (lm) {  // late peers (rare): one divergent loop for all the thread's events
-                const int j = __ffs(lm) - 1;
-                lm &= lm - 1;
-                const uint32_t word = pick(cv, j);
-                const uint32_t cell = word >> kLogIdx;
-                if (COUNT_REP && kRepL2) red_or_global_if(rep + (cell >> 5), 1u << (cell & 31u), true);
-                if (COUNT_REP && !kRepL2) atomicOr(&s_map[cell >> 4], 1u << (16 + (cell & 15)));
-                uint32_t s = hslot(cell);
-                for (;;) {
-                    const uint32_t o = atomicCAS(&late_tbl[s], kEmpty, word);
-                    if (o == kEmpty) break;
-                    if ((o >> kLogIdx) == cell) {  // keep the lowest index of the cell
-                        atomicMin(&late_tbl[s], word);
-                        break;
-                    }
-                    s = (s + 1) & (kHash - 1);
-                }
-#pragma unroll
-                for (int q = 0; q < kPer; q++)
-                    if (j == q) cv[q] = kEmpty;
-            }
-            prod_sync<NT>();  // S1: every claim of the tile is in the bitmap, s_late is complete
-            // ---- resolve: the claimant is the new voxel unless a late peer has a lower index
-            uint32_t w0[kPer], pm = 0;
-#pragma unroll
-            for (int j = 0; j < kPer; j++) {  // first probe: nearly always an empty slot
-                w0[j] = cv[j] != kEmpty ? late_tbl[hslot(cv[j] >> kLogIdx)] : kEmpty;
-                if (w0[j] != kEmpty) pm |= 1u << j;
-            }
-            while (pm) {  // occupied slot (rare): follow the probe sequence
-                const int j = __ffs(pm) - 1;
-                pm &= pm - 1;
-                const uint32_t mine = pick(cv, j);
-                const uint32_t cell = mine >> kLogIdx;
-                uint32_t s = hslot(cell), w = pick(w0, j);
-                for (;;) {
-                    if ((w >> kLogIdx) == cell) {
-                        if (w < mine) {  // lower index: that event is the representative
-                            const uint32_t nxy = __ldg(reinterpret_cast<const uint32_t*>(
-                                evs + (base + (w & kIdxMask))));
-#pragma unroll
-                            for (int q = 0; q < kPer; q++)
-                                if (j == q) {
-                                    cv[q] = w;
-                                    cxy[q] = nxy;
-                                }
-                        }
-                        break;
-                    }
-                    s = (s + 1) & (kHash - 1);
-                    w = late_tbl[s];
-                    if (w == kEmpty) break;
-                }
-            }
-            uint32_t bal[kPer], wtot = 0;
-#pragma unroll
-            for (int j = 0; j < kPer; j++) {
-                bal[j] = __ballot_sync(0xffffffffu, cv[j] != kEmpty);
-                wtot += __popc(bal[j]);
-            }
-            // the other parity's table was last read one tile ago: clean it for the next tile
-            if (tid < kHash / 4)
-                reinterpret_cast<uint4*>(s_late + (par ^ 1) * kHash)[tid] =
-                    make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-            uint32_t wbase = 0;
-            if (lane == 0)
-                asm volatile("atom.shared.add.u32 %0, [%1], %2;"
-                             : "=r"(wbase)
-                             : "r"(smem_u32(&s_cursor[par])), "r"(wtot)
-                             : "memory");
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-            {
-                const uint32_t pos0 = s_chunk_pos, nxt0 = s_next_base;
-                const uint32_t room = s_chunk_end - pos0;
-                const uint32_t lt = (1u << lane) - 1u;
-#pragma unroll
-                for (int j = 0; j < kPer; j++) {
-                    if (cv[j] != kEmpty) {
-                        const uint32_t o = wbase + __popc(bal[j] & lt);
-                        const uint32_t p = o < room ? pos0 + o : nxt0 + (o - room);
-                        a.keys[p] = key_base + (cv[j] >> kLogIdx);
-                        a.first[p] = base + (cv[j] & kIdxMask) + first_offset;
-                        a.xy[p] = cxy[j];
-                    }
-                    wbase += __popc(bal[j]);
-                }
-            }
-            if (tid == 0) book_par = par;
-        }
-    }
-    prod_sync<NT>();
-    if (tid == 0) book();
-    if (COUNT_REP && !first_bin) count_rep();  // the last bin's repeated cells
-    if (viol) atomicOr(&cnt->slab_violation, 1u);
-    if (tid == 0) {  // publish the two chunks this CTA leaves partly filled
-        if (pend_chunk != kNoChunk) s_next_base = pend_chunk * kChunk;
-        uint32_t* cl = a.chunk_list + 4 * blockIdx.x;
-        cl[0] = s_chunk_end - kChunk;
-        cl[1] = kChunk - (s_chunk_end - s_chunk_pos);
-        cl[2] = s_next_base;
-        cl[3] = 0;
-    }
-}
-}  // namespace duo
 
 // ---- fix-up: make the voxel shard dense -------------------------------------------------------
 // Chunks not listed are full.  U = total filled.  Every live slot at a position >= U is moved into
@@ -1266,7 +589,7 @@ __device__ __forceinline__ uint32_t plan_locate(const uint32_t* start, const uin
 }
 
 __global__ void __launch_bounds__(kFixThreads)
-    k_slab_fix(const uint32_t* chunk_list, uint32_t n_list, DsCounters* cnt, uint64_t* keys,
+    k_slab_fix(const ChunkTail* chunk_list, uint32_t n_ctas, DsCounters* cnt, uint64_t* keys,
                uint32_t* first, uint32_t* xy, unsigned long long* sticky) {
     __shared__ uint32_t s_base[kMaxList], s_fill[kMaxList];
     __shared__ uint32_t s_src_start[kMaxList + 1], s_src_prefix[kMaxList + 1];
@@ -1278,10 +601,12 @@ __global__ void __launch_bounds__(kFixThreads)
     }
     const uint32_t M = (uint32_t)cnt->scratch[3];  // chunks handed out
     const uint32_t i = threadIdx.x;
+    const uint32_t n_list = 2 * n_ctas;  // two listed chunks per CTA
     uint32_t hole = 0;
     if (i < n_list) {
-        s_base[i] = chunk_list[2 * i];
-        s_fill[i] = chunk_list[2 * i + 1];
+        const ChunkTail ct = chunk_list[i >> 1];
+        s_base[i] = (i & 1) ? ct.next_base : ct.cur_base;
+        s_fill[i] = (i & 1) ? ct.next_filled : ct.cur_filled;
         hole = kChunk - s_fill[i];
     }
     uint32_t holes;
@@ -1350,46 +675,26 @@ __global__ void __launch_bounds__(kFixThreads)
     }
 }
 
-#ifndef EVK_SLAB_KERNEL
-#define EVK_SLAB_KERNEL 3  // 1: k_slab_main (round 1), 2: k_slab_pipe, 3: k_slab_duo (two CTAs / SM)
-#endif
-constexpr int kVariant = EVK_SLAB_KERNEL;
-constexpr int kIdxBits = kVariant == 3 ? duo::kLogIdx : kVariant == 2 ? pipe::kLogIdx : kLogTile;
-constexpr int kGridPerSm = kVariant == 3 ? duo::kCtas : kCtasPerSm;
-constexpr int kBlockThreads = kVariant == 3 ? duo::NT : kVariant == 2 ? pipe::NT : kThreads;
-// "hit twice" bits: upper half of the bitmap words (variants 1, 2) or a global bitmap (variant 3)
-constexpr bool kRepInMap = kVariant != 3 || !duo::kRepL2;
-
 uint32_t map_words(uint64_t cells, bool count_rep) {
-    return (uint32_t)(count_rep && kRepInMap ? (cells + 15) / 16 : (cells + 31) / 32);
+    return (uint32_t)(count_rep ? (cells + 15) / 16 : (cells + 31) / 32);
 }
 size_t slab_smem_bytes(uint64_t cells, bool count_rep) {
-    const size_t ring = kVariant == 3   ? (size_t)duo::kStages * duo::TILE * 16
-                        : kVariant == 2 ? (size_t)pipe::kStages * pipe::TILE * 16
-                                        : (size_t)kStages * kTile * 16;
-    const size_t late = kVariant == 3   ? (size_t)2 * duo::kHash * 4
-                        : kVariant == 2 ? (size_t)2 * pipe::kHash * 4
-                                        : (size_t)2 * kHash * 4;
-    return ring + late + (size_t)((map_words(cells, count_rep) + 3) & ~3u) * 4;
+    return (size_t)kStages * kTile * 16 + (size_t)2 * kHash * 4 +
+           (size_t)((map_words(cells, count_rep) + 3) & ~3u) * 4;
 }
 constexpr size_t kSmemLimit = 232448 - 1024;  // 227 KB opt-in maximum minus the static part
-constexpr size_t kListBytes = 16384;          // chunk list (4 words per CTA), then the rep bitmaps
 
 }  // namespace
 
 size_t evk_slab_scratch_bytes(int sm_count) {
-    const size_t ctas = (size_t)sm_count * kGridPerSm;
-    return kListBytes + (kVariant == 3 && duo::kRepL2 ? ctas * duo::kRepStride * sizeof(uint32_t) : 0);
+    return (size_t)sm_count * kCtasPerSm * sizeof(ChunkTail);
 }
-int evk_slab_ctas_per_sm() { return kGridPerSm; }
+int evk_slab_ctas_per_sm() { return kCtasPerSm; }
 
 bool evk_slab_supported(const evk_handle* h, const KeyParams& kp) {
     if (kp.keyfn != EVK_KEY_VOXEL || kp.vt <= 0 || h->n_events == 0) return false;
-    if (kp.cells >= (1ull << (32 - kIdxBits))) return false;  // packed (cell, index) word
-    if (2 * kGridPerSm * h->sm_count > kMaxList) return false;
-    if ((size_t)kGridPerSm * h->sm_count * 16 > kListBytes) return false;
-    if (kVariant == 3 && duo::kRepL2 && map_words(kp.cells, true) > duo::kRepStride) return false;
-    // (variant 3 with a key space too large for two CTAs per SM still runs, one CTA per SM)
+    if (kp.cells >= (1ull << (32 - kLogTile))) return false;  // packed (cell, index) word
+    if (2 * kCtasPerSm * h->sm_count > kMaxList) return false;
     return slab_smem_bytes(kp.cells, true) <= kSmemLimit;
 }
 
@@ -1397,7 +702,7 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
                         int* launches, bool sync, const unsigned long long* range,
                         const long long* t0_dev) {
     *ok = false;
-    const int grid = h->sm_count * kGridPerSm;
+    const int grid = h->sm_count * kCtasPerSm;
     SlabArgs a;
     a.kp = kp;
     a.ev = h->d_events;
@@ -1407,8 +712,7 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
     a.first = h->d_first;
     a.xy = h->d_xy;
     a.cnt = h->d_cnt;
-    a.chunk_list = reinterpret_cast<uint32_t*>(h->d_slab_scratch);
-    a.rep_bits = reinterpret_cast<uint32_t*>(static_cast<char*>(h->d_slab_scratch) + kListBytes);
+    a.chunk_list = reinterpret_cast<ChunkTail*>(h->d_slab_scratch);
     a.first_offset = (uint32_t)h->shard_first;
     a.words = map_words(kp.cells, count_repeated != 0);
     a.max_bins = (uint32_t)h->max_bins;
@@ -1418,28 +722,18 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
     a.t0_dev = t0_dev;
     const size_t smem = slab_smem_bytes(kp.cells, count_repeated != 0);
     const bool pow2 = kp.sx >= 0 && kp.sy >= 0;
-    void (*kern)(SlabArgs);
-    if (kVariant == 3)
-        kern = count_repeated ? (pow2 ? duo::k_slab_duo<true, true> : duo::k_slab_duo<true, false>)
-                              : (pow2 ? duo::k_slab_duo<false, true> : duo::k_slab_duo<false, false>);
-    else if (kVariant == 2)
-        kern = count_repeated ? (pow2 ? pipe::k_slab_pipe<true, true> : pipe::k_slab_pipe<true, false>)
-                              : (pow2 ? pipe::k_slab_pipe<false, true> : pipe::k_slab_pipe<false, false>);
-    else
-        kern = count_repeated ? (pow2 ? k_slab_main<true, true> : k_slab_main<true, false>)
-                              : (pow2 ? k_slab_main<false, true> : k_slab_main<false, false>);
+    void (*kern)(SlabArgs) =
+        count_repeated ? (pow2 ? k_slab_main<true, true> : k_slab_main<true, false>)
+                       : (pow2 ? k_slab_main<false, true> : k_slab_main<false, false>);
     EVK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kSmemLimit));
-    if (kVariant == 3)  // both CTAs of an SM need their full shared-memory share
-        EVK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                         cudaSharedmemCarveoutMaxShared));
     k_slab_bins<<<2 * grid, 256, 0, h->stream>>>(a);
     EVK_CUDA(h, cudaGetLastError());
     evk_prof_rec(h, 5);
-    kern<<<grid, kBlockThreads, smem, h->stream>>>(a);
+    kern<<<grid, kThreads, smem, h->stream>>>(a);
     EVK_CUDA(h, cudaGetLastError());
     evk_prof_rec(h, 6);
-    k_slab_fix<<<grid, kFixThreads, 0, h->stream>>>(a.chunk_list, 2 * grid, h->d_cnt, h->d_keys,
+    k_slab_fix<<<grid, kFixThreads, 0, h->stream>>>(a.chunk_list, grid, h->d_cnt, h->d_keys,
                                                    h->d_first, h->d_xy, h->d_sticky);
     EVK_CUDA(h, cudaGetLastError());
     *launches += 3;
