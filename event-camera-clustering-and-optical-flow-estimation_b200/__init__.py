@@ -19,7 +19,7 @@ EVENT_DTYPE = np.dtype(
 assert EVENT_DTYPE.itemsize == 16
 
 KEY_VOXEL, KEY_REF_HASH8192 = 0, 1
-ALGO_AUTO, ALGO_TABLE, ALGO_SORT, ALGO_SLAB = 0, 1, 2, 3
+ALGO_AUTO, ALGO_TABLE, ALGO_SORT, ALGO_SLAB, ALGO_PARTITION = 0, 1, 2, 3, 4
 OWNER_TIME_RANGE, OWNER_MIX64 = 0, 1
 STATUS = {0: "EVK_OK", -1: "EVK_ERR_INVALID", -2: "EVK_ERR_CUDA", -3: "EVK_ERR_NOMEM",
           -4: "EVK_ERR_STATE", -5: "EVK_ERR_CAPACITY", -6: "EVK_ERR_IO", -7: "EVK_ERR_COMM"}

@@ -275,6 +275,7 @@ int evk_destroy(evk_handle* h) {
     evk_aec_destroy(h);
     evk_ts_destroy(h);
     evk_dbscan_destroy(h);
+    evk_partition_free(h);
     // graphs first: they reference the buffers, events and streams released below
     if (h->fused_exec) chk(cudaGraphExecDestroy(h->fused_exec), "fused graph");
     if (h->loop_exec) chk(cudaGraphExecDestroy(h->loop_exec), "loop graph");
@@ -558,7 +559,20 @@ int evk_downsample_local(evk_handle* h, const evk_ds_params* p) {
     if (algo == EVK_ALGO_SLAB) {
         bool ok = false;
         if (evk_slab_supported(h, kp)) EVK_TRY(evk_downsample_slab(h, kp, p->count_repeated, &ok, &launches));
-        if (!ok) {  // not partitioned by time bin (or unsupported shape): general path
+        if (!ok) {  // not partitioned by time bin (or unsupported shape)
+            algo = EVK_ALGO_PARTITION;
+            EVK_CUDA(h, cudaMemsetAsync(h->d_sticky, 0, sizeof(unsigned long long), h->stream));
+        } else {
+            prof_rec(h, 1);
+            prof_rec(h, 2);
+        }
+    }
+    if (algo == EVK_ALGO_PARTITION) {  // bring the stream into bin order first, then the slab kernel
+        bool ok = false;
+        EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
+        prof_rec(h, 0);
+        EVK_TRY(evk_downsample_partitioned(h, kp, p->count_repeated, &ok, &launches));
+        if (!ok) {  // key space or bin count the partition does not take: the general table
             algo = EVK_ALGO_TABLE;
             EVK_CUDA(h, cudaMemsetAsync(h->d_sticky, 0, sizeof(unsigned long long), h->stream));
             EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
@@ -583,7 +597,7 @@ int evk_downsample_local(evk_handle* h, const evk_ds_params* p) {
         EVK_TRY(evk_downsample_sort(h, kp, &launches));
         prof_rec(h, 1);
         prof_rec(h, 2);
-    } else if (algo != EVK_ALGO_SLAB) {
+    } else if (algo != EVK_ALGO_SLAB && algo != EVK_ALGO_PARTITION) {
         return evk_fail(h, EVK_ERR_INVALID, "unknown algo %d", p->algo);
     }
     EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,

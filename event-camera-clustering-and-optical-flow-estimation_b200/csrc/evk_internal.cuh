@@ -148,6 +148,13 @@ struct evk_handle {
     uint32_t *d_si_in = nullptr, *d_si_out = nullptr;
     void* d_sv_tmp = nullptr;
     size_t sv_tmp_bytes = 0;
+    // partition path (lazy): events in time-bin order, their original indices, strip x bin offsets
+    evk_event* d_part_events = nullptr;
+    uint32_t* d_part_orig = nullptr;
+    uint32_t* d_part_hist = nullptr;
+    size_t part_hist_cap = 0;
+    evk_event* d_part_events2 = nullptr;  // two-level partition of scattered streams: level-1 copy
+    uint32_t* d_part_orig2 = nullptr;
     // slab scratch
     uint32_t* d_bin_start = nullptr;  // [max_bins + 1]
     void* d_slab_scratch = nullptr;   // fix-up plan + per-CTA chunk list
@@ -312,6 +319,10 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
                         const unsigned long long* range = nullptr,
                         const long long* t0_dev = nullptr);
 bool evk_slab_supported(const evk_handle* h, const KeyParams& kp);
+// unordered streams: stable partition by time bin + the slab kernel (evk_partition.cu)
+int evk_downsample_partitioned(evk_handle* h, const KeyParams& kp, int count_repeated, bool* ok,
+                               int* launches);
+void evk_partition_free(evk_handle* h);
 size_t evk_slab_scratch_bytes(int sm_count);
 int evk_slab_ctas_per_sm();
 // canonical order

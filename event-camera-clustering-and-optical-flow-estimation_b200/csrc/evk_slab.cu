@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
     __shared__ __align__(8) uint64_t s_bar[kStages];
     __shared__ uint32_t s_cursor[2];  // voxels emitted by the current tile (by tile parity)
     __shared__ uint32_t s_chunk_pos, s_chunk_end, s_next_base;
+    __shared__ uint32_t s_stop;  // some CTA has found the stream unordered: stop early
 
     DsCounters* cnt = a.cnt;
     if (cnt->slab_violation) return;
@@ -353,7 +354,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
         const uint64_t tb = tb0 + b;
         const int64_t t_lo = t0 + (int64_t)(tb * (uint64_t)kp.vt);
         const uint64_t key_base = tb * kp.cells;
+        if (tid == 0) s_stop = *reinterpret_cast<volatile unsigned int*>(&cnt->slab_violation);
         prod_sync<NT>();  // every thread has left the previous bin (bitmap, cursor)
+        if (s_stop) break;  // (an early stop inside the tile loop also ends here)
         if (tid == 0) book();
         {  // count the previous bin's repeated cells and clear the bitmap in one pass
             uint32_t r = 0;
@@ -420,7 +423,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 cb[j] = sbit;
 #endif
             }
+            // a rejected stream is rerun on a general path: publish the violation at once and let
+            // every CTA stop at its next tile (uniformly: thread 0 reads, the barrier broadcasts)
+            const bool poll = (tile_seq & 3u) == 0;  // (every fourth tile: ~1 instruction per tile)
+            if (poll) {
+                if (viol == 1) {
+                    atomicOr(&cnt->slab_violation, 1u);
+                    viol = 3;
+                }
+                if (tid == 0)
+                    s_stop = *reinterpret_cast<volatile unsigned int*>(&cnt->slab_violation);
+            }
             prod_sync<NT>();  // B0: every bitmap read of this tile precedes every claim below
+            if (poll && s_stop) break;
             // EARLY_FREE: this tile's ring slot has been drained into registers; else the ring slot
             // of the previous tile is no longer in use.  Either way: the next tile of the stream
             if (tid == kTmaThread) fetch();
@@ -523,6 +538,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
             if (tid == 0) book_par = par;
         }
     }
+    // (early stop: bulk copies still in flight must land before the CTA gives up its shared memory)
+    if (tid == kTmaThread)
+        for (uint32_t q = tile_seq; q < tma_seq; q++) mbar_wait(&s_bar[q % kStages], (q / kStages) & 1);
     prod_sync<NT>();
     if (tid == 0) book();
     if (COUNT_REP) {  // the last bin's repeated cells

@@ -73,11 +73,13 @@ typedef struct evk_event {
 enum { EVK_KEY_VOXEL = 0, EVK_KEY_REF_HASH8192 = 1 };
 /* downsample algorithm selector */
 enum {
-    EVK_ALGO_AUTO = 0,  /* time-slab kernel when the stream allows it, else the table        */
+    EVK_ALGO_AUTO = 0,  /* time-slab kernel when the stream allows it, else partition, else table */
     EVK_ALGO_TABLE = 1, /* global open-addressing table, 64-bit keys, atomicCAS insert       */
     EVK_ALGO_SORT = 2,  /* radix sort + unique (cross-check variant)                         */
-    EVK_ALGO_SLAB = 3   /* per-time-bin shared-memory kernel; fails over to TABLE if the
-                           stream is not partitioned by time bin                            */
+    EVK_ALGO_SLAB = 3,  /* per-time-bin shared-memory kernel; a stream that is not partitioned by
+                           time bin fails over to PARTITION, then to TABLE                  */
+    EVK_ALGO_PARTITION = 4 /* reported in ds_algo_used (also selectable): stable partition of
+                           the stream by time bin on the device, then the time-slab kernel  */
 };
 
 /* Downsample parameters.  Replaces the compile-time constants of the reference kernel

@@ -234,7 +234,8 @@ def test_kmeans_extensions(evk, orc):
 
 def test_unordered_stream_falls_back_to_table(evk, orc):
     """the slab kernel requires a stream partitioned by time bin; anything else must be detected
-    and handled by the general table with identical results"""
+    and handled by the general paths (stable partition by time bin + slab kernel, else the
+    table) with identical results"""
     n, W, H = 200_000, 346, 260
     ev = orc.synth(orc.synth_params(0xE7CA0001, n, W, H, 10_000_000, 8))
     rng = np.random.default_rng(7)
@@ -248,10 +249,13 @@ def test_unordered_stream_falls_back_to_table(evk, orc):
     with evk.Evk(n) as h:
         for name, e in cases.items():
             h.load_events(e)
-            for algo in ("AUTO", "SLAB", "TABLE", "SORT"):
+            for algo in ("AUTO", "SLAB", "PARTITION", "TABLE", "SORT"):
                 run_ds(evk, orc, h, e, W, H, 4, 4, 1000, 1, algo)
-                if algo in ("AUTO", "SLAB"):
-                    assert h.stage_times().ds_algo_used == evk.ALGO_TABLE, name
+                if algo in ("AUTO", "SLAB", "PARTITION"):
+                    assert h.stage_times().ds_algo_used == evk.ALGO_PARTITION, name
+            # a key space the partition does not take (no time bins): the table
+            run_ds(evk, orc, h, e, W, H, 4, 4, 0, 1, "PARTITION")
+            assert h.stage_times().ds_algo_used == evk.ALGO_TABLE, name
 
 
 def test_edge_cases(evk, orc):
