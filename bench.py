@@ -585,6 +585,28 @@ def _main(args, real_stdout):
     ms_per_step = max_over_ranks(total_ms) / args.steps
     value = n * world / (ms_per_step * 1e-3) / 1e6
 
+    if strong:   # C4 is a device-resident scaling measurement: no host legs
+        if rank == 0:
+            peak, _ = peaks()
+            U = state["U_local"]
+            step_bytes = 16.0 * n + 36.0 * U
+            line = {"metric": "Mevents/s downsample+k-means iteration", "value": value,
+                    "unit": "Mevents/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                    "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+                    "vs_baseline": None, "dtype": "u64 keys / f32 distances / exact u64 sums",
+                    "data": "synthetic", "config": workload_config(args, world),
+                    "owner": args.owner, "unique_voxels_rank0": U, "unique_voxels_total": state["U"],
+                    "ds_algo": {1: "table", 2: "sort", 3: "slab", 4: "partition"}.get(algo_used),
+                    "stage_ms": {"downsample_dominant_kernel": ds_main / args.steps,
+                                 "downsample_total": ds_total / args.steps,
+                                 "kmeans_iteration": km_total / args.steps},
+                    "step_roofline_frac_per_gpu": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                    "gpu_launches": launches, "clocks": clocks, "e2e": None}
+            print(json.dumps(line), file=real_stdout, flush=True)
+        h.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     # ---- end to end through the C-ABI with host buffers ----------------------------------------
     # (a) everything the reference reads back (e2e), (b) centroids + counts only, (c) the bare H2D
     U_cap = state["U_local"] + (1 << 16)
@@ -720,7 +742,8 @@ def _main(args, real_stdout):
             "vs_baseline": None, "dtype": "u64 keys / f32 distances / exact u64 sums",
             "data": "synthetic", "config": workload_config(args, world),
             "unique_voxels_per_gpu": U, "repeated": state.get("R"),
-            "ds_algo": {1: "table", 2: "sort", 3: "slab"}.get(algo_used, str(algo_used)),
+            "ds_algo": {1: "table", 2: "sort", 3: "slab", 4: "partition"}.get(algo_used, str(algo_used)),
+            "owner": args.owner if world > 1 else None,
             "roofline": {"bound": "hbm", "kernel": kern, "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "frac_of_8000_nominal": achieved / 8000.0,

@@ -58,6 +58,7 @@ void invalidate_results(evk_handle* h) {
     h->have_voxels = false;
     h->perm_valid = false;
     h->reps_valid = false;
+    h->voxels_foreign = false;
     h->n_unique = h->n_repeated = 0;
     h->n_labels = 0;
     h->pix_valid = false;
@@ -655,6 +656,9 @@ int evk_get_voxels(evk_handle* h, uint64_t* keys, evk_event* reps, uint32_t* fir
     const size_t n = h->n_unique;
     if (cap < n) return evk_fail(h, EVK_ERR_CAPACITY, "cap %zu < %zu voxels", cap, n);
     if (!n) return EVK_OK;
+    if (reps && h->voxels_foreign && !h->reps_valid)
+        return evk_fail(h, EVK_ERR_STATE, "the representatives of hash-owned voxels were not "
+                        "exchanged by the fused step: use evk_downsample_sharded");
     DeviceGuard g(h->device);
     EVK_TRY(evk_ensure_perm(h));
     // gather into the (now idle) sort-variant / scratch buffers, one column at a time
@@ -701,7 +705,7 @@ int evk_init_centroids_first_k(evk_handle* h, const evk_km_params* p) {
     KmLaunch kl = km_launch_params(h, p);
     unsigned long long* d_count = &h->d_cnt->scratch[0];
     // fast path: walk the head of the stream until K distinct keys have been met
-    if (!h->reps_valid && h->n_events) {
+    if (!h->voxels_foreign && h->n_events) {
         const size_t n_scan = h->n_events < (1u << 20) ? h->n_events : (1u << 20);
         EVK_CUDA(h, evk_launch_init_first_k_walk(h->kp, kl, h->d_events, n_scan, h->d_cent, d_count,
                                                  h->stream));
@@ -756,7 +760,7 @@ int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_done,
     const size_t n = p->on_events ? h->n_events : h->n_unique;
     const uint32_t* xy = p->on_events ? nullptr : h->d_xy;
     const evk_event* ev = p->on_events ? h->d_events : h->d_events - h->shard_first;
-    if (!p->on_events && p->D > 2 && h->reps_valid)
+    if (!p->on_events && p->D > 2 && h->voxels_foreign)
         return evk_fail(h, EVK_ERR_INVALID, "D > 2 is not supported on a sharded voxel table");
     h->times.km_total_ms = h->times.km_assign_ms = 0.f;
     int it = 0, launches = 0;

@@ -93,6 +93,22 @@ struct Mailbox {
     unsigned long long seq;                             // my step counter
     unsigned long long err;                             // a wait timed out
     float cent[EVK_MAX_K * 2];
+    // hash-owned exchange (k_mix_*): what every rank tells every other rank, by step parity
+    unsigned long long mix_info[2][kMaxWorld][4];       // [src]: first bin, last bin, all-suspect, seq
+    unsigned long long mix_cnt[2][kMaxWorld][kMaxWorld][2];  // [src][dst]: records (plain, suspect)
+    unsigned long long mix_cnt_flag[2][kMaxWorld];      // seq of row src
+    unsigned long long mix_done_flag[2][kMaxWorld];     // seq: src has finished writing into me
+};
+
+struct MixPeer {  // one rank's buffers as seen from this process
+    uint64_t* keys;
+    uint32_t* first;
+    uint32_t* xy;
+    evk_event* reps;
+    uint64_t* sk;  // suspect staging
+    uint32_t* sf;
+    uint32_t* sx;
+    evk_event* sr;
 };
 
 struct CommState {
@@ -113,6 +129,17 @@ struct CommState {
     Mailbox* peer_mail[64] = {};                    // [r]: rank r's mailbox mapped into this process
     const evk_event* peer_events[64] = {};          // [r]: rank r's event buffer
     Mailbox** d_peer_mail = nullptr;                // the table above, on the device
+    // hash-owned exchange over peer memory: the local downsample writes into (lk, lf, lx), the
+    // bucket scatter writes every record straight into its owner's voxel shard (d_keys / d_first /
+    // d_xy / d_reps, mapped below) or, for keys another rank may also hold, into the owner's
+    // staging (rk / rf / rx / rr) for the merge
+    bool mix_p2p = false;
+    uint64_t* lk = nullptr;
+    uint32_t *lf = nullptr, *lx = nullptr;
+    struct MixPeer* d_mix_peers = nullptr;      // [world], device
+    unsigned long long* d_mix = nullptr;        // device scratch (see MX_*)
+    unsigned long long* h_mix = nullptr;        // pinned mirror of the tail
+    void* ipc_opened[64][8] = {};
     cudaGraphExec_t step_exec = nullptr;  // the fused sharded step as one graph
     int step_owner = 0;                   // evk_downsample_kmeans_sharded_submit: owner mode,
     bool step_fusable = false;            // and whether the submission went out as the graph
@@ -375,8 +402,22 @@ __global__ void k_pack_step_stats(const DsCounters* cnt, const unsigned long lon
     tail[2] = cnt->n_repeated;
 }
 
+// owner of a key: the top 32 bits of mix64(key ^ golden) range-reduced to [0, G) by a multiply
+// (a 64-bit modulo costs ~40 instructions per record; the rule is restated in sharding.py)
+// the same for the hash-owned step: the exchange's error word instead of the halo range flag
+__global__ void k_pack_mix_stats(const DsCounters* cnt, const unsigned long long* mx_tail,
+                                 unsigned long long found_want, int check_found,
+                                 const Mailbox* mail, unsigned long long* tail) {
+    unsigned long long flag = mx_tail[2];
+    if (check_found && cnt->scratch[4] != found_want) flag |= 1;
+    tail[0] = (flag ? 1 : 0) + ((mail && mail->err) ? (1ull << 32) : 0ull);
+    tail[1] = cnt->n_unique;
+    tail[2] = 0;
+}
+
 __device__ __forceinline__ int owner_of(uint64_t key, int world) {
-    return (int)(evk_mix64(key ^ 0x9E3779B97F4A7C15ull) % (uint64_t)world);
+    const uint32_t hi = (uint32_t)(evk_mix64(key ^ 0x9E3779B97F4A7C15ull) >> 32);
+    return (int)__umulhi(hi, (uint32_t)world);
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -502,6 +543,371 @@ __global__ void __launch_bounds__(kBlock)
         tkeys[slot] = EVK_EMPTY_KEY;
         tfirst[slot] = EVK_EMPTY_IDX;
     }
+}
+
+// ---- hash-owned exchange over peer memory ------------------------------------------------------
+// owner = mix64(key) % G (the north star's design).  Every rank downsamples its own index shard,
+// then writes each voxel record STRAIGHT into its owner's voxel shard over NVLink: no staging copy,
+// no NCCL call, no host round trip between the local downsample and the last kernel.
+//   k_mix_publish_info  my first / last time bin (or "unordered") into every mailbox
+//   k_mix_hist          records per owner, split into plain and SUSPECT ones: a key can only exist
+//                       on two ranks when its time bin straddles a shard boundary (index-sharded,
+//                       time-ordered stream), i.e. when its bin is some rank's first or last bin;
+//                       a rank whose shard is not time-ordered marks everything suspect
+//   k_mix_publish_counts / k_mix_offsets   the G x G count matrix travels through the mailboxes;
+//                       every rank derives where its records start in every owner's arrays
+//   k_mix_scatter       block-aggregated bucket cursors; plain records go into the owner's
+//                       d_keys / d_first / d_xy (/ d_reps), suspects into the owner's staging
+//   k_mix_done          "my writes into you are complete" to everyone, wait for everyone's
+//   k_merge_*           the owner resolves the (few) suspects in its hash-owned table: lowest
+//                       global first index wins; winners are appended behind the plain records
+enum { MX_HIST = 0, MX_OFF_PLAIN = 2 * kMaxWorld, MX_OFF_SUSP = 3 * kMaxWorld,
+       MX_CUR = 4 * kMaxWorld, MX_TAIL = 6 * kMaxWorld, MX_WORDS = 6 * kMaxWorld + 8 };
+// tail: [0] plain records I own, [1] suspects I own, [2] error (capacity / time-out)
+
+__global__ void __launch_bounds__(64)
+    k_mix_publish_info(Mailbox* mine, Mailbox* const* peers, int rank, int world,
+                       unsigned long long tb_first, unsigned long long tb_last,
+                       unsigned long long all_suspect) {
+    const unsigned long long seq = mine->seq;
+    const int par = (int)(seq & 1);
+    const int r = threadIdx.x;
+    if (r < world) {
+        unsigned long long* info = peers[r]->mix_info[par][rank];
+        info[0] = tb_first;
+        info[1] = tb_last;
+        info[2] = all_suspect;
+        __threadfence_system();
+        st_release_sys(&info[3], seq);
+    }
+}
+
+// exact key / cells without a 64-bit division: q = hi64(key * ceil(2^64 / cells)) is the quotient
+// or the quotient + 1
+struct MixDiv {
+    uint64_t cells, magic;  // magic = floor(2^64 / cells) + 1 (0 when cells == 1)
+};
+__device__ __forceinline__ uint64_t mix_tbin(uint64_t key, const MixDiv& d) {
+    if (d.cells <= 1) return key;
+    uint64_t q = __umul64hi(key, d.magic);
+    if (q * d.cells > key) q--;
+    return q;
+}
+__device__ __forceinline__ bool mix_suspect(uint64_t key, const MixDiv& d, const uint64_t* s_bins,
+                                            int n_bins, bool all) {
+    if (all) return true;
+    const uint64_t tb = mix_tbin(key, d);
+    bool s = false;
+    for (int i = 0; i < n_bins; i++) s |= s_bins[i] == tb;
+    return s;
+}
+
+// shared by the histogram and the scatter: wait for every rank's info, list the suspect bins
+__device__ __forceinline__ bool mix_load_info(Mailbox* mine, int world, uint64_t* s_bins,
+                                              int* s_flags) {
+    const unsigned long long seq = mine->seq;
+    const int par = (int)(seq & 1);
+    if (threadIdx.x == 0) {
+        s_flags[0] = 0;  // all suspect
+        s_flags[1] = 1;  // ok
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        unsigned long long* info = mine->mix_info[par][threadIdx.x];
+        if (!wait_flag(&info[3], seq)) {
+            s_flags[1] = 0;
+            mine->err = 1;
+        } else {
+            s_bins[2 * threadIdx.x] = __ldcg(&info[0]);
+            s_bins[2 * threadIdx.x + 1] = __ldcg(&info[1]);
+            if (__ldcg(&info[2])) s_flags[0] = 1;
+        }
+    }
+    __syncthreads();
+    return s_flags[1] != 0;
+}
+
+// bucket of every record (2 * owner + suspect) -> bkt[], and the bucket sizes
+__global__ void __launch_bounds__(kBlock)
+    k_mix_hist(const uint64_t* __restrict__ keys, size_t n, int world, MixDiv dv, Mailbox* mine,
+               unsigned long long* mx, uint8_t* bkt) {
+    __shared__ uint64_t s_bins[2 * kMaxWorld];
+    __shared__ int s_flags[2];
+    __shared__ unsigned int s_h[2 * kMaxWorld];
+    if (!mix_load_info(mine, world, s_bins, s_flags)) {
+        if (threadIdx.x == 0) mx[MX_TAIL + 2] = 1;
+        return;
+    }
+    for (int i = threadIdx.x; i < 2 * world; i += kBlock) s_h[i] = 0;
+    __syncthreads();
+    const bool all = s_flags[0] != 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t k = keys[i];
+        const int b = 2 * owner_of(k, world) + (mix_suspect(k, dv, s_bins, 2 * world, all) ? 1 : 0);
+        bkt[i] = (uint8_t)b;
+        atomicAdd(&s_h[b], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * world; i += kBlock)
+        if (s_h[i]) atomicAdd(&mx[MX_HIST + i], (unsigned long long)s_h[i]);
+}
+
+// my row of the count matrix into every mailbox
+__global__ void __launch_bounds__(kBlock)
+    k_mix_publish_counts(Mailbox* mine, Mailbox* const* peers, int rank, int world,
+                         const unsigned long long* mx) {
+    const unsigned long long seq = mine->seq;
+    const int par = (int)(seq & 1);
+    for (int i = threadIdx.x; i < world * 2 * world; i += kBlock) {
+        const int r = i / (2 * world), j = i % (2 * world);
+        peers[r]->mix_cnt[par][rank][j >> 1][j & 1] = mx[MX_HIST + j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) st_release_sys(&peers[threadIdx.x]->mix_cnt_flag[par][rank], seq);
+}
+
+// where my records start in every owner's arrays; how many records I own
+__global__ void __launch_bounds__(64)
+    k_mix_offsets(Mailbox* mine, int rank, int world, unsigned long long cap_plain,
+                  unsigned long long cap_susp, unsigned long long* mx, DsCounters* cnt) {
+    __shared__ int s_ok;
+    const unsigned long long seq = mine->seq;
+    const int par = (int)(seq & 1);
+    if (threadIdx.x == 0) s_ok = 1;
+    __syncthreads();
+    if ((int)threadIdx.x < world && !wait_flag(&mine->mix_cnt_flag[par][threadIdx.x], seq)) {
+        s_ok = 0;
+        mine->err = 1;
+    }
+    __syncthreads();
+    if (!s_ok) {
+        if (threadIdx.x == 0) mx[MX_TAIL + 2] = 1;
+        return;
+    }
+    const int d = threadIdx.x;  // one owner per thread
+    if (d < world) {
+        unsigned long long op = 0, os = 0, tp = 0, ts = 0;
+        for (int s = 0; s < world; s++) {
+            const unsigned long long cp = __ldcg(&mine->mix_cnt[par][s][d][0]);
+            const unsigned long long cs = __ldcg(&mine->mix_cnt[par][s][d][1]);
+            if (s < rank) {
+                op += cp;
+                os += cs;
+            }
+            tp += cp;
+            ts += cs;
+        }
+        mx[MX_OFF_PLAIN + d] = op;
+        mx[MX_OFF_SUSP + d] = os;
+        if (d == rank) {
+            mx[MX_TAIL + 0] = tp;
+            mx[MX_TAIL + 1] = ts;
+            cnt->n_unique = tp;  // the merge appends its winners behind the plain records
+        }
+        // every rank checks every owner's capacity: all of them see the same matrix and agree
+        if (tp + ts > cap_plain || ts > cap_susp) mx[MX_TAIL + 2] = 1;
+    }
+}
+
+// Bucket scatter into the owners' memory.  A block sorts a tile of kScTile records by bucket in
+// shared memory, claims one range per bucket with one global atomic each, and then writes the
+// tile out with consecutive threads on consecutive slots: every bucket's run is one contiguous,
+// coalesced burst over NVLink instead of 8 / 4 / 4-byte stores scattered across the owner's arrays.
+constexpr int kScPer = 4, kScTile = kBlock * kScPer;
+__global__ void __launch_bounds__(kBlock)
+    k_mix_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ first,
+                  const uint32_t* __restrict__ xy, const evk_event* __restrict__ ev0,
+                  const uint8_t* __restrict__ bkt, size_t n, int world,
+                  const MixPeer* __restrict__ peers, unsigned long long* mx, int want_reps) {
+    __shared__ unsigned int s_cnt[2 * kMaxWorld], s_start[2 * kMaxWorld + 1];
+    __shared__ unsigned long long s_dst[2 * kMaxWorld];  // first slot of this tile's run per bucket
+    __shared__ uint64_t s_k[kScTile];
+    __shared__ uint32_t s_f[kScTile], s_x[kScTile];
+    __shared__ uint8_t s_b[kScTile];
+    if (mx[MX_TAIL + 2]) return;  // capacity error or time-out: nothing is written anywhere
+    const int nb = 2 * world;
+    const size_t n_tiles = (n + kScTile - 1) / kScTile;
+    for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int o = threadIdx.x; o < nb; o += kBlock) s_cnt[o] = 0;
+        __syncthreads();
+        uint64_t k[kScPer];
+        uint32_t f[kScPer], x[kScPer], loc[kScPer];
+        int b[kScPer];
+#pragma unroll
+        for (int j = 0; j < kScPer; j++) {
+            const size_t i = t * kScTile + (size_t)j * kBlock + threadIdx.x;
+            b[j] = -1;
+            if (i < n) {
+                k[j] = keys[i];
+                f[j] = first[i];
+                x[j] = xy[i];
+                b[j] = bkt[i];
+                loc[j] = atomicAdd(&s_cnt[b[j]], 1u);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {  // exclusive scan of the bucket sizes (<= 128 buckets: 4 per lane)
+            unsigned int v[4], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int o = threadIdx.x * 4 + q;
+                v[q] = o < nb ? s_cnt[o] : 0u;
+                sum += v[q];
+            }
+            unsigned int inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned int u = __shfl_up_sync(0xffffffffu, inc, d);
+                if ((int)threadIdx.x >= d) inc += u;
+            }
+            unsigned int run = inc - sum;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int o = threadIdx.x * 4 + q;
+                if (o < nb) {
+                    s_start[o] = run;
+                    // the tile's run of bucket o in its owner's arrays
+                    const unsigned long long off = mx[((o & 1) ? MX_OFF_SUSP : MX_OFF_PLAIN) + (o >> 1)];
+                    s_dst[o] = off + (v[q] ? atomicAdd(&mx[MX_CUR + o], (unsigned long long)v[q]) : 0ull);
+                }
+                run += v[q];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kScPer; j++) {
+            if (b[j] < 0) continue;
+            const unsigned int slot = s_start[b[j]] + loc[j];
+            s_k[slot] = k[j];
+            s_f[slot] = f[j];
+            s_x[slot] = x[j];
+            s_b[slot] = (uint8_t)b[j];
+        }
+        __syncthreads();
+        const size_t left = n - t * kScTile;
+        const unsigned int in_tile = left < (size_t)kScTile ? (unsigned int)left : (unsigned int)kScTile;
+#pragma unroll
+        for (int j = 0; j < kScPer; j++) {
+            const unsigned int slot = j * kBlock + threadIdx.x;
+            if (slot >= in_tile) continue;
+            const int bb = s_b[slot];
+            const MixPeer& pr = peers[bb >> 1];
+            const size_t p = (size_t)s_dst[bb] + (slot - s_start[bb]);
+            const uint32_t ff = s_f[slot];
+            if (bb & 1) {
+                pr.sk[p] = s_k[slot];
+                pr.sf[p] = ff;
+                pr.sx[p] = s_x[slot];
+                if (want_reps) pr.sr[p] = ev0[ff];  // ev0 is indexable by global index
+            } else {
+                pr.keys[p] = s_k[slot];
+                pr.first[p] = ff;
+                pr.xy[p] = s_x[slot];
+                if (want_reps) pr.reps[p] = ev0[ff];
+            }
+        }
+        __syncthreads();
+    }
+    __threadfence_system();
+}
+
+__global__ void __launch_bounds__(64)
+    k_mix_done(Mailbox* mine, Mailbox* const* peers, int rank, int world, unsigned long long* mx) {
+    __shared__ int s_ok;
+    const unsigned long long seq = mine->seq;
+    const int par = (int)(seq & 1);
+    if (threadIdx.x == 0) s_ok = 1;
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        st_release_sys(&peers[threadIdx.x]->mix_done_flag[par][rank], seq);
+        if (!wait_flag(&mine->mix_done_flag[par][threadIdx.x], seq)) {
+            s_ok = 0;
+            mine->err = 1;
+        }
+    }
+    __syncthreads();
+    if (!s_ok && threadIdx.x == 0) mx[MX_TAIL + 2] = 1;
+}
+
+// the suspect merge with its record count read on the device (mx[MX_TAIL + 1])
+__global__ void __launch_bounds__(kBlock)
+    k_mix_merge_insert(const uint64_t* __restrict__ rk, const uint32_t* __restrict__ rf,
+                       const unsigned long long* mx, uint64_t* tkeys, uint32_t* tfirst,
+                       uint64_t mask) {
+    const size_t m = mx[MX_TAIL + 2] ? 0 : (size_t)mx[MX_TAIL + 1];
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        const uint64_t key = rk[i];
+        uint64_t slot = evk_mix64(key) & mask;
+        for (;;) {
+            uint64_t cur = ld_relaxed_u64(tkeys + slot);
+            if (cur == EVK_EMPTY_KEY)
+                cur = atomicCAS((unsigned long long*)(tkeys + slot), EVK_EMPTY_KEY, key);
+            if (cur == EVK_EMPTY_KEY || cur == key) {
+                atomicMin(tfirst + slot, rf[i]);
+                break;
+            }
+            slot = (slot + 1) & mask;
+        }
+    }
+}
+__global__ void __launch_bounds__(kBlock)
+    k_mix_merge_emit(const uint64_t* __restrict__ rk, const uint32_t* __restrict__ rf,
+                     const uint32_t* __restrict__ rx, const evk_event* __restrict__ rr,
+                     const unsigned long long* mx, const uint64_t* __restrict__ tkeys,
+                     const uint32_t* __restrict__ tfirst, uint64_t mask, uint64_t* keys,
+                     uint32_t* first, uint32_t* xy, evk_event* reps, uint32_t* slot_out,
+                     DsCounters* cnt, int want_reps) {
+    const size_t m = mx[MX_TAIL + 2] ? 0 : (size_t)mx[MX_TAIL + 1];
+    const int lane = threadIdx.x & 31;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t m_pad = (m + 31) & ~(size_t)31;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m_pad; i += stride) {
+        bool win = false;
+        uint64_t key = 0;
+        uint32_t f = 0;
+        if (i < m) {
+            key = rk[i];
+            f = rf[i];
+            uint64_t slot = evk_mix64(key) & mask;
+            while (tkeys[slot] != key) slot = (slot + 1) & mask;
+            win = tfirst[slot] == f;
+            slot_out[i] = (uint32_t)slot;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, win);
+        unsigned long long base = 0;
+        if (lane == 0 && bal) base = atomicAdd(&cnt->n_unique, (unsigned long long)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (win) {
+            const size_t o = (size_t)base + __popc(bal & ((1u << lane) - 1u));
+            keys[o] = key;
+            first[o] = f;
+            xy[o] = rx[i];
+            if (want_reps) reps[o] = rr[i];
+        }
+    }
+}
+__global__ void __launch_bounds__(kBlock)
+    k_mix_merge_reset(const uint32_t* __restrict__ slots, const unsigned long long* mx,
+                      uint64_t* tkeys, uint32_t* tfirst) {
+    const size_t m = mx[MX_TAIL + 2] ? 0 : (size_t)mx[MX_TAIL + 1];
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        const uint32_t slot = slots[i];
+        tkeys[slot] = EVK_EMPTY_KEY;
+        tfirst[slot] = EVK_EMPTY_IDX;
+    }
+}
+
+// flag = sum over ranks of (1 if the basic set-up failed) + (2 if the hash-owned set-up failed)
+bool ok_all(unsigned long long sum, int world, int what) {
+    // decode: each rank contributes 0..3; without carries between the two bits this needs them
+    // separated, so ranks add 1 and 2 * (world + 1) instead (see the callers)
+    (void)world;
+    return what == 1 ? (sum & 0xFFFFull) == 0 : (sum >> 16) == 0;
 }
 
 int grid_for(size_t n, int sm) {
@@ -677,12 +1083,123 @@ int sharded_mix64(evk_handle* h, const evk_ds_params* p) {
     h->n_repeated = 0;  // per-key hit counts are not exchanged in this mode
     h->perm_valid = false;
     h->reps_valid = true;
+    h->voxels_foreign = true;
     h->have_voxels = true;
     c->h_stats[ST_FLAG] = 0;
     c->h_stats[ST_U] = h->n_unique;
     c->h_stats[ST_R] = 0;
     EVK_CUDA(h, cudaMemcpyAsync(c->d_stats, c->h_stats, 3 * 8, cudaMemcpyHostToDevice, h->stream));
     EVK_TRY(stats_allreduce(h, c, 3));
+    return EVK_OK;
+}
+
+// Hash-owned downsample over peer memory (see the k_mix_* kernels).  One host synchronisation after
+// the local downsample (its algorithm -- slab, partition, table -- is chosen on the host) and one at
+// the end.  want_reps: also deliver the representative events (evk_get_voxels needs them; the fused
+// step does not).
+int sharded_mix64_p2p(evk_handle* h, const evk_ds_params* p, bool want_reps) {
+    CommState* c = h->comm;
+    const int G = c->world;
+    if (h->table_cap > (1ull << 32))
+        return evk_fail(h, EVK_ERR_CAPACITY, "hash-owned exchange supports max_events < 2^31");
+    // 1. local downsample into the local voxel buffers (the shard arrays are written by peers)
+    evk_ds_params q = *p;
+    if (q.algo == EVK_ALGO_SLAB) q.algo = EVK_ALGO_AUTO;
+    std::swap(h->d_keys, c->lk);
+    std::swap(h->d_first, c->lf);
+    std::swap(h->d_xy, c->lx);
+    const int st = evk_downsample_local(h, &q);
+    std::swap(h->d_keys, c->lk);
+    std::swap(h->d_first, c->lf);
+    std::swap(h->d_xy, c->lx);
+    // (an error on one rank only would leave the others waiting: it is reported after the exchange)
+    const size_t U = st == EVK_OK ? h->n_unique : 0;
+    const bool ordered = st == EVK_OK && h->times.ds_algo_used == EVK_ALGO_SLAB;
+    // the slab kernels leave the first bin and the bin count behind (DsCounters::scratch[2], [0])
+    const unsigned long long tb_first = ordered ? h->h_cnt->scratch[2] : 0;
+    const unsigned long long tb_last = ordered ? tb_first + h->h_cnt->scratch[0] - 1 : 0;
+    KeyParams kp;
+    EVK_TRY(evk_make_key_params(h, p, &kp));
+    MixDiv dv;
+    dv.cells = kp.cells ? kp.cells : 1;
+    dv.magic = dv.cells > 1 ? ~0ull / dv.cells + 1 : 0;
+    uint8_t* bkt = reinterpret_cast<uint8_t*>(c->sx);  // (idle send staging: one byte per record)
+    const bool all_suspect = !ordered || kp.keyfn != EVK_KEY_VOXEL || kp.vt <= 0;
+    unsigned long long* mx = c->d_mix;
+    static const bool trace = getenv("EVK_MIX_TRACE") != nullptr;
+    static cudaEvent_t tev[8] = {};
+    auto mark = [&](int i) {
+        if (!trace) return;
+        if (!tev[i]) cudaEventCreate(&tev[i]);
+        cudaEventRecord(tev[i], h->stream);
+    };
+    EVK_CUDA(h, cudaMemsetAsync(mx, 0, MX_WORDS * sizeof(unsigned long long), h->stream));
+    EVK_CUDA(h, cudaMemsetAsync(h->d_cnt, 0, sizeof(DsCounters), h->stream));
+    evk_prof_rec(h, 0);
+    mark(0);
+    k_p2p_tick<<<1, 1, 0, h->stream>>>(c->mail, c->d_peer_mail, 0);  // seq++ (no neighbour flag)
+    k_mix_publish_info<<<1, 64, 0, h->stream>>>(c->mail, c->d_peer_mail, c->rank, G, tb_first,
+                                                tb_last, all_suspect ? 1ull : 0ull);
+    const int grid = grid_for(U ? U : 1, h->sm_count);
+    k_mix_hist<<<grid, kBlock, 0, h->stream>>>(c->lk, U, G, dv, c->mail, mx, bkt);
+    mark(1);
+    k_mix_publish_counts<<<1, kBlock, 0, h->stream>>>(c->mail, c->d_peer_mail, c->rank, G, mx);
+    k_mix_offsets<<<1, 64, 0, h->stream>>>(c->mail, c->rank, G, (unsigned long long)h->out_cap,
+                                           (unsigned long long)c->stage_cap, mx, h->d_cnt);
+    const evk_event* ev0 = h->d_events - h->shard_first;
+    mark(2);
+    k_mix_scatter<<<h->sm_count * 8, kBlock, 0, h->stream>>>(c->lk, c->lf, c->lx, ev0, bkt, U, G,
+                                                             c->d_mix_peers, mx, want_reps ? 1 : 0);
+    mark(3);
+    k_mix_done<<<1, 64, 0, h->stream>>>(c->mail, c->d_peer_mail, c->rank, G, mx);
+    mark(4);
+    // 2. the owner resolves its suspects: lowest global first index wins, winners are appended
+    {
+        const uint64_t mask = (uint64_t)h->table_cap - 1;
+        const int mg = h->sm_count * 8;
+        k_mix_merge_insert<<<mg, kBlock, 0, h->stream>>>(c->rk, c->rf, mx, h->d_tkeys, h->d_tfirst,
+                                                         mask);
+        k_mix_merge_emit<<<mg, kBlock, 0, h->stream>>>(c->rk, c->rf, c->rx, c->rr, mx, h->d_tkeys,
+                                                       h->d_tfirst, mask, h->d_keys, h->d_first,
+                                                       h->d_xy, h->d_reps, c->sf, h->d_cnt,
+                                                       want_reps ? 1 : 0);
+        k_mix_merge_reset<<<mg, kBlock, 0, h->stream>>>(c->sf, mx, h->d_tkeys, h->d_tfirst);
+    }
+    EVK_CUDA(h, cudaGetLastError());
+    mark(5);
+    if (trace) {
+        cudaEventSynchronize(tev[5]);
+        float t[5];
+        for (int i = 0; i < 5; i++) cudaEventElapsedTime(&t[i], tev[i], tev[i + 1]);
+        fprintf(stderr, "[evk mix64 rank %d] U=%zu hist %.3f counts+offsets %.3f scatter %.3f "
+                "done-wait %.3f merge %.3f ms\n", c->rank, U, t[0], t[1], t[2], t[3], t[4]);
+    }
+    evk_prof_rec(h, 1);
+    evk_prof_rec(h, 2);
+    EVK_CUDA(h, cudaMemcpyAsync(c->h_mix, mx + MX_TAIL, 8 * sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, h->stream));
+    EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,
+                                h->stream));
+    return st;
+}
+
+// collection half of the exchange: counters to the host, state of the handle
+int sharded_mix64_p2p_finish(evk_handle* h, int st_local, bool want_reps) {
+    CommState* c = h->comm;
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (c->h_mix[2])
+        return evk_fail(h, EVK_ERR_CAPACITY, "hash-owned exchange: a rank would own more voxels than "
+                        "its capacity, or a peer did not answer (rank %d owns %llu + %llu)", c->rank,
+                        c->h_mix[0], c->h_mix[1]);
+    EVK_TRY(st_local);
+    h->n_unique = (size_t)h->h_cnt->n_unique;
+    h->n_repeated = 0;  // per-key hit counts are not exchanged in this mode
+    h->perm_valid = false;
+    h->reps_valid = want_reps;
+    h->voxels_foreign = true;
+    h->have_voxels = true;
+    h->pix_valid = false;
+    h->times.ds_launches += 10;
     return EVK_OK;
 }
 
@@ -727,14 +1244,69 @@ void p2p_setup(evk_handle* h, CommState* c) {
         ok = cudaMalloc((void**)&c->d_peer_mail, sizeof(Mailbox*) * kMaxWorld) == cudaSuccess &&
              cudaMemcpy(c->d_peer_mail, c->peer_mail, sizeof(Mailbox*) * kMaxWorld,
                         cudaMemcpyHostToDevice) == cudaSuccess;
+    // hash-owned exchange: every rank's voxel shard and staging arrays, mapped the same way
+    bool mix = ok && getenv("EVK_NO_MIX_P2P") == nullptr;
+    struct MixHandles {
+        cudaIpcMemHandle_t a[8];
+    };
+    MixHandles mh;
+    memset(&mh, 0, sizeof mh);
+    MixHandles* d_mh = nullptr;
+    std::vector<MixHandles> allm(c->world);
+    if (mix) {
+        mix = stage_alloc(h, c) == EVK_OK &&
+              cudaMalloc((void**)&c->lk, h->out_cap * 8) == cudaSuccess &&
+              cudaMalloc((void**)&c->lf, h->out_cap * 4) == cudaSuccess &&
+              cudaMalloc((void**)&c->lx, h->out_cap * 4) == cudaSuccess &&
+              cudaMalloc((void**)&c->d_mix, MX_WORDS * 8) == cudaSuccess &&
+              cudaMallocHost((void**)&c->h_mix, 8 * 8) == cudaSuccess &&
+              cudaMalloc((void**)&c->d_mix_peers, sizeof(MixPeer) * kMaxWorld) == cudaSuccess;
+        void* mineptr[8] = {h->d_keys, h->d_first, h->d_xy, h->d_reps, c->rk, c->rf, c->rx, c->rr};
+        for (int i = 0; mix && i < 8; i++)
+            mix = cudaIpcGetMemHandle(&mh.a[i], mineptr[i]) == cudaSuccess;
+    }
+    // (collectives below are reached by every rank whatever happened above)
+    bool coll2 = cudaMalloc((void**)&d_mh, sizeof(MixHandles) * c->world) == cudaSuccess;
+    coll2 = coll2 && cudaMemcpy(d_mh + c->rank, &mh, sizeof mh, cudaMemcpyHostToDevice) == cudaSuccess;
+    coll2 = g_nccl.AllGather(d_mh ? d_mh + c->rank : nullptr, d_mh, sizeof(MixHandles), ncclUint8,
+                             c->comm, h->stream) == ncclSuccess && coll2;
+    coll2 = cudaStreamSynchronize(h->stream) == cudaSuccess && coll2;
+    coll2 = coll2 && cudaMemcpy(allm.data(), d_mh, sizeof(MixHandles) * c->world,
+                                cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (d_mh) cudaFree(d_mh);
+    mix = mix && coll2;
+    std::vector<MixPeer> mp(kMaxWorld);
+    for (int r = 0; mix && r < c->world; r++) {
+        void* ptr[8] = {h->d_keys, h->d_first, h->d_xy, h->d_reps, c->rk, c->rf, c->rx, c->rr};
+        if (r != c->rank)
+            for (int i = 0; mix && i < 8; i++) {
+                mix = cudaIpcOpenMemHandle(&ptr[i], allm[r].a[i], cudaIpcMemLazyEnablePeerAccess) ==
+                      cudaSuccess;
+                c->ipc_opened[r][i] = mix ? ptr[i] : nullptr;
+            }
+        mp[r].keys = static_cast<uint64_t*>(ptr[0]);
+        mp[r].first = static_cast<uint32_t*>(ptr[1]);
+        mp[r].xy = static_cast<uint32_t*>(ptr[2]);
+        mp[r].reps = static_cast<evk_event*>(ptr[3]);
+        mp[r].sk = static_cast<uint64_t*>(ptr[4]);
+        mp[r].sf = static_cast<uint32_t*>(ptr[5]);
+        mp[r].sx = static_cast<uint32_t*>(ptr[6]);
+        mp[r].sr = static_cast<evk_event*>(ptr[7]);
+    }
+    if (mix)
+        mix = cudaMemcpy(c->d_mix_peers, mp.data(), sizeof(MixPeer) * kMaxWorld,
+                         cudaMemcpyHostToDevice) == cudaSuccess;
     // all ranks agree: P2P only if it works everywhere
-    unsigned long long flag = ok ? 0 : 1;
+    unsigned long long flag = (ok ? 0 : 1) + (mix ? 0 : (1ull << 16));
     if (cudaMemcpy(c->d_stats, &flag, 8, cudaMemcpyHostToDevice) == cudaSuccess &&
         g_nccl.AllReduce(c->d_stats, c->d_stats, 1, ncclUint64, ncclSum, c->comm, h->stream) ==
             ncclSuccess &&
         cudaStreamSynchronize(h->stream) == cudaSuccess &&
-        cudaMemcpy(&flag, c->d_stats, 8, cudaMemcpyDeviceToHost) == cudaSuccess)
-        c->p2p = flag == 0;
+        cudaMemcpy(&flag, c->d_stats, 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+        // (sum over ranks: bit 0 of any rank -> odd contributions; test the two conditions apart)
+        c->p2p = ok_all(flag, c->world, 1);
+        c->mix_p2p = c->p2p && ok_all(flag, c->world, 2);
+    }
     cudaGetLastError();
 }
 
@@ -799,8 +1371,15 @@ int evk_comm_destroy(evk_handle* h) {
         if (c->peer_mail[r]) cudaIpcCloseMemHandle(c->peer_mail[r]);
         if (c->peer_events[r]) cudaIpcCloseMemHandle(const_cast<evk_event*>(c->peer_events[r]));
     }
+    for (int r = 0; r < c->world; r++)
+        for (int i = 0; i < 8; i++)
+            if (c->ipc_opened[r][i]) cudaIpcCloseMemHandle(c->ipc_opened[r][i]);
     if (c->d_peer_mail) cudaFree(c->d_peer_mail);
     if (c->mail) cudaFree(c->mail);
+    void* mixptrs[] = {c->lk, c->lf, c->lx, c->d_mix, c->d_mix_peers};
+    for (void* q : mixptrs)
+        if (q) cudaFree(q);
+    if (c->h_mix) cudaFreeHost(c->h_mix);
     cudaGetLastError();
     if (c->comm && g_nccl.ok) g_nccl.CommDestroy(c->comm);
     void* ptrs[] = {c->d_stats, c->sk, c->rk, c->sf, c->rf, c->sx, c->rx, c->sr, c->rr};
@@ -835,7 +1414,19 @@ int evk_downsample_sharded(evk_handle* h, const evk_ds_params* p, int owner_mode
         return evk_fail(h, EVK_ERR_INVALID, "unknown owner mode %d", owner_mode);
     }
     if (!done) {
-        EVK_TRY(sharded_mix64(h, p));
+        if (c->mix_p2p) {
+            const int st_local = sharded_mix64_p2p(h, p, true);
+            EVK_TRY(sharded_mix64_p2p_finish(h, st_local, true));
+            // the global voxel count for the caller (and for the fallback of the fused step)
+            c->h_stats[ST_FLAG] = 0;
+            c->h_stats[ST_U] = h->n_unique;
+            c->h_stats[ST_R] = 0;
+            EVK_CUDA(h, cudaMemcpyAsync(c->d_stats, c->h_stats, 3 * 8, cudaMemcpyHostToDevice,
+                                        h->stream));
+            EVK_TRY(stats_allreduce(h, c, 3));
+        } else {
+            EVK_TRY(sharded_mix64(h, p));
+        }
         c->last_mode = EVK_OWNER_MIX64;
     }
     if (n_unique_local) *n_unique_local = h->n_unique;
@@ -993,8 +1584,67 @@ int evk_downsample_kmeans_sharded_submit(evk_handle* h, const evk_ds_params* ds,
     h->step_iters = 0;
     c->step_owner = owner_mode;
     c->step_fusable = fusable;
+    // hash ownership over peer memory: local downsample (host-synchronous: its algorithm is chosen
+    // on the host), then exchange + merge + the k-means pass + the allreduce as one stream of
+    // kernels with a single synchronisation in _wait.  Representatives are not exchanged here.
+    const bool mix_fused = owner_mode == EVK_OWNER_MIX64 && c->mix_p2p && km->D == 2 &&
+                           !km->on_events && km->K <= 254 && km->iters == 1 && km->tol < 0.f &&
+                           ds->keyfn == EVK_KEY_VOXEL &&
+                           (uint64_t)ds->width * ds->height <= (64ull << 20);
+    if (mix_fused) {
+        if (h->step_pending)
+            EVK_TRY(evk_downsample_kmeans_sharded_wait(h, nullptr, nullptr, nullptr));
+        if (!evk_ensure_images(h, ds->width, ds->height))
+            return evk_fail(h, EVK_ERR_NOMEM, "pixel images");
+        c->step_fusable = false;
+        const int st_local = sharded_mix64_p2p(h, ds, false);
+        EVK_TRY(st_local);  // (a local failure after the exchange was queued: peers see U = 0)
+        h->ds = *ds;
+        h->kp = kp;
+        h->have_ds = true;
+        const KmLaunch kl = evk_km_launch_params(h, km);
+        unsigned long long* tail = h->d_acc + (size_t)km->K * 5;
+        EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+        EVK_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+        if (init_first_k) {
+            if (c->rank == 0) {
+                const size_t n_scan = n_own < (1u << 20) ? n_own : (1u << 20);
+                if (n_scan)
+                    EVK_CUDA(h, evk_launch_init_first_k_walk(kp, kl, h->d_events, n_scan, h->d_cent,
+                                                             &h->d_cnt->scratch[4], h->side));
+                k_p2p_push_cent<<<1, 256, 0, h->side>>>(c->mail, c->d_peer_mail, c->world, h->d_cent,
+                                                        km->K);
+            } else {
+                k_p2p_cent<<<1, 256, 0, h->side>>>(c->mail, h->d_cent, km->K);
+            }
+            EVK_CUDA(h, cudaGetLastError());
+        }
+        EVK_CUDA(h, evk_launch_km_image(kl, ds->width, ds->height, h->d_prune_lists, h->d_cent,
+                                        nullptr, h->d_label_map, h->d_quads, h->d_acc, h->side));
+        EVK_CUDA(h, cudaEventRecord(h->ev_join, h->side));
+        EVK_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));
+        evk_prof_rec(h, 3);
+        EVK_CUDA(h, evk_launch_km_assign_tiles(kl, ds->width, ds->height, h->d_quads, h->d_label_map,
+                                               h->d_xy, h->out_cap, &h->d_cnt->n_unique, true,
+                                               h->d_acc, h->d_labels, h->sm_count, h->stream));
+        k_pack_mix_stats<<<1, 1, 0, h->stream>>>(h->d_cnt, c->d_mix + MX_TAIL,
+                                                 (unsigned long long)km->K,
+                                                 init_first_k && c->rank == 0, c->mail, tail);
+        k_p2p_allreduce<<<1, 1024, 0, h->stream>>>(c->mail, c->d_peer_mail, c->rank, c->world,
+                                                   h->d_acc, km->K * 5 + 3);
+        EVK_CUDA(h, cudaGetLastError());
+        EVK_CUDA(h, cudaMemcpyAsync(c->h_stats, tail, 3 * 8, cudaMemcpyDeviceToHost, h->stream));
+        EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
+                                           h->stream));
+        evk_prof_rec(h, 4);
+        EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,
+                                    h->stream));
+        h->step_pending = 3;  // hash-owned step in flight
+        h->step_sharded = true;
+        return EVK_OK;
+    }
     if (!fusable) {
-        if (h->step_pending == 1)
+        if (h->step_pending == 1 || h->step_pending == 3)
             EVK_TRY(evk_downsample_kmeans_sharded_wait(h, nullptr, nullptr, nullptr));
         h->step_pending = 0;
         EVK_TRY(evk_downsample_sharded(h, ds, owner_mode, nullptr, nullptr));
@@ -1064,6 +1714,32 @@ int evk_downsample_kmeans_sharded_wait(evk_handle* h, size_t* n_unique_local,
     CommState* c = h->comm;
     const int pending = h->step_pending;
     h->step_pending = 0;
+    if (pending == 3) {  // hash-owned step: exchange + k-means pass were queued by submit
+        DeviceGuard dev_guard(h->device);
+        const evk_km_params* km = &h->step_km;
+        EVK_TRY(sharded_mix64_p2p_finish(h, EVK_OK, false));
+        if (c->h_stats[0])
+            return evk_fail(h, (c->h_stats[0] >> 32) ? EVK_ERR_COMM : EVK_ERR_CAPACITY,
+                            "hash-owned step abandoned (a peer timed out, a rank ran out of room, "
+                            "or rank 0 holds fewer than K distinct voxels in its first 2^20 events)");
+        c->h_stats[ST_U] = c->h_stats[1];
+        h->K = km->K;
+        h->D = km->D;
+        h->have_centroids = true;
+        h->n_labels = h->n_unique;
+        h->labels_on_events = false;
+        h->km_last = *km;
+        c->last_mode = EVK_OWNER_MIX64;
+        h->times.km_launches = 6;
+        h->times.km_iters = 1;
+        if (h->profiling) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]) == cudaSuccess)
+                h->times.km_total_ms = h->times.km_assign_ms = ms;
+            cudaGetLastError();
+        }
+        h->step_iters = 1;
+    }
     if (pending == 1) {
         DeviceGuard dev_guard(h->device);
         const evk_ds_params* ds = &h->step_ds;

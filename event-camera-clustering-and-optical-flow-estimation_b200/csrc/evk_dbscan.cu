@@ -397,7 +397,7 @@ int evk_dbscan_voxels(evk_handle* h, const evk_dbscan_params* p, size_t* n_clust
     EVK_TRY(evk_collect_pending(h));
     if (!h->have_voxels) return evk_fail(h, EVK_ERR_STATE, "evk_dbscan_voxels: no voxel shard");
     if (p->D != 2 && p->D != 3) return evk_fail(h, EVK_ERR_INVALID, "dbscan: D must be 2 or 3");
-    if (p->D == 3 && (h->comm || h->reps_valid))
+    if (p->D == 3 && (h->comm || h->reps_valid || h->voxels_foreign))
         return evk_fail(h, EVK_ERR_INVALID, "dbscan: D = 3 needs the shard's own events (not sharded)");
     cudaSetDevice(h->device);
     const size_t n = h->n_unique;

@@ -400,7 +400,7 @@ int evk_ensure_perm(evk_handle* h) {
         EVK_CUDA(h, cudaMalloc(&h->d_sort_a, (m + 64) * sizeof(uint32_t)));
         EVK_CUDA(h, cudaMalloc(&h->d_sort_b, (m + 64) * sizeof(uint32_t)));
     }
-    if (n && !h->reps_valid) {
+    if (n && !h->voxels_foreign) {
         // local voxels: first indices lie in [shard_first, shard_first + max_events)
         const uint32_t base = (uint32_t)h->shard_first;
         const size_t words = (m + 31) / 32 + 1;

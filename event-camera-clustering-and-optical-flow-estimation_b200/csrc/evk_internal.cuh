@@ -137,6 +137,7 @@ struct evk_handle {
     size_t n_unique = 0, n_repeated = 0;
     bool have_voxels = false;
     bool reps_valid = false;
+    bool voxels_foreign = false;  // the shard holds voxels of other ranks' events (hash ownership)
     // canonical order (lazy): d_perm[i] = emission position of the i-th voxel by first index
     uint32_t* d_perm = nullptr;
     bool perm_valid = false;

@@ -77,9 +77,11 @@ def mix64(z):
 
 
 def owner_mix64(keys, world):
-    """EVK_OWNER_MIX64: owner = mix64(key ^ golden) % world (csrc/evk_comm.cu: owner_of)"""
+    """EVK_OWNER_MIX64: the top 32 bits of mix64(key ^ golden), range-reduced to [0, world) by a
+    multiply: (hi32 * world) >> 32 (csrc/evk_comm.cu: owner_of)"""
     k = np.asarray(keys, dtype=np.uint64) ^ np.uint64(0x9E3779B97F4A7C15)
-    return (mix64(k) % np.uint64(world)).astype(np.int64)
+    hi = mix64(k) >> np.uint64(32)
+    return ((hi * np.uint64(world)) >> np.uint64(32)).astype(np.int64)
 
 
 def merge_lowest_index(keys, first):

@@ -113,6 +113,26 @@ def main():
         assert (h.get_labels() == ol1[np.searchsorted(of, first2)]).all()
         if rank == 0:
             print(f"mg ok: {name} fused sharded step world={world} U={ug} (also queued x3)", flush=True)
+        # the hash-owned step (owner = mix64(key) range-reduced to the ranks): local downsample, records
+        # written straight into their owners' shards over peer memory, suspects merged, one k-means
+        # pass -- the union of the shards is the oracle's voxel set, centroids and counts agree
+        for rep in range(2):
+            h.synth(evk.synth_params(seed, n, W, H, rate, blobs, first_index=rank * n))
+            ul, ug, it = h.downsample_kmeans_sharded(ds, km1, True, evk.OWNER_MIX64)
+            assert (ug, it) == (len(ok), 1), (name, rank, ug, len(ok))
+            keys, _, first = h.get_voxels(reps=False)
+            assert len(keys) == ul and (np.diff(first.astype(np.int64)) > 0).all()
+            all_keys = np.concatenate(gather_arrays(keys, rank, world))
+            all_first = np.concatenate(gather_arrays(first, rank, world))
+            order = np.argsort(all_first, kind="stable")
+            assert len(all_keys) == len(ok), "a key is owned by two ranks or lost"
+            assert (all_keys[order] == ok).all() and (all_first[order] == of).all()
+            cent, counts = h.get_centroids(K, 2)
+            assert (counts == ocnt1).all() and np.allclose(cent, oc1, rtol=1e-5, atol=0)
+            lab = h.get_labels()
+            assert (lab == ol1[np.searchsorted(of, first)]).all()
+        if rank == 0:
+            print(f"mg ok: {name} hash-owned fused step world={world} U={ug}", flush=True)
         # unordered stream: the time-range scheme must detect it on every rank and fall back
         rng = np.random.default_rng(5)
         perm = rng.permutation(total)
@@ -135,6 +155,15 @@ def main():
         assert ug == len(ok2) and (all_keys[order] == ok2).all() and (all_first[order] == of2).all()
         pts2 = orc.points(ev_shuf, of2, 2)
         oc2, _, ocnt2, _ = orc.kmeans(pts2, pts2[:K], iters=1, threads=4)
+        cent, counts = h.get_centroids(K, 2)
+        assert (counts == ocnt2).all() and np.allclose(cent, oc2, rtol=1e-5, atol=0)
+        h.load_events(ev_shuf[rank * n:(rank + 1) * n])
+        ul, ug, it = h.downsample_kmeans_sharded(ds, km1, True, evk.OWNER_MIX64)
+        keys, _, first = h.get_voxels(reps=False)
+        all_keys = np.concatenate(gather_arrays(keys, rank, world))
+        all_first = np.concatenate(gather_arrays(first, rank, world))
+        order = np.argsort(all_first, kind="stable")
+        assert ug == len(ok2) and (all_keys[order] == ok2).all() and (all_first[order] == of2).all()
         cent, counts = h.get_centroids(K, 2)
         assert (counts == ocnt2).all() and np.allclose(cent, oc2, rtol=1e-5, atol=0)
         if rank == 0:

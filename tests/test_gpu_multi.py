@@ -27,4 +27,4 @@ def test_sharded_downsample_and_kmeans(world):
     sys.stdout.write(r.stdout[-3000:])
     sys.stderr.write(r.stderr[-3000:])
     assert r.returncode == 0
-    assert r.stdout.count("mg ok") == 8
+    assert r.stdout.count("mg ok") == 10
