@@ -425,7 +425,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
             }
             // a rejected stream is rerun on a general path: publish the violation at once and let
             // every CTA stop at its next tile (uniformly: thread 0 reads, the barrier broadcasts)
-            const bool poll = (tile_seq & 3u) == 0;  // (every fourth tile: ~1 instruction per tile)
+#ifndef EVK_SLAB_POLL_MASK
+#define EVK_SLAB_POLL_MASK 15u
+#endif
+            const bool poll = (tile_seq & EVK_SLAB_POLL_MASK) == 0;  // (every 16th tile: polling every 4th cost 2 %)
             if (poll) {
                 if (viol == 1) {
                     atomicOr(&cnt->slab_violation, 1u);
