@@ -59,6 +59,7 @@ void invalidate_results(evk_handle* h) {
     h->perm_valid = false;
     h->reps_valid = false;
     h->voxels_foreign = false;
+    h->t_range_valid = false;
     h->n_unique = h->n_repeated = 0;
     h->n_labels = 0;
     h->pix_valid = false;
@@ -285,7 +286,7 @@ int evk_destroy(evk_handle* h) {
                     h->d_sort_c, h->d_sk_in,  h->d_sk_out, h->d_si_in,  h->d_si_out, h->d_sv_tmp,
                     h->d_bin_start, h->d_slab_scratch, h->d_cnt, h->d_cent,   h->d_acc,    h->d_counts, h->d_shift,
                     h->d_cand,   h->d_flush, h->d_prune_lists, h->d_label_map, h->d_pixcnt, h->d_quads,
-                    h->d_win_stage, h->d_n_points, h->d_raw, h->d_raw_blk, h->d_sticky, h->d_t0};
+                    h->d_win_stage, h->d_n_points, h->d_raw, h->d_raw_blk, h->d_sticky, h->d_t0, h->d_prune3_lists};
     for (void* p : ptrs)
         if (p) chk(cudaFree(p), "free");
     if (h->h_cnt) chk(cudaFreeHost(h->h_cnt), "free host");
@@ -607,6 +608,13 @@ int evk_downsample_local(evk_handle* h, const evk_ds_params* p) {
     h->n_unique = (size_t)h->h_cnt->n_unique;
     h->n_repeated = p->count_repeated ? (size_t)h->h_cnt->n_repeated : 0;
     h->have_voxels = true;
+    // the slab kernels leave the first time bin and the bin count behind: every representative's
+    // timestamp lies in that range (used by the space-time pruning of the D = 3 / 4 k-means)
+    if ((algo == EVK_ALGO_SLAB || algo == EVK_ALGO_PARTITION) && kp.vt > 0 && h->n_unique) {
+        h->t_range_lo = kp.t0 + (long long)h->h_cnt->scratch[2] * kp.vt;
+        h->t_range_hi = h->t_range_lo + (long long)h->h_cnt->scratch[0] * kp.vt - 1;
+        h->t_range_valid = true;
+    }
     h->times.ds_algo_used = algo;
     h->times.ds_launches = launches;
     if (h->profiling) {
@@ -868,7 +876,21 @@ int evk_kmeans_run(evk_handle* h, const evk_km_params* p, int* iters_done,
                                                 h->d_label_map, xy, n, nullptr, true, h->d_acc,
                                                 h->d_labels, h->sm_count, h->stream);
         } else {
-            if (in_frame)  // voxels are gated to the frame: exact candidate pruning applies
+            if (in_frame && p->D > 2 && h->t_range_valid && !h->voxels_foreign) {
+                // D = 3 / 4: candidate lists per (time slab, pixel tile)
+                if (!h->d_prune3_lists &&
+                    cudaMalloc(&h->d_prune3_lists, (size_t)EVK_PRUNE3_LISTS * 16) != cudaSuccess) {
+                    cudaGetLastError();
+                    h->d_prune3_lists = nullptr;
+                }
+                if (h->d_prune3_lists)
+                    ce = evk_launch_km_assign_pruned3(kl, h->ds.width, h->ds.height,
+                                                      h->d_prune3_lists, h->t_range_lo,
+                                                      h->t_range_hi, xy, ev, h->d_first, n,
+                                                      h->d_cent, h->d_acc, h->d_labels,
+                                                      h->sm_count, h->stream);
+            }
+            if (ce == cudaErrorNotSupported && in_frame)  // D = 2: exact candidate pruning per tile
                 ce = evk_launch_km_assign_pruned(kl, h->ds.width, h->ds.height, h->d_prune_lists,
                                                  xy, n, h->d_cent, h->d_acc, h->d_labels,
                                                  h->sm_count, h->stream);
@@ -1093,6 +1115,11 @@ int evk_downsample_kmeans_wait(evk_handle* h, size_t* n_unique, size_t* n_repeat
             h->n_unique = (size_t)h->h_cnt->n_unique;
             h->n_repeated = ds->count_repeated ? (size_t)h->h_cnt->n_repeated : 0;
             h->have_voxels = true;
+            if (ds->vt_us > 0 && h->n_unique) {
+                h->t_range_lo = ds->t0_us + (long long)h->h_cnt->scratch[2] * ds->vt_us;
+                h->t_range_hi = h->t_range_lo + (long long)h->h_cnt->scratch[0] * ds->vt_us - 1;
+                h->t_range_valid = true;
+            }
             h->K = km->K;
             h->D = km->D;
             h->have_centroids = true;

@@ -174,6 +174,10 @@ struct evk_handle {
     unsigned long long* d_acc = nullptr;     // [EVK_MAX_K * (EVK_MAX_D + 1)]
     unsigned long long* d_counts = nullptr;  // [EVK_MAX_K] counts of the last iteration
     void* d_prune_lists = nullptr;           // [EVK_PRUNE_TILES] uint4 candidate lists
+    void* d_prune3_lists = nullptr;          // [EVK_PRUNE3_LISTS] uint4, lazy (D == 3 / 4)
+    // microsecond range of the current voxel shard's time bins (slab / partition paths)
+    bool t_range_valid = false;
+    long long t_range_lo = 0, t_range_hi = 0;
     // pixel-image k-means (lazy, D == 2): label of every pixel, voxel representatives per pixel
     uint8_t* d_label_map = nullptr;          // [height * width]
     uint32_t* d_pixcnt = nullptr;            // [height * width]
@@ -361,6 +365,13 @@ cudaError_t evk_launch_km_assign_pruned(const KmLaunch& kl, int width, int heigh
                                         const uint32_t* xy, size_t n, const float* cent,
                                         unsigned long long* acc, int32_t* labels, int sm_count,
                                         cudaStream_t s);
+// D == 3 / 4 with pruning in space and time: lists3 = EVK_PRUNE3_LISTS uint4 candidate lists
+#define EVK_PRUNE3_LISTS (64 * EVK_PRUNE_TILES)
+cudaError_t evk_launch_km_assign_pruned3(const KmLaunch& kl, int width, int height, void* lists3,
+                                         long long t_lo, long long t_hi, const uint32_t* xy,
+                                         const evk_event* ev, const uint32_t* first, size_t n,
+                                         const float* cent, unsigned long long* acc,
+                                         int32_t* labels, int sm_count, cudaStream_t s);
 // pixel-image k-means (D == 2, K <= 254; evk_kmeans.cu)
 cudaError_t evk_launch_pix_hist(const uint32_t* xy, size_t n, int width, int height,
                                 uint32_t* pixcnt, int sm_count, cudaStream_t s,

@@ -395,6 +395,272 @@ __global__ void __launch_bounds__(kBlock)
     }
 }
 
+// ---- exact candidate pruning in space AND time (D == 3 / 4, voxels) ---------------------------
+// The per-point scan of K centroids is issue-bound (K x 9 instructions per point).  Voxel
+// representatives lie inside the frame and inside the downsample's time-bin range, so the same
+// exact pruning as above works on boxes [16 x 16 px tile] x [time slab of 2^sh us] (x [0, p_scale]
+// for D == 4): for a box B and centroid k, dmin(k) / dmax(k) are the smallest / largest distance
+// from c_k to any point of B; only centroids with dmin(k) <= min_k dmax(k) (+ slack far above
+// fp32 rounding) can be the nearest of a point of B.  lists[slab][tile] = up to 16 ascending
+// centroid indices (keeps the lowest-k tie rule), 0xFE = scan all K.  A point looks its list up
+// with its tile and the slab of its representative's timestamp, then runs the CONTRACT arithmetic
+// on the listed centroids only: same operands, operations and order, bit-identical labels.
+struct Prune3 {
+    int32_t shift_us;   // slab width = 2^shift_us microseconds
+    int32_t n_slabs;
+    long long t_lo;     // first microsecond of slab 0
+};
+
+template <int D>
+__global__ void __launch_bounds__(128)
+    k_km_candidates3(KmLaunch kl, PruneGrid pg, Prune3 p3, const float* __restrict__ cent,
+                     uint4* lists) {
+    extern __shared__ float s_cc3[];  // [K * D]
+    for (int i = threadIdx.x; i < kl.K * D; i += blockDim.x) s_cc3[i] = cent[i];
+    __syncthreads();
+    const int tiles = pg.tx * pg.ty;
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= tiles * p3.n_slabs) return;
+    const int slab = id / tiles, t = id - slab * tiles;
+    const int ty = t / pg.tx, tx = t - ty * pg.tx;
+    float lo[4], hi[4];
+    lo[0] = (float)(tx << pg.shift);
+    lo[1] = (float)(ty << pg.shift);
+    hi[0] = (float)min(pg.width - 1, ((tx + 1) << pg.shift) - 1);
+    hi[1] = (float)min(pg.height - 1, ((ty + 1) << pg.shift) - 1);
+    // the point coordinate is fmul_rn((float)(t - t0), t_scale): monotone in t
+    const long long ta = p3.t_lo + ((long long)slab << p3.shift_us);
+    const long long tb = ta + (1ll << p3.shift_us) - 1;
+    lo[2] = __fmul_rn((float)(ta - kl.t0), kl.t_scale);
+    hi[2] = __fmul_rn((float)(tb - kl.t0), kl.t_scale);
+    if (lo[2] > hi[2]) {  // (negative t_scale)
+        const float sw = lo[2];
+        lo[2] = hi[2];
+        hi[2] = sw;
+    }
+    lo[3] = fminf(0.f, kl.p_scale);
+    hi[3] = fmaxf(0.f, kl.p_scale);
+    // Reference centroid r = the one with the smallest worst-case distance at the slab's mid time.
+    // Centroid k can be dropped when it is farther than r from EVERY point of the box:
+    //   d_k - d_r = [s_k - s_r] + g(t),  s = squared distance in the spatial (+ polarity) dimensions,
+    //   g(t) = (ct_k - t)^2 - (ct_r - t)^2 is LINEAR in t, so its minimum over the slab is at an end.
+    // (A box bound that takes the worst t for k and for r independently loses 2 |dt| x slab width,
+    // which is more than the spatial separation of the centroids once |dt| is a few hundred.)
+    const float tm = 0.5f * (lo[2] + hi[2]);
+    float ub = INFINITY;
+    int kr = 0;
+    for (int k = 0; k < kl.K; k++) {
+        float m = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            if (d == 2) continue;
+            const float c = s_cc3[k * D + d];
+            const float a = fmaxf(fabsf(c - lo[d]), fabsf(c - hi[d]));
+            m += a * a;
+        }
+        const float dt = s_cc3[k * D + 2] - tm;
+        m += dt * dt;
+        if (m < ub) {
+            ub = m;
+            kr = k;
+        }
+    }
+    float smax_r = 0.f;  // largest spatial (+ polarity) squared distance from r to the box
+#pragma unroll
+    for (int d = 0; d < D; d++) {
+        if (d == 2) continue;
+        const float c = s_cc3[kr * D + d];
+        const float a = fmaxf(fabsf(c - lo[d]), fabsf(c - hi[d]));
+        smax_r += a * a;
+    }
+    const float ctr = s_cc3[kr * D + 2];
+    const float dra = ctr - lo[2], drb = ctr - hi[2];
+    // slack: far above the rounding of this test and of the fp32 contract arithmetic it guards
+    const float scale = smax_r + fmaxf(dra * dra, drb * drb);
+    const float tol = scale * 1.0e-4f + 0.5f;
+    unsigned char out[kListLen];
+#pragma unroll
+    for (int i = 0; i < kListLen; i++) out[i] = 0xFF;
+    int cnt = 0;
+    for (int k = 0; k < kl.K; k++) {
+        float smin = 0.f;
+#pragma unroll
+        for (int d = 0; d < D; d++) {
+            if (d == 2) continue;
+            const float c = s_cc3[k * D + d];
+            const float a = fmaxf(0.f, fmaxf(lo[d] - c, c - hi[d]));
+            smin += a * a;
+        }
+        const float ctk = s_cc3[k * D + 2];
+        const float ka = ctk - lo[2], kb = ctk - hi[2];
+        const float g = fminf(ka * ka - dra * dra, kb * kb - drb * drb);
+        const float ktol = tol + (smin + fmaxf(ka * ka, kb * kb)) * 1.0e-4f;
+        if (smin - smax_r + g <= ktol) {
+#pragma unroll
+            for (int i = 0; i < kListLen; i++)
+                if (i == cnt) out[i] = (unsigned char)k;
+            cnt++;
+        }
+    }
+    if (cnt > kListLen || !(ub < INFINITY)) out[0] = 0xFE;  // too many candidates: full scan
+    uint4 w;
+    w.x = out[0] | (out[1] << 8) | (out[2] << 16) | ((uint32_t)out[3] << 24);
+    w.y = out[4] | (out[5] << 8) | (out[6] << 16) | ((uint32_t)out[7] << 24);
+    w.z = out[8] | (out[9] << 8) | (out[10] << 16) | ((uint32_t)out[11] << 24);
+    w.w = out[12] | (out[13] << 8) | (out[14] << 16) | ((uint32_t)out[15] << 24);
+    lists[id] = w;
+}
+
+template <int D>
+__device__ __forceinline__ float km_d2(const float* c, float px, float py, float pt, float pp) {
+    const float dx = __fsub_rn(c[0], px), dy = __fsub_rn(c[1], py);
+    float d2 = __fmaf_rn(dy, dy, __fmul_rn(dx, dx));
+    const float dt = __fsub_rn(c[2], pt);
+    d2 = __fmaf_rn(dt, dt, d2);
+    if (D > 3) {
+        const float dp = __fsub_rn(c[3], pp);
+        d2 = __fmaf_rn(dp, dp, d2);
+    }
+    return d2;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kBlock)
+    k_km_assign_pruned3(KmLaunch kl, PruneGrid pg, Prune3 p3, const uint4* __restrict__ lists,
+                        const uint32_t* __restrict__ xy, const evk_event* __restrict__ ev,
+                        const uint32_t* __restrict__ first, size_t n,
+                        const float* __restrict__ cent, unsigned long long* __restrict__ acc,
+                        int32_t* __restrict__ labels, int n_rep) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = kl.K;
+    float* s_c = reinterpret_cast<float*>(smem_raw);                                   // [K * D]
+    // sum of (t - t0): 16-bit limbs in u32 accumulators (a 64-bit shared atomicAdd is a CAS spin
+    // loop); bits 32 and up, zero for streams shorter than 71 minutes, keep the 64-bit path
+    unsigned long long* s_t = reinterpret_cast<unsigned long long*>(s_c + ((K * D + 3) & ~3));  // [n_rep][K]
+    uint32_t* s_acc = reinterpret_cast<uint32_t*>(s_t + n_rep * K);                    // [n_rep][6][K]
+    for (int i = threadIdx.x; i < K * D; i += kBlock) s_c[i] = cent[i];
+    for (int i = threadIdx.x; i < n_rep * K; i += kBlock) s_t[i] = 0;
+    for (int i = threadIdx.x; i < n_rep * 6 * K; i += kBlock) s_acc[i] = 0;
+    __syncthreads();
+    uint32_t* my_acc = s_acc + (threadIdx.x & (n_rep - 1)) * 6 * K;
+    unsigned long long* my_t = s_t + (threadIdx.x & (n_rep - 1)) * K;
+    const int tiles = pg.tx * pg.ty;
+
+    const size_t n_chunks = (n + kChunk - 1) / kChunk;
+    for (size_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+        const size_t cbase = c * (size_t)kChunk;
+        for (int r = 0; r < kChunk / (kBlock * kPPT); r++) {
+            const size_t base = cbase + (size_t)r * (kBlock * kPPT);
+            if (base >= n) break;
+            uint32_t w[kPPT], ip[kPPT];
+            long long it[kPPT];
+            uint4 lst[kPPT];
+#pragma unroll
+            for (int q = 0; q < kPPT; q++) {  // all gathers of the pass in flight together
+                const size_t i = base + (size_t)q * kBlock + threadIdx.x;
+                w[q] = 0;
+                it[q] = 0;
+                ip[q] = 0;
+                if (i < n) {
+                    w[q] = xy[i];
+                    const evk_event* src = ev + first[i];
+                    if (D > 3) {
+                        const uint4 e = ld_event(src);
+                        ip[q] = ev_pbit(e);
+                        it[q] = ev_t(e);
+                    } else {
+                        it[q] = __ldg(reinterpret_cast<const long long*>(
+                            reinterpret_cast<const char*>(src) + 8));
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < kPPT; q++) {
+                const uint32_t t = ((w[q] >> 16) >> pg.shift) * pg.tx + ((w[q] & 0xFFFFu) >> pg.shift);
+                long long sl = (it[q] - p3.t_lo) >> p3.shift_us;
+                // (a representative outside the announced time range: scan everything)
+                const bool in = sl >= 0 && sl < p3.n_slabs;
+                lst[q] = in ? __ldg(lists + (size_t)sl * tiles + t) : make_uint4(0xFEu, 0, 0, 0);
+                it[q] -= kl.t0;
+            }
+#pragma unroll
+            for (int q = 0; q < kPPT; q++) {
+                const size_t i = base + (size_t)q * kBlock + threadIdx.x;
+                const bool ok = i < n;
+                const uint32_t ix = w[q] & 0xFFFFu, iy = w[q] >> 16;
+                const float px = (float)ix, py = (float)iy;
+                const float pt = __fmul_rn((float)it[q], kl.t_scale);
+                const float pp = D > 3 ? __fmul_rn(ip[q] ? 1.0f : 0.0f, kl.p_scale) : 0.f;
+                float best = kl.best2;
+                int lab = -1;
+                const bool full = (lst[q].x & 0xFFu) == 0xFEu;
+                if (__any_sync(0xffffffffu, full)) {
+                    if (full) {
+                        for (int k = 0; k < K; k++) {
+                            const float d2 = km_d2<D>(s_c + k * D, px, py, pt, pp);
+                            if (d2 < best) {
+                                best = d2;
+                                lab = k;
+                            }
+                        }
+                    }
+                }
+                if (!full) {
+                    const uint32_t lw[4] = {lst[q].x, lst[q].y, lst[q].z, lst[q].w};
+#pragma unroll
+                    for (int s = 0; s < kListLen; s++) {
+                        const uint32_t k = (lw[s >> 2] >> (8 * (s & 3))) & 0xFFu;
+                        if (k == 0xFFu) break;
+                        const float d2 = km_d2<D>(s_c + k * D, px, py, pt, pp);
+                        if (d2 < best) {
+                            best = d2;
+                            lab = (int)k;
+                        }
+                    }
+                }
+                if (ok) {
+                    if (kl.write_labels) labels[i] = lab;
+                    if (lab >= 0) {
+                        atomicAdd(&my_acc[lab], 1u);
+                        atomicAdd(&my_acc[K + lab], ix);
+                        atomicAdd(&my_acc[2 * K + lab], iy);
+                        const unsigned long long ut = (unsigned long long)it[q];
+                        atomicAdd(&my_acc[4 * K + lab], (uint32_t)(ut & 0xFFFFu));
+                        atomicAdd(&my_acc[5 * K + lab], (uint32_t)((ut >> 16) & 0xFFFFu));
+                        if (ut >> 32) atomicAdd(&my_t[lab], ut >> 32);
+                        if (D > 3) atomicAdd(&my_acc[3 * K + lab], ip[q]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += kBlock) {
+            unsigned long long sc = 0, sx = 0, sy = 0, st = 0, sp = 0;
+#pragma unroll
+            for (int rr = 0; rr < n_rep; rr++) {
+                uint32_t* a = s_acc + rr * 6 * K;
+                sc += a[k];
+                sx += a[K + k];
+                sy += a[2 * K + k];
+                sp += a[3 * K + k];
+                st += (unsigned long long)a[4 * K + k] + ((unsigned long long)a[5 * K + k] << 16) +
+                      (s_t[rr * K + k] << 32);
+#pragma unroll
+                for (int f = 0; f < 6; f++) a[f * K + k] = 0;
+                s_t[rr * K + k] = 0;
+            }
+            if (sc) {
+                atomicAdd(&acc[k * ACC_STRIDE + ACC_CNT], sc);
+                atomicAdd(&acc[k * ACC_STRIDE + ACC_X], sx);
+                atomicAdd(&acc[k * ACC_STRIDE + ACC_Y], sy);
+                atomicAdd(&acc[k * ACC_STRIDE + ACC_T], st);
+                if (D > 3) atomicAdd(&acc[k * ACC_STRIDE + ACC_P], sp);
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---- pixel-image k-means (D == 2, voxels, K <= 254) -------------------------------------------
 // Voxel representatives have integer pixel coordinates, so with D == 2 everything an iteration
 // needs from the voxel list is the histogram pixcnt[y][x] = number of representatives at that pixel
@@ -750,6 +1016,53 @@ cudaError_t evk_launch_km_assign_pruned(const KmLaunch& kl, int width, int heigh
     size_t smem = (size_t)kl.K * sizeof(float2) + (size_t)kRep * 3 * kl.K * sizeof(uint32_t);
     k_km_assign_pruned<<<grid, kBlock, smem, s>>>(kl, pg, reinterpret_cast<const uint4*>(lists),
                                                   xy, n, cent, acc, labels);
+    return cudaGetLastError();
+}
+
+// D == 3 / 4 on voxels whose representatives' timestamps lie in [t_lo, t_hi] (the downsample's
+// time-bin range): lists3 holds n_slabs x tiles candidate lists (EVK_PRUNE3_LISTS at most)
+cudaError_t evk_launch_km_assign_pruned3(const KmLaunch& kl, int width, int height, void* lists3,
+                                         long long t_lo, long long t_hi, const uint32_t* xy,
+                                         const evk_event* ev, const uint32_t* first, size_t n,
+                                         const float* cent, unsigned long long* acc,
+                                         int32_t* labels, int sm_count, cudaStream_t s) {
+    if ((kl.D != 3 && kl.D != 4) || kl.K <= 8 || kl.K > 254 || t_hi < t_lo)
+        return cudaErrorNotSupported;
+    if (n == 0) return cudaSuccess;
+    const PruneGrid pg = evk_make_prune_grid(width, height);
+    const int tiles = pg.tx * pg.ty;
+    Prune3 p3;
+    const int want = EVK_PRUNE3_LISTS / tiles < 64 ? EVK_PRUNE3_LISTS / tiles : 64;
+    if (want < 1) return cudaErrorNotSupported;
+    p3.t_lo = t_lo;
+    p3.shift_us = 0;
+    const unsigned long long span = (unsigned long long)(t_hi - t_lo) + 1;
+    while (((span + (1ull << p3.shift_us) - 1) >> p3.shift_us) > (unsigned long long)want) p3.shift_us++;
+    p3.n_slabs = (int)((span + (1ull << p3.shift_us) - 1) >> p3.shift_us);
+    const int n_lists = tiles * p3.n_slabs;
+    const size_t csmem = (size_t)kl.K * kl.D * sizeof(float);
+    if (kl.D == 3)
+        k_km_candidates3<3><<<(n_lists + 127) / 128, 128, csmem, s>>>(
+            kl, pg, p3, cent, reinterpret_cast<uint4*>(lists3));
+    else
+        k_km_candidates3<4><<<(n_lists + 127) / 128, 128, csmem, s>>>(
+            kl, pg, p3, cent, reinterpret_cast<uint4*>(lists3));
+    size_t chunks = (n + kChunk - 1) / kChunk;
+    size_t cap = (size_t)sm_count * 8;
+    int grid = (int)(chunks < cap ? chunks : cap);
+    const int n_rep = kl.K > 128 ? 4 : 8;  // accumulator copies (fewer same-address atomics)
+    const size_t smem = (size_t)((kl.K * kl.D + 3) & ~3) * sizeof(float) +
+                        (size_t)n_rep * kl.K * sizeof(unsigned long long) +
+                        (size_t)n_rep * 6 * kl.K * sizeof(uint32_t);
+    if (smem > 48 * 1024) return cudaErrorNotSupported;
+    if (kl.D == 3)
+        k_km_assign_pruned3<3><<<grid, kBlock, smem, s>>>(
+            kl, pg, p3, reinterpret_cast<const uint4*>(lists3), xy, ev, first, n, cent, acc, labels,
+            n_rep);
+    else
+        k_km_assign_pruned3<4><<<grid, kBlock, smem, s>>>(
+            kl, pg, p3, reinterpret_cast<const uint4*>(lists3), xy, ev, first, n, cent, acc, labels,
+            n_rep);
     return cudaGetLastError();
 }
 

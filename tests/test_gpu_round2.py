@@ -232,3 +232,38 @@ def test_queued_steps_report_a_rejected_slice(evk, orc):
             h.downsample_kmeans_submit(ds, km, True)
         ok, of, orr = orc.downsample(ev, orc.ds_params(W, H, 2, 2, 500, 0, 1))
         assert h.downsample_kmeans_wait()[:2] == (len(ok), orr)
+
+
+# ------------------------------------------------- D = 3 / 4 k-means with space-time pruning --
+@pytest.mark.parametrize("D,K,md", [(3, 32, 0.0), (4, 64, 0.0), (3, 64, 90.0), (4, 12, 0.0)])
+def test_kmeans_d3_d4_pruned_vs_oracle(evk, orc, D, K, md):
+    """D = 3 / 4 on voxels takes the candidate lists per (time slab, pixel tile) when K > 8: labels,
+    counts and centroids must equal the oracle's full scan (ties within 1e-6 aside)"""
+    n, W, H = 1_200_000, 640, 480
+    ts, ps = 2e-3, 40.0
+    ev = orc.synth(orc.synth_params(0xE7CA0007, n, W, H, 20_000_000, 24))
+    ok, of, _ = orc.downsample(ev, orc.ds_params(W, H, 2, 2, 500, 0, 1))
+    pts = orc.points(ev, of, D, 0, ts, ps)
+    iters = 3
+    oc_prev, _, _, _ = orc.kmeans(pts, pts[:K], md, iters=iters - 1, threads=orc.max_threads())
+    oc, ol, ocnt, _ = orc.kmeans(pts, pts[:K], md, iters=iters, threads=orc.max_threads())
+    with evk.Evk(n) as h:
+        h.load_events(ev)
+        for algo in (evk.ALGO_SLAB, evk.ALGO_PARTITION):
+            h.downsample(evk.ds_params(W, H, 2, 2, 500, 0, 1, algo=algo))
+            assert h.stage_times().ds_algo_used == algo
+            km = evk.km_params(K, D, max_dist=md, iters=iters, t_scale=ts, p_scale=ps)
+            h.init_centroids_first_k(km)
+            assert h.kmeans(km) == iters
+            lab = h.get_labels()
+            cent, counts = h.get_centroids(K, D)
+            bad = np.nonzero(lab != ol)[0]
+            for i in bad:
+                assert lab[i] >= 0 and ol[i] >= 0
+                dg = ((oc_prev[lab[i]].astype(np.float64) - pts[i]) ** 2).sum()
+                dw = ((oc_prev[ol[i]].astype(np.float64) - pts[i]) ** 2).sum()
+                assert abs(dg - dw) <= 1e-6 * max(dg, dw)
+            if md > 0:
+                assert (lab < 0).any()
+            assert (counts == ocnt).all()
+            np.testing.assert_allclose(cent, oc, rtol=CENT_RTOL, atol=1e-6)
