@@ -65,6 +65,7 @@ class AecParams(C.Structure):
     ]
 
 
+CORNER_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("label", "<i4")])
 AEC_CLUSTER_DTYPE = np.dtype([("id", "<i4"), ("n", "<i4"), ("mu", "<f8", (2,)),
                               ("centroid", "<f8", (2,))], align=True)
 AEC_FLOW_DTYPE = np.dtype([("id", "<i4"), ("n", "<i4"), ("centroid", "<f8", (2,)),
@@ -103,6 +104,8 @@ SYMBOLS = [
     "evk_aec_get_clusters", "evk_aec_get_points", "evk_aec_report",
     "evk_dbscan_points", "evk_dbscan_voxels", "evk_dbscan_get", "evk_dbscan_destroy",
     "evk_ts_create", "evk_ts_destroy", "evk_ts_corners", "evk_ts_get_corners", "evk_ts_get_surface",
+    "evk_ts_filter_corners", "evk_filter_corners", "evk_get_filtered_corners",
+    "evk_filter_corners_destroy",
 ]
 
 _lib = None
@@ -163,6 +166,10 @@ def lib():
         "evk_ts_corners": [vp, i32, psz],
         "evk_ts_get_corners": [vp, vp, sz],
         "evk_ts_get_surface": [vp, vp, sz],
+        "evk_ts_filter_corners": [vp, i32, psz],
+        "evk_filter_corners": [vp, vp, sz, i32, i32, i32, psz],
+        "evk_get_filtered_corners": [vp, vp, sz],
+        "evk_filter_corners_destroy": [vp],
         "evk_get_centroids": [vp, vp, vp],
         "evk_window_config": [vp, C.POINTER(DsParams), C.POINTER(KmParams), C.c_int64],
         "evk_window_config_events": [vp, C.POINTER(DsParams), C.POINTER(KmParams), sz],
@@ -489,6 +496,26 @@ class Evk:
         if n.value:
             self._ck(self._L.evk_ts_get_corners(self._h, _p(idx), len(idx)))
         return idx
+
+    def _filtered(self, n):
+        out = np.zeros(n, CORNER_DTYPE)
+        if n:
+            self._ck(self._L.evk_get_filtered_corners(self._h, _p(out), n))
+        return out
+
+    def ts_filter_corners(self, box_size=15):
+        """box non-maximum suppression of the last ts_corners list -> records (x, y, label)"""
+        n = C.c_size_t(0)
+        self._ck(self._L.evk_ts_filter_corners(self._h, box_size, C.byref(n)))
+        return self._filtered(n.value)
+
+    def filter_corners(self, xy, width, height, box_size=15):
+        """the same on a host list of (x, y) pairs"""
+        xy = np.ascontiguousarray(xy, dtype=np.int32).reshape(-1, 2)
+        n = C.c_size_t(0)
+        self._ck(self._L.evk_filter_corners(self._h, _p(xy), len(xy), width, height, box_size,
+                                            C.byref(n)))
+        return self._filtered(n.value)
 
     def ts_surface(self):
         out = np.zeros(self._ts_shape, np.int64)

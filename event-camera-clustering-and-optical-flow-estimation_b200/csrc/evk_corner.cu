@@ -331,3 +331,248 @@ int evk_ts_get_surface(evk_handle* h, int64_t* out, size_t cap_pixels) {
 }
 
 }  // extern "C"
+
+// ---- corner post-processing: box non-maximum suppression -----------------------------------------
+// CornerFilter::filterCorners of the reference's corner tracker (FCT:81-151, call site FCT:832 with
+// box size 15): corners in input order; a corner is kept when its box [x - h, x + h] x [y - h, y + h]
+// (h = box / 2, clipped to the image) touches no box of a corner kept before it; kept corners are
+// labelled 0, 1, 2, ... in order.  The reference walks the list with a mask image.  Here the same
+// greedy rule runs on the pairwise relation "boxes intersect":
+//   k_nms_boxes   the clipped box of every corner
+//   k_nms_mask    upper triangle of the n x n conflict matrix as 64-bit words (one thread per word)
+//   k_nms_scan    one CTA walks the corners 64 at a time: the 64 x 64 diagonal block is resolved
+//                 sequentially from shared memory by one thread (the only serial part), then every
+//                 thread ORs the rows of the corners just kept into its word of the "suppressed" set
+// Exact for any order and density; n <= 32768 corners per call (the matrix is n^2 / 8 bytes).
+namespace {
+
+constexpr int kNmsMaxWords = 512;  // 64-bit words of the suppressed set = threads of the scan CTA
+
+__global__ void __launch_bounds__(256)
+    k_nms_xy_from_events(const evk_event* __restrict__ ev, const uint32_t* __restrict__ idx,
+                         uint32_t n, int32_t* xy) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(ev + idx[i]);
+    xy[2 * i] = (int32_t)(w & 0xFFFFu);
+    xy[2 * i + 1] = (int32_t)(w >> 16);
+}
+
+__global__ void __launch_bounds__(256)
+    k_nms_boxes(const int32_t* __restrict__ xy, uint32_t n, int W, int H, int half, int4* box) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int x = xy[2 * i], y = xy[2 * i + 1];
+    // (64-bit: coordinates come from the caller)
+    const long long sx = max(0ll, (long long)x - half), ex = min((long long)W - 1, (long long)x + half);
+    const long long sy = max(0ll, (long long)y - half), ey = min((long long)H - 1, (long long)y + half);
+    const bool empty = sx > ex || sy > ey;  // centre outside the image: touches and marks nothing
+    box[i] = empty ? make_int4(1, 0, 1, 0) : make_int4((int)sx, (int)ex, (int)sy, (int)ey);
+}
+
+// mask[i][w] bit b: corner j = 64 w + b comes after corner i and their boxes intersect
+__global__ void __launch_bounds__(256)
+    k_nms_mask(const int4* __restrict__ box, uint32_t n, uint32_t n_w, unsigned long long* mask) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t i = blockIdx.y;
+    if (w >= n_w || w < (i >> 6)) return;
+    const int4 a = box[i];
+    unsigned long long bits = 0;
+    const uint32_t j0 = w << 6;
+#pragma unroll 4
+    for (uint32_t b = 0; b < 64; b++) {
+        const uint32_t j = j0 + b;
+        if (j <= i || j >= n) continue;
+        const int4 c = box[j];
+        const bool hit = max(a.x, c.x) <= min(a.y, c.y) && max(a.z, c.z) <= min(a.w, c.w);
+        bits |= (unsigned long long)hit << b;
+    }
+    mask[(size_t)i * n_w + w] = bits;
+}
+
+__global__ void __launch_bounds__(kNmsMaxWords)
+    k_nms_scan(const unsigned long long* __restrict__ mask, uint32_t n, uint32_t n_w,
+               uint32_t* kept, unsigned long long* n_kept) {
+    __shared__ unsigned long long s_diag[64];
+    __shared__ unsigned long long s_rem, s_keep;
+    __shared__ uint32_t s_count;
+    const uint32_t t = threadIdx.x;
+    unsigned long long rem = 0;  // suppressed corners of word t
+    if (t == 0) s_count = 0;
+    for (uint32_t W0 = 0; W0 < n_w; W0++) {
+        const uint32_t base = W0 << 6;
+        if (t == W0) s_rem = rem;
+        if (t < 64) s_diag[t] = base + t < n ? mask[(size_t)(base + t) * n_w + W0] : 0ull;
+        __syncthreads();
+        if (t == 0) {  // the 64 corners of this word, in order
+            unsigned long long r = s_rem, keep = 0;
+            uint32_t c = s_count;
+            const uint32_t m = n - base < 64 ? n - base : 64;
+            for (uint32_t b = 0; b < m; b++) {
+                if (!((r >> b) & 1ull)) {
+                    keep |= 1ull << b;
+                    r |= s_diag[b];
+                    kept[c++] = base + b;
+                }
+            }
+            s_keep = keep;
+            s_count = c;
+        }
+        __syncthreads();
+        if (t > W0 && t < n_w) {  // the kept corners suppress later ones
+            unsigned long long k = s_keep;
+            while (k) {
+                const int b = __ffsll((long long)k) - 1;
+                k &= k - 1;
+                rem |= mask[(size_t)(base + b) * n_w + t];
+            }
+        }
+        __syncthreads();
+    }
+    if (t == 0) *n_kept = s_count;
+}
+
+__global__ void __launch_bounds__(256)
+    k_nms_emit(const int32_t* __restrict__ xy, const uint32_t* __restrict__ kept, uint32_t m,
+               evk_corner* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    evk_corner c;
+    c.x = xy[2 * kept[i]];
+    c.y = xy[2 * kept[i] + 1];
+    c.label = (int32_t)i;
+    out[i] = c;
+}
+
+}  // namespace
+
+struct NmsHost {
+    size_t cap = 0;  // corners
+    int32_t* d_xy = nullptr;
+    int4* d_box = nullptr;
+    unsigned long long* d_mask = nullptr;
+    size_t mask_words = 0;
+    uint32_t* d_kept = nullptr;
+    evk_corner* d_out = nullptr;
+    unsigned long long* d_n = nullptr;
+    size_t n_kept = 0;
+    bool have = false;
+};
+
+static int nms_reserve(evk_handle* h, size_t n) {
+    if (!h->nms) h->nms = new NmsHost;
+    NmsHost* s = h->nms;
+    const size_t n_w = (n + 63) / 64;
+    if (s->cap < n) {
+        void* ptrs[] = {s->d_xy, s->d_box, s->d_kept, s->d_out};
+        for (void* p : ptrs)
+            if (p) cudaFree(p);
+        s->cap = 0;
+        const size_t c = n < 1024 ? 1024 : n;
+        EVK_CUDA(h, cudaMalloc((void**)&s->d_xy, c * 2 * sizeof(int32_t)));
+        EVK_CUDA(h, cudaMalloc((void**)&s->d_box, c * sizeof(int4)));
+        EVK_CUDA(h, cudaMalloc((void**)&s->d_kept, c * sizeof(uint32_t)));
+        EVK_CUDA(h, cudaMalloc((void**)&s->d_out, c * sizeof(evk_corner)));
+        s->cap = c;
+    }
+    if (s->mask_words < n * n_w) {
+        if (s->d_mask) cudaFree(s->d_mask);
+        s->d_mask = nullptr;
+        s->mask_words = 0;
+        EVK_CUDA(h, cudaMalloc((void**)&s->d_mask, n * n_w * sizeof(unsigned long long)));
+        s->mask_words = n * n_w;
+    }
+    if (!s->d_n) EVK_CUDA(h, cudaMalloc((void**)&s->d_n, sizeof(unsigned long long)));
+    return EVK_OK;
+}
+
+// the corners are in s->d_xy[0 .. n)
+static int nms_run(evk_handle* h, size_t n, int width, int height, int box_size, size_t* n_kept) {
+    NmsHost* s = h->nms;
+    s->n_kept = 0;
+    s->have = true;
+    if (n_kept) *n_kept = 0;
+    if (n == 0) return EVK_OK;
+    const uint32_t n32 = (uint32_t)n, n_w = (uint32_t)((n + 63) / 64);
+    k_nms_boxes<<<(n32 + 255) / 256, 256, 0, h->stream>>>(s->d_xy, n32, width, height, box_size / 2,
+                                                         s->d_box);
+    k_nms_mask<<<dim3((n_w + 255) / 256, n32), 256, 0, h->stream>>>(s->d_box, n32, n_w, s->d_mask);
+    k_nms_scan<<<1, kNmsMaxWords, 0, h->stream>>>(s->d_mask, n32, n_w, s->d_kept, s->d_n);
+    EVK_CUDA(h, cudaGetLastError());
+    unsigned long long m = 0;
+    EVK_CUDA(h, cudaMemcpyAsync(&m, s->d_n, sizeof m, cudaMemcpyDeviceToHost, h->stream));
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (m) {
+        k_nms_emit<<<((uint32_t)m + 255) / 256, 256, 0, h->stream>>>(s->d_xy, s->d_kept, (uint32_t)m,
+                                                                    s->d_out);
+        EVK_CUDA(h, cudaGetLastError());
+    }
+    s->n_kept = (size_t)m;
+    if (n_kept) *n_kept = s->n_kept;
+    return EVK_OK;
+}
+
+extern "C" {
+
+int evk_filter_corners_destroy(evk_handle* h) {
+    if (!h || !h->nms) return EVK_OK;
+    NmsHost* s = h->nms;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    void* ptrs[] = {s->d_xy, s->d_box, s->d_mask, s->d_kept, s->d_out, s->d_n};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete s;
+    h->nms = nullptr;
+    return EVK_OK;
+}
+
+int evk_filter_corners(evk_handle* h, const int32_t* xy, size_t n, int width, int height,
+                       int box_size, size_t* n_kept) {
+    if (!h) return EVK_ERR_INVALID;
+    if (n && !xy) return evk_fail(h, EVK_ERR_INVALID, "xy is NULL");
+    if (width < 1 || height < 1 || box_size < 0)
+        return evk_fail(h, EVK_ERR_INVALID, "evk_filter_corners: %d x %d, box %d", width, height, box_size);
+    if (n > (size_t)kNmsMaxWords * 64)
+        return evk_fail(h, EVK_ERR_CAPACITY, "at most %d corners per call", kNmsMaxWords * 64);
+    DeviceGuard g(h->device);
+    EVK_TRY(nms_reserve(h, n ? n : 1));
+    if (n)
+        EVK_CUDA(h, cudaMemcpyAsync(h->nms->d_xy, xy, n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice,
+                                    h->stream));
+    return nms_run(h, n, width, height, box_size, n_kept);
+}
+
+int evk_ts_filter_corners(evk_handle* h, int box_size, size_t* n_kept) {
+    if (!h) return EVK_ERR_INVALID;
+    if (!h->ts || !h->ts->have) return evk_fail(h, EVK_ERR_STATE, "evk_ts_corners has not run");
+    if (box_size < 0) return evk_fail(h, EVK_ERR_INVALID, "box size %d", box_size);
+    TsHost* t = h->ts;
+    const size_t n = t->n_corners;
+    if (n > (size_t)kNmsMaxWords * 64)
+        return evk_fail(h, EVK_ERR_CAPACITY, "%zu corners: at most %d per call", n, kNmsMaxWords * 64);
+    DeviceGuard g(h->device);
+    EVK_TRY(nms_reserve(h, n ? n : 1));
+    if (n) {
+        k_nms_xy_from_events<<<((uint32_t)n + 255) / 256, 256, 0, h->stream>>>(
+            h->d_events, t->d_corners, (uint32_t)n, h->nms->d_xy);
+        EVK_CUDA(h, cudaGetLastError());
+    }
+    return nms_run(h, n, t->W, t->H, box_size, n_kept);
+}
+
+int evk_get_filtered_corners(evk_handle* h, evk_corner* out, size_t cap) {
+    if (!h) return EVK_ERR_INVALID;
+    if (!h->nms || !h->nms->have) return evk_fail(h, EVK_ERR_STATE, "no corner list has been filtered");
+    NmsHost* s = h->nms;
+    if (s->n_kept == 0) return EVK_OK;
+    if (!out || cap < s->n_kept)
+        return evk_fail(h, EVK_ERR_CAPACITY, "%zu corners, room for %zu", s->n_kept, cap);
+    DeviceGuard g(h->device);
+    EVK_CUDA(h, cudaMemcpyAsync(out, s->d_out, s->n_kept * sizeof(evk_corner), cudaMemcpyDeviceToHost,
+                                h->stream));
+    EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+    return EVK_OK;
+}
+
+}  // extern "C"
+

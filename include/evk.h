@@ -337,6 +337,21 @@ EVK_API int evk_ts_corners(evk_handle* h, int literal_break, size_t* n_corners);
 /* stream indices (ascending) of the corner events of the last evk_ts_corners = the events pushed to
  * `corners` at FCT:1050 */
 EVK_API int evk_ts_get_corners(evk_handle* h, uint32_t* event_index, size_t cap);
+/* Corner post-processing: CornerFilter::filterCorners of the same file (FCT:81-151; call site
+ * FCT:832 with box_size 15 -- its `threshold` argument and response sort are commented out there).
+ * Corners in list order; a corner is kept when its box [x - box_size / 2, x + box_size / 2]^2, clipped
+ * to the image, touches no box of a corner kept before it; kept corners are labelled 0, 1, 2, ...
+ * At most 32768 corners per call. */
+typedef struct evk_corner {
+    int32_t x, y, label;
+} evk_corner;
+/* on the corner list of the last evk_ts_corners (device-resident) */
+EVK_API int evk_ts_filter_corners(evk_handle* h, int box_size, size_t* n_kept);
+/* on a host list of n (x, y) pairs, as the reference's std::vector<Corner> */
+EVK_API int evk_filter_corners(evk_handle* h, const int32_t* xy, size_t n, int width, int height,
+                               int box_size, size_t* n_kept);
+EVK_API int evk_get_filtered_corners(evk_handle* h, evk_corner* out, size_t cap);
+EVK_API int evk_filter_corners_destroy(evk_handle* h);
 /* the surface, row-major [height][width] */
 EVK_API int evk_ts_get_surface(evk_handle* h, int64_t* out, size_t cap_pixels);
 

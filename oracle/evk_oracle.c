@@ -764,3 +764,41 @@ size_t orc_ts_corners(const evk_event* ev, size_t n, int W, int H, int64_t* surf
     }
     return nc;
 }
+
+/* ---- corner post-processing: box non-maximum suppression ---------------------
+ * Restates CornerFilter::filterCorners, event-cam-tracking/event-cam-fast-corner-tracker/
+ * metavision_time_surface_periodic_group_track.cpp:81-151 (call site :832, box size 15; the
+ * `threshold` argument and the response sort are commented out there, :93-98,112).  Corners are
+ * taken in input order; a corner is kept when no pixel of its box [x - h, x + h] x [y - h, y + h]
+ * (h = box_size / 2, clipped to the image, :118-121) has been marked by a corner kept before it
+ * (:124-136); a kept corner gets label = its rank among the kept ones (:144) and marks its box
+ * (:148-151).  Unlike the reference, a corner whose clipped box is empty (centre outside the image)
+ * reads nothing here -- the reference would read outside its mask.  Pinned against the reference's
+ * own class compiled where it lies (oracle/_ref/libref_fct.so, tests/test_corner_filter.py).
+ * kept[i] = index of the i-th kept corner.  Returns the number kept. */
+size_t orc_filter_corners(const int32_t* xy, size_t n, int width, int height, int box_size,
+                          uint32_t* kept) {
+    if (n == 0 || width < 1 || height < 1) return 0;
+    uint8_t* mask = (uint8_t*)calloc((size_t)width * height, 1);
+    const int half = box_size / 2;
+    size_t nk = 0;
+    for (size_t i = 0; i < n; i++) {
+        const int x = xy[2 * i], y = xy[2 * i + 1];
+        const int sx = x - half > 0 ? x - half : 0, ex = x + half < width - 1 ? x + half : width - 1;
+        const int sy = y - half > 0 ? y - half : 0, ey = y + half < height - 1 ? y + half : height - 1;
+        int is_max = 1;
+        for (int yy = sy; yy <= ey && is_max; yy++)
+            for (int xx = sx; xx <= ex; xx++)
+                if (mask[(size_t)yy * width + xx]) {
+                    is_max = 0;
+                    break;
+                }
+        if (is_max) {
+            kept[nk++] = (uint32_t)i;
+            for (int yy = sy; yy <= ey; yy++)
+                for (int xx = sx; xx <= ex; xx++) mask[(size_t)yy * width + xx] = 255;
+        }
+    }
+    free(mask);
+    return nk;
+}

@@ -127,4 +127,8 @@ size_t orc_evt3_encode(const evk_event* ev, size_t n, uint16_t* words, size_t ca
 #ifdef __cplusplus
 }
 #endif
+/* box non-maximum suppression of a corner list (the reference's CornerFilter::filterCorners) */
+size_t orc_filter_corners(const int32_t* xy, size_t n, int width, int height, int box_size,
+                          uint32_t* kept);
+
 #endif
