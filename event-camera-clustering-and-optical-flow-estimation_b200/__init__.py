@@ -106,6 +106,8 @@ SYMBOLS = [
     "evk_ts_create", "evk_ts_destroy", "evk_ts_corners", "evk_ts_get_corners", "evk_ts_get_surface",
     "evk_ts_filter_corners", "evk_filter_corners", "evk_get_filtered_corners",
     "evk_filter_corners_destroy",
+    "evk_optics_points", "evk_optics_voxels", "evk_optics_get", "evk_optics_clusters",
+    "evk_optics_destroy",
 ]
 
 _lib = None
@@ -170,6 +172,11 @@ def lib():
         "evk_filter_corners": [vp, vp, sz, i32, i32, i32, psz],
         "evk_get_filtered_corners": [vp, vp, sz],
         "evk_filter_corners_destroy": [vp],
+        "evk_optics_points": [vp, vp, sz, i32, i32, C.c_double],
+        "evk_optics_voxels": [vp, i32, C.c_double],
+        "evk_optics_get": [vp, vp, vp, sz, psz],
+        "evk_optics_clusters": [vp, C.c_double, vp, sz, psz],
+        "evk_optics_destroy": [vp],
         "evk_get_centroids": [vp, vp, vp],
         "evk_window_config": [vp, C.POINTER(DsParams), C.POINTER(KmParams), C.c_int64],
         "evk_window_config_events": [vp, C.POINTER(DsParams), C.POINTER(KmParams), sz],
@@ -516,6 +523,32 @@ class Evk:
         self._ck(self._L.evk_filter_corners(self._h, _p(xy), len(xy), width, height, box_size,
                                             C.byref(n)))
         return self._filtered(n.value)
+
+    # ---- OPTICS (evk_optics_*)
+    def _optics_result(self):
+        n = C.c_size_t(0)
+        self._ck(self._L.evk_optics_get(self._h, None, None, 0, C.byref(n)))
+        order, reach = np.zeros(n.value, np.uint32), np.zeros(n.value, np.float64)
+        if n.value:
+            self._ck(self._L.evk_optics_get(self._h, _p(order), _p(reach), n.value, C.byref(n)))
+        return order, reach
+
+    def optics_points(self, pts, min_pts, eps):
+        """pts: [n, 2 or 3] integers -> (order, reachability by ordering position; -1 = none)"""
+        pts = np.ascontiguousarray(pts, dtype=np.int32)
+        self._ck(self._L.evk_optics_points(self._h, _p(pts), len(pts), pts.shape[1], min_pts, eps))
+        return self._optics_result()
+
+    def optics_voxels(self, min_pts, eps):
+        self._ck(self._L.evk_optics_voxels(self._h, min_pts, eps))
+        return self._optics_result()
+
+    def optics_clusters(self, threshold):
+        n = C.c_size_t(0)
+        self._ck(self._L.evk_optics_get(self._h, None, None, 0, C.byref(n)))
+        cl, nc = np.zeros(n.value, np.uint32), C.c_size_t(0)
+        self._ck(self._L.evk_optics_clusters(self._h, threshold, _p(cl), n.value, C.byref(nc)))
+        return cl, nc.value
 
     def ts_surface(self):
         out = np.zeros(self._ts_shape, np.int64)

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libevk.so")
 SOURCES = ["evk_api.cu", "evk_downsample.cu", "evk_slab.cu", "evk_partition.cu", "evk_kmeans.cu", "evk_synth.cu",
-           "evk_comm.cu", "evk_evt2.cu", "evk_evt3.cu", "evk_aec.cu", "evk_corner.cu", "evk_dbscan.cu"]
+           "evk_comm.cu", "evk_evt2.cu", "evk_evt3.cu", "evk_aec.cu", "evk_corner.cu", "evk_dbscan.cu", "evk_optics.cu"]
 NVCC = os.environ.get("EVK_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = os.environ.get("EVK_NVCC_EXTRA", "").split() + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall",

@@ -277,6 +277,7 @@ int evk_destroy(evk_handle* h) {
     evk_aec_destroy(h);
     evk_ts_destroy(h);
     evk_filter_corners_destroy(h);
+    evk_optics_destroy(h);
     evk_dbscan_destroy(h);
     evk_partition_free(h);
     // graphs first: they reference the buffers, events and streams released below

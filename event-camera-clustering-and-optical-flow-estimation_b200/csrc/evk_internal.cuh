@@ -108,7 +108,8 @@ struct CommState;
 struct AecHost;  // evk_aec.cu
 struct TsHost;   // evk_corner.cu
 struct DbHost;   // evk_dbscan.cu
-struct NmsHost;  // evk_corner.cu (box non-maximum suppression of corner lists)
+struct NmsHost;  // evk_corner.cu
+struct OpticsHost;  // evk_optics.cu (box non-maximum suppression of corner lists)
 
 struct FusedKey {  // what the captured fused-step graph depends on
     size_t n;
@@ -250,6 +251,7 @@ struct evk_handle {
     // time surface + corner test (evk_corner.cu), created by evk_ts_create
     TsHost* ts = nullptr;
     NmsHost* nms = nullptr;
+    OpticsHost* optics = nullptr;
     // DBSCAN buffers and last results (evk_dbscan.cu), created on first use
     DbHost* db = nullptr;
     uint64_t shard_first = 0;

@@ -385,6 +385,26 @@ EVK_API int evk_dbscan_get(evk_handle* h, int32_t* labels, size_t cap_points, ui
                            size_t cap_extra);
 EVK_API int evk_dbscan_destroy(evk_handle* h);
 
+/* OPTICS reachability ordering as the reference computes it on event coordinates (event-cam-
+ * clustering/optics-clustering/include/optics/optics.hpp:413-590 compute_reachability_dists; app:
+ * test/cluster_event_data.cpp:333-338 with min_pts 2, epsilon 10, threshold 10): neighbours are the
+ * points with squared distance <= epsilon^2 (the point itself included), the core distance is the
+ * distance to the neighbour of rank min_pts - 1, seeds are popped in (reachability, index) order.
+ * Integer coordinates, D = 2 or 3; at most 65536 points, min_pts <= 32.  The neighbourhood work runs
+ * on the device, the priority-queue walk on the host. */
+EVK_API int evk_optics_points(evk_handle* h, const int32_t* pts, size_t n, int D, int min_pts,
+                              double eps);
+/* the current voxel shard: point i = (x, y) of the representative of the i-th voxel, canonical order */
+EVK_API int evk_optics_voxels(evk_handle* h, int min_pts, double eps);
+/* order[k] = index of the k-th point of the ordering, reach[k] = its reachability (-1: none);
+ * either may be NULL; *n = number of points */
+EVK_API int evk_optics_get(evk_handle* h, uint32_t* order, double* reach, size_t cap, size_t* n);
+/* get_cluster_indices(reach_dists, threshold) (optics.hpp:674-690): cluster[k] = id of the cluster of
+ * the k-th point of the ordering (a point without reachability or with one >= threshold opens one) */
+EVK_API int evk_optics_clusters(evk_handle* h, double threshold, uint32_t* cluster, size_t cap,
+                                size_t* n_clusters);
+EVK_API int evk_optics_destroy(evk_handle* h);
+
 /* ---- profiling / measurement --------------------------------------------------------------- */
 EVK_API int evk_set_profiling(evk_handle* h, int enabled);
 EVK_API int evk_get_stage_times(const evk_handle* h, evk_stage_times* out);

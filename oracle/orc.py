@@ -38,7 +38,8 @@ class SynthParams(C.Structure):
 
 
 def build(force=False):
-    src = [os.path.join(_HERE, f) for f in ("evk_oracle.c", "evk_oracle.h", "aec_oracle.c", "dbscan_oracle.c")]
+    src = [os.path.join(_HERE, f) for f in ("evk_oracle.c", "evk_oracle.h", "aec_oracle.c", "dbscan_oracle.c",
+                                             "optics_oracle.c")]
     if (not force and os.path.exists(_LIB)
             and all(os.path.getmtime(_LIB) >= os.path.getmtime(s) for s in src)):
         return _LIB
