@@ -941,10 +941,12 @@ int evk_kmeans(evk_handle* h, const evk_km_params* p, int* iters_done) {
 }
 
 // ---- fused step -----------------------------------------------------------------------------
-// One submission, one host synchronisation: bins -> (first-K walk) -> candidate lists -> slab
-// kernel whose consumer warps assign + accumulate every voxel it emits -> fix-up -> finalise.
-// Shapes the fused kernel does not take (unordered stream, D > 2, K > 254, raw-event clustering,
-// key space too large for shared memory) run the three separate calls: same results either way.
+// One submission, one host synchronisation: a replayed CUDA graph of nine kernels -- bins -> slab
+// -> fix-up on the main stream, first-K walk -> candidate lists -> label map -> quads beside them on
+// the side stream, then assign + accumulate over the new voxels -> finalise.  (Assigning inside the
+// slab kernel with consumer warps was measured slower)  Shapes the fused pass
+// does not take (unordered stream, D > 2, K > 254, raw-event clustering, key space too large for
+// shared memory) run the three separate calls: same results either way.
 static int step_unfused(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
                         int init_first_k, int* iters_done) {
     EVK_TRY(evk_downsample_local(h, ds));

@@ -50,6 +50,9 @@ namespace {
 #ifndef EVK_SLAB_STAGES
 #define EVK_SLAB_STAGES 2
 #endif
+#ifndef EVK_SLAB_LEAN
+#define EVK_SLAB_LEAN 0  // 1: fewer integer-ALU operations in the classify pass
+#endif
 #ifndef EVK_SLAB_KEEP_BITS
 #define EVK_SLAB_KEEP_BITS 1  // 1: the claim pass reuses the classify pass's word index and bit
 #endif
@@ -347,6 +350,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
         for (int s = 0; s < (EVK_SLAB_EARLY_FREE ? kStages : kStages - 1); s++) fetch();
     }
 
+#if EVK_SLAB_LEAN
+    const uint32_t y_lim = ((uint32_t)(kp.height - 1) << 16) | 0xFFFFu;
+    const uint32_t ysh = 16u + (uint32_t)(kp.sy >= 0 ? kp.sy : 0);
+#endif
     for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
         const uint32_t lo = a.bin_start[b], hi = a.bin_start[b + 1];
         if (hi < lo) viol = 1;  // ranges do not partition the stream: not time-ordered
@@ -386,7 +393,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 const uint32_t li = j * NT + tid;
                 const uint4 ev = tile[li];
                 const uint32_t x = ev.x & 0xFFFFu, y = ev.x >> 16;
-#if EVK_SLAB_VIOLX == 1
+#if EVK_SLAB_LEAN
+                // y < height  <=>  (y << 16 | x) <= ((height - 1) << 16 | 0xFFFF): no need to extract y
+                const bool gate = (base + li < hi) & (x < (uint32_t)kp.width) & (ev.x <= y_lim);
+                const bool inbin = (uint64_t)(ev_t(ev) - t_lo) < (uint64_t)kp.vt;
+                const bool ok = gate & inbin;
+                viol |= (uint32_t)(gate != ok);  // a gated-in event that is not of this bin
+#elif EVK_SLAB_VIOLX == 1
                 const bool gate = (base + li < hi) & (x < (uint32_t)kp.width) & (y < (uint32_t)kp.height);
                 const bool inbin = (uint64_t)(ev_t(ev) - t_lo) < (uint64_t)kp.vt;
                 const bool ok = gate & inbin;
@@ -403,18 +416,31 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 ok &= inbin;
 #endif
                 uint32_t cell;
+#if EVK_SLAB_LEAN
+                if (POW2) cell = (ev.x >> ysh) * kp.NX + (x >> kp.sx);
+                else cell = (kp.sy >= 0 ? y >> kp.sy : __umulhi(y, kp.my)) * kp.NX +
+                            (kp.sx >= 0 ? x >> kp.sx : __umulhi(x, kp.mx));
+                // polarity bit = (int16)p > 0: the sign test on the halfword moved to bit 31
+                if (kp.use_p) cell = cell * 2u + ((int32_t)(ev.y << 16) > 0 ? 1u : 0u);
+#else
                 if (POW2) cell = (y >> kp.sy) * kp.NX + (x >> kp.sx);
                 else cell = (kp.sy >= 0 ? y >> kp.sy : __umulhi(y, kp.my)) * kp.NX +
                             (kp.sx >= 0 ? x >> kp.sx : __umulhi(x, kp.mx));
                 if (kp.use_p) cell = cell * 2u + ev_pbit(ev);
+#endif
                 const uint32_t w = COUNT_REP ? cell >> 4 : cell >> 5;
                 const uint32_t sbit = 1u << (cell & (COUNT_REP ? 15u : 31u));
                 const uint32_t wv = ok ? s_map[w] : 0xFFFFFFFFu;  // gated events: nothing to do
                 if (COUNT_REP) {  // duplicate of an earlier tile's voxel: mark it "hit twice"
                     // (a predicated reduction: the branch the compiler builds around an atomicOr
                     // here costs 2 % of the kernel)
-                    const uint32_t need = (wv & sbit) && !(wv & (sbit << 16)) && ok;
-                    sred_or_if(&s_map[w], sbit << 16, need);
+#if EVK_SLAB_LEAN
+                    const uint32_t hbit = sbit * 0x10000u;
+#else
+                    const uint32_t hbit = sbit << 16;
+#endif
+                    const uint32_t need = (wv & sbit) && !(wv & hbit) && ok;
+                    sred_or_if(&s_map[w], hbit, need);
                 }
                 cv[j] = (wv & sbit) ? kEmpty : ((cell << kLogTile) | li);
                 cxy[j] = ev.x;

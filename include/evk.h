@@ -219,9 +219,13 @@ EVK_API int evk_kmeans(evk_handle* h, const evk_km_params* p, int* iters_done);
 
 /* Fused step: the same results as evk_downsample, then (init_first_k != 0) evk_init_centroids_first_k
  * or (== 0) the centroids already held by the handle (warm start), then evk_kmeans -- submitted as
- * one pass with a single host synchronisation.  On time-ordered streams with D = 2 the first Lloyd
- * iteration runs inside the downsample kernel (every voxel is assigned and accumulated as it is
- * emitted); other shapes run the three calls one after the other.  Replaces the per-slice sequence
+ * one pass with a single host synchronisation.  On time-ordered streams with D = 2, K <= 254 and one
+ * iteration the pass is ONE replayed CUDA graph of nine kernels -- time-slab downsample (bins, slab,
+ * fix-up) with the centroid-only work (first-K walk, candidate lists, label map, quads) beside it
+ * on a second stream, then one assign + accumulate pass over the new voxels and the finalise; the
+ * voxel count never leaves the device in between.  (Assigning inside the downsample kernel was
+ * measured slower: DESIGN.md section 7.)  Other shapes run the three calls one after the other
+ * with the same results.  Replaces the per-slice sequence
  * launch -> clFinish -> read -> consumer of ACCEL/store.cpp:397-445 when the consumer is k-means. */
 EVK_API int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const evk_km_params* km,
                                   int init_first_k, size_t* n_unique, size_t* n_repeated,
@@ -232,9 +236,11 @@ EVK_API int evk_downsample_kmeans(evk_handle* h, const evk_ds_params* ds, const 
  * reports its counts.  Steps may be queued behind each other (each one works on the events resident
  * at its turn in stream order); wait then reports the last one.  evk_downsample_kmeans ==
  * submit + wait.  Shapes the fused pass does not take run synchronously inside submit.
- * Loading the next slice's events behind a queued step is allowed (the copy is stream-ordered
- * behind the step); results that refer back to the events -- the representatives of
- * evk_get_voxels -- must then be read before that load. */
+ * A loader called while steps are queued collects them first (their results refer back to the
+ * events they ran on), so results must be read before the next load.  Queued steps need
+ * time-ordered slices: if the time-slab path rejects an EARLIER queued step, wait returns
+ * EVK_ERR_STATE instead of silently skipping that slice (one step at a time falls back to the
+ * general path). */
 EVK_API int evk_downsample_kmeans_submit(evk_handle* h, const evk_ds_params* ds,
                                          const evk_km_params* km, int init_first_k);
 EVK_API int evk_downsample_kmeans_wait(evk_handle* h, size_t* n_unique, size_t* n_repeated,
