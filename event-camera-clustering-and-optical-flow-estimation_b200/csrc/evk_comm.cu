@@ -585,7 +585,8 @@ __global__ void __launch_bounds__(64)
 // exact key / cells without a 64-bit division: q = hi64(key * ceil(2^64 / cells)) is the quotient
 // or the quotient + 1
 struct MixDiv {
-    uint64_t cells, magic;  // magic = floor(2^64 / cells) + 1 (0 when cells == 1)
+    uint64_t cells, magic;    // magic = floor(2^64 / cells) + 1 (0 when cells == 1)
+    uint64_t lo_key, hi_key;  // keys in [lo_key, hi_key) lie strictly inside this rank's bin range
 };
 __device__ __forceinline__ uint64_t mix_tbin(uint64_t key, const MixDiv& d) {
     if (d.cells <= 1) return key;
@@ -596,6 +597,9 @@ __device__ __forceinline__ uint64_t mix_tbin(uint64_t key, const MixDiv& d) {
 __device__ __forceinline__ bool mix_suspect(uint64_t key, const MixDiv& d, const uint64_t* s_bins,
                                             int n_bins, bool all) {
     if (all) return true;
+    // a time-ordered shard can share a bin with another rank only in its own first or last bin:
+    // keys strictly between them need no division and no search
+    if (key >= d.lo_key && key < d.hi_key) return false;
     const uint64_t tb = mix_tbin(key, d);
     bool s = false;
     for (int i = 0; i < n_bins; i++) s |= s_bins[i] == tb;
@@ -641,12 +645,34 @@ __global__ void __launch_bounds__(kBlock)
     for (int i = threadIdx.x; i < 2 * world; i += kBlock) s_h[i] = 0;
     __syncthreads();
     const bool all = s_flags[0] != 0;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint64_t k = keys[i];
-        const int b = 2 * owner_of(k, world) + (mix_suspect(k, dv, s_bins, 2 * world, all) ? 1 : 0);
-        bkt[i] = (uint8_t)b;
-        atomicAdd(&s_h[b], 1u);
+    const int lane = threadIdx.x & 31;
+    constexpr int kU = 4;  // keys in flight per thread (one load per iteration is latency-bound)
+    const size_t tile = (size_t)kBlock * kU;
+    const size_t n_tiles = (n + tile - 1) / tile;
+    for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        uint64_t k[kU];
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            const size_t i = t * tile + (size_t)u * kBlock + threadIdx.x;
+            k[u] = i < n ? keys[i] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < kU; u++) {
+            const size_t i = t * tile + (size_t)u * kBlock + threadIdx.x;
+            int b = -1;
+            if (i < n) {
+                b = 2 * owner_of(k[u], world) + (mix_suspect(k[u], dv, s_bins, 2 * world, all) ? 1 : 0);
+                bkt[i] = (uint8_t)b;
+            }
+            // one shared atomic per (warp, bucket present)
+            uint32_t rest = __ballot_sync(0xffffffffu, b >= 0);
+            while (rest) {
+                const int b0 = __shfl_sync(0xffffffffu, b, __ffs(rest) - 1);
+                const uint32_t m = __ballot_sync(0xffffffffu, b == b0);
+                if (lane == __ffs(m) - 1) atomicAdd(&s_h[b0], (unsigned int)__popc(m));
+                rest &= ~m;
+            }
+        }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * world; i += kBlock)
@@ -715,12 +741,14 @@ __global__ void __launch_bounds__(64)
 // shared memory, claims one range per bucket with one global atomic each, and then writes the
 // tile out with consecutive threads on consecutive slots: every bucket's run is one contiguous,
 // coalesced burst over NVLink instead of 8 / 4 / 4-byte stores scattered across the owner's arrays.
-constexpr int kScPer = 4, kScTile = kBlock * kScPer;
-__global__ void __launch_bounds__(kBlock)
+constexpr int kScPer = 2, kScTile = kBlock * kScPer;
+constexpr int kScCtas = 8;  // resident CTAs per SM (registers capped accordingly)
+__global__ void __launch_bounds__(kBlock, kScCtas)
     k_mix_scatter(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ first,
                   const uint32_t* __restrict__ xy, const evk_event* __restrict__ ev0,
                   const uint8_t* __restrict__ bkt, size_t n, int world,
-                  const MixPeer* __restrict__ peers, unsigned long long* mx, int want_reps) {
+                  const MixPeer* __restrict__ peers, unsigned long long* mx, int want_reps,
+                  int local_only) {
     __shared__ unsigned int s_cnt[2 * kMaxWorld], s_start[2 * kMaxWorld + 1];
     __shared__ unsigned long long s_dst[2 * kMaxWorld];  // first slot of this tile's run per bucket
     __shared__ uint64_t s_k[kScTile];
@@ -735,16 +763,29 @@ __global__ void __launch_bounds__(kBlock)
         uint64_t k[kScPer];
         uint32_t f[kScPer], x[kScPer], loc[kScPer];
         int b[kScPer];
+        const int lane = threadIdx.x & 31;
+        const uint32_t lt = (1u << lane) - 1u;
 #pragma unroll
         for (int j = 0; j < kScPer; j++) {
             const size_t i = t * kScTile + (size_t)j * kBlock + threadIdx.x;
             b[j] = -1;
+            loc[j] = 0;
             if (i < n) {
                 k[j] = keys[i];
                 f[j] = first[i];
                 x[j] = xy[i];
                 b[j] = bkt[i];
-                loc[j] = atomicAdd(&s_cnt[b[j]], 1u);
+            }
+            // slot inside the tile's bucket: one shared atomic per (warp, bucket present)
+            uint32_t rest = __ballot_sync(0xffffffffu, b[j] >= 0);
+            while (rest) {
+                const int b0 = __shfl_sync(0xffffffffu, b[j], __ffs(rest) - 1);
+                const uint32_t m = __ballot_sync(0xffffffffu, b[j] == b0);
+                unsigned int base = 0;
+                if (lane == __ffs(m) - 1) base = atomicAdd(&s_cnt[b0], (unsigned int)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                if (b[j] == b0) loc[j] = base + __popc(m & lt);
+                rest &= ~m;
             }
         }
         __syncthreads();
@@ -793,7 +834,7 @@ __global__ void __launch_bounds__(kBlock)
             const unsigned int slot = j * kBlock + threadIdx.x;
             if (slot >= in_tile) continue;
             const int bb = s_b[slot];
-            const MixPeer& pr = peers[bb >> 1];
+            const MixPeer& pr = peers[local_only >= 0 ? local_only : (bb >> 1)];
             const size_t p = (size_t)s_dst[bb] + (slot - s_start[bb]);
             const uint32_t ff = s_f[slot];
             if (bb & 1) {
@@ -810,7 +851,8 @@ __global__ void __launch_bounds__(kBlock)
         }
         __syncthreads();
     }
-    __threadfence_system();
+    // (no fence here: a system-scope fence per thread costs more than the scatter itself; the
+    // kernel boundary orders these writes before k_mix_done, which fences once and raises the flags)
 }
 
 __global__ void __launch_bounds__(64)
@@ -1123,6 +1165,12 @@ int sharded_mix64_p2p(evk_handle* h, const evk_ds_params* p, bool want_reps) {
     MixDiv dv;
     dv.cells = kp.cells ? kp.cells : 1;
     dv.magic = dv.cells > 1 ? ~0ull / dv.cells + 1 : 0;
+    dv.lo_key = dv.hi_key = 0;
+    if (ordered && kp.vt > 0 && kp.keyfn == EVK_KEY_VOXEL) {
+        dv.lo_key = (tb_first + 1) * dv.cells;  // first key behind my first bin
+        dv.hi_key = tb_last * dv.cells;         // first key of my last bin
+        if (dv.hi_key < dv.lo_key) dv.hi_key = dv.lo_key;
+    }
     uint8_t* bkt = reinterpret_cast<uint8_t*>(c->sx);  // (idle send staging: one byte per record)
     const bool all_suspect = !ordered || kp.keyfn != EVK_KEY_VOXEL || kp.vt <= 0;
     unsigned long long* mx = c->d_mix;
@@ -1148,8 +1196,14 @@ int sharded_mix64_p2p(evk_handle* h, const evk_ds_params* p, bool want_reps) {
                                            (unsigned long long)c->stage_cap, mx, h->d_cnt);
     const evk_event* ev0 = h->d_events - h->shard_first;
     mark(2);
-    k_mix_scatter<<<h->sm_count * 8, kBlock, 0, h->stream>>>(c->lk, c->lf, c->lx, ev0, bkt, U, G,
-                                                             c->d_mix_peers, mx, want_reps ? 1 : 0);
+    static bool carve_set = false;
+    if (!carve_set) {  // (latency-bound: ncu showed 3 resident CTAs at 72 registers)
+        cudaFuncSetAttribute(k_mix_scatter, cudaFuncAttributePreferredSharedMemoryCarveout, 60);
+        carve_set = true;
+    }
+    k_mix_scatter<<<h->sm_count * kScCtas, kBlock, 0, h->stream>>>(c->lk, c->lf, c->lx, ev0, bkt, U, G,
+                                                             c->d_mix_peers, mx, want_reps ? 1 : 0,
+                                                             getenv("EVK_MIX_TIMING_LOCAL_ONLY") ? c->rank : -1);
     mark(3);
     k_mix_done<<<1, 64, 0, h->stream>>>(c->mail, c->d_peer_mail, c->rank, G, mx);
     mark(4);
@@ -1356,7 +1410,9 @@ int evk_comm_init(evk_handle* h, int rank, int world, const uint8_t* id128) {
     }
     if ((size_t)c->halo * 4 > h->max_events) c->halo = (uint32_t)(h->max_events / 4);
     h->comm = c;
-    if (world > 1 && !getenv("EVK_NO_P2P")) p2p_setup(h, c);  // best effort: NCCL stays the fallback
+    // (EVK_P2P_SINGLE: the peer-memory paths with one rank, for profiling their kernels under ncu)
+    if ((world > 1 || getenv("EVK_P2P_SINGLE")) && !getenv("EVK_NO_P2P"))
+        p2p_setup(h, c);  // best effort: NCCL stays the fallback
     return EVK_OK;
 }
 
