@@ -50,8 +50,18 @@ namespace {
 #ifndef EVK_SLAB_STAGES
 #define EVK_SLAB_STAGES 2
 #endif
+#ifndef EVK_SLAB_CHECKS
+#define EVK_SLAB_CHECKS 0  // 1: every index of the hot kernel is bounds-checked on the device (a failed
+#endif                     //    check sets DsCounters::overflow bit 1); compute-sanitizer is closed
+                           //    on this pool, so the parity / stress tests are run against this build
+#ifndef EVK_SLAB_TRIM
+#define EVK_SLAB_TRIM 8  // instruction trims, adopted one by one (A/B: profiles/r02/slab_ab_runs.md)
+#endif
 #ifndef EVK_SLAB_LEAN
-#define EVK_SLAB_LEAN 0  // 1: fewer integer-ALU operations in the classify pass
+#define EVK_SLAB_LEAN 1  // 1: fewer integer-ALU operations in the classify pass
+#endif
+#if EVK_SLAB_TRIM >= 7 && !EVK_SLAB_LEAN
+#error "EVK_SLAB_TRIM >= 7 pads short tiles and needs the EVK_SLAB_LEAN frame test"
 #endif
 #ifndef EVK_SLAB_KEEP_BITS
 #define EVK_SLAB_KEEP_BITS 1  // 1: the claim pass reuses the classify pass's word index and bit
@@ -85,6 +95,15 @@ struct ChunkTail {
     uint32_t next_base, next_filled;  // chunk claimed ahead (kNoChunk-based if none); always 0 filled
 };
 
+#if EVK_SLAB_CHECKS
+#define SLAB_CHECK(cond)                                   \
+    do {                                                   \
+        if (!(cond)) atomicOr(&cnt->overflow, 2u);         \
+    } while (0)
+#else
+#define SLAB_CHECK(cond) ((void)0)
+#endif
+
 struct SlabArgs {
     KeyParams kp;
     const evk_event* ev;
@@ -99,6 +118,7 @@ struct SlabArgs {
     uint32_t words;         // bitmap words per bin
     uint32_t max_bins;
     uint32_t min_bins;
+    uint32_t out_cap;       // slots of keys / first / xy (checked build)
     // sharded runs: [0] != 0 -> give up; [3] = leading events that belong to the previous rank's
     // last bin; [4] = events received behind my own that belong to my last bin.  Read on the device
     // so that the halo exchange and the downsample need no host round trip in between.
@@ -274,6 +294,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
     __shared__ uint32_t s_cursor[2];  // voxels emitted by the current tile (by tile parity)
     __shared__ uint32_t s_chunk_pos, s_chunk_end, s_next_base;
     __shared__ uint32_t s_stop;  // some CTA has found the stream unordered: stop early
+#if EVK_SLAB_TRIM >= 3
+    __shared__ uint64_t s_key_base;  // first key of the current bin (see the output pass)
+#endif
+#if EVK_SLAB_TRIM >= 4
+    __shared__ int64_t s_t_lo;       // first microsecond of the current bin
+#endif
+#if EVK_SLAB_TRIM >= 6
+    __shared__ uint64_t s_out[3];    // global addresses of the key / first-index / xy columns
+#endif
 
     DsCounters* cnt = a.cnt;
     if (cnt->slab_violation) return;
@@ -285,6 +314,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
     const SlabRange rg = slab_range(a);
     const evk_event* const evs = rg.ev;
     const uint32_t first_offset = rg.first_offset;
+#if EVK_SLAB_TRIM >= 1
+    uint32_t lane_lt;  // lanes below mine (the output pass ranks a lane among the emitting lanes)
+    asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lane_lt));
+#endif
+#if EVK_SLAB_TRIM == 2
+    // output array bases in registers (else three constant-bank loads in front of every record)
+    uint64_t* keys_p = a.keys;
+    uint32_t* first_p = a.first;
+    uint32_t* xy_p = a.xy;
+    asm volatile("" : "+l"(keys_p), "+l"(first_p), "+l"(xy_p));
+#endif
 
     for (int i = tid; i < 2 * kHash; i += NT) s_late[i] = kEmpty;
     for (uint32_t i = tid; i < a.words; i += NT) s_map[i] = 0;
@@ -292,6 +332,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
         for (int s = 0; s < kStages; s++) mbar_init(&s_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_cursor[0] = s_cursor[1] = 0;
+#if EVK_SLAB_TRIM >= 6
+        s_out[0] = (uint64_t)__cvta_generic_to_global(a.keys);
+        s_out[1] = (uint64_t)__cvta_generic_to_global(a.first);
+        s_out[2] = (uint64_t)__cvta_generic_to_global(a.xy);
+#endif
         // two chunks up front: the current one and the one after it
         const uint32_t c0 = (uint32_t)atomicAdd(&cnt->scratch[3], 2ull);
         s_chunk_pos = c0 * kChunk;
@@ -360,8 +405,21 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
         if (hi <= lo) continue;
         const uint64_t tb = tb0 + b;
         const int64_t t_lo = t0 + (int64_t)(tb * (uint64_t)kp.vt);
-        const uint64_t key_base = tb * kp.cells;
+        uint64_t key_base = tb * kp.cells;
+#if EVK_SLAB_TRIM >= 1
+        // (kept in registers for the whole bin: the compiler otherwise rematerialises the 64-bit
+        // product, six instructions, in front of every key store: ncu source page, round 2)
+        asm volatile("" : "+l"(key_base));
+#endif
         if (tid == 0) s_stop = *reinterpret_cast<volatile unsigned int*>(&cnt->slab_violation);
+#if EVK_SLAB_TRIM >= 3
+        // (one 8-byte shared load per record instead of the 64-bit product, which ptxas
+        // rematerialises -- six instructions -- in front of every key store)
+        if (tid == 0) s_key_base = key_base;
+#endif
+#if EVK_SLAB_TRIM >= 4
+        if (tid == 0) s_t_lo = t_lo;
+#endif
         prod_sync<NT>();  // every thread has left the previous bin (bitmap, cursor)
         if (s_stop) break;  // (an early stop inside the tile loop also ends here)
         if (tid == 0) book();
@@ -383,6 +441,24 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
             const uint4* tile = s_ev + stage * kTile;
             uint32_t* late_tbl = s_late + par * kHash;
             mbar_wait(&s_bar[stage], (tile_seq / kStages) & 1);
+#if EVK_SLAB_TRIM >= 4
+            // (one shared load per tile instead of rematerialising t0 + tb * vt, a 64-bit product)
+            const int64_t t_lo = *reinterpret_cast<volatile int64_t*>(&s_t_lo);
+#endif
+#if EVK_SLAB_TRIM >= 7
+            // the last tile of a bin is short: its unused slots still hold an older tile.  Overwrite
+            // them with an event outside the frame (x = y = 0xFFFF), so that the per-event test
+            // "index < end of bin" -- two instructions per event of every tile -- is not needed
+            if (hi - base < (uint32_t)TILE) {  // (uniform over the CTA)
+                const uint32_t live = hi - base;
+#pragma unroll
+                for (int j = 0; j < kPer; j++)
+                    if ((uint32_t)(j * NT + tid) >= live)
+                        const_cast<uint4*>(tile)[j * NT + tid] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+                // (the slot is next written by a bulk copy: order the two proxies)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+#endif
             // ---- classify: cv = candidate word (cell << kLogTile | index in tile) or kEmpty
             uint32_t cv[kPer], cxy[kPer];
 #if EVK_SLAB_KEEP_BITS
@@ -395,7 +471,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 const uint32_t x = ev.x & 0xFFFFu, y = ev.x >> 16;
 #if EVK_SLAB_LEAN
                 // y < height  <=>  (y << 16 | x) <= ((height - 1) << 16 | 0xFFFF): no need to extract y
+#if EVK_SLAB_TRIM >= 7
+                const bool gate = (x < (uint32_t)kp.width) & (ev.x <= y_lim);
+#else
                 const bool gate = (base + li < hi) & (x < (uint32_t)kp.width) & (ev.x <= y_lim);
+#endif
                 const bool inbin = (uint64_t)(ev_t(ev) - t_lo) < (uint64_t)kp.vt;
                 const bool ok = gate & inbin;
                 viol |= (uint32_t)(gate != ok);  // a gated-in event that is not of this bin
@@ -430,6 +510,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
 #endif
                 const uint32_t w = COUNT_REP ? cell >> 4 : cell >> 5;
                 const uint32_t sbit = 1u << (cell & (COUNT_REP ? 15u : 31u));
+                SLAB_CHECK(!ok || (w < a.words && li < (uint32_t)kTile));
                 const uint32_t wv = ok ? s_map[w] : 0xFFFFFFFFu;  // gated events: nothing to do
                 if (COUNT_REP) {  // duplicate of an earlier tile's voxel: mark it "hit twice"
                     // (a predicated reduction: the branch the compiler builds around an atomicOr
@@ -474,6 +555,19 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
 #pragma unroll
             for (int j = 0; j < kPer; j++) {
                 late[j] = false;
+#if EVK_SLAB_TRIM >= 4 && EVK_SLAB_KEEP_BITS
+                {   // predicated returning atomic, no branch (old = 0 for lanes without a candidate)
+                    uint32_t old = 0;
+                    asm volatile(
+                        "{ .reg .pred q; setp.ne.u32 q, %3, 0xFFFFFFFF; "
+                        "@q atom.shared.or.b32 %0, [%1], %2; }"
+                        : "+r"(old)
+                        : "r"(smem_u32(&s_map[cw[j]])), "r"(cb[j]), "r"(cv[j])
+                        : "memory");
+                    late[j] = (old & cb[j]) != 0;
+                    continue;
+                }
+#endif
                 if (cv[j] == kEmpty) continue;
 #if EVK_SLAB_KEEP_BITS
                 uint32_t* wp = &s_map[cw[j]];
@@ -492,7 +586,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 const uint32_t cell = cv[j] >> kLogTile;
                 if (COUNT_REP) atomicOr(&s_map[cell >> 4], 1u << (16 + (cell & 15)));
                 uint32_t s = hash_slot(cell);
+#if EVK_SLAB_CHECKS
+                uint32_t probes = 0;
+#endif
                 for (;;) {
+                    SLAB_CHECK(s < (uint32_t)kHash && ++probes <= (uint32_t)kHash);
                     const uint32_t old = atomicCAS(&late_tbl[s], kEmpty, cv[j]);
                     if (old == kEmpty) break;
                     if ((old >> kLogTile) == cell) {  // keep the lowest index of the cell
@@ -506,11 +604,47 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
             prod_sync<NT>();  // S1: every claim of the tile is in the bitmap, s_late is complete
             // ---- resolve: the claimant is the new voxel unless a late peer has a lower index
             uint32_t bal[kPer], wtot = 0, w0[kPer];
-#pragma unroll
-            for (int j = 0; j < kPer; j++)  // first probe: nearly always an empty slot
-                w0[j] = cv[j] != kEmpty ? late_tbl[hash_slot(cv[j] >> kLogTile)] : kEmpty;
+#define EVK_SLAB_HBIT_PROBE (EVK_SLAB_TRIM >= 8 && EVK_SLAB_KEEP_BITS)
 #pragma unroll
             for (int j = 0; j < kPer; j++) {
+                // COUNT_REP: a late peer has set the cell's "hit twice" bit (so may a warp already
+                // classifying the next tile: then the probe finds nothing) -- one load of a word
+                // whose address and bit are in registers instead of hashing the cell for a probe
+#if EVK_SLAB_HBIT_PROBE
+                if (COUNT_REP) w0[j] = cv[j] != kEmpty ? s_map[cw[j]] : 0u;
+                else
+#endif
+                    // first probe: nearly always an empty slot
+                    w0[j] = cv[j] != kEmpty ? late_tbl[hash_slot(cv[j] >> kLogTile)] : kEmpty;
+            }
+#pragma unroll
+            for (int j = 0; j < kPer; j++) {
+#if EVK_SLAB_HBIT_PROBE
+                if (COUNT_REP) {
+                    if (w0[j] & (cb[j] << 16)) {
+                        const uint32_t cell = cv[j] >> kLogTile;
+                        uint32_t s = hash_slot(cell);
+                        for (;;) {
+                            const uint32_t w = late_tbl[s];
+                            if (w == kEmpty) break;
+                            if ((w >> kLogTile) == cell) {
+                                if (w < cv[j]) {  // lower index: that event is the representative
+                                    cv[j] = w;
+#if EVK_SLAB_EARLY_FREE
+                                    SLAB_CHECK((size_t)base + (w & kIdxMask) < rg.n);
+                                    cxy[j] = __ldg(reinterpret_cast<const uint32_t*>(
+                                        evs + (base + (w & kIdxMask))));
+#else
+                                    cxy[j] = tile[w & kIdxMask].x;
+#endif
+                                }
+                                break;
+                            }
+                            s = (s + 1) & (kHash - 1);
+                        }
+                    }
+                } else
+#endif
                 if (w0[j] != kEmpty) {
                     const uint32_t cell = cv[j] >> kLogTile;
                     uint32_t s = hash_slot(cell), w = w0[j];
@@ -519,6 +653,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                             if (w < cv[j]) {  // lower index: that event is the representative
                                 cv[j] = w;
 #if EVK_SLAB_EARLY_FREE
+                                SLAB_CHECK((size_t)base + (w & kIdxMask) < rg.n);
                                 cxy[j] = __ldg(reinterpret_cast<const uint32_t*>(
                                     evs + (base + (w & kIdxMask))));
 #else
@@ -542,24 +677,79 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
             uint32_t wbase = 0;
             // one shared atomic per warp, written as PTX: the compiler's own warp-aggregation of an
             // atomicAdd under a condition (leader election + redux) costs a dozen instructions
+#if EVK_SLAB_TRIM >= 5
+            // (elect.sync names the one lane: behind a lane test ptxas cannot prove the atomic is
+            // single-lane and wraps it in its own same-address aggregation -- VOTE / FLO / POPC /
+            // SHFL, a dozen instructions)
+            uint32_t leader;
+            asm volatile(
+                "{ .reg .pred q; elect.sync %1|q, 0xffffffff; @q atom.shared.add.u32 %0, [%2], %3; }"
+                : "+r"(wbase), "=r"(leader)
+                : "r"(smem_u32(&s_cursor[par])), "r"(wtot)
+                : "memory");
+            wbase = __shfl_sync(0xffffffffu, wbase, leader);
+#elif EVK_SLAB_TRIM >= 4
+            // (predicated inside the asm: around a branch the compiler builds a leader election --
+            // S2R / VOTEU / FLO / POPC, about twenty instructions)
+            asm volatile(
+                "{ .reg .pred q; setp.eq.u32 q, %3, 0; @q atom.shared.add.u32 %0, [%1], %2; }"
+                : "+r"(wbase)
+                : "r"(smem_u32(&s_cursor[par])), "r"(wtot), "r"((uint32_t)lane)
+                : "memory");
+#else
             if (lane == 0)
                 asm volatile("atom.shared.add.u32 %0, [%1], %2;"
                              : "=r"(wbase)
                              : "r"(smem_u32(&s_cursor[par])), "r"(wtot)
                              : "memory");
+#endif
+#if EVK_SLAB_TRIM < 5
             wbase = __shfl_sync(0xffffffffu, wbase, 0);
+#endif
             {
                 const uint32_t pos0 = s_chunk_pos, nxt0 = s_next_base;
                 const uint32_t room = s_chunk_end - pos0;  // slots left in the current chunk
+#if EVK_SLAB_TRIM >= 6
+                // (the column bases and the bin's first key: read once per tile through shared
+                // memory, else three constant-bank loads and a shared load in front of every record)
+                const uint64_t keys_g = *reinterpret_cast<volatile uint64_t*>(&s_out[0]);
+                const uint64_t first_g = *reinterpret_cast<volatile uint64_t*>(&s_out[1]);
+                const uint64_t xy_g = *reinterpret_cast<volatile uint64_t*>(&s_out[2]);
+                const uint64_t key_base_t = *reinterpret_cast<volatile uint64_t*>(&s_key_base);
+#endif
+#if EVK_SLAB_TRIM >= 1
+                const uint32_t lt = lane_lt;
+#else
                 const uint32_t lt = (1u << lane) - 1u;
+#endif
 #pragma unroll
                 for (int j = 0; j < kPer; j++) {
                     if (cv[j] != kEmpty) {
                         const uint32_t o = wbase + __popc(bal[j] & lt);
                         const uint32_t p = o < room ? pos0 + o : nxt0 + (o - room);
+                        SLAB_CHECK(p < a.out_cap && (o < room || nxt0 != kNoChunk));
+#if EVK_SLAB_TRIM >= 6
+                        asm volatile("st.global.u64 [%0], %1;" ::"l"(keys_g + (uint64_t)p * 8u),
+                                     "l"(key_base_t + (cv[j] >> kLogTile))
+                                     : "memory");
+                        asm volatile("st.global.u32 [%0], %1;" ::"l"(first_g + (uint64_t)p * 4u),
+                                     "r"(base + (cv[j] & kIdxMask) + first_offset)
+                                     : "memory");
+                        asm volatile("st.global.u32 [%0], %1;" ::"l"(xy_g + (uint64_t)p * 4u), "r"(cxy[j])
+                                     : "memory");
+#elif EVK_SLAB_TRIM >= 3
+                        a.keys[p] = *reinterpret_cast<volatile uint64_t*>(&s_key_base) + (cv[j] >> kLogTile);
+                        a.first[p] = base + (cv[j] & kIdxMask) + first_offset;
+                        a.xy[p] = cxy[j];
+#elif EVK_SLAB_TRIM >= 2
+                        keys_p[p] = key_base + (cv[j] >> kLogTile);
+                        first_p[p] = base + (cv[j] & kIdxMask) + first_offset;
+                        xy_p[p] = cxy[j];
+#else
                         a.keys[p] = key_base + (cv[j] >> kLogTile);
                         a.first[p] = base + (cv[j] & kIdxMask) + first_offset;
                         a.xy[p] = cxy[j];
+#endif
                     }
                     wbase += __popc(bal[j]);
                 }
@@ -742,6 +932,10 @@ bool evk_slab_supported(const evk_handle* h, const KeyParams& kp) {
     if (kp.keyfn != EVK_KEY_VOXEL || kp.vt <= 0 || h->n_events == 0) return false;
     if (kp.cells >= (1ull << (32 - kLogTile))) return false;  // packed (cell, index) word
     if (2 * kCtasPerSm * h->sm_count > kMaxList) return false;
+#if EVK_SLAB_TRIM >= 7
+    // (short tiles are padded with the event x = y = 0xFFFF, which must be outside the frame)
+    if (kp.width > 65535 && kp.height > 65535) return false;
+#endif
     return slab_smem_bytes(kp.cells, true) <= kSmemLimit;
 }
 
@@ -765,6 +959,7 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
     a.max_bins = (uint32_t)h->max_bins;
     // a single CTA walks a bin sequentially: with few bins and many events the table is faster
     a.min_bins = h->n_events > (1u << 22) ? 32 : 1;
+    a.out_cap = (uint32_t)(h->out_cap > 0xFFFFFFFFull ? 0xFFFFFFFFull : h->out_cap);
     a.range = range;
     a.t0_dev = t0_dev;
     const size_t smem = slab_smem_bytes(kp.cells, count_repeated != 0);
