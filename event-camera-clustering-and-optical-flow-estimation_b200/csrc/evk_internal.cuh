@@ -381,7 +381,7 @@ cudaError_t evk_launch_pix_hist(const uint32_t* xy, size_t n, int width, int hei
                                 uint32_t* pixcnt, int sm_count, cudaStream_t s,
                                 const unsigned long long* n_dev = nullptr);
 cudaError_t evk_launch_set_u64(unsigned long long* dst, unsigned long long v, cudaStream_t s);
-#define EVK_MAX_QUADS 16384
+#define EVK_MAX_QUADS 65536  // 4 x 4-px quads for a 1280 x 720 sensor (57 600)
 struct QuadGrid {  // squares of (1 << shift) pixels, tx * ty <= EVK_MAX_QUADS
     int32_t width, shift, tx, ty;
 };

@@ -794,14 +794,15 @@ __global__ void __launch_bounds__(128)
 // ACC: also accumulate the exact sums (single-iteration path); else labels only (gather at the end
 // of the image iterations).  Accumulators: one private column per lane (bank == lane: no conflicts)
 // shared by the CTA's warps through 32-bit shared atomics, flushed with 64-bit global atomics.
-constexpr int kTlMax = EVK_MAX_QUADS;
-constexpr int kUnit = kBlock * 8;  // points per work unit
-constexpr int kFlushUnits = 64;
+constexpr int kTilesBlock = 512;        // two CTAs per SM share the SM's shared memory: a table of
+                                        // 4 x 4-px quads for Gen4 (57.6 KB) + the accumulators
+constexpr int kUnit = kTilesBlock * 8;  // points per work unit
+constexpr int kFlushUnits = 32;
 
 __device__ __forceinline__ void tiles_flush(uint32_t* s_acc, int K, int copies,
                                             unsigned long long* acc) {
     __syncthreads();
-    for (int j = threadIdx.x; j < 3 * K; j += kBlock) {
+    for (int j = threadIdx.x; j < 3 * K; j += kTilesBlock) {
         unsigned long long sum = 0;
         for (int cc = 0; cc < copies; cc++) {
             const int idx = j * copies + ((cc + threadIdx.x) & (copies - 1));  // skewed: no conflicts
@@ -816,20 +817,20 @@ __device__ __forceinline__ void tiles_flush(uint32_t* s_acc, int K, int copies,
 }
 
 template <bool ACC>
-__global__ void __launch_bounds__(kBlock)
-    k_km_assign_tiles(KmLaunch kl, QuadGrid pg, const uint8_t* __restrict__ quads,
+__global__ void __launch_bounds__(kTilesBlock, 2)
+    k_km_assign_tiles(KmLaunch kl, QuadGrid pg, uint32_t tl_bytes, const uint8_t* __restrict__ quads,
                       const uint8_t* __restrict__ map, const uint32_t* __restrict__ xy, size_t n,
                       const unsigned long long* __restrict__ n_dev, int copies,
                       unsigned long long* __restrict__ acc, int32_t* __restrict__ labels) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint8_t* s_tl = smem_raw;                                         // [kTlMax]
-    uint32_t* s_acc = reinterpret_cast<uint32_t*>(smem_raw + kTlMax);  // [3][K][copies]
+    uint8_t* s_tl = smem_raw;                                            // [tl_bytes]
+    uint32_t* s_acc = reinterpret_cast<uint32_t*>(smem_raw + tl_bytes);  // [3][K][copies]
     const int K = kl.K;
     if (n_dev) n = (size_t)*n_dev;  // voxel count still on the device (fused step)
-    for (int t = threadIdx.x; t < (pg.tx * pg.ty + 3) / 4; t += kBlock)  // table is padded to 4
+    for (int t = threadIdx.x; t < (pg.tx * pg.ty + 3) / 4; t += kTilesBlock)  // table is padded to 4
         reinterpret_cast<uint32_t*>(s_tl)[t] = __ldg(reinterpret_cast<const uint32_t*>(quads) + t);
     if (ACC)
-        for (int i = threadIdx.x; i < 3 * K * copies; i += kBlock) s_acc[i] = 0;
+        for (int i = threadIdx.x; i < 3 * K * copies; i += kTilesBlock) s_acc[i] = 0;
     __syncthreads();
     const uint32_t col = threadIdx.x & (copies - 1);
     // work unit: kUnit points = two 16-B loads per thread, units dealt round-robin to the CTAs
@@ -900,8 +901,9 @@ __global__ void __launch_bounds__(kBlock)
                     atomicAdd(a + 2 * K * copies, w[q] >> 16);
                 }
             }
-            // a column receives at most 8 * (kBlock / 32) * 8 = 512 points per unit:
-            // 512 * kFlushUnits * 65535 < 2^32
+            // per unit a column receives 8 points from each of the kTilesBlock / 32 = 16 warps,
+            // times 32 / copies lanes per column (copies >= 8 for K <= 254): at most 512 points,
+            // and 512 * kFlushUnits * 65535 < 2^32
             if (++since_flush == kFlushUnits) {
                 since_flush = 0;
                 tiles_flush(s_acc, K, copies, acc);
@@ -1146,26 +1148,32 @@ cudaError_t evk_launch_km_assign_tiles(const KmLaunch& kl, int width, int height
     const QuadGrid pg = evk_make_quad_grid(width, height);
     int copies = 32;
     while (copies > 1 && (size_t)3 * kl.K * copies * 4 > 48 * 1024) copies >>= 1;
-    const size_t smem = kTlMax + (accumulate ? (size_t)3 * kl.K * copies * 4 : 0);
-    if (accumulate)
+    const uint32_t tl_bytes = (uint32_t)((pg.tx * pg.ty + 15) & ~15);
+    const size_t smem = tl_bytes + (accumulate ? (size_t)3 * kl.K * copies * 4 : 0);
+    static bool attr_set = false;
+    if (!attr_set) {
         cudaFuncSetAttribute(k_km_assign_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             64 * 1024);
+                             EVK_MAX_QUADS + 48 * 1024);
+        cudaFuncSetAttribute(k_km_assign_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             EVK_MAX_QUADS);
+        attr_set = true;
+    }
     // one wave: as many CTAs as are resident at once, units dealt round-robin
     int per_sm = 1;
     if (accumulate)
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_km_assign_tiles<true>, kBlock, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_km_assign_tiles<true>, kTilesBlock, smem);
     else
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_km_assign_tiles<false>, kBlock, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_km_assign_tiles<false>, kTilesBlock, smem);
     if (per_sm < 1) per_sm = 1;
     const size_t units = (n + kUnit - 1) / kUnit;
     const size_t cap = (size_t)sm_count * per_sm;
     const int grid = (int)(units < cap ? units : cap);
     if (accumulate) {
-        k_km_assign_tiles<true><<<grid, kBlock, smem, s>>>(kl, pg, quads, map, xy, n, n_dev, copies,
-                                                           acc, labels);
+        k_km_assign_tiles<true><<<grid, kTilesBlock, smem, s>>>(kl, pg, tl_bytes, quads, map, xy, n,
+                                                                n_dev, copies, acc, labels);
     } else {
-        k_km_assign_tiles<false><<<grid, kBlock, smem, s>>>(kl, pg, quads, map, xy, n, n_dev,
-                                                            copies, acc, labels);
+        k_km_assign_tiles<false><<<grid, kTilesBlock, smem, s>>>(kl, pg, tl_bytes, quads, map, xy, n,
+                                                                 n_dev, copies, acc, labels);
     }
     return cudaGetLastError();
 }

@@ -38,9 +38,6 @@
 
 namespace {
 
-#ifndef EVK_SLAB_VIOLX
-#define EVK_SLAB_VIOLX 1  // how the out-of-bin check is written (A/B'd: see DESIGN.md section 7)
-#endif
 #ifndef EVK_SLAB_THREADS
 #define EVK_SLAB_THREADS 1024
 #endif
@@ -54,21 +51,25 @@ namespace {
 #define EVK_SLAB_CHECKS 0  // 1: every index of the hot kernel is bounds-checked on the device (a failed
 #endif                     //    check sets DsCounters::overflow bit 1); compute-sanitizer is closed
                            //    on this pool, so the parity / stress tests are run against this build
-#ifndef EVK_SLAB_TRIM
-#define EVK_SLAB_TRIM 8  // instruction trims, adopted one by one (A/B: profiles/r02/slab_ab_runs.md)
+// A/B switches of round 2 (profiles/r02/slab_ab_runs.md); the defaults are what was adopted
+#ifndef EVK_SLAB_UNCOND_CLAIM
+#define EVK_SLAB_UNCOND_CLAIM 0  // 1: the claim pass's atomic is issued by every lane (see there)
 #endif
-#ifndef EVK_SLAB_LEAN
-#define EVK_SLAB_LEAN 1  // 1: fewer integer-ALU operations in the classify pass
+#ifndef EVK_SLAB_UNCOND_RED
+#define EVK_SLAB_UNCOND_RED 1  // 1: the classify pass's hit-twice reduction is issued by every lane
 #endif
-#if EVK_SLAB_TRIM >= 7 && !EVK_SLAB_LEAN
-#error "EVK_SLAB_TRIM >= 7 pads short tiles and needs the EVK_SLAB_LEAN frame test"
+#ifndef EVK_SLAB_SHORT_ROWS
+#define EVK_SLAB_SHORT_ROWS 1  // 1: a bin's last (short) tile skips its empty rows in the classify pass
 #endif
-#ifndef EVK_SLAB_KEEP_BITS
-#define EVK_SLAB_KEEP_BITS 1  // 1: the claim pass reuses the classify pass's word index and bit
+#ifndef EVK_SLAB_PRED_OUT
+#define EVK_SLAB_PRED_OUT 1  // 1: the output pass's stores are predicated instead of branched around
 #endif
-#ifndef EVK_SLAB_EARLY_FREE
-#define EVK_SLAB_EARLY_FREE 1  // 1: a ring slot is refilled right after the classify pass drained it
-#endif                         //    (a late peer's coordinates are then re-read from global memory)
+#ifndef EVK_SLAB_LATE_REG
+#define EVK_SLAB_LATE_REG 1  // 1: a late peer sets its hit-twice bit through the classify pass's registers
+#endif
+#ifndef EVK_SLAB_PVIOL
+#define EVK_SLAB_PVIOL 1  // 1: the out-of-bin check accumulates in a predicate, folded once per tile
+#endif
 constexpr int kThreads = EVK_SLAB_THREADS;  // CTA size (the hardware maximum by default)
 constexpr int kCtasPerSm = kThreads <= 512 ? 2 : 1;
 constexpr int kPer = EVK_SLAB_PER;          // events per thread per tile
@@ -279,7 +280,7 @@ __device__ __forceinline__ void it_enter(TileIt& it, const uint32_t* bin_start, 
     }
 }
 
-template <bool COUNT_REP, bool POW2>
+template <bool COUNT_REP, bool POW2, bool USE_P>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) {
     constexpr int NT = kThreads;
     constexpr int TILE = NT * kPer;  // events per tile
@@ -294,15 +295,13 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
     __shared__ uint32_t s_cursor[2];  // voxels emitted by the current tile (by tile parity)
     __shared__ uint32_t s_chunk_pos, s_chunk_end, s_next_base;
     __shared__ uint32_t s_stop;  // some CTA has found the stream unordered: stop early
-#if EVK_SLAB_TRIM >= 3
-    __shared__ uint64_t s_key_base;  // first key of the current bin (see the output pass)
-#endif
-#if EVK_SLAB_TRIM >= 4
+    // Per-bin and per-launch constants the passes read back ONCE PER TILE through shared memory.
+    // Held in registers across the tile loop they do not survive: ptxas rematerialises the 64-bit
+    // products (six instructions in front of every key store, ncu source page of round 2) and
+    // re-reads the column bases from the constant bank in front of every record.
+    __shared__ uint64_t s_key_base;  // first key of the current bin
     __shared__ int64_t s_t_lo;       // first microsecond of the current bin
-#endif
-#if EVK_SLAB_TRIM >= 6
     __shared__ uint64_t s_out[3];    // global addresses of the key / first-index / xy columns
-#endif
 
     DsCounters* cnt = a.cnt;
     if (cnt->slab_violation) return;
@@ -310,21 +309,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
     const int64_t t0 = a.t0_dev ? *a.t0_dev : a.kp.t0;  // (replayed graphs: device-side origin)
     const uint32_t nb = (uint32_t)cnt->scratch[0];
     const uint64_t tb0 = cnt->scratch[2];
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x;
     const SlabRange rg = slab_range(a);
     const evk_event* const evs = rg.ev;
     const uint32_t first_offset = rg.first_offset;
-#if EVK_SLAB_TRIM >= 1
     uint32_t lane_lt;  // lanes below mine (the output pass ranks a lane among the emitting lanes)
     asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(lane_lt));
-#endif
-#if EVK_SLAB_TRIM == 2
-    // output array bases in registers (else three constant-bank loads in front of every record)
-    uint64_t* keys_p = a.keys;
-    uint32_t* first_p = a.first;
-    uint32_t* xy_p = a.xy;
-    asm volatile("" : "+l"(keys_p), "+l"(first_p), "+l"(xy_p));
-#endif
 
     for (int i = tid; i < 2 * kHash; i += NT) s_late[i] = kEmpty;
     for (uint32_t i = tid; i < a.words; i += NT) s_map[i] = 0;
@@ -332,11 +322,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
         for (int s = 0; s < kStages; s++) mbar_init(&s_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         s_cursor[0] = s_cursor[1] = 0;
-#if EVK_SLAB_TRIM >= 6
         s_out[0] = (uint64_t)__cvta_generic_to_global(a.keys);
         s_out[1] = (uint64_t)__cvta_generic_to_global(a.first);
         s_out[2] = (uint64_t)__cvta_generic_to_global(a.xy);
-#endif
         // two chunks up front: the current one and the one after it
         const uint32_t c0 = (uint32_t)atomicAdd(&cnt->scratch[3], 2ull);
         s_chunk_pos = c0 * kChunk;
@@ -392,34 +380,22 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
     if (tid == kTmaThread) {
         it_enter(tma, a.bin_start, nb);
 #pragma unroll
-        for (int s = 0; s < (EVK_SLAB_EARLY_FREE ? kStages : kStages - 1); s++) fetch();
+        for (int s = 0; s < kStages; s++) fetch();
     }
 
-#if EVK_SLAB_LEAN
+    // y < height  <=>  (y << 16 | x) <= ((height - 1) << 16 | 0xFFFF): no need to extract y
     const uint32_t y_lim = ((uint32_t)(kp.height - 1) << 16) | 0xFFFFu;
     const uint32_t ysh = 16u + (uint32_t)(kp.sy >= 0 ? kp.sy : 0);
-#endif
     for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
         const uint32_t lo = a.bin_start[b], hi = a.bin_start[b + 1];
         if (hi < lo) viol = 1;  // ranges do not partition the stream: not time-ordered
         if (hi <= lo) continue;
-        const uint64_t tb = tb0 + b;
-        const int64_t t_lo = t0 + (int64_t)(tb * (uint64_t)kp.vt);
-        uint64_t key_base = tb * kp.cells;
-#if EVK_SLAB_TRIM >= 1
-        // (kept in registers for the whole bin: the compiler otherwise rematerialises the 64-bit
-        // product, six instructions, in front of every key store: ncu source page, round 2)
-        asm volatile("" : "+l"(key_base));
-#endif
-        if (tid == 0) s_stop = *reinterpret_cast<volatile unsigned int*>(&cnt->slab_violation);
-#if EVK_SLAB_TRIM >= 3
-        // (one 8-byte shared load per record instead of the 64-bit product, which ptxas
-        // rematerialises -- six instructions -- in front of every key store)
-        if (tid == 0) s_key_base = key_base;
-#endif
-#if EVK_SLAB_TRIM >= 4
-        if (tid == 0) s_t_lo = t_lo;
-#endif
+        if (tid == 0) {
+            const uint64_t tb = tb0 + b;
+            s_stop = *reinterpret_cast<volatile unsigned int*>(&cnt->slab_violation);
+            s_key_base = tb * kp.cells;
+            s_t_lo = t0 + (int64_t)(tb * (uint64_t)kp.vt);
+        }
         prod_sync<NT>();  // every thread has left the previous bin (bitmap, cursor)
         if (s_stop) break;  // (an early stop inside the tile loop also ends here)
         if (tid == 0) book();
@@ -431,111 +407,105 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
             }
             if (COUNT_REP) {
                 r = __reduce_add_sync(0xffffffffu, r);
-                if (lane == 0 && r) atomicAdd(&cnt->n_repeated, (unsigned long long)r);
+                if ((tid & 31) == 0 && r) atomicAdd(&cnt->n_repeated, (unsigned long long)r);
             }
         }
         prod_sync<NT>();
 
         for (uint32_t base = lo; base < hi; base += TILE, tile_seq++) {
             const uint32_t stage = tile_seq % kStages, par = tile_seq & 1;
-            const uint4* tile = s_ev + stage * kTile;
+            uint4* tile = s_ev + stage * kTile;
             uint32_t* late_tbl = s_late + par * kHash;
             mbar_wait(&s_bar[stage], (tile_seq / kStages) & 1);
-#if EVK_SLAB_TRIM >= 4
-            // (one shared load per tile instead of rematerialising t0 + tb * vt, a 64-bit product)
             const int64_t t_lo = *reinterpret_cast<volatile int64_t*>(&s_t_lo);
+            // ---- classify: cv = candidate word (cell << kLogTile | index in tile) or kEmpty;
+            // cw / cb = bitmap word index and bit of the event's cell (reused by the claim pass)
+            uint32_t cv[kPer], cxy[kPer], cw[kPer], cb[kPer];
+#if EVK_SLAB_PVIOL
+            bool tile_viol = false;
 #endif
-#if EVK_SLAB_TRIM >= 7
-            // the last tile of a bin is short: its unused slots still hold an older tile.  Overwrite
-            // them with an event outside the frame (x = y = 0xFFFF), so that the per-event test
-            // "index < end of bin" -- two instructions per event of every tile -- is not needed
-            if (hi - base < (uint32_t)TILE) {  // (uniform over the CTA)
-                const uint32_t live = hi - base;
-#pragma unroll
-                for (int j = 0; j < kPer; j++)
-                    if ((uint32_t)(j * NT + tid) >= live)
-                        const_cast<uint4*>(tile)[j * NT + tid] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
-                // (the slot is next written by a bulk copy: order the two proxies)
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            }
-#endif
-            // ---- classify: cv = candidate word (cell << kLogTile | index in tile) or kEmpty
-            uint32_t cv[kPer], cxy[kPer];
-#if EVK_SLAB_KEEP_BITS
-            uint32_t cw[kPer], cb[kPer];  // bitmap word index and bit of each candidate (claim pass)
-#endif
-#pragma unroll
-            for (int j = 0; j < kPer; j++) {
+            auto classify_row = [&](int j) {
                 const uint32_t li = j * NT + tid;
                 const uint4 ev = tile[li];
                 const uint32_t x = ev.x & 0xFFFFu, y = ev.x >> 16;
-#if EVK_SLAB_LEAN
-                // y < height  <=>  (y << 16 | x) <= ((height - 1) << 16 | 0xFFFF): no need to extract y
-#if EVK_SLAB_TRIM >= 7
                 const bool gate = (x < (uint32_t)kp.width) & (ev.x <= y_lim);
-#else
-                const bool gate = (base + li < hi) & (x < (uint32_t)kp.width) & (ev.x <= y_lim);
-#endif
                 const bool inbin = (uint64_t)(ev_t(ev) - t_lo) < (uint64_t)kp.vt;
                 const bool ok = gate & inbin;
-                viol |= (uint32_t)(gate != ok);  // a gated-in event that is not of this bin
-#elif EVK_SLAB_VIOLX == 1
-                const bool gate = (base + li < hi) & (x < (uint32_t)kp.width) & (y < (uint32_t)kp.height);
-                const bool inbin = (uint64_t)(ev_t(ev) - t_lo) < (uint64_t)kp.vt;
-                const bool ok = gate & inbin;
-                viol |= (uint32_t)(gate != ok);  // a gated-in event that is not of this bin
-#elif EVK_SLAB_VIOLX == 2
-                bool ok = (base + li < hi) & (x < (uint32_t)kp.width) & (y < (uint32_t)kp.height);
-                const bool inbin = (uint64_t)(ev_t(ev) - t_lo) < (uint64_t)kp.vt;
-                viol |= (uint32_t)(ok & !inbin);
-                ok &= inbin;
+                // a gated-in event that is not of this bin: the stream is not what the bins say
+#if EVK_SLAB_PVIOL
+                tile_viol |= gate != ok;
 #else
-                bool ok = (base + li < hi) & (x < (uint32_t)kp.width) & (y < (uint32_t)kp.height);
-                const bool inbin = (uint64_t)(ev_t(ev) - t_lo) < (uint64_t)kp.vt;
-                if (ok & !inbin) viol = 1;  // not an event of this bin
-                ok &= inbin;
+                viol |= (uint32_t)(gate != ok);
 #endif
                 uint32_t cell;
-#if EVK_SLAB_LEAN
                 if (POW2) cell = (ev.x >> ysh) * kp.NX + (x >> kp.sx);
                 else cell = (kp.sy >= 0 ? y >> kp.sy : __umulhi(y, kp.my)) * kp.NX +
                             (kp.sx >= 0 ? x >> kp.sx : __umulhi(x, kp.mx));
                 // polarity bit = (int16)p > 0: the sign test on the halfword moved to bit 31
-                if (kp.use_p) cell = cell * 2u + ((int32_t)(ev.y << 16) > 0 ? 1u : 0u);
-#else
-                if (POW2) cell = (y >> kp.sy) * kp.NX + (x >> kp.sx);
-                else cell = (kp.sy >= 0 ? y >> kp.sy : __umulhi(y, kp.my)) * kp.NX +
-                            (kp.sx >= 0 ? x >> kp.sx : __umulhi(x, kp.mx));
-                if (kp.use_p) cell = cell * 2u + ev_pbit(ev);
-#endif
-                const uint32_t w = COUNT_REP ? cell >> 4 : cell >> 5;
+                if (USE_P) cell = cell * 2u + ((int32_t)(ev.y << 16) > 0 ? 1u : 0u);
+                uint32_t w = COUNT_REP ? cell >> 4 : cell >> 5;
                 const uint32_t sbit = 1u << (cell & (COUNT_REP ? 15u : 31u));
                 SLAB_CHECK(!ok || (w < a.words && li < (uint32_t)kTile));
+                if (EVK_SLAB_UNCOND_CLAIM || EVK_SLAB_UNCOND_RED) w = ok ? w : 0u;  // (any lane may touch it)
                 const uint32_t wv = ok ? s_map[w] : 0xFFFFFFFFu;  // gated events: nothing to do
                 if (COUNT_REP) {  // duplicate of an earlier tile's voxel: mark it "hit twice"
+#if EVK_SLAB_UNCOND_RED
+                    // every lane issues the reduction, most with a zero (gated events read all
+                    // ones, so theirs is zero too): ptxas turns a predicated shared atomic into a
+                    // branch around it (BSSY / BRA / BSYNC) although some lane of the warp nearly
+                    // always takes it
+                    atomicOr(&s_map[w], ((wv & sbit) << 16) & ~wv);
+#else
                     // (a predicated reduction: the branch the compiler builds around an atomicOr
                     // here costs 2 % of the kernel)
-#if EVK_SLAB_LEAN
                     const uint32_t hbit = sbit * 0x10000u;
-#else
-                    const uint32_t hbit = sbit << 16;
-#endif
                     const uint32_t need = (wv & sbit) && !(wv & hbit) && ok;
                     sred_or_if(&s_map[w], hbit, need);
+#endif
                 }
                 cv[j] = (wv & sbit) ? kEmpty : ((cell << kLogTile) | li);
                 cxy[j] = ev.x;
-#if EVK_SLAB_KEEP_BITS
                 cw[j] = w;
                 cb[j] = sbit;
-#endif
+            };
+            if (hi - base < (uint32_t)TILE) {  // (uniform over the CTA)
+                // the last tile of a bin is short: its unused slots still hold an older tile.
+                // Overwrite them with an event outside the frame (x = y = 0xFFFF), so that the
+                // per-event test "index < end of bin" -- two instructions per event of every tile
+                // -- is not needed
+                const uint32_t live = hi - base;
+#pragma unroll
+                for (int j = 0; j < kPer; j++)
+                    if ((uint32_t)(j * NT + tid) >= live)
+                        tile[j * NT + tid] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+                // (the slot is next written by a bulk copy: order the two proxies)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#if EVK_SLAB_SHORT_ROWS
+                // (its own copy of the classify pass: the rows beyond the end of the bin -- on
+                // average a tile's worth of rows per bin -- are skipped)
+#pragma unroll
+                for (int j = 0; j < kPer; j++) {
+                    if ((uint32_t)(j * NT) < live) {
+                        classify_row(j);
+                    } else {
+                        cv[j] = kEmpty;
+                        cxy[j] = cw[j] = cb[j] = 0;
+                    }
+                }
+            } else {
+#else
             }
+            {
+#endif
+#pragma unroll
+                for (int j = 0; j < kPer; j++) classify_row(j);
+            }
+#if EVK_SLAB_PVIOL
+            if (tile_viol) viol |= 1u;
+#endif
             // a rejected stream is rerun on a general path: publish the violation at once and let
             // every CTA stop at its next tile (uniformly: thread 0 reads, the barrier broadcasts)
-#ifndef EVK_SLAB_POLL_MASK
-#define EVK_SLAB_POLL_MASK 15u
-#endif
-            const bool poll = (tile_seq & EVK_SLAB_POLL_MASK) == 0;  // (every 16th tile: polling every 4th cost 2 %)
+            const bool poll = (tile_seq & 15u) == 0;  // (every 16th tile: polling every 4th cost 2 %)
             if (poll) {
                 if (viol == 1) {
                     atomicOr(&cnt->slab_violation, 1u);
@@ -546,45 +516,39 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
             }
             prod_sync<NT>();  // B0: every bitmap read of this tile precedes every claim below
             if (poll && s_stop) break;
-            // EARLY_FREE: this tile's ring slot has been drained into registers; else the ring slot
-            // of the previous tile is no longer in use.  Either way: the next tile of the stream
+            // this tile's ring slot has been drained into registers: refill it with the tile after
+            // the next one
             if (tid == kTmaThread) fetch();
             if (tid == 0) book();
             // ---- claim: one returning atomic per unseen event
             bool late[kPer];
 #pragma unroll
             for (int j = 0; j < kPer; j++) {
-                late[j] = false;
-#if EVK_SLAB_TRIM >= 4 && EVK_SLAB_KEEP_BITS
-                {   // predicated returning atomic, no branch (old = 0 for lanes without a candidate)
-                    uint32_t old = 0;
-                    asm volatile(
-                        "{ .reg .pred q; setp.ne.u32 q, %3, 0xFFFFFFFF; "
-                        "@q atom.shared.or.b32 %0, [%1], %2; }"
-                        : "+r"(old)
-                        : "r"(smem_u32(&s_map[cw[j]])), "r"(cb[j]), "r"(cv[j])
-                        : "memory");
-                    late[j] = (old & cb[j]) != 0;
-                    continue;
-                }
-#endif
-                if (cv[j] == kEmpty) continue;
-#if EVK_SLAB_KEEP_BITS
-                uint32_t* wp = &s_map[cw[j]];
-                const uint32_t sbit = cb[j];
+#if EVK_SLAB_UNCOND_CLAIM
+                // (every lane issues the atomic, lanes without a candidate OR in a zero)
+                const uint32_t bitv = cv[j] != kEmpty ? cb[j] : 0u;
+                const uint32_t old = atomicOr(&s_map[cw[j]], bitv);
+                late[j] = (old & bitv) != 0;
 #else
-                const uint32_t cell = cv[j] >> kLogTile;
-                uint32_t* wp = COUNT_REP ? &s_map[cell >> 4] : &s_map[cell >> 5];
-                const uint32_t sbit = 1u << (cell & (COUNT_REP ? 15u : 31u));
+                uint32_t old = 0;  // (stays 0 for lanes without a candidate)
+                asm volatile(
+                    "{ .reg .pred q; setp.ne.u32 q, %3, 0xFFFFFFFF; "
+                    "@q atom.shared.or.b32 %0, [%1], %2; }"
+                    : "+r"(old)
+                    : "r"(smem_u32(&s_map[cw[j]])), "r"(cb[j]), "r"(cv[j])
+                    : "memory");
+                late[j] = (old & cb[j]) != 0;
 #endif
-                const uint32_t old = atomicOr(wp, sbit);
-                late[j] = (old & sbit) != 0;
             }
 #pragma unroll
             for (int j = 0; j < kPer; j++) {  // a peer of this tile claimed the cell first (rare)
                 if (!late[j]) continue;
                 const uint32_t cell = cv[j] >> kLogTile;
-                if (COUNT_REP) atomicOr(&s_map[cell >> 4], 1u << (16 + (cell & 15)));
+#if EVK_SLAB_LATE_REG
+                if (COUNT_REP) atomicOr(&s_map[cw[j]], cb[j] << 16);  // the cell is hit twice
+#else
+                if (COUNT_REP) atomicOr(&s_map[cell >> 4], 1u << (16 + (cell & 15)));  // hit twice
+#endif
                 uint32_t s = hash_slot(cell);
 #if EVK_SLAB_CHECKS
                 uint32_t probes = 0;
@@ -602,69 +566,36 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 cv[j] = kEmpty;
             }
             prod_sync<NT>();  // S1: every claim of the tile is in the bitmap, s_late is complete
-            // ---- resolve: the claimant is the new voxel unless a late peer has a lower index
+            // ---- resolve: the claimant is the new voxel unless a late peer has a lower index.
+            // COUNT_REP: a late peer has set the cell's "hit twice" bit (so may a warp already
+            // classifying the next tile: then the probe finds nothing) -- one load of a word whose
+            // address and bit are in registers answers "is there a late peer" without hashing the
+            // cell; else the first probe of the table (nearly always an empty slot) does
             uint32_t bal[kPer], wtot = 0, w0[kPer];
-#define EVK_SLAB_HBIT_PROBE (EVK_SLAB_TRIM >= 8 && EVK_SLAB_KEEP_BITS)
 #pragma unroll
             for (int j = 0; j < kPer; j++) {
-                // COUNT_REP: a late peer has set the cell's "hit twice" bit (so may a warp already
-                // classifying the next tile: then the probe finds nothing) -- one load of a word
-                // whose address and bit are in registers instead of hashing the cell for a probe
-#if EVK_SLAB_HBIT_PROBE
-                if (COUNT_REP) w0[j] = cv[j] != kEmpty ? s_map[cw[j]] : 0u;
-                else
-#endif
-                    // first probe: nearly always an empty slot
-                    w0[j] = cv[j] != kEmpty ? late_tbl[hash_slot(cv[j] >> kLogTile)] : kEmpty;
+                if (COUNT_REP) w0[j] = cv[j] != kEmpty ? s_map[cw[j]] & (cb[j] << 16) : 0u;
+                else w0[j] = cv[j] != kEmpty ? ~late_tbl[hash_slot(cv[j] >> kLogTile)] : 0u;
             }
 #pragma unroll
             for (int j = 0; j < kPer; j++) {
-#if EVK_SLAB_HBIT_PROBE
-                if (COUNT_REP) {
-                    if (w0[j] & (cb[j] << 16)) {
-                        const uint32_t cell = cv[j] >> kLogTile;
-                        uint32_t s = hash_slot(cell);
-                        for (;;) {
-                            const uint32_t w = late_tbl[s];
-                            if (w == kEmpty) break;
-                            if ((w >> kLogTile) == cell) {
-                                if (w < cv[j]) {  // lower index: that event is the representative
-                                    cv[j] = w;
-#if EVK_SLAB_EARLY_FREE
-                                    SLAB_CHECK((size_t)base + (w & kIdxMask) < rg.n);
-                                    cxy[j] = __ldg(reinterpret_cast<const uint32_t*>(
-                                        evs + (base + (w & kIdxMask))));
-#else
-                                    cxy[j] = tile[w & kIdxMask].x;
-#endif
-                                }
-                                break;
-                            }
-                            s = (s + 1) & (kHash - 1);
-                        }
-                    }
-                } else
-#endif
-                if (w0[j] != kEmpty) {
+                if (w0[j]) {
                     const uint32_t cell = cv[j] >> kLogTile;
-                    uint32_t s = hash_slot(cell), w = w0[j];
+                    uint32_t s = hash_slot(cell);
                     for (;;) {
+                        const uint32_t w = late_tbl[s];
+                        if (w == kEmpty) break;
                         if ((w >> kLogTile) == cell) {
                             if (w < cv[j]) {  // lower index: that event is the representative
                                 cv[j] = w;
-#if EVK_SLAB_EARLY_FREE
+                                // (its ring slot may already hold a later tile: rare, L2-resident)
                                 SLAB_CHECK((size_t)base + (w & kIdxMask) < rg.n);
                                 cxy[j] = __ldg(reinterpret_cast<const uint32_t*>(
                                     evs + (base + (w & kIdxMask))));
-#else
-                                cxy[j] = tile[w & kIdxMask].x;
-#endif
                             }
                             break;
                         }
                         s = (s + 1) & (kHash - 1);
-                        w = late_tbl[s];
-                        if (w == kEmpty) break;
                     }
                 }
                 bal[j] = __ballot_sync(0xffffffffu, cv[j] != kEmpty);
@@ -674,83 +605,57 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
             if (tid < kHash / 4)
                 reinterpret_cast<uint4*>(s_late + (par ^ 1) * kHash)[tid] =
                     make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
-            uint32_t wbase = 0;
-            // one shared atomic per warp, written as PTX: the compiler's own warp-aggregation of an
-            // atomicAdd under a condition (leader election + redux) costs a dozen instructions
-#if EVK_SLAB_TRIM >= 5
-            // (elect.sync names the one lane: behind a lane test ptxas cannot prove the atomic is
-            // single-lane and wraps it in its own same-address aggregation -- VOTE / FLO / POPC /
-            // SHFL, a dozen instructions)
-            uint32_t leader;
+            // one shared atomic per warp claims the warp's output slots.  elect.sync names the one
+            // lane: behind a lane test ptxas cannot prove the atomic is single-lane and wraps it in
+            // its own same-address aggregation (VOTE / FLO / POPC / SHFL, a dozen instructions)
+            uint32_t wbase = 0, leader;
             asm volatile(
                 "{ .reg .pred q; elect.sync %1|q, 0xffffffff; @q atom.shared.add.u32 %0, [%2], %3; }"
                 : "+r"(wbase), "=r"(leader)
                 : "r"(smem_u32(&s_cursor[par])), "r"(wtot)
                 : "memory");
             wbase = __shfl_sync(0xffffffffu, wbase, leader);
-#elif EVK_SLAB_TRIM >= 4
-            // (predicated inside the asm: around a branch the compiler builds a leader election --
-            // S2R / VOTEU / FLO / POPC, about twenty instructions)
-            asm volatile(
-                "{ .reg .pred q; setp.eq.u32 q, %3, 0; @q atom.shared.add.u32 %0, [%1], %2; }"
-                : "+r"(wbase)
-                : "r"(smem_u32(&s_cursor[par])), "r"(wtot), "r"((uint32_t)lane)
-                : "memory");
-#else
-            if (lane == 0)
-                asm volatile("atom.shared.add.u32 %0, [%1], %2;"
-                             : "=r"(wbase)
-                             : "r"(smem_u32(&s_cursor[par])), "r"(wtot)
-                             : "memory");
-#endif
-#if EVK_SLAB_TRIM < 5
-            wbase = __shfl_sync(0xffffffffu, wbase, 0);
-#endif
             {
                 const uint32_t pos0 = s_chunk_pos, nxt0 = s_next_base;
                 const uint32_t room = s_chunk_end - pos0;  // slots left in the current chunk
-#if EVK_SLAB_TRIM >= 6
-                // (the column bases and the bin's first key: read once per tile through shared
-                // memory, else three constant-bank loads and a shared load in front of every record)
                 const uint64_t keys_g = *reinterpret_cast<volatile uint64_t*>(&s_out[0]);
                 const uint64_t first_g = *reinterpret_cast<volatile uint64_t*>(&s_out[1]);
                 const uint64_t xy_g = *reinterpret_cast<volatile uint64_t*>(&s_out[2]);
-                const uint64_t key_base_t = *reinterpret_cast<volatile uint64_t*>(&s_key_base);
-#endif
-#if EVK_SLAB_TRIM >= 1
-                const uint32_t lt = lane_lt;
-#else
-                const uint32_t lt = (1u << lane) - 1u;
-#endif
+                const uint64_t key_base = *reinterpret_cast<volatile uint64_t*>(&s_key_base);
 #pragma unroll
                 for (int j = 0; j < kPer; j++) {
+#if EVK_SLAB_PRED_OUT
+                    {   // every lane computes a slot, the three stores are predicated: some lane of
+                        // the warp nearly always emits, so a branch around the record only adds
+                        // BSSY / BRA / BSYNC
+                        const uint32_t o = wbase + __popc(bal[j] & lane_lt);
+                        const uint32_t p = o < room ? pos0 + o : nxt0 + (o - room);
+                        SLAB_CHECK(cv[j] == kEmpty || (p < a.out_cap && (o < room || nxt0 != kNoChunk)));
+                        asm volatile(
+                            "{ .reg .pred q; setp.ne.u32 q, %6, 0xFFFFFFFF;\n\t"
+                            "@q st.global.u64 [%0], %1;\n\t"
+                            "@q st.global.u32 [%2], %3;\n\t"
+                            "@q st.global.u32 [%4], %5; }" ::"l"(keys_g + (uint64_t)p * 8u),
+                            "l"(key_base + (cv[j] >> kLogTile)), "l"(first_g + (uint64_t)p * 4u),
+                            "r"(base + (cv[j] & kIdxMask) + first_offset),
+                            "l"(xy_g + (uint64_t)p * 4u), "r"(cxy[j]), "r"(cv[j])
+                            : "memory");
+                    }
+#else
                     if (cv[j] != kEmpty) {
-                        const uint32_t o = wbase + __popc(bal[j] & lt);
+                        const uint32_t o = wbase + __popc(bal[j] & lane_lt);
                         const uint32_t p = o < room ? pos0 + o : nxt0 + (o - room);
                         SLAB_CHECK(p < a.out_cap && (o < room || nxt0 != kNoChunk));
-#if EVK_SLAB_TRIM >= 6
                         asm volatile("st.global.u64 [%0], %1;" ::"l"(keys_g + (uint64_t)p * 8u),
-                                     "l"(key_base_t + (cv[j] >> kLogTile))
+                                     "l"(key_base + (cv[j] >> kLogTile))
                                      : "memory");
                         asm volatile("st.global.u32 [%0], %1;" ::"l"(first_g + (uint64_t)p * 4u),
                                      "r"(base + (cv[j] & kIdxMask) + first_offset)
                                      : "memory");
                         asm volatile("st.global.u32 [%0], %1;" ::"l"(xy_g + (uint64_t)p * 4u), "r"(cxy[j])
                                      : "memory");
-#elif EVK_SLAB_TRIM >= 3
-                        a.keys[p] = *reinterpret_cast<volatile uint64_t*>(&s_key_base) + (cv[j] >> kLogTile);
-                        a.first[p] = base + (cv[j] & kIdxMask) + first_offset;
-                        a.xy[p] = cxy[j];
-#elif EVK_SLAB_TRIM >= 2
-                        keys_p[p] = key_base + (cv[j] >> kLogTile);
-                        first_p[p] = base + (cv[j] & kIdxMask) + first_offset;
-                        xy_p[p] = cxy[j];
-#else
-                        a.keys[p] = key_base + (cv[j] >> kLogTile);
-                        a.first[p] = base + (cv[j] & kIdxMask) + first_offset;
-                        a.xy[p] = cxy[j];
-#endif
                     }
+#endif
                     wbase += __popc(bal[j]);
                 }
             }
@@ -766,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
         uint32_t r = 0;
         for (uint32_t i = tid; i < a.words; i += NT) r += __popc(s_map[i] >> 16);
         r = __reduce_add_sync(0xffffffffu, r);
-        if (lane == 0 && r) atomicAdd(&cnt->n_repeated, (unsigned long long)r);
+        if ((tid & 31) == 0 && r) atomicAdd(&cnt->n_repeated, (unsigned long long)r);
     }
     if (viol) atomicOr(&cnt->slab_violation, 1u);
     if (tid == 0) {  // publish the two chunks this CTA leaves partly filled
@@ -862,13 +767,19 @@ __global__ void __launch_bounds__(kFixThreads)
     uint32_t dtot;
     const uint32_t dpre = block_exclusive_scan(dlen, s_warp, &dtot);
     if (i < n_list) s_dst_prefix[i] = dpre;
-    // source segments: live slots at positions >= U, chunk by chunk
+    // source segments: live slots at positions >= U, chunk by chunk (a chunk that is not listed is
+    // full; the listed ones scatter their fill into the table)
+    if (i < n_src) s_src_prefix[i] = kChunk;
+    __syncthreads();
+    if (i < n_list && s_base[i] % kChunk == 0) {
+        const uint32_t m = s_base[i] / kChunk;
+        if (m >= m0 && m - m0 < n_src) s_src_prefix[m - m0] = s_fill[i];
+    }
+    __syncthreads();
     uint32_t slen = 0;
     if (i < n_src) {
         const uint32_t m = m0 + i;
-        uint32_t fill = kChunk;
-        for (uint32_t q = 0; q < n_list; q++)
-            if (s_base[q] == m * kChunk) fill = s_fill[q];
+        const uint32_t fill = s_src_prefix[i];
         const uint64_t l0 = (uint64_t)m * kChunk, l1 = l0 + fill;
         const uint64_t s = l0 > U ? l0 : U;
         s_src_start[i] = (uint32_t)s;
@@ -932,10 +843,8 @@ bool evk_slab_supported(const evk_handle* h, const KeyParams& kp) {
     if (kp.keyfn != EVK_KEY_VOXEL || kp.vt <= 0 || h->n_events == 0) return false;
     if (kp.cells >= (1ull << (32 - kLogTile))) return false;  // packed (cell, index) word
     if (2 * kCtasPerSm * h->sm_count > kMaxList) return false;
-#if EVK_SLAB_TRIM >= 7
     // (short tiles are padded with the event x = y = 0xFFFF, which must be outside the frame)
     if (kp.width > 65535 && kp.height > 65535) return false;
-#endif
     return slab_smem_bytes(kp.cells, true) <= kSmemLimit;
 }
 
@@ -964,9 +873,12 @@ int evk_downsample_slab(evk_handle* h, const KeyParams& kp, int count_repeated, 
     a.t0_dev = t0_dev;
     const size_t smem = slab_smem_bytes(kp.cells, count_repeated != 0);
     const bool pow2 = kp.sx >= 0 && kp.sy >= 0;
-    void (*kern)(SlabArgs) =
-        count_repeated ? (pow2 ? k_slab_main<true, true> : k_slab_main<true, false>)
-                       : (pow2 ? k_slab_main<false, true> : k_slab_main<false, false>);
+    static void (*const kerns[8])(SlabArgs) = {
+        k_slab_main<false, false, false>, k_slab_main<false, false, true>,
+        k_slab_main<false, true, false>,  k_slab_main<false, true, true>,
+        k_slab_main<true, false, false>,  k_slab_main<true, false, true>,
+        k_slab_main<true, true, false>,   k_slab_main<true, true, true>};
+    void (*kern)(SlabArgs) = kerns[(count_repeated ? 4 : 0) + (pow2 ? 2 : 0) + (kp.use_p ? 1 : 0)];
     EVK_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)kSmemLimit));
     k_slab_bins<<<2 * grid, 256, 0, h->stream>>>(a);
