@@ -52,9 +52,6 @@ namespace {
 #endif                     //    check sets DsCounters::overflow bit 1); compute-sanitizer is closed
                            //    on this pool, so the parity / stress tests are run against this build
 // A/B switches of round 2 (profiles/r02/slab_ab_runs.md); the defaults are what was adopted
-#ifndef EVK_SLAB_UNCOND_CLAIM
-#define EVK_SLAB_UNCOND_CLAIM 0  // 1: the claim pass's atomic is issued by every lane (see there)
-#endif
 #ifndef EVK_SLAB_UNCOND_RED
 #define EVK_SLAB_UNCOND_RED 1  // 1: the classify pass's hit-twice reduction is issued by every lane
 #endif
@@ -252,7 +249,7 @@ __device__ __forceinline__ uint32_t hash_slot(uint32_t cell) {
 // bookkeeping
 
 // predicated shared-memory reduction: no branch, no return value
-__device__ __forceinline__ void sred_or_if(uint32_t* addr, uint32_t v, uint32_t pred) {
+[[maybe_unused]] __device__ __forceinline__ void sred_or_if(uint32_t* addr, uint32_t v, uint32_t pred) {
     asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q red.shared.or.b32 [%0], %1; }" ::"r"(
                      smem_u32(addr)),
                  "r"(v), "r"(pred)
@@ -446,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 uint32_t w = COUNT_REP ? cell >> 4 : cell >> 5;
                 const uint32_t sbit = 1u << (cell & (COUNT_REP ? 15u : 31u));
                 SLAB_CHECK(!ok || (w < a.words && li < (uint32_t)kTile));
-                if (EVK_SLAB_UNCOND_CLAIM || EVK_SLAB_UNCOND_RED) w = ok ? w : 0u;  // (any lane may touch it)
+                if (EVK_SLAB_UNCOND_RED) w = ok ? w : 0u;  // (any lane may touch it)
                 const uint32_t wv = ok ? s_map[w] : 0xFFFFFFFFu;  // gated events: nothing to do
                 if (COUNT_REP) {  // duplicate of an earlier tile's voxel: mark it "hit twice"
 #if EVK_SLAB_UNCOND_RED
@@ -524,12 +521,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
             bool late[kPer];
 #pragma unroll
             for (int j = 0; j < kPer; j++) {
-#if EVK_SLAB_UNCOND_CLAIM
-                // (every lane issues the atomic, lanes without a candidate OR in a zero)
-                const uint32_t bitv = cv[j] != kEmpty ? cb[j] : 0u;
-                const uint32_t old = atomicOr(&s_map[cw[j]], bitv);
-                late[j] = (old & bitv) != 0;
-#else
+                // (issued by every lane with a zero for lanes without a candidate, this returning
+                // atomic costs more than the branch ptxas builds around the predicated one: A/B)
                 uint32_t old = 0;  // (stays 0 for lanes without a candidate)
                 asm volatile(
                     "{ .reg .pred q; setp.ne.u32 q, %3, 0xFFFFFFFF; "
@@ -538,7 +531,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                     : "r"(smem_u32(&s_map[cw[j]])), "r"(cb[j]), "r"(cv[j])
                     : "memory");
                 late[j] = (old & cb[j]) != 0;
-#endif
             }
 #pragma unroll
             for (int j = 0; j < kPer; j++) {  // a peer of this tile claimed the cell first (rare)
