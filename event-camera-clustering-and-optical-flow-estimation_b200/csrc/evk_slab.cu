@@ -34,6 +34,8 @@
 // (evk_downsample.cu), which remains the general path: the kernel verifies on the fly that
 // [bin_start[b], bin_start[b+1]) holds only events of bin b and that the ranges partition the
 // stream; any violation makes the host fall back to the table.
+#include <type_traits>
+
 #include "evk_internal.cuh"
 
 namespace {
@@ -57,9 +59,6 @@ namespace {
 #endif
 #ifndef EVK_SLAB_SHORT_ROWS
 #define EVK_SLAB_SHORT_ROWS 1  // 1: a bin's last (short) tile skips its empty rows in the classify pass
-#endif
-#ifndef EVK_SLAB_PRED_OUT
-#define EVK_SLAB_PRED_OUT 1  // 1: the output pass's stores are predicated instead of branched around
 #endif
 #ifndef EVK_SLAB_LATE_REG
 #define EVK_SLAB_LATE_REG 1  // 1: a late peer sets its hit-twice bit through the classify pass's registers
@@ -290,15 +289,21 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
     uint32_t* s_map = s_late + 2 * kHash;  // [words]
     __shared__ __align__(8) uint64_t s_bar[kStages];
     __shared__ uint32_t s_cursor[2];  // voxels emitted by the current tile (by tile parity)
-    __shared__ uint32_t s_chunk_pos, s_chunk_end, s_next_base;
-    __shared__ uint32_t s_stop;  // some CTA has found the stream unordered: stop early
+    // output chunk state + the early-stop flag (some CTA has found the stream unordered), one
+    // 16-byte group: the output pass reads it with one load
+    __shared__ __align__(16) uint32_t s_chunk[4];
+    uint32_t& s_chunk_pos = s_chunk[0];
+    uint32_t& s_chunk_end = s_chunk[1];
+    uint32_t& s_next_base = s_chunk[2];
+    uint32_t& s_stop = s_chunk[3];
     // Per-bin and per-launch constants the passes read back ONCE PER TILE through shared memory.
     // Held in registers across the tile loop they do not survive: ptxas rematerialises the 64-bit
     // products (six instructions in front of every key store, ncu source page of round 2) and
     // re-reads the column bases from the constant bank in front of every record.
-    __shared__ uint64_t s_key_base;  // first key of the current bin
-    __shared__ int64_t s_t_lo;       // first microsecond of the current bin
-    __shared__ uint64_t s_out[3];    // global addresses of the key / first-index / xy columns
+    __shared__ int64_t s_t_lo;  // first microsecond of the current bin
+    // [0..2] global addresses of the key / first-index / xy columns, [3] first key of the current bin
+    __shared__ __align__(16) uint64_t s_out[4];
+    uint64_t& s_key_base = s_out[3];
 
     DsCounters* cnt = a.cnt;
     if (cnt->slab_violation) return;
@@ -608,20 +613,32 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 : "memory");
             wbase = __shfl_sync(0xffffffffu, wbase, leader);
             {
-                const uint32_t pos0 = s_chunk_pos, nxt0 = s_next_base;
-                const uint32_t room = s_chunk_end - pos0;  // slots left in the current chunk
-                const uint64_t keys_g = *reinterpret_cast<volatile uint64_t*>(&s_out[0]);
-                const uint64_t first_g = *reinterpret_cast<volatile uint64_t*>(&s_out[1]);
-                const uint64_t xy_g = *reinterpret_cast<volatile uint64_t*>(&s_out[2]);
-                const uint64_t key_base = *reinterpret_cast<volatile uint64_t*>(&s_key_base);
+                // chunk state, column bases and the bin's first key: three 16-byte shared loads
+                uint32_t pos0, end0, nxt0, stop_unused;
+                asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(pos0), "=r"(end0), "=r"(nxt0), "=r"(stop_unused)
+                             : "r"(smem_u32(s_chunk)));
+                (void)stop_unused;
+                uint64_t keys_g, first_g, xy_g, key_base;
+                asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];"
+                             : "=l"(keys_g), "=l"(first_g)
+                             : "r"(smem_u32(&s_out[0])));
+                asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];"
+                             : "=l"(xy_g), "=l"(key_base)
+                             : "r"(smem_u32(&s_out[2])));
+                const uint32_t room = end0 - pos0;  // slots left in the current chunk
+                // the warp's slots [wbase, wbase + wtot) nearly always lie on one side of the chunk
+                // boundary: then slot = rank + one warp-uniform offset, no per-record select
+                const bool straddle = (wbase < room) & (wbase + wtot > room);
+                auto emit = [&](auto per_lane) {
+                    const uint32_t off = wbase < room ? pos0 : nxt0 - room;
+                    uint32_t wb = wbase;
 #pragma unroll
-                for (int j = 0; j < kPer; j++) {
-#if EVK_SLAB_PRED_OUT
-                    {   // every lane computes a slot, the three stores are predicated: some lane of
-                        // the warp nearly always emits, so a branch around the record only adds
-                        // BSSY / BRA / BSYNC
-                        const uint32_t o = wbase + __popc(bal[j] & lane_lt);
-                        const uint32_t p = o < room ? pos0 + o : nxt0 + (o - room);
+                    for (int j = 0; j < kPer; j++) {
+                        const uint32_t o = wb + __popc(bal[j] & lane_lt);
+                        uint32_t p;
+                        if (decltype(per_lane)::value) p = o < room ? pos0 + o : nxt0 + (o - room);
+                        else p = o + off;
                         SLAB_CHECK(cv[j] == kEmpty || (p < a.out_cap && (o < room || nxt0 != kNoChunk)));
                         asm volatile(
                             "{ .reg .pred q; setp.ne.u32 q, %6, 0xFFFFFFFF;\n\t"
@@ -632,24 +649,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                             "r"(base + (cv[j] & kIdxMask) + first_offset),
                             "l"(xy_g + (uint64_t)p * 4u), "r"(cxy[j]), "r"(cv[j])
                             : "memory");
+                        wb += __popc(bal[j]);
                     }
-#else
-                    if (cv[j] != kEmpty) {
-                        const uint32_t o = wbase + __popc(bal[j] & lane_lt);
-                        const uint32_t p = o < room ? pos0 + o : nxt0 + (o - room);
-                        SLAB_CHECK(p < a.out_cap && (o < room || nxt0 != kNoChunk));
-                        asm volatile("st.global.u64 [%0], %1;" ::"l"(keys_g + (uint64_t)p * 8u),
-                                     "l"(key_base + (cv[j] >> kLogTile))
-                                     : "memory");
-                        asm volatile("st.global.u32 [%0], %1;" ::"l"(first_g + (uint64_t)p * 4u),
-                                     "r"(base + (cv[j] & kIdxMask) + first_offset)
-                                     : "memory");
-                        asm volatile("st.global.u32 [%0], %1;" ::"l"(xy_g + (uint64_t)p * 4u), "r"(cxy[j])
-                                     : "memory");
-                    }
-#endif
-                    wbase += __popc(bal[j]);
-                }
+                };
+                if (straddle) emit(std::true_type{});
+                else emit(std::false_type{});
             }
             if (tid == 0) book_par = par;
         }
