@@ -255,38 +255,56 @@ __global__ void k_p2p_tick(Mailbox* mine, Mailbox* const* peers, int rank) {
 // previous rank's last time bin are counted HERE (a 32-way search over my own, local events) and the
 // count travels with the flag, so the receiver pulls exactly those events and needs no search of its
 // own (k_halo_range's two searches would otherwise sit between the pull and the downsample).
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(1024)
     k_p2p_tick_range(KeyParams kp, const evk_event* ev, uint32_t n_own, uint32_t halo, int rank,
                      int world, Mailbox* mine, Mailbox* const* peers, unsigned long long* stats) {
-    const int lane = threadIdx.x;
+    // One CTA of 1024 threads: a 1024-way search finds the end of the first bin's run inside the
+    // boundary block in two rounds of (independent) global loads -- the search sits in front of the
+    // flag the previous rank's pull is waiting for, and of this rank's own downsample.
+    __shared__ unsigned int s_first;  // lowest thread whose probe lies behind the run
+    const unsigned int tid = threadIdx.x, NT = blockDim.x;
     const unsigned long long seq = mine->seq + 1;
-    __syncwarp();
-    if (lane == 0) mine->seq = seq;
+    __syncthreads();
+    if (tid == 0) mine->seq = seq;
     unsigned long long flag = n_own < halo ? 1 : 0, skip = 0;
-    if (!flag && rank > 0) {
+    if (!flag && rank > 0) {  // (uniform over the CTA)
         const int64_t t0v = ev[0].t;
         if (t0v < kp.t0) {
             flag = 1;
         } else {
             const uint64_t b0 = evk_tbin(kp, t0v);
-            uint32_t lo = 0, hi = halo;  // first offset whose bin differs from the first event's
+            uint32_t lo = 0, hi = halo;  // the first offset whose bin differs lies in [lo, hi]
             while (lo < hi) {
                 const uint32_t span = hi - lo;
-                const uint32_t p = lo + (uint32_t)((uint64_t)span * (uint32_t)(lane + 1) / 33u);
-                const int64_t t = ev[p].t;
-                const bool differs = !(t >= kp.t0 && evk_tbin(kp, t) == b0);
-                const uint32_t m = __ballot_sync(0xffffffffu, differs);
-                const int f = m ? __ffs(m) - 1 : 32;
-                const uint32_t p_f = __shfl_sync(0xffffffffu, p, f < 32 ? f : 0);
-                const uint32_t p_b = __shfl_sync(0xffffffffu, p, f > 0 ? f - 1 : 0);
-                if (f < 32) hi = p_f;
-                if (f > 0) lo = p_b + 1;
+                const bool dense = span <= NT;  // every offset of the range has its own thread
+                const uint32_t p = dense ? lo + tid
+                                         : lo + (uint32_t)((uint64_t)span * (tid + 1) / (NT + 1));
+                if (tid == 0) s_first = NT;
+                __syncthreads();
+                if (!dense || tid < span) {
+                    const int64_t t = ev[p].t;
+                    if (!(t >= kp.t0 && evk_tbin(kp, t) == b0)) atomicMin(&s_first, tid);
+                }
+                __syncthreads();
+                const uint32_t f = s_first;
+                __syncthreads();  // (s_first is reset at the top of the next round)
+                if (dense) {
+                    lo = hi = f < NT ? lo + f : hi;
+                } else {
+                    // probe of thread q: lo + span * (q + 1) / (NT + 1), increasing in q
+                    const uint32_t p_f = lo + (uint32_t)((uint64_t)span * (f + 1) / (NT + 1));
+                    const uint32_t p_b = lo + (uint32_t)((uint64_t)span * f / (NT + 1));  // thread f - 1
+                    const uint32_t lo_old = lo;
+                    if (f < NT) hi = p_f;
+                    if (f > 0) lo = p_b + 1;
+                    (void)lo_old;
+                }
             }
             skip = lo;
             if (skip >= halo || skip >= n_own) flag = 1;  // first bin does not end inside the block
         }
     }
-    if (lane == 0) {
+    if (tid == 0) {
         stats[ST_FLAG] = flag;
         stats[ST_SKIP] = flag ? 0 : skip;
         stats[ST_KEEP] = 0;
@@ -400,6 +418,51 @@ __global__ void k_pack_step_stats(const DsCounters* cnt, const unsigned long lon
     tail[0] = (flag ? 1 : 0) + ((mail && mail->err) ? (1ull << 32) : 0ull);
     tail[1] = cnt->n_unique;
     tail[2] = cnt->n_repeated;
+}
+
+// The fused time-range step's tail as ONE kernel (three launches and a copy node in round 1):
+// pack the step's stats behind the partial sums, the one-shot allreduce over peer memory, the
+// allreduced stats into the counters block (it travels to the host with the step's one D2H copy),
+// the centroid update.
+__global__ void __launch_bounds__(1024)
+    k_p2p_step_tail(Mailbox* mine, Mailbox* const* peers, int rank, int world,
+                    unsigned long long* acc, int n, DsCounters* cnt, const unsigned long long* range,
+                    unsigned long long found_want, int check_found, KmLaunch kl, float* cent,
+                    unsigned long long* counts, float* shift) {
+    __shared__ int s_ok;
+    const unsigned long long seq = mine->seq;
+    const int par = (int)(seq & 1);
+    if (threadIdx.x == 0) {
+        s_ok = 1;
+        unsigned long long flag = cnt->slab_violation | cnt->overflow | range[ST_FLAG];
+        if (check_found && cnt->scratch[4] != found_want) flag |= 1;
+        acc[n - 3] = (flag ? 1 : 0) + (mine->err ? (1ull << 32) : 0ull);
+        acc[n - 2] = cnt->n_unique;
+        acc[n - 1] = cnt->n_repeated;
+    }
+    __syncthreads();
+    for (int r = 0; r < world; r++)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) peers[r]->sums[par][rank][i] = acc[i];
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < world) st_release_sys(&peers[threadIdx.x]->sum_flag[par][rank], seq);
+    if ((int)threadIdx.x < world && !wait_flag(&mine->sum_flag[par][threadIdx.x], seq)) {
+        s_ok = 0;
+        mine->err = 1;
+    }
+    __syncthreads();
+    if (s_ok) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            unsigned long long sum = 0;
+            for (int r = 0; r < world; r++) sum += __ldcg(&mine->sums[par][r][i]);  // written by peers
+            acc[i] = sum;
+        }
+    } else if (threadIdx.x == 0) {
+        acc[n - 3] = 1ull << 32;  // give up: the host drops to NCCL everywhere
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) cnt->step_tail[threadIdx.x] = acc[n - 3 + threadIdx.x];
+    evk_km_finalise_body(kl, cent, acc, counts, shift);
 }
 
 // owner of a key: the top 32 bits of mix64(key ^ golden) range-reduced to [0, G) by a multiply
@@ -1524,7 +1587,7 @@ static int enqueue_fused_sharded(evk_handle* h, const KeyParams& kp, const evk_d
     if (c->p2p) {  // peer memory over NVLink: flags + direct loads / stores (see k_p2p_*)
         // who keeps what is decided by the SENDER of a boundary block (a search over its own events)
         // and travels with the flag; the receiver pulls exactly its share
-        k_p2p_tick_range<<<1, 32, 0, h->stream>>>(kp, h->d_events, (uint32_t)n_own, halo, c->rank,
+        k_p2p_tick_range<<<1, 1024, 0, h->stream>>>(kp, h->d_events, (uint32_t)n_own, halo, c->rank,
                                                   c->world, c->mail, c->d_peer_mail, c->d_stats);
         EVK_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));  // the side stream reads the new seq
         if (c->rank < c->world - 1)
@@ -1576,21 +1639,23 @@ static int enqueue_fused_sharded(evk_handle* h, const KeyParams& kp, const evk_d
     EVK_CUDA(h, evk_launch_km_assign_tiles(kl, ds->width, ds->height, h->d_quads, h->d_label_map,
                                            h->d_xy, n_own + halo, &h->d_cnt->n_unique, true,
                                            h->d_acc, h->d_labels, h->sm_count, h->stream));
-    k_pack_step_stats<<<1, 1, 0, h->stream>>>(h->d_cnt, c->d_stats, (unsigned long long)km->K,
-                                              init_first_k && c->rank == 0,
-                                              c->p2p ? c->mail : nullptr, tail);
-    EVK_CUDA(h, cudaGetLastError());
     if (c->p2p) {
-        k_p2p_allreduce<<<1, 1024, 0, h->stream>>>(c->mail, c->d_peer_mail, c->rank, c->world,
-                                                   h->d_acc, km->K * 5 + 3);
+        k_p2p_step_tail<<<1, 1024, 0, h->stream>>>(
+            c->mail, c->d_peer_mail, c->rank, c->world, h->d_acc, km->K * 5 + 3, h->d_cnt, c->d_stats,
+            (unsigned long long)km->K, init_first_k && c->rank == 0, kl, h->d_cent, h->d_counts,
+            h->d_shift);
         EVK_CUDA(h, cudaGetLastError());
     } else {
+        k_pack_step_stats<<<1, 1, 0, h->stream>>>(h->d_cnt, c->d_stats, (unsigned long long)km->K,
+                                                  init_first_k && c->rank == 0, nullptr, tail);
+        EVK_CUDA(h, cudaGetLastError());
         EVK_NCCL(h, g_nccl.AllReduce(h->d_acc, h->d_acc, (size_t)km->K * 5 + 3, ncclUint64,
                                      ncclSum, c->comm, h->stream));
+        EVK_CUDA(h, cudaMemcpyAsync(h->d_cnt->step_tail, tail, 3 * 8, cudaMemcpyDeviceToDevice,
+                                    h->stream));
+        EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
+                                           h->stream));
     }
-    EVK_CUDA(h, cudaMemcpyAsync(c->h_stats, tail, 3 * 8, cudaMemcpyDeviceToHost, h->stream));
-    EVK_CUDA(h, evk_launch_km_finalise(kl, h->d_cent, h->d_acc, h->d_counts, h->d_shift,
-                                       h->stream));
     evk_prof_rec(h, 4);
     EVK_CUDA(h, cudaMemcpyAsync(h->h_cnt, h->d_cnt, sizeof(DsCounters), cudaMemcpyDeviceToHost,
                                 h->stream));
@@ -1803,6 +1868,7 @@ int evk_downsample_kmeans_sharded_wait(evk_handle* h, size_t* n_unique_local,
         const int init_first_k = h->step_init;
         const int launches = c->step_launches;
         EVK_CUDA(h, cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < 3; i++) c->h_stats[i] = h->h_cnt->step_tail[i];  // (with the counters)
         if (c->h_stats[0] >> 32) {  // a peer-memory wait timed out somewhere: NCCL from now on
             c->p2p = false;
             cudaGraphExecDestroy(c->step_exec);

@@ -102,6 +102,9 @@ struct DsCounters {  // device-side counters, mirrored into pinned host memory a
     unsigned int slab_violation;  // slab kernel found an event outside its bin's index range
     unsigned int overflow;
     unsigned long long scratch[6];
+    // fused sharded step: [0] = any reason to abandon the pass (+ 2^32: a peer-memory wait timed
+    // out), [1] = voxels of all ranks, [2] = repeated cells of all ranks (k_p2p_step_tail)
+    unsigned long long step_tail[3];
 };
 
 struct CommState;
@@ -351,6 +354,45 @@ struct KmLaunch {
     int write_labels;
 };
 KmLaunch evk_km_launch_params(const evk_handle* h, const evk_km_params* p);
+#ifdef __CUDACC__
+// centroid = exact sum / count rounded once to fp32; empty clusters keep their centroid;
+// shift = max_k |delta c_k|_inf; accumulators are zeroed for the next iteration.  Threads
+// [0, K) of one CTA (k_km_finalise; the tail kernel of the fused sharded step).
+__device__ __forceinline__ void evk_km_finalise_body(const KmLaunch& kl, float* cent,
+                                                     unsigned long long* acc,
+                                                     unsigned long long* counts, float* shift) {
+    __shared__ unsigned int s_shift;
+    if (threadIdx.x == 0) s_shift = 0;
+    __syncthreads();
+    const int k = threadIdx.x;
+    if (k < kl.K) {
+        unsigned long long c = acc[k * ACC_STRIDE + ACC_CNT];
+        counts[k] = c;
+        float mx = 0.f;
+        if (c) {
+            for (int d = 0; d < kl.D; d++) {
+                double s;
+                if (d == 0) s = (double)acc[k * ACC_STRIDE + ACC_X];
+                else if (d == 1) s = (double)acc[k * ACC_STRIDE + ACC_Y];
+                else if (d == 2) s = (double)(long long)acc[k * ACC_STRIDE + ACC_T];
+                else s = (double)acc[k * ACC_STRIDE + ACC_P];
+                double m = s / (double)c;
+                if (d == 2) m *= (double)kl.t_scale;
+                if (d == 3) m *= (double)kl.p_scale;
+                float nc = (float)m;
+                float dl = fabsf(nc - cent[k * kl.D + d]);
+                mx = fmaxf(mx, dl);
+                cent[k * kl.D + d] = nc;
+            }
+        }
+        atomicMax(&s_shift, __float_as_uint(mx));  // non-negative floats order like uints
+#pragma unroll
+        for (int j = 0; j < ACC_STRIDE; j++) acc[k * ACC_STRIDE + j] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *shift = __uint_as_float(s_shift);
+}
+#endif
 cudaError_t evk_launch_km_assign(const KmLaunch& kl, const uint32_t* xy, const evk_event* ev,
                                  const uint32_t* first, size_t n, const float* cent,
                                  unsigned long long* acc, int32_t* labels, int sm_count,

@@ -160,43 +160,11 @@ __global__ void __launch_bounds__(kBlock)
     }
 }
 
-// centroid = exact sum / count rounded once to fp32; empty clusters keep their centroid;
-// shift = max_k |delta c_k|_inf; accumulators are zeroed for the next iteration
+// centroid update on the device (evk_km_finalise_body, evk_internal.cuh)
 __global__ void __launch_bounds__(EVK_MAX_K)
     k_km_finalise(KmLaunch kl, float* cent, unsigned long long* acc, unsigned long long* counts,
                   float* shift) {
-    __shared__ unsigned int s_shift;
-    if (threadIdx.x == 0) s_shift = 0;
-    __syncthreads();
-    const int k = threadIdx.x;
-    if (k < kl.K) {
-        unsigned long long c = acc[k * ACC_STRIDE + ACC_CNT];
-        counts[k] = c;
-        float mx = 0.f;
-        if (c) {
-            const double inv = 1.0 / (double)c;
-            (void)inv;
-            for (int d = 0; d < kl.D; d++) {
-                double s;
-                if (d == 0) s = (double)acc[k * ACC_STRIDE + ACC_X];
-                else if (d == 1) s = (double)acc[k * ACC_STRIDE + ACC_Y];
-                else if (d == 2) s = (double)(long long)acc[k * ACC_STRIDE + ACC_T];
-                else s = (double)acc[k * ACC_STRIDE + ACC_P];
-                double m = s / (double)c;
-                if (d == 2) m *= (double)kl.t_scale;
-                if (d == 3) m *= (double)kl.p_scale;
-                float nc = (float)m;
-                float dl = fabsf(nc - cent[k * kl.D + d]);
-                mx = fmaxf(mx, dl);
-                cent[k * kl.D + d] = nc;
-            }
-        }
-        atomicMax(&s_shift, __float_as_uint(mx));  // non-negative floats order like uints
-#pragma unroll
-        for (int j = 0; j < ACC_STRIDE; j++) acc[k * ACC_STRIDE + j] = 0;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *shift = __uint_as_float(s_shift);
+    evk_km_finalise_body(kl, cent, acc, counts, shift);
 }
 
 // candidates for "first K voxels in canonical order": voxels whose first index is below `bound`
