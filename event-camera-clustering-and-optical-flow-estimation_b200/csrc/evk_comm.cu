@@ -1889,7 +1889,7 @@ int evk_downsample_kmeans_sharded_wait(evk_handle* h, size_t* n_unique_local,
             c->last_mode = EVK_OWNER_TIME_RANGE;
             h->times.ds_algo_used = EVK_ALGO_SLAB;
             h->times.ds_launches = launches + 2;
-            h->times.km_launches = 6;
+            h->times.km_launches = c->p2p ? 5 : 6;  // candidates, image, quads, assign, tail (NCCL: + pack, finalise)
             h->times.km_iters = 1;
             if (h->profiling) {
                 float ms = 0.f;

@@ -392,15 +392,17 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
         const uint32_t lo = a.bin_start[b], hi = a.bin_start[b + 1];
         if (hi < lo) viol = 1;  // ranges do not partition the stream: not time-ordered
         if (hi <= lo) continue;
+        if (tid == 0) s_stop = *reinterpret_cast<volatile unsigned int*>(&cnt->slab_violation);
+        prod_sync<NT>();  // every thread has left the previous bin (bitmap, cursor, key base)
+        if (s_stop) break;  // (an early stop inside the tile loop also ends here)
         if (tid == 0) {
+            // (only now: slower warps were still writing the previous bin's records, which read
+            // s_key_base, until the barrier above)
             const uint64_t tb = tb0 + b;
-            s_stop = *reinterpret_cast<volatile unsigned int*>(&cnt->slab_violation);
             s_key_base = tb * kp.cells;
             s_t_lo = t0 + (int64_t)(tb * (uint64_t)kp.vt);
+            book();
         }
-        prod_sync<NT>();  // every thread has left the previous bin (bitmap, cursor)
-        if (s_stop) break;  // (an early stop inside the tile loop also ends here)
-        if (tid == 0) book();
         {  // count the previous bin's repeated cells and clear the bitmap in one pass
             uint32_t r = 0;
             for (uint32_t i = tid; i < a.words; i += NT) {

@@ -88,7 +88,8 @@ def main():
             h.synth(evk.synth_params(seed, n, W, H, rate, blobs, first_index=rank * n))
             ul, ug, it = h.downsample_kmeans_sharded(ds, km1, True, evk.OWNER_TIME_RANGE)
             assert (ug, it) == (len(ok), 1), (name, rank, ug, len(ok))
-            assert h.stage_times().km_launches == 6, "fused sharded pass did not run"
+            # (5 kernels with the peer-memory tail, 6 on the NCCL path; the separate calls report others)
+            assert h.stage_times().km_launches in (5, 6), "fused sharded pass did not run"
             keys, reps, first = h.get_voxels()
             assert len(keys) == ul and reps.tobytes() == ev_all[first].tobytes()
             all_keys = np.concatenate(gather_arrays(keys, rank, world))

@@ -25,6 +25,10 @@ def test_sharded_downsample_and_kmeans(world):
            os.path.join(ROOT, "tests", "mg_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     sys.stdout.write(r.stdout[-3000:])
-    sys.stderr.write(r.stderr[-3000:])
+    if r.returncode != 0:  # the workers' own tracebacks come before torchrun's failure summary
+        at = r.stderr.find("Traceback")
+        sys.stderr.write(r.stderr[max(0, at - 500):at + 6000] if at >= 0 else r.stderr[-6000:])
+    else:
+        sys.stderr.write(r.stderr[-3000:])
     assert r.returncode == 0
     assert r.stdout.count("mg ok") == 10

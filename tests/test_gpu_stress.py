@@ -75,3 +75,37 @@ def test_slab_stress(evk, orc, case):
         cent, counts = h.get_centroids(K, 2)
         assert (counts == ocnt).all() and (cent == oc).all()
         assert (h.get_labels() == ol).all()
+
+
+def test_slab_many_one_tile_bins(evk, orc):
+    """Regression (round 2): with bins of one short tile each, every tile is the last tile of its
+    bin, and the per-bin constants the output pass reads back through shared memory (first key of
+    the bin) must not be replaced before every warp has written the previous bin's records.
+    Found by the 4- and 8-GPU parity runs on shuffled shards (280 bins of 2 500 events per rank):
+    voxels came out with the NEXT bin's key base.  Two shapes: that shard through the partition
+    path, and an ordered stream with bins of about 2 000 events through the slab path."""
+    W, H, vx, vy, vt, up = 346, 260, 4, 4, 1000, 1
+    n, world = 700_000, 4
+    ev_all = orc.synth(orc.synth_params(0xE7CA0002, n * world, W, H, 10_000_000, 32), threads=4)
+    shard = ev_all[np.random.default_rng(5).permutation(n * world)][:n]
+    ok, of, orr = orc.downsample(shard, orc.ds_params(W, H, vx, vy, vt, 0, up))
+    with evk.Evk(n) as h:
+        for rep in range(3):
+            h.load_events(shard)
+            U, R = h.downsample(evk.ds_params(W, H, vx, vy, vt, 0, up, algo=evk.ALGO_PARTITION))
+            assert h.stage_times().ds_algo_used == evk.ALGO_PARTITION
+            keys, _, first = h.get_voxels(reps=False)
+            assert (U, R) == (len(ok), orr)
+            assert (keys == ok).all() and (first == of).all()
+    n2 = 2_000_000
+    ev = orc.synth(orc.synth_params(0xE7CA0005, n2, 1280, 720, 100_000_000, 64), threads=4)
+    p = (1280, 720, 2, 2, 20, 0, 1)   # 20 us bins: 1 000 bins of 2 000 events
+    ok, of, orr = orc.downsample(ev, orc.ds_params(*p))
+    with evk.Evk(n2) as h:
+        h.load_events(ev)
+        for rep in range(3):
+            U, R = h.downsample(evk.ds_params(*p, algo=evk.ALGO_SLAB))
+            assert h.stage_times().ds_algo_used == evk.ALGO_SLAB
+            keys, _, first = h.get_voxels(reps=False)
+            assert (U, R) == (len(ok), orr)
+            assert (keys == ok).all() and (first == of).all()
