@@ -13,18 +13,20 @@
 //            the prefetch distance of a three-stage ring at two thirds of the memory, which is
 //            what lets a tile hold three events per thread (round 2: -3.8 %, profiles/r02)
 //   s_late   two small tables (one per tile parity) for the rare events that lose a claim race
-// Per tile:  classify  one bitmap load per event: seen -> duplicate of an earlier tile
+// Per tile:  classify  one bitmap load per event: seen -> duplicate of an earlier tile (its cell's
+//                      "hit twice" bit is set by a reduction every lane issues, most with a zero)
 //            -- barrier: every read of the tile precedes every claim of the tile --
 //            claim     each unseen event does ONE returning atomicOr on the bitmap: bit was clear
 //                      -> it owns the cell ("claimant"); bit was set -> a peer of the SAME tile got
 //                      there first ("late peer"): its packed (cell, index) word goes into s_late,
-//                      where a 32-bit atomicMin keeps the lowest index of the cell
+//                      where a 32-bit atomicMin keeps the lowest index of the cell, and the cell's
+//                      "hit twice" bit is set
 //            -- barrier --
-//            resolve   a claimant probes s_late once: a late peer with a lower index replaces it
-//                      as representative (lowest stream index wins; its coordinates are
-//                      re-read from global memory: rare, L2-resident); then warp ballot
-//                      + one shared atomic per warp claim output slots and the 16-B record goes
-//                      to HBM from registers
+//            resolve   a claimant whose cell is now "hit twice" probes s_late: a late peer with a
+//                      lower index replaces it as representative (lowest stream index wins, SURVEY
+//                      8a; its coordinates are re-read from global memory: rare, L2-resident); then
+//                      warp ballot + one shared atomic per warp claim output slots and the 16-B
+//                      record goes to HBM from registers through predicated stores
 // Two block barriers per tile and no global atomic: output slots come from a CTA-private chunk of
 // the output arrays (claimed from a global counter one chunk ahead); a small fix-up pass moves
 // the tail of the last chunks into the holes so the voxel shard is dense.  HBM sees each event
@@ -53,19 +55,8 @@ namespace {
 #define EVK_SLAB_CHECKS 0  // 1: every index of the hot kernel is bounds-checked on the device (a failed
 #endif                     //    check sets DsCounters::overflow bit 1); compute-sanitizer is closed
                            //    on this pool, so the parity / stress tests are run against this build
-// A/B switches of round 2 (profiles/r02/slab_ab_runs.md); the defaults are what was adopted
-#ifndef EVK_SLAB_UNCOND_RED
-#define EVK_SLAB_UNCOND_RED 1  // 1: the classify pass's hit-twice reduction is issued by every lane
-#endif
-#ifndef EVK_SLAB_SHORT_ROWS
-#define EVK_SLAB_SHORT_ROWS 1  // 1: a bin's last (short) tile skips its empty rows in the classify pass
-#endif
-#ifndef EVK_SLAB_LATE_REG
-#define EVK_SLAB_LATE_REG 1  // 1: a late peer sets its hit-twice bit through the classify pass's registers
-#endif
-#ifndef EVK_SLAB_PVIOL
-#define EVK_SLAB_PVIOL 1  // 1: the out-of-bin check accumulates in a predicate, folded once per tile
-#endif
+// (round 2's A/B switches -- every-lane hit-twice reduction, short-row skip, predicate for the
+// out-of-bin check, ... -- are folded into the code: profiles/r02/slab_ab_runs.md has the runs)
 constexpr int kThreads = EVK_SLAB_THREADS;  // CTA size (the hardware maximum by default)
 constexpr int kCtasPerSm = kThreads <= 512 ? 2 : 1;
 constexpr int kPer = EVK_SLAB_PER;          // events per thread per tile
@@ -247,13 +238,6 @@ __device__ __forceinline__ uint32_t hash_slot(uint32_t cell) {
 // lane 0 of the last producer warp issues the bulk copies; thread 0 keeps the output-chunk
 // bookkeeping
 
-// predicated shared-memory reduction: no branch, no return value
-[[maybe_unused]] __device__ __forceinline__ void sred_or_if(uint32_t* addr, uint32_t v, uint32_t pred) {
-    asm volatile("{ .reg .pred q; setp.ne.u32 q, %2, 0; @q red.shared.or.b32 [%0], %1; }" ::"r"(
-                     smem_u32(addr)),
-                 "r"(v), "r"(pred)
-                 : "memory");
-}
 template <int NT>
 __device__ __forceinline__ void prod_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory");
@@ -425,9 +409,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
             // ---- classify: cv = candidate word (cell << kLogTile | index in tile) or kEmpty;
             // cw / cb = bitmap word index and bit of the event's cell (reused by the claim pass)
             uint32_t cv[kPer], cxy[kPer], cw[kPer], cb[kPer];
-#if EVK_SLAB_PVIOL
             bool tile_viol = false;
-#endif
             auto classify_row = [&](int j) {
                 const uint32_t li = j * NT + tid;
                 const uint4 ev = tile[li];
@@ -436,11 +418,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 const bool inbin = (uint64_t)(ev_t(ev) - t_lo) < (uint64_t)kp.vt;
                 const bool ok = gate & inbin;
                 // a gated-in event that is not of this bin: the stream is not what the bins say
-#if EVK_SLAB_PVIOL
                 tile_viol |= gate != ok;
-#else
-                viol |= (uint32_t)(gate != ok);
-#endif
                 uint32_t cell;
                 if (POW2) cell = (ev.x >> ysh) * kp.NX + (x >> kp.sx);
                 else cell = (kp.sy >= 0 ? y >> kp.sy : __umulhi(y, kp.my)) * kp.NX +
@@ -450,22 +428,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                 uint32_t w = COUNT_REP ? cell >> 4 : cell >> 5;
                 const uint32_t sbit = 1u << (cell & (COUNT_REP ? 15u : 31u));
                 SLAB_CHECK(!ok || (w < a.words && li < (uint32_t)kTile));
-                if (EVK_SLAB_UNCOND_RED) w = ok ? w : 0u;  // (any lane may touch it)
+                w = ok ? w : 0u;  // (every lane issues the reduction below: a word any lane may touch)
                 const uint32_t wv = ok ? s_map[w] : 0xFFFFFFFFu;  // gated events: nothing to do
                 if (COUNT_REP) {  // duplicate of an earlier tile's voxel: mark it "hit twice"
-#if EVK_SLAB_UNCOND_RED
                     // every lane issues the reduction, most with a zero (gated events read all
                     // ones, so theirs is zero too): ptxas turns a predicated shared atomic into a
                     // branch around it (BSSY / BRA / BSYNC) although some lane of the warp nearly
                     // always takes it
                     atomicOr(&s_map[w], ((wv & sbit) << 16) & ~wv);
-#else
-                    // (a predicated reduction: the branch the compiler builds around an atomicOr
-                    // here costs 2 % of the kernel)
-                    const uint32_t hbit = sbit * 0x10000u;
-                    const uint32_t need = (wv & sbit) && !(wv & hbit) && ok;
-                    sred_or_if(&s_map[w], hbit, need);
-#endif
                 }
                 cv[j] = (wv & sbit) ? kEmpty : ((cell << kLogTile) | li);
                 cxy[j] = ev.x;
@@ -484,7 +454,6 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                         tile[j * NT + tid] = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
                 // (the slot is next written by a bulk copy: order the two proxies)
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-#if EVK_SLAB_SHORT_ROWS
                 // (its own copy of the classify pass: the rows beyond the end of the bin -- on
                 // average a tile's worth of rows per bin -- are skipped)
 #pragma unroll
@@ -497,16 +466,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
                     }
                 }
             } else {
-#else
-            }
-            {
-#endif
 #pragma unroll
                 for (int j = 0; j < kPer; j++) classify_row(j);
             }
-#if EVK_SLAB_PVIOL
             if (tile_viol) viol |= 1u;
-#endif
             // a rejected stream is rerun on a general path: publish the violation at once and let
             // every CTA stop at its next tile (uniformly: thread 0 reads, the barrier broadcasts)
             const bool poll = (tile_seq & 15u) == 0;  // (every 16th tile: polling every 4th cost 2 %)
@@ -543,11 +506,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) k_slab_main(SlabArgs a) 
             for (int j = 0; j < kPer; j++) {  // a peer of this tile claimed the cell first (rare)
                 if (!late[j]) continue;
                 const uint32_t cell = cv[j] >> kLogTile;
-#if EVK_SLAB_LATE_REG
                 if (COUNT_REP) atomicOr(&s_map[cw[j]], cb[j] << 16);  // the cell is hit twice
-#else
-                if (COUNT_REP) atomicOr(&s_map[cell >> 4], 1u << (16 + (cell & 15)));  // hit twice
-#endif
                 uint32_t s = hash_slot(cell);
 #if EVK_SLAB_CHECKS
                 uint32_t probes = 0;
