@@ -1118,14 +1118,13 @@ cudaError_t evk_launch_km_assign_tiles(const KmLaunch& kl, int width, int height
     while (copies > 1 && (size_t)3 * kl.K * copies * 4 > 48 * 1024) copies >>= 1;
     const uint32_t tl_bytes = (uint32_t)((pg.tx * pg.ty + 15) & ~15);
     const size_t smem = tl_bytes + (accumulate ? (size_t)3 * kl.K * copies * 4 : 0);
-    static bool attr_set = false;
-    if (!attr_set) {
+    // (a function attribute is per device: set on every call, whichever device the handle lives on)
+    if (accumulate)
         cudaFuncSetAttribute(k_km_assign_tiles<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              EVK_MAX_QUADS + 48 * 1024);
+    else
         cudaFuncSetAttribute(k_km_assign_tiles<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              EVK_MAX_QUADS);
-        attr_set = true;
-    }
     // one wave: as many CTAs as are resident at once, units dealt round-robin
     int per_sm = 1;
     if (accumulate)
